@@ -1,0 +1,167 @@
+"""GPU parity: Planet::GenerateChunk(s) / GeneratePlatform / edits on sm_100a against the CPU oracle — block ids bit-exact."""
+import numpy as np
+import pytest
+
+import oracle as O
+import thisspaceofmine_b200 as T
+from helpers import assert_mesh_equal
+
+pytestmark = pytest.mark.gpu
+
+# ServerPlanetEnvironment.cpp:60-63: the four start platforms of the default planet
+PLATFORMS = [(T.Direction.Right, (65, -18, -39)), (T.Direction.Back, (-34, 2, 53)), (T.Direction.Front, (22, -35, -59)), (T.Direction.Down, (23, -62, 26))]
+
+
+def _planets(ctx, seed, count, platforms=False):
+    lib = ctx.blockLibrary
+    n = int(np.prod(count))
+    gp = T.Planet(ctx, 1.0, 16.0, 9.81, capacity=n)
+    gp.GenerateChunks(lib, seed, count)
+    op = O.Planet(1.0, 16.0)
+    assert op.generate(seed, count, nthreads=8)
+    if platforms:
+        for d, c in PLATFORMS:
+            gp.GeneratePlatform(lib, d, c)
+            op.generate_platform(d, c)
+    return gp, op
+
+
+def _assert_blocks_equal(gp, op, grid):
+    got = gp.GetContent(grid)
+    for i, idx in enumerate(grid):
+        want = op.get_blocks(idx)
+        if not np.array_equal(got[i], want):
+            bad = np.flatnonzero(got[i] != want)
+            k = int(bad[0])
+            raise AssertionError(f"chunk {tuple(idx)}: {len(bad)} ids differ, first at local {(k % 32, (k // 32) % 32, k // 1024)}: gpu {got[i][k]} oracle {want[k]}")
+
+
+@pytest.mark.parametrize("seed,count", [(42, (5, 5, 5)), (42, (3, 3, 3)), (7, (1, 1, 1)), (123456789, (3, 5, 1)), (0xFFFFFFFE, (7, 3, 5))])
+def test_generate_chunks_bit_exact(ctx, seed, count):
+    gp, op = _planets(ctx, seed, count)
+    _assert_blocks_equal(gp, op, T.Planet.chunk_grid(count))
+
+
+def test_default_planet_with_platforms_and_meshes(ctx):
+    """BASELINE config 1/3: seed 42, 5x5x5, the 4 GeneratePlatform scripts, then every chunk meshed with real neighbours."""
+    count = (5, 5, 5)
+    gp, op = _planets(ctx, 42, count, platforms=True)
+    grid = T.Planet.chunk_grid(count)
+    _assert_blocks_equal(gp, op, grid)
+    batch = gp.BuildMeshes(grid, render=True, collider=True)
+    total = inexact = 0
+    for i, idx in enumerate(grid):
+        s = assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"chunk {tuple(idx)}")
+        total += s["faces"]
+        inexact += s["inexact"]
+    assert total == batch.total_faces and total > 50000
+    # dirty set after generation + platforms = every chunk (OnReset -> DirectionMask_All)
+    assert np.array_equal(gp.CollectInvalidated(), op.collect_dirty())
+
+
+def test_even_chunk_count_is_rejected(ctx):
+    """chunkCount 4 puts blocks beyond +-maxHeight: the reference asserts (Nz::SafeCaster, Planet.cpp:199); we refuse."""
+    gp = T.Planet(ctx, capacity=64)
+    with pytest.raises(T.TsomError) as e:
+        gp.GenerateChunks(ctx.blockLibrary, 42, (4, 4, 4))
+    assert e.value.code == 3
+    _, ok = O.generate_chunk(42, (4, 4, 4), (-2, 0, 0))
+    assert not ok
+
+
+def test_regen_single_chunk(ctx):
+    """/regenchunk: Planet::GenerateChunk on one chunk of an existing planet (PlayerSessionHandler.cpp:290)."""
+    gp, op = _planets(ctx, 42, (3, 3, 3))
+    gp.UpdateBlocks(np.array([[1, 1, 0, 3, 4, 5, 13]]))
+    gp.GenerateChunk(ctx.blockLibrary, [(1, 1, 0)], 42, (3, 3, 3))
+    _assert_blocks_equal(gp, op, np.array([[1, 1, 0]], np.int32))
+
+
+def test_edit_stream_and_dirty_set(ctx):
+    """BASELINE config 4 in small: random UpdateBlock ops per tick, dirty set = edited chunks + masked neighbours, remesh them."""
+    count = (3, 3, 3)
+    gp, op = _planets(ctx, 42, count)
+    grid = T.Planet.chunk_grid(count)
+    gp.CollectInvalidated()
+    op.collect_dirty()
+    rng = np.random.default_rng(2025)
+    for tick in range(4):
+        n = 2000
+        edits = np.zeros((n, 7), np.int64)
+        edits[:, 0:3] = grid[rng.integers(0, len(grid), n)]
+        # bias towards boundaries so the neighbour-mask rule (Planet.cpp:39-58) is exercised, and repeat blocks so order matters
+        edits[:, 3:6] = rng.choice([0, 1, 15, 30, 31], size=(n, 3))
+        edits[:, 6] = rng.choice([0, 2, 7, 13], size=n)
+        if tick == 3:
+            edits[:, 0:3] = (9, 9, 9)  # edits to a chunk that does not exist are skipped
+        gp.UpdateBlocks(edits)
+        op.apply_edits(edits)
+        dg, do = gp.CollectInvalidated(), op.collect_dirty()
+        assert np.array_equal(dg, do), f"tick {tick}: dirty sets differ"
+        if len(dg):
+            batch = gp.BuildMeshes(dg)
+            for i, idx in enumerate(dg):
+                assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"tick {tick} chunk {tuple(idx)}")
+    _assert_blocks_equal(gp, op, grid)
+
+
+def test_interior_edit_invalidates_only_its_chunk(ctx):
+    gp, op = _planets(ctx, 42, (3, 3, 3))
+    gp.CollectInvalidated()
+    gp.UpdateBlock((0, 0, 0), (5, 5, 5), 7)
+    assert gp.CollectInvalidated().tolist() == [[0, 0, 0]]
+    gp.UpdateBlock((0, 0, 0), (0, 5, 31), 7)  # x == 0 -> Left, z == 31 -> Up
+    assert gp.CollectInvalidated().tolist() == [[-1, 0, 0], [0, 0, 0], [0, 1, 0]]
+
+
+def test_box_collider(ctx):
+    """FlatChunk::BuildCollider greedy merge (FlatChunk.cpp:56-153): same boxes, same order."""
+    gp, op = _planets(ctx, 42, (3, 3, 3))
+    for idx in [(0, 1, 0), (1, 1, 1), (0, 0, 0), (-1, 0, 1)]:
+        got, want = gp.BuildBoxCollider(idx), op.box_collider(idx)
+        assert got.shape == want.shape and np.array_equal(got, want), f"{idx}: {got.shape} vs {want.shape}"
+
+
+def test_halo_pull_between_two_shards(ctx):
+    """Multi-GPU path on one GPU: the planet split into two containers ("ranks"); each pulls the other's boundary slabs
+    (the P2P kernel, here over local pointers) and must produce the meshes of the unsplit planet."""
+    import ctypes as C
+    from thisspaceofmine_b200 import _lib as L
+
+    count = (3, 3, 3)
+    whole, op = _planets(ctx, 42, count)
+    grid = T.Planet.chunk_grid(count)
+    content = whole.GetContent(grid)
+    half = len(grid) // 2 + 1
+    parts = [(grid[:half], content[:half]), (grid[half:], content[half:])]
+    shards = []
+    for g, b in parts:
+        s = T.ChunkContainer(ctx, len(g))
+        s.ResetChunks(g, b)
+        shards.append(s)
+    owner = {tuple(idx): (r, i) for r, (g, _) in enumerate(parts) for i, idx in enumerate(g)}
+    for r, s in enumerate(shards):
+        other = 1 - r
+        L.check(L.lib().tsom_peer_attach_local(s._h, other, shards[other]._h))
+        rem = []
+        for idx in parts[r][0]:
+            for d in range(6):
+                n = tuple(int(v) for v in idx + T.host.s_chunkDirOffset[d])
+                if n in owner and owner[n][0] == other:
+                    rem.append(n)
+        rem = sorted(set(rem))
+        if rem:
+            ri = np.array(rem, np.int32)
+            slots = np.zeros(len(rem), np.uint32)
+            for k, n in enumerate(rem):
+                sl = C.c_uint32()
+                L.check(L.lib().tsom_chunk_slot(shards[other]._h, ri[k].ctypes.data_as(C.POINTER(C.c_int32)), C.byref(sl)))
+                slots[k] = sl.value
+            ranks = np.full(len(rem), other, np.int32)
+            L.check(L.lib().tsom_container_add_remote_chunks(s._h, ri.ctypes.data_as(C.POINTER(C.c_int32)), slots.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                             ranks.ctypes.data_as(C.POINTER(C.c_int32)), len(rem)))
+        L.check(L.lib().tsom_halo_pull(s._h))
+    for r, s in enumerate(shards):
+        batch = s.BuildMeshes(parts[r][0])
+        for i, idx in enumerate(parts[r][0]):
+            assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"rank {r} chunk {tuple(idx)}")

@@ -1,0 +1,152 @@
+"""GPU parity: Chunk::BuildMesh on sm_100a (through the C ABI) against the CPU oracle, same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle as O
+import thisspaceofmine_b200 as T
+from helpers import NBLK, assert_mesh_equal, hash_fill, lidx, random_chunk
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(ctx, chunks, tile=1.0):
+    """Build the same container on both sides: chunks = {idx: blocks or None}."""
+    gc = T.ChunkContainer(ctx, max(len(chunks), 1), tile)
+    op = O.Planet(tile)
+    for idx, b in chunks.items():
+        op.add_chunk(idx, b)
+        gc.AddChunk(idx, None if b is None else b[None, :])
+    return gc, op
+
+
+def _compare_all(gc, op, indices, **kw):
+    batch = gc.BuildMeshes(indices, **{k: v for k, v in kw.items() if k in ("render", "collider", "deformed", "deformRadius", "gravityCenters")})
+    inexact = faces = 0
+    for i, idx in enumerate(indices):
+        g = None if kw.get("gravityCenters") is None else kw["gravityCenters"][i]
+        om = op.mesh(idx, deformed=kw.get("deformed", False), deform_radius=kw.get("deformRadius", 0.0), gravity_center=g)
+        s = assert_mesh_equal(batch.chunk(i), om, what=f"chunk {tuple(idx)}", check_attr=kw.get("render", True))
+        inexact += s["inexact"]
+        faces += s["faces"]
+    return faces, inexact
+
+
+def test_single_block(ctx):
+    b = np.zeros(NBLK, np.uint16)
+    b[lidx(7, 6, 5)] = 7
+    gc, op = _pair(ctx, {(0, 0, 0): b})
+    faces, inexact = _compare_all(gc, op, [(0, 0, 0)])
+    assert faces == 6
+
+
+def test_empty_and_full_chunk(ctx):
+    gc, op = _pair(ctx, {(0, 0, 0): np.zeros(NBLK, np.uint16), (5, 0, 0): np.full(NBLK, 7, np.uint16)})
+    batch = gc.BuildMeshes([(0, 0, 0), (5, 0, 0)])
+    assert batch.chunk(0) is None  # null mesh, ClientChunkEntities.cpp:161-162
+    assert batch.face_counts[1] == 6 * 32 * 32
+    _compare_all(gc, op, [(0, 0, 0), (5, 0, 0)])
+
+
+@pytest.mark.parametrize("p", [0.05, 0.5, 0.95])
+def test_random_isolated(ctx, p):
+    rng = np.random.default_rng(1234)
+    chunks = {(i, 0, 2 * i): random_chunk(rng, p) for i in range(3)}
+    chunks = {(2 * i, 0, 0): b for i, (k, b) in enumerate(chunks.items())}  # isolated: no face-adjacent chunk
+    gc, op = _pair(ctx, chunks)
+    faces, inexact = _compare_all(gc, op, list(chunks))
+    assert faces > 0
+
+
+def test_benchmark_fill_matches_oracle(ctx):
+    """The hash fill bench.py uses (BASELINE config 2): same face counts as the oracle."""
+    chunks = {(3 * i, 0, 0): hash_fill(1234, i) for i in range(4)}
+    gc, op = _pair(ctx, chunks)
+    _compare_all(gc, op, list(chunks))
+
+
+def test_mixed_ids_transparency_and_double_sided(ctx):
+    """ids {0,2,3,7,8,9,13}: same-type suppression, transparent neighbours, double-sided glass twins (Chunk.cpp:190-205)."""
+    rng = np.random.default_rng(99)
+    chunks = {(0, 0, 0): random_chunk(rng, 0.7, ids=(2, 3, 7, 8, 9, 13)), (2, 0, 0): random_chunk(rng, 0.9, ids=(9, 13)), (4, 0, 0): np.full(NBLK, 13, np.uint16)}
+    gc, op = _pair(ctx, chunks)
+    _compare_all(gc, op, list(chunks))
+
+
+def test_glass_next_to_stone_and_air(ctx):
+    b = np.zeros(NBLK, np.uint16)
+    b[lidx(10, 10, 10)] = 13  # glass
+    b[lidx(11, 10, 10)] = 7   # stone
+    gc, op = _pair(ctx, {(0, 0, 0): b})
+    batch = gc.BuildMeshes([(0, 0, 0)])
+    # glass: 5 air sides x 2 (double sided), nothing towards stone; stone: 5 air sides + 1 towards glass (transparent)
+    assert batch.face_counts[0] == 10 + 6
+    _compare_all(gc, op, [(0, 0, 0)])
+
+
+def test_neighbours_3x3x3(ctx):
+    """Halo slabs from all six neighbours, including chunks without content and missing chunks (Chunk.cpp:104-172)."""
+    rng = np.random.default_rng(7)
+    chunks = {}
+    for cx in range(-1, 2):
+        for cy in range(-1, 2):
+            for cz in range(-1, 2):
+                chunks[(cx, cy, cz)] = random_chunk(rng, 0.6, ids=(2, 7, 9, 13))
+    chunks[(1, 0, 0)] = None   # exists, no content -> faces towards it are drawn
+    del chunks[(0, -1, 0)]     # missing -> faces drawn
+    gc, op = _pair(ctx, chunks)
+    todo = [k for k, v in chunks.items() if v is not None]
+    faces, inexact = _compare_all(gc, op, todo)
+    assert faces > 0
+
+
+def test_tile_size_and_custom_gravity(ctx):
+    rng = np.random.default_rng(5)
+    chunks = {(1, -2, 3): random_chunk(rng, 0.3, ids=(3, 7))}
+    gc, op = _pair(ctx, chunks, tile=0.5)
+    _compare_all(gc, op, [(1, -2, 3)])
+    g = np.array([[3.25, -100.0, 17.5]], np.float32)
+    _compare_all(gc, op, [(1, -2, 3)], gravityCenters=g)
+
+
+def test_collider_reuses_face_list(ctx):
+    """DeformedChunk::BuildCollider path: positions only + the same indices, from the same compacted face list."""
+    rng = np.random.default_rng(11)
+    chunks = {(0, 0, 0): random_chunk(rng, 0.4, ids=(7, 9, 13))}
+    gc, op = _pair(ctx, chunks)
+    both = gc.BuildMeshes([(0, 0, 0)], render=True, collider=True).chunk(0)
+    only = gc.BuildMeshes([(0, 0, 0)], render=False, collider=True).chunk(0)
+    om = op.mesh((0, 0, 0))
+    assert_mesh_equal(both, om, "render+collider")
+    assert only.vertices is None
+    assert np.array_equal(only.indices, om.indices)
+    assert np.array_equal(only.collider_positions, both.collider_positions)
+    np.testing.assert_allclose(only.collider_positions, om.position, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("radius", [0.0, 16.0, 40.0])
+def test_deformed_corners(ctx, radius):
+    """DeformedChunk::ComputeVoxelCorners + DeformPosition (DeformedChunk.cpp:115-154)."""
+    rng = np.random.default_rng(3)
+    chunks = {(1, 1, 0): random_chunk(rng, 0.3, ids=(3, 7, 13)), (0, 0, 0): random_chunk(rng, 0.2)}
+    gc, op = _pair(ctx, chunks)
+    _compare_all(gc, op, list(chunks), deformed=True, deformRadius=radius)
+    _compare_all(gc, op, list(chunks), deformed=True, deformRadius=radius, render=False, collider=True)
+
+
+def test_batch_order_and_views(ctx):
+    """One batched call: per-chunk views are dense, in job order, and each equals the single-chunk result."""
+    rng = np.random.default_rng(21)
+    chunks = {(2 * i, 0, 0): random_chunk(rng, 0.1 * (i + 1)) for i in range(6)}
+    gc, op = _pair(ctx, chunks)
+    order = list(chunks)[::-1]
+    batch = gc.BuildMeshes(order)
+    assert batch.first_faces[0] == 0
+    assert np.array_equal(batch.first_faces[1:], np.cumsum(batch.face_counts.astype(np.uint64))[:-1])
+    for i, idx in enumerate(order):
+        assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"{idx}")
+
+
+def test_unknown_chunk_is_an_error(ctx):
+    gc, _ = _pair(ctx, {(0, 0, 0): np.zeros(NBLK, np.uint16)})
+    with pytest.raises(T.TsomError):
+        gc.BuildMeshes([(9, 9, 9)])

@@ -1,0 +1,638 @@
+// gen_kernels.cu — planet chunk generation on sm_100a (replaces Planet::GenerateChunk, reference src/CommonLib/Planet.cpp:160-383)
+// plus the small maintenance kernels (x-slab packing, edit scatter, platform script, greedy box collider, P2P halo pull).
+//
+// B200-first decomposition of GenerateChunk:
+//   terrain_kernel  : the Perlin height function depends only on the planet column, not on the chunk.  It is evaluated ONCE per
+//                     column and direction (FP64, explicit round-to-nearest intrinsics, no FMA contraction) into int16
+//                     `terrainDepth` tiles of 32x32; the reference re-evaluates it in every chunk stacked along the axis.
+//   generate_kernel : one CTA per chunk, pure integer work.  Each thread produces 8 consecutive ids and stores them with one
+//                     16-byte store (the chunk is written exactly once, 64 KiB, fully coalesced).  The sequential
+//                     std::minstd_rand / std::bernoulli_distribution(0.9) stream of Planet.cpp:167-168,219 is reproduced by LCG
+//                     skip-ahead: the blocks that consume a draw form an axis-aligned box in the chunk, so the draw index of a
+//                     block is closed-form and x_k = 48271^k * x_0 mod (2^31-1) is reached with three table multiplications.
+//                     The six terrain passes (Planet.cpp:233-381) commute into "Empty if above any column start, grass if dirt at
+//                     a column start", evaluated per block from six per-column start tables in shared memory.
+#include "tsom_kernels.h"
+#include "tsom_device.cuh"
+
+namespace tsomk
+{
+	// ------------------------------------------------------------------------------------------------ siv::PerlinNoise v3.0.0
+	__device__ __forceinline__ double pn_fade(double t)
+	{
+		// t * t * t * (t * (t * 6 - 15) + 10)
+		double inner = __dadd_rn(__dmul_rn(t, __dsub_rn(__dmul_rn(t, 6.0), 15.0)), 10.0);
+		return __dmul_rn(__dmul_rn(__dmul_rn(t, t), t), inner);
+	}
+
+	__device__ __forceinline__ double pn_lerp(double a, double b, double t) { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), t)); }
+
+	__device__ __forceinline__ double pn_grad(unsigned hash, double x, double y, double z)
+	{
+		const unsigned h = hash & 15u;
+		const double u = h < 8u ? x : y;
+		const double v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+		return __dadd_rn((h & 1u) == 0u ? u : -u, (h & 2u) == 0u ? v : -v);
+	}
+
+	__device__ double pn_noise3d(const uint8_t* __restrict__ p, double x, double y, double z)
+	{
+		const double _x = floor(x), _y = floor(y), _z = floor(z);
+		const int ix = int(_x) & 255, iy = int(_y) & 255, iz = int(_z) & 255;
+		const double fx = __dsub_rn(x, _x), fy = __dsub_rn(y, _y), fz = __dsub_rn(z, _z);
+		const double u = pn_fade(fx), v = pn_fade(fy), w = pn_fade(fz);
+
+		const unsigned A = (p[ix & 255] + iy) & 255u;
+		const unsigned B = (p[(ix + 1) & 255] + iy) & 255u;
+		const unsigned AA = (p[A] + iz) & 255u;
+		const unsigned AB = (p[(A + 1) & 255] + iz) & 255u;
+		const unsigned BA = (p[B] + iz) & 255u;
+		const unsigned BB = (p[(B + 1) & 255] + iz) & 255u;
+
+		const double fx1 = __dsub_rn(fx, 1.0), fy1 = __dsub_rn(fy, 1.0), fz1 = __dsub_rn(fz, 1.0);
+		const double p0 = pn_grad(p[AA], fx, fy, fz);
+		const double p1 = pn_grad(p[BA], fx1, fy, fz);
+		const double p2 = pn_grad(p[AB], fx, fy1, fz);
+		const double p3 = pn_grad(p[BB], fx1, fy1, fz);
+		const double p4 = pn_grad(p[(AA + 1) & 255], fx, fy, fz1);
+		const double p5 = pn_grad(p[(BA + 1) & 255], fx1, fy, fz1);
+		const double p6 = pn_grad(p[(AB + 1) & 255], fx, fy1, fz1);
+		const double p7 = pn_grad(p[(BB + 1) & 255], fx1, fy1, fz1);
+
+		const double q0 = pn_lerp(p0, p1, u), q1 = pn_lerp(p2, p3, u), q2 = pn_lerp(p4, p5, u), q3 = pn_lerp(p6, p7, u);
+		const double r0 = pn_lerp(q0, q1, v), r1 = pn_lerp(q2, q3, v);
+		return pn_lerp(r0, r1, w);
+	}
+
+	// normalizedOctave2D_01(x, y, 4) with persistence 0.5: sum / 1.875 * 0.5 + 0.5
+	__device__ double pn_octave01(const uint8_t* __restrict__ p, double x, double y)
+	{
+		double result = 0.0, amplitude = 1.0;
+#pragma unroll 1
+		for (int i = 0; i < 4; ++i)
+		{
+			result = __dadd_rn(result, __dmul_rn(pn_noise3d(p, x, y, 0.34567), amplitude));
+			x = __dmul_rn(x, 2.0);
+			y = __dmul_rn(y, 2.0);
+			amplitude = __dmul_rn(amplitude, 0.5);
+		}
+		const double n = __ddiv_rn(result, 1.875);
+		return __dadd_rn(__dmul_rn(n, 0.5), 0.5);
+	}
+
+	// Tiles: direction d, tile (ta, tb), column (i, j) -> terrain[offset[d] + ((tb * nA + ta) * 1024) + j * 32 + i]
+	//   Right/Left : A = world Y (up, local z), B = world Z (local y); i = local y, j = local z; noise(a = wy, b = wz)
+	//   Up/Down    : A = world X (local x),     B = world Z (local y); i = local x, j = local y; noise(a = wx, b = wz)
+	//   Back/Front : A = world X (local x),     B = world Y (local z); i = local x, j = local z; noise(a = wx, b = wy)
+	__global__ void __launch_bounds__(1024) terrain_kernel(const TerrainArgs a, int dir, int nA, int nB, int axA, int axB, int axH)
+	{
+		__shared__ uint8_t perm[256];
+		if (threadIdx.x < 256)
+			perm[threadIdx.x] = a.perm[dir * 256 + threadIdx.x];
+		__syncthreads();
+
+		const int tile = blockIdx.x;
+		const int ta = tile % nA, tb = tile / nA;
+		const int i = threadIdx.x & 31, j = threadIdx.x >> 5;
+
+		// world block coordinates of the column along the two table axes (GetBlockIndices: chunk*32 + local - 16)
+		int wa, wb;
+		if (dir == D_RIGHT || dir == D_LEFT)
+		{
+			wa = (a.tileOrigin[axA] + ta) * CS + j - CS / 2; // world Y from local z = j
+			wb = (a.tileOrigin[axB] + tb) * CS + i - CS / 2; // world Z from local y = i
+		}
+		else
+		{
+			wa = (a.tileOrigin[axA] + ta) * CS + i - CS / 2; // world X from local x = i
+			wb = (a.tileOrigin[axB] + tb) * CS + j - CS / 2; // world Z (local y) or world Y (local z) = j
+		}
+
+		const double scale = double(0.02f);
+		const double heightScale = double(1.5f);
+		const double height = __dmul_rn(pn_octave01(perm, __dmul_rn(double(wa), scale), __dmul_rn(double(wb), scale)), heightScale);
+
+		// int terrainDepth = std::round(std::min<double>(height * (maxH / 2 - freeSpace) + freeSpace, maxH / 2));  freeSpace is size_t
+		const int half = a.maxH[axH] / 2;
+		const unsigned long long span = static_cast<unsigned long long>(static_cast<long long>(half)) - 30ull;
+		double t = __dadd_rn(__dmul_rn(height, __ull2double_rn(span)), 30.0);
+		const double cap = double(half);
+		if (cap < t)
+			t = cap;
+		a.terrain[a.terrainOffset[dir] + size_t(tile) * SLAB + j * CS + i] = int16_t(int(round(t)));
+	}
+
+	void launch_terrain(const TerrainArgs& a, cudaStream_t st)
+	{
+		// axis ids: 0 = world X, 1 = world Y (up), 2 = world Z
+		struct { int dir, axA, axB, axH; } plan[6] = {
+			{ D_RIGHT, 1, 2, 0 }, { D_LEFT, 1, 2, 0 }, { D_UP, 0, 2, 1 }, { D_DOWN, 0, 2, 1 }, { D_BACK, 0, 1, 2 }, { D_FRONT, 0, 1, 2 },
+		};
+		for (auto& p : plan)
+		{
+			int nA = a.tileCount[p.axA], nB = a.tileCount[p.axB];
+			terrain_kernel<<<nA * nB, 1024, 0, st>>>(a, p.dir, nA, nB, p.axA, p.axB, p.axH);
+		}
+	}
+
+	// ------------------------------------------------------------------------------------------------ std::minstd_rand skip-ahead
+	constexpr uint32_t LCG_A = 48271u;
+	constexpr uint32_t LCG_M = 2147483647u;
+
+	__host__ __device__ __forceinline__ uint32_t mulmod31(uint32_t x, uint32_t y)
+	{
+		const unsigned long long p = static_cast<unsigned long long>(x) * y;
+		uint32_t s = uint32_t(p & LCG_M) + uint32_t(p >> 31);
+		return s >= LCG_M ? s - LCG_M : s;
+	}
+
+	__host__ __device__ inline uint32_t powmod31(uint32_t base, unsigned long long e)
+	{
+		uint32_t r = 1u;
+		while (e)
+		{
+			if (e & 1ull)
+				r = mulmod31(r, base);
+			base = mulmod31(base, base);
+			e >>= 1;
+		}
+		return r;
+	}
+
+	constexpr int GEN_THREADS = 256;
+	constexpr int ROWS_PER_CHUNK = CS * CS;
+
+	struct GenSmem
+	{
+		uint8_t start[6][SLAB]; // per pass and column: start height (32 = pass does not touch the column)
+		uint32_t powX[CS], powY[CS], powZ[CS];
+	};
+
+	__global__ void __launch_bounds__(GEN_THREADS) generate_kernel(const GenArgs a)
+	{
+		__shared__ GenSmem sm;
+		const int tid = threadIdx.x;
+		const uint32_t job = blockIdx.x;
+		if (job >= a.nJobs)
+			return;
+		const uint32_t slot = a.jobSlot[job];
+		const int4 ci = a.chunkIdx[slot];
+
+		// world coordinates of local (0,0,0): GetBlockIndices = chunk * 32 + (x, z, y) - 16
+		const int wx0 = ci.x * CS - CS / 2; // + local x
+		const int wy0 = ci.y * CS - CS / 2; // + local z (up)
+		const int wz0 = ci.z * CS - CS / 2; // + local y
+
+		// ---- terrain passes: column start heights (Planet.cpp:241-248 and the five twins)
+		// pass order in sm.start: 0 +X(Right) 1 -X(Left) 2 +Y(Up) 3 -Y(Down) 4 +Z(Back) 5 -Z(Front)
+		{
+			const int passDir[6] = { D_RIGHT, D_LEFT, D_UP, D_DOWN, D_BACK, D_FRONT };
+			const int blockDepth[6] = {
+				a.maxH[0] - wx0 + 1, a.maxH[0] + (wx0 + CS - 1) + 1,
+				a.maxH[1] - wy0 + 1, a.maxH[1] + (wy0 + CS - 1) + 1,
+				a.maxH[2] - wz0 + 1, a.maxH[2] + (wz0 + CS - 1) + 1,
+			};
+			const int tx = ci.x - a.tileOrigin[0], ty = ci.y - a.tileOrigin[1], tz = ci.z - a.tileOrigin[2];
+			const size_t tileIdx[6] = {
+				size_t(tz) * a.tileCount[1] + ty, size_t(tz) * a.tileCount[1] + ty, // (A = Y, B = Z)
+				size_t(tz) * a.tileCount[0] + tx, size_t(tz) * a.tileCount[0] + tx, // (A = X, B = Z)
+				size_t(ty) * a.tileCount[0] + tx, size_t(ty) * a.tileCount[0] + tx, // (A = X, B = Y)
+			};
+#pragma unroll
+			for (int p = 0; p < 6; ++p)
+			{
+				const int16_t* tile = a.terrain + a.terrainOffset[passDir[p]] + tileIdx[p] * SLAB;
+				const int bd = blockDepth[p];
+				for (int c = tid; c < SLAB; c += GEN_THREADS)
+				{
+					const int td = tile[c];
+					int s = 32;
+					if (bd >= td && bd - td < CS)
+						s = bd - td;
+					sm.start[p][c] = uint8_t(s);
+				}
+			}
+		}
+
+		// ---- RNG: the blocks that draw (depth - 30 > 18, Planet.cpp:218-219) form a box in local coordinates
+		const int Lx = a.maxH[0] - 49, Ly = a.maxH[1] - 49, Lz = a.maxH[2] - 49; // |wx| <= Lx, |wz| <= Ly, |wy| <= Lz (y/z crossed, :199-203)
+		const int ax0 = max(0, -Lx - wx0), ax1 = min(CS - 1, Lx - wx0);
+		const int ay0 = max(0, -Ly - wz0), ay1 = min(CS - 1, Ly - wz0); // local y <-> world Z
+		const int az0 = max(0, -Lz - wy0), az1 = min(CS - 1, Lz - wy0); // local z <-> world Y
+		const int NX = ax1 - ax0 + 1, NY = ay1 - ay0 + 1;
+		const bool anyDraw = (NX > 0) && (NY > 0) && (az1 >= az0);
+		if (anyDraw && tid < 3 * CS)
+		{
+			const int j = tid & 31;
+			const unsigned long long stride = tid < CS ? 2ull : (tid < 2 * CS ? 2ull * NX : 2ull * NX * NY);
+			uint32_t* dst = tid < CS ? sm.powX : (tid < 2 * CS ? sm.powY : sm.powZ);
+			dst[j] = powmod31(LCG_A, stride * j);
+		}
+		__syncthreads();
+
+		uint32_t chunkSeed = a.seed + uint32_t(ci.x) + uint32_t(ci.y) + uint32_t(ci.z);
+		uint32_t x0 = chunkSeed % LCG_M; // std::linear_congruential_engine::seed: 0 -> 1
+		if (x0 == 0u)
+			x0 = 1u;
+		const uint32_t base2 = mulmod31(x0, mulmod31(LCG_A, LCG_A)); // second engine output of draw 0
+
+		uint16_t* out = a.blocks + size_t(slot) * NB;
+		uint16_t* xs = a.xslabs + size_t(slot) * 2 * SLAB;
+
+		const int xq = tid & 3;
+		const int y = (tid >> 2) & 31;
+		const int wz = wz0 + y;
+		const int absWz = abs(wz);
+
+#pragma unroll 1
+		for (int it = 0; it < CS / 2; ++it)
+		{
+			const int z = 2 * it + (tid >> 7);
+			const int wy = wy0 + z;
+			const int mYZ = min(a.maxH[1] - absWz, a.maxH[2] - abs(wy));
+
+			const bool rowDraws = anyDraw && y >= ay0 && y <= ay1 && z >= az0 && z <= az1;
+			uint32_t rowMul = 0u;
+			if (rowDraws)
+				rowMul = mulmod31(mulmod31(base2, sm.powY[y - ay0]), sm.powZ[z - az0]);
+
+			const int col = z * CS + y;  // X passes: [local z][local y]
+			const int sXp = sm.start[0][col], sXm = sm.start[1][col];
+
+			uint32_t packed[4];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				const int x = xq * 8 + j;
+				const int wx = wx0 + x;
+				const int depth = min(a.maxH[0] - abs(wx), mYZ);
+
+				unsigned id;
+				if (depth < 30)
+					id = 0u;
+				else
+				{
+					const int d = depth - 30;
+					if (d <= 6)
+						id = a.snow;
+					else if (d <= 18)
+						id = a.dirt;
+					else
+					{
+						// draw n of the chunk: u1 = x_{2n+1}, u2 = x_{2n+2}; bernoulli(0.9) == (u2-1, u1-1) lexicographically below (bStar, aStar)
+						const uint32_t u2 = mulmod31(rowMul, sm.powX[x - ax0]);
+						bool stone = (u2 - 1u) < a.bStar;
+						if ((u2 - 1u) == a.bStar)
+						{
+							const uint32_t u1 = mulmod31(u2, a.aInv);
+							stone = (u1 - 1u) < a.aStar;
+						}
+						id = stone ? a.stone : a.stoneMossy;
+					}
+					if (abs(wx) <= 2 && absWz <= 2)
+						id = 0u; // central shaft, after the draw (Planet.cpp:221-222)
+				}
+
+				// terrain carve: height along each pass's axis
+				const int sYp = sm.start[2][y * CS + x], sYm = sm.start[3][y * CS + x]; // Y passes: [local y][local x], along local z
+				const int sZp = sm.start[4][z * CS + x], sZm = sm.start[5][z * CS + x]; // Z passes: [local z][local x], along local y
+				const int hXp = x, hXm = CS - 1 - x, hYp = z, hYm = CS - 1 - z, hZp = y, hZm = CS - 1 - y;
+				const bool above = (hXp > sXp) | (hXm > sXm) | (hYp > sYp) | (hYm > sYm) | (hZp > sZp) | (hZm > sZm);
+				const bool at = (hXp == sXp) | (hXm == sXm) | (hYp == sYp) | (hYm == sYm) | (hZp == sZp) | (hZm == sZm);
+				if (above)
+					id = 0u;
+				else if (at && id == a.dirt)
+					id = a.grass;
+
+				if (j & 1)
+					packed[j >> 1] |= id << 16;
+				else
+					packed[j >> 1] = id;
+
+				if (x == 0)
+					xs[col] = uint16_t(id);
+				if (x == CS - 1)
+					xs[SLAB + col] = uint16_t(id);
+			}
+			*reinterpret_cast<uint4*>(out + (size_t(z) * CS + y) * CS + xq * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+		}
+	}
+
+	void launch_generate(const GenArgs& a, int grid, cudaStream_t st)
+	{
+		generate_kernel<<<grid, GEN_THREADS, 0, st>>>(a);
+	}
+
+	// ------------------------------------------------------------------------------------------------ x-slab packing
+	// xslabs[slot][0][z][y] = ids[z][y][0], xslabs[slot][1][z][y] = ids[z][y][31]: what the Left/Right neighbours stage as halo
+	__global__ void __launch_bounds__(256) build_xslabs_kernel(const uint16_t* __restrict__ blocks, uint16_t* __restrict__ xslabs, const uint32_t* __restrict__ slots, uint32_t n)
+	{
+		const uint32_t i = blockIdx.x;
+		if (i >= n)
+			return;
+		const uint32_t slot = slots ? slots[i] : i;
+		const uint16_t* src = blocks + size_t(slot) * NB;
+		uint16_t* dst = xslabs + size_t(slot) * 2 * SLAB;
+		for (int c = threadIdx.x; c < SLAB; c += 256)
+		{
+			dst[c] = src[c * CS];
+			dst[SLAB + c] = src[c * CS + CS - 1];
+		}
+	}
+
+	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, const uint32_t* slots, uint32_t n, cudaStream_t st)
+	{
+		if (n)
+			build_xslabs_kernel<<<n, 256, 0, st>>>(blocks, xslabs, slots, n);
+	}
+
+	// ------------------------------------------------------------------------------------------------ edits
+	// Chunk::UpdateBlock (Chunk.cpp:348-366) + the neighbour-mask rule of Planet.cpp:39-58.  Edits must land in order (a later
+	// edit of the same block wins): every thread scans the whole list and applies only the edits of the chunk slots it owns.
+	__device__ __forceinline__ void device_update_block(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint32_t slot, int x, int y, int z, uint16_t id)
+	{
+		blocks[size_t(slot) * NB + (z * CS + y) * CS + x] = id;
+		unsigned mask = 0x80u; // bit 7: "is in m_invalidatedChunks" (a mask of 0 still invalidates the chunk itself)
+		if (x == 0)
+		{
+			xslabs[size_t(slot) * 2 * SLAB + z * CS + y] = id;
+			mask |= 1u << D_LEFT;
+		}
+		else if (x == CS - 1)
+		{
+			xslabs[size_t(slot) * 2 * SLAB + SLAB + z * CS + y] = id;
+			mask |= 1u << D_RIGHT;
+		}
+		if (y == 0)
+			mask |= 1u << D_FRONT;
+		else if (y == CS - 1)
+			mask |= 1u << D_BACK;
+		if (z == 0)
+			mask |= 1u << D_DOWN;
+		else if (z == CS - 1)
+			mask |= 1u << D_UP;
+		invalidMask[slot] |= uint8_t(mask);
+	}
+
+	constexpr int EDIT_THREADS = 256;
+	constexpr int EDIT_CTAS = 16;
+
+	__global__ void __launch_bounds__(EDIT_THREADS) apply_edits_kernel(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* __restrict__ edits, uint32_t n)
+	{
+		__shared__ EditDev tile[1024];
+		const uint32_t g = blockIdx.x * EDIT_THREADS + threadIdx.x;
+		const uint32_t G = gridDim.x * EDIT_THREADS;
+		for (uint32_t base = 0; base < n; base += 1024u)
+		{
+			const uint32_t m = min(1024u, n - base);
+			for (uint32_t i = threadIdx.x; i < m; i += EDIT_THREADS)
+				tile[i] = edits[base + i];
+			__syncthreads();
+			for (uint32_t i = 0; i < m; ++i)
+			{
+				const EditDev e = tile[i];
+				if (e.slot != 0xFFFFFFFFu && e.slot % G == g)
+					device_update_block(blocks, xslabs, invalidMask, e.slot, int(e.packed & 31u), int((e.packed >> 5) & 31u), int((e.packed >> 10) & 31u), uint16_t(e.packed >> 16));
+			}
+			__syncthreads();
+		}
+	}
+
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, cudaStream_t st)
+	{
+		if (n)
+			apply_edits_kernel<<<EDIT_CTAS, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, edits, n);
+	}
+
+	// ------------------------------------------------------------------------------------------------ Planet::GeneratePlatform
+	// A data-dependent sequential edit script (Planet.cpp:405-512); run by one thread against the device-resident blocks.
+	struct PlatformAxis { int forwardAxis, rightAxis, upAxis, forwardDir, rightDir, upDir; };
+	__constant__ PlatformAxis c_dirAxis[6] = {
+		{ 1, 0, 2,  1,  1,  1 }, { 2, 0, 1,  1,  1, -1 }, { 1, 0, 2, -1,  1, -1 },
+		{ 2, 1, 0, -1,  1, -1 }, { 2, 1, 0, -1, -1,  1 }, { 2, 0, 1, -1,  1,  1 },
+	};
+
+	// GetChunkIndicesByBlockIndices (ChunkContainer.inl:19-42) + slot lookup; returns -1 when the chunk is absent
+	__device__ int platform_locate(const PlatformArgs& a, const int coord[3], int local[3])
+	{
+		int chunk[3], adj[3];
+		for (int k = 0; k < 3; ++k)
+		{
+			adj[k] = coord[k] + CS / 2;
+			int off = adj[k] < 0 ? adj[k] - CS + 1 : adj[k];
+			chunk[k] = off / CS;
+		}
+		int l[3];
+		for (int k = 0; k < 3; ++k)
+		{
+			l[k] = adj[k] - chunk[k] * CS;
+			if (l[k] < 0)
+				l[k] += CS;
+		}
+		local[0] = l[0];
+		local[1] = l[2];
+		local[2] = l[1]; // (x, z, y)
+		for (int k = 0; k < 3; ++k)
+		{
+			int g = chunk[k] - a.gridOrigin[k];
+			if (g < 0 || g >= a.gridDim[k])
+				return -1;
+		}
+		return a.slotGrid[((chunk[2] - a.gridOrigin[2]) * a.gridDim[1] + (chunk[1] - a.gridOrigin[1])) * a.gridDim[0] + (chunk[0] - a.gridOrigin[0])];
+	}
+
+	__global__ void platform_kernel(const PlatformArgs a)
+	{
+		if (threadIdx.x != 0 || blockIdx.x != 0)
+			return;
+		const int platformSize = 15;
+		const unsigned freeHeight = 10;
+		const PlatformAxis ax = c_dirAxis[a.upDirection];
+
+		int coord[3] = { a.center[0], a.center[1], a.center[2] };
+		coord[ax.rightAxis] += -ax.rightDir * platformSize / 2;
+		coord[ax.forwardAxis] += -ax.forwardDir * platformSize / 2;
+		int orig[3] = { coord[0], coord[1], coord[2] };
+
+		for (unsigned y = 0; y < freeHeight; ++y)
+		{
+			const int startingZ = coord[ax.forwardAxis];
+			for (int z = 0; z < platformSize; ++z)
+			{
+				const int startingX = coord[ax.rightAxis];
+				for (int x = 0; x < platformSize; ++x)
+				{
+					uint16_t id;
+					if (y != 0)
+						id = 0;
+					else if (x == 0 || x == platformSize - 1 || z == 0 || z == platformSize - 1)
+						id = a.copper;
+					else
+						id = a.stoneBricks;
+					int local[3];
+					int slot = platform_locate(a, coord, local);
+					if (slot >= 0)
+						device_update_block(a.blocks, a.xslabs, a.invalidMask, uint32_t(slot), local[0], local[1], local[2], id);
+					coord[ax.rightAxis] += ax.rightDir;
+				}
+				coord[ax.rightAxis] = startingX;
+				coord[ax.forwardAxis] += ax.forwardDir;
+			}
+			if (coord[ax.upAxis] == 0 && ax.upDir < 0)
+				break;
+			coord[ax.upAxis] += ax.upDir;
+			coord[ax.forwardAxis] = startingZ;
+		}
+
+		coord[0] = orig[0];
+		coord[1] = orig[1];
+		coord[2] = orig[2];
+		for (unsigned y = 1;; ++y)
+		{
+			coord[ax.upAxis] -= ax.upDir;
+			bool hasEmpty = false;
+			const int startingZ = coord[ax.forwardAxis];
+			for (int z = 0; z < platformSize; ++z)
+			{
+				const int startingX = coord[ax.rightAxis];
+				for (int x = 0; x < platformSize; ++x)
+				{
+					int local[3];
+					int slot = platform_locate(a, coord, local);
+					if (slot < 0)
+						continue; // before the x position advances, as Planet.cpp:478-482
+					coord[ax.rightAxis] += ax.rightDir;
+
+					if (y % 3 == 0)
+					{
+						if (x != 0 && x != platformSize - 1 && z != 0 && z != platformSize - 1)
+							continue;
+					}
+					else
+					{
+						if (a.blocks[size_t(slot) * NB + (local[2] * CS + local[1]) * CS + local[0]] != 0)
+							continue;
+						if ((x != 0 && x != platformSize - 1) || (z != 0 && z != platformSize - 1))
+							continue;
+					}
+					hasEmpty = true;
+					device_update_block(a.blocks, a.xslabs, a.invalidMask, uint32_t(slot), local[0], local[1], local[2], a.planks);
+				}
+				coord[ax.rightAxis] = startingX;
+				coord[ax.forwardAxis] += ax.forwardDir;
+			}
+			if (!hasEmpty)
+				break;
+			coord[ax.forwardAxis] = startingZ;
+		}
+	}
+
+	void launch_platform(const PlatformArgs& a, cudaStream_t st) { platform_kernel<<<1, 32, 0, st>>>(a); }
+
+	// ------------------------------------------------------------------------------------------------ FlatChunk::BuildCollider
+	// Greedy box merge (FlatChunk.cpp:56-153): order dependent, so one thread walks the bitmask exactly like the reference;
+	// the mask itself (Chunk::OnChunkReset, Chunk.cpp:368-384) is built by the whole CTA with ballots.
+	__global__ void __launch_bounds__(256) box_collider_kernel(const uint16_t* __restrict__ ids, const uint8_t* __restrict__ blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count)
+	{
+		__shared__ uint32_t mask[ROWS_PER_CHUNK];
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		for (int r = warp; r < ROWS_PER_CHUNK; r += 8)
+		{
+			unsigned id = ids[r * CS + lane];
+			unsigned f = blkFlags[id < nTypes ? id : nTypes - 1];
+			uint32_t m = __ballot_sync(0xffffffffu, (f & BF_COLLIDES) != 0);
+			if (lane == 0)
+				mask[r] = m;
+		}
+		__syncthreads();
+		if (threadIdx.x != 0)
+			return;
+
+		uint32_t nBoxes = 0;
+		auto bit = [&](int x, int y, int z) { return (mask[z * CS + y] >> x) & 1u; };
+		for (int z = 0; z < CS; ++z)
+		{
+			for (int y = 0; y < CS; ++y)
+			{
+				int x = 0;
+				while (x < CS)
+				{
+					uint32_t m = mask[z * CS + y] >> x;
+					if (!m)
+						break;
+					x += __ffs(m) - 1;          // start of the run
+					uint32_t run = mask[z * CS + y] >> x;
+					int len = (~run == 0u) ? 32 - x : __ffs(~run) - 1;
+					if (len > CS - x)
+						len = CS - x;
+					const int sx = x, endX = x + len - 1;
+					const uint32_t rowBits = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << sx;
+					int endY = y, endZ = z;
+					for (endY += 1; endY < CS; ++endY)
+						if ((mask[z * CS + endY] & rowBits) != rowBits)
+							break;
+					endY--;
+					for (endZ += 1; endZ < CS; ++endZ)
+					{
+						bool ok = true;
+						for (int yy = y; yy <= endY; ++yy)
+							if ((mask[endZ * CS + yy] & rowBits) != rowBits)
+							{
+								ok = false;
+								break;
+							}
+						if (!ok)
+							break;
+					}
+					endZ--;
+					for (int zz = z; zz <= endZ; ++zz)
+						for (int yy = y; yy <= endY; ++yy)
+							mask[zz * CS + yy] &= ~rowBits;
+					if (nBoxes < cap)
+					{
+						float* o = boxes + size_t(nBoxes) * 6;
+						const float half = float(CS) * 0.5f;
+						o[0] = float(sx) - half;
+						o[1] = float(z) - half;
+						o[2] = float(y) - half;
+						o[3] = float(endX + 1) - float(sx);
+						o[4] = float(endZ + 1) - float(z);
+						o[5] = float(endY + 1) - float(y);
+					}
+					++nBoxes;
+					x = endX + 1;
+					(void)bit;
+				}
+			}
+		}
+		*count = nBoxes;
+	}
+
+	void launch_box_collider(const uint16_t* chunkBlocks, const uint8_t* blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count, cudaStream_t st)
+	{
+		box_collider_kernel<<<1, 256, 0, st>>>(chunkBlocks, blkFlags, nTypes, boxes, cap, count);
+	}
+
+	// ------------------------------------------------------------------------------------------------ P2P halo pull
+	// One CTA per ghost slab: 2 KiB read straight from the owner GPU's HBM over NVLink (peer-mapped pointer), written locally.
+	__global__ void __launch_bounds__(128) halo_pull_kernel(const GhostDesc* __restrict__ descs, uint32_t n, uint16_t* __restrict__ ghostSlabs)
+	{
+		const uint32_t i = blockIdx.x;
+		if (i >= n)
+			return;
+		const GhostDesc d = descs[i];
+		const int t = threadIdx.x; // 128 x 16 B = 2 KiB
+		const uint4* src;
+		if (d.contig)
+			src = reinterpret_cast<const uint4*>(d.src) + t;
+		else
+			src = reinterpret_cast<const uint4*>(d.src + size_t(t >> 2) * SLAB) + (t & 3);
+		reinterpret_cast<uint4*>(ghostSlabs + size_t(d.ghost) * SLAB)[t] = *src;
+	}
+
+	void launch_halo_pull(const GhostDesc* descs, uint32_t n, uint16_t* ghostSlabs, cudaStream_t st)
+	{
+		if (n)
+			halo_pull_kernel<<<n, 128, 0, st>>>(descs, n, ghostSlabs);
+	}
+}

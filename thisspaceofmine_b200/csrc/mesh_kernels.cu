@@ -1,0 +1,760 @@
+// mesh_kernels.cu — face-culled chunk meshing on sm_100a (replaces Chunk::BuildMesh, reference src/CommonLib/Chunk.cpp:20-250).
+//
+// Two kernels share one staging / visibility front end:
+//   mesh_count_kernel : per chunk, stage ids + 6 halo slabs into shared memory with TMA bulk copies (cp.async.bulk + mbarrier),
+//                       build per-row bit masks with warp ballots, derive the 6 visibility masks per row, sum faces.
+//   mesh_emit_kernel  : same front end, then a block-wide prefix scan over the 1024 rows gives every face its ordinal in the
+//                       reference's emission order (z, y, x, Up/Down/Front/Back/Left/Right + double-sided twin); warps take
+//                       tiles of 32 consecutive faces, compute them one face per lane, transpose through shared memory and
+//                       stream them out with fully coalesced 16-byte stores (vertices 48 B x 4, indices u32 x 6,
+//                       collider positions 12 B x 4 from the same face list).
+// A face is drawn iff self != Empty and (neighbour chunk absent, or neighbour id != self and neighbour is transparent)
+// (Chunk.cpp:190-201).  An absent neighbour chunk is staged as a slab of Empty ids, which is equivalent.
+//
+// Compiled with -fmad=false: the float math reproduces the reference's operation order without FMA contraction.
+#include "tsom_kernels.h"
+#include "tsom_device.cuh"
+
+namespace tsomk
+{
+	constexpr int MESH_THREADS = 512;
+	constexpr int MESH_WARPS = MESH_THREADS / 32;
+	constexpr int ROWS = CS * CS; // 1024 x-rows per chunk
+
+	// staging: one face = 12 float4 (4 vertices x 48 B) padded to 13 so lane-strided 16-byte stores are conflict free
+	constexpr int STAGE_FACE_F4 = 13;
+	constexpr int STAGE_WARP_BYTES = 32 * STAGE_FACE_F4 * 16; // 6656
+
+	// emission order of the reference (Chunk.cpp:200-246) as Direction values
+	__constant__ int c_slotDir[6] = { D_UP, D_DOWN, D_FRONT, D_BACK, D_LEFT, D_RIGHT };
+
+	// Per emission slot, the 4 quad corners as bit codes dX | dY<<1 | dZ<<2 in world-local axes (X = local x, Y = up = local z,
+	// Z = local y) — the effective Nz::BoxCorner semantics derived in SURVEY.md §8.1.  The double-sided twin swaps v0<->v1, v2<->v3.
+	__constant__ unsigned char c_faceCorners[6][4] = {
+		{ 0b011, 0b111, 0b010, 0b110 }, // Up    : (1,1,0) (1,1,1) (0,1,0) (0,1,1)
+		{ 0b101, 0b001, 0b100, 0b000 }, // Down  : (1,0,1) (1,0,0) (0,0,1) (0,0,0)
+		{ 0b001, 0b011, 0b000, 0b010 }, // Front : (1,0,0) (1,1,0) (0,0,0) (0,1,0)
+		{ 0b111, 0b101, 0b110, 0b100 }, // Back  : (1,1,1) (1,0,1) (0,1,1) (0,0,1)
+		{ 0b010, 0b110, 0b000, 0b100 }, // Left  : (0,1,0) (0,1,1) (0,0,0) (0,0,1)
+		{ 0b111, 0b011, 0b101, 0b001 }, // Right : (1,1,1) (1,1,0) (1,0,1) (1,0,0)
+	};
+
+	// order in which the 8 corners are summed for the block centre (enum order of Nz::BoxCorner as listed at
+	// DeformedChunk.cpp:123-130 under the §8.1 mapping)
+	__constant__ unsigned char c_cornerSumOrder[8] = { 0b100, 0b101, 0b000, 0b001, 0b110, 0b111, 0b010, 0b011 };
+
+	struct MeshSmem
+	{
+		// persistent for the whole chunk
+		uint16_t ids[NB];          // 65536 B, TMA destination
+		uint32_t mD[ROWS];         // double-sided mask per row
+		uint32_t V[6][ROWS];       // visibility mask per emission slot and row
+		uint32_t rowOff[ROWS + 4]; // exclusive prefix of faces per row (+ total at [ROWS])
+		uint32_t desc[MESH_WARPS][32];
+		uint32_t warpSum[MESH_WARPS + 1];
+		uint32_t job;
+		uint32_t total;
+		alignas(8) uint64_t bar;
+		// phase 1-2 only; the emit kernel reuses this area as the face staging buffer
+		union
+		{
+			struct
+			{
+				uint16_t halo[6][SLAB]; // Direction order
+				uint32_t mT[ROWS];      // transparent mask per row
+				uint32_t mE[ROWS];      // non-empty mask per row
+				uint32_t hT[6][CS];     // transparent masks of the halo slabs (Left/Right: bit = y, row = z)
+			} front;
+			float4 stage[MESH_WARPS][32 * STAGE_FACE_F4];
+		} u;
+	};
+
+	struct CountSmem
+	{
+		uint16_t ids[NB];
+		uint16_t halo[6][SLAB];
+		uint32_t mT[ROWS];
+		uint32_t mE[ROWS];
+		uint32_t mD[ROWS];
+		uint32_t hT[6][CS];
+		uint32_t warpSum[MESH_WARPS + 1];
+		uint32_t job;
+		alignas(8) uint64_t bar;
+	};
+
+	__device__ __forceinline__ unsigned block_flags(const MeshArgs& a, unsigned id)
+	{
+		return __ldg(a.blkFlags + (id < a.nTypes ? id : a.nTypes - 1));
+	}
+
+	// ---- stage one chunk: 64 KiB of ids + six 2 KiB halo slabs, by TMA bulk copies completing on one mbarrier ----
+	__device__ __forceinline__ void stage_chunk(const MeshArgs& a, uint32_t slot, uint16_t* ids, uint16_t (*halo)[SLAB], uint64_t* bar)
+	{
+		const int tid = threadIdx.x;
+		const int lane = tid & 31;
+		const int warp = tid >> 5;
+		const unsigned long long* hp = a.halo + size_t(slot) * 6;
+
+		if (warp == 0)
+		{
+			uint32_t bytes = NB * 2;
+#pragma unroll
+			for (int d = 0; d < 6; ++d)
+				bytes += (hp[d] != 0ull) ? SLAB * 2 : 0;
+
+			fence_proxy_async(); // earlier generic reads of these buffers (previous chunk) happen-before the async writes
+			if (lane == 0)
+			{
+				mbar_arrive_expect_tx(bar, bytes);
+				// the chunk itself, in 4 pieces so several copy engines' worth of requests are in flight
+				const uint16_t* src = a.blocks + size_t(slot) * NB;
+#pragma unroll
+				for (int p = 0; p < 4; ++p)
+					tma_load_1d(ids + p * (NB / 4), src + p * (NB / 4), NB / 2, bar);
+			}
+			__syncwarp();
+#pragma unroll
+			for (int d = 0; d < 6; ++d)
+			{
+				unsigned long long e = hp[d];
+				if (e == 0ull)
+					continue;
+				const uint16_t* src = reinterpret_cast<const uint16_t*>(e & ~HALO_KIND_MASK);
+				if ((e & HALO_KIND_MASK) == HALO_ROWS)
+					tma_load_1d(&halo[d][lane * CS], src + size_t(lane) * SLAB, CS * 2, bar); // 32 rows of 64 B, stride 2 KiB
+				else if (lane == 0)
+					tma_load_1d(&halo[d][0], src, SLAB * 2, bar);
+			}
+		}
+		// absent neighbours read as Empty (generic stores; visible after the block barrier that follows the mbarrier wait)
+#pragma unroll
+		for (int d = 0; d < 6; ++d)
+		{
+			if (hp[d] == 0ull)
+			{
+				uint32_t* z = reinterpret_cast<uint32_t*>(&halo[d][0]);
+				for (int i = tid; i < SLAB / 2; i += MESH_THREADS)
+					z[i] = 0u;
+			}
+		}
+	}
+
+	// ---- phase 1: per-row bit masks via warp ballots (lane = x) ----
+	__device__ __forceinline__ void build_masks(const MeshArgs& a, const uint16_t* ids, const uint16_t (*halo)[SLAB],
+	                                            uint32_t* mT, uint32_t* mE, uint32_t* mD, uint32_t (*hT)[CS])
+	{
+		const int lane = threadIdx.x & 31;
+		const int warp = threadIdx.x >> 5;
+
+		for (int r = warp; r < ROWS; r += MESH_WARPS)
+		{
+			unsigned id = ids[r * CS + lane];
+			unsigned f = block_flags(a, id);
+			uint32_t t = __ballot_sync(0xffffffffu, (f & BF_TRANSPARENT) != 0);
+			uint32_t e = __ballot_sync(0xffffffffu, id != 0);
+			uint32_t d = __ballot_sync(0xffffffffu, (f & BF_DOUBLE_SIDED) != 0);
+			if (lane == 0)
+			{
+				mT[r] = t;
+				mE[r] = e;
+				mD[r] = d;
+			}
+		}
+		// halo slabs: 6 x 32 rows
+		for (int r = warp; r < 6 * CS; r += MESH_WARPS)
+		{
+			int d = r >> 5, j = r & 31;
+			unsigned id = halo[d][j * CS + lane];
+			uint32_t t = __ballot_sync(0xffffffffu, (block_flags(a, id) & BF_TRANSPARENT) != 0);
+			if (lane == 0)
+				hT[d][j] = t;
+		}
+	}
+
+	// neighbour id of block (x,y,z) towards emission slot s, staged halo included
+	__device__ __forceinline__ unsigned neighbour_id(const uint16_t* ids, const uint16_t (*halo)[SLAB], int x, int y, int z, int s)
+	{
+		switch (s)
+		{
+			case 0: return z < CS - 1 ? ids[((z + 1) * CS + y) * CS + x] : halo[D_UP][y * CS + x];
+			case 1: return z > 0 ? ids[((z - 1) * CS + y) * CS + x] : halo[D_DOWN][y * CS + x];
+			case 2: return y > 0 ? ids[(z * CS + y - 1) * CS + x] : halo[D_FRONT][z * CS + x];
+			case 3: return y < CS - 1 ? ids[(z * CS + y + 1) * CS + x] : halo[D_BACK][z * CS + x];
+			case 4: return x > 0 ? ids[(z * CS + y) * CS + x - 1] : halo[D_LEFT][z * CS + y];
+			default: return x < CS - 1 ? ids[(z * CS + y) * CS + x + 1] : halo[D_RIGHT][z * CS + y];
+		}
+	}
+
+	// ---- phase 2: visibility masks of the two rows owned by this thread (rows 2*tid, 2*tid+1), in emission-slot order ----
+	// Returns the face count of both rows; v[j][s] receives the masks.
+	__device__ __forceinline__ void row_visibility(const uint16_t* ids, const uint16_t (*halo)[SLAB], const uint32_t* mT, const uint32_t* mE,
+	                                               const uint32_t (*hT)[CS], uint32_t v[2][6])
+	{
+		const int tid = threadIdx.x;
+		const int lane = tid & 31;
+		uint32_t need[2];
+
+#pragma unroll
+		for (int j = 0; j < 2; ++j)
+		{
+			const int r = 2 * tid + j;
+			const int z = r >> 5, y = r & 31;
+			const uint32_t t = mT[r], e = mE[r];
+
+			uint32_t tUp = z < CS - 1 ? mT[r + CS] : hT[D_UP][y];
+			uint32_t tDown = z > 0 ? mT[r - CS] : hT[D_DOWN][y];
+			uint32_t tFront = y > 0 ? mT[r - 1] : hT[D_FRONT][z];
+			uint32_t tBack = y < CS - 1 ? mT[r + 1] : hT[D_BACK][z];
+			uint32_t tLeft = (t << 1) | ((hT[D_LEFT][z] >> y) & 1u);
+			uint32_t tRight = (t >> 1) | (((hT[D_RIGHT][z] >> y) & 1u) << 31);
+
+			v[j][0] = e & tUp;
+			v[j][1] = e & tDown;
+			v[j][2] = e & tFront;
+			v[j][3] = e & tBack;
+			v[j][4] = e & tLeft;
+			v[j][5] = e & tRight;
+			need[j] = e & t; // transparent non-empty blocks: "same type" suppression needs the ids (Chunk.cpp:192-194)
+		}
+
+		// rare path: rows holding transparent non-empty blocks compare ids, one row per step, lane = x
+#pragma unroll
+		for (int j = 0; j < 2; ++j)
+		{
+			uint32_t flagged = __ballot_sync(0xffffffffu, need[j] != 0);
+			while (flagged)
+			{
+				const int b = __ffs(flagged) - 1;
+				flagged &= flagged - 1;
+				const int r = 2 * ((tid & ~31) + b) + j;
+				const int z = r >> 5, y = r & 31;
+				const unsigned self = ids[r * CS + lane];
+#pragma unroll
+				for (int s = 0; s < 6; ++s)
+				{
+					uint32_t same = __ballot_sync(0xffffffffu, neighbour_id(ids, halo, lane, y, z, s) == self);
+					if (lane == b)
+						v[j][s] &= ~same;
+				}
+			}
+		}
+	}
+
+	__device__ __forceinline__ uint32_t row_faces(const uint32_t v[6], uint32_t d)
+	{
+		uint32_t c = 0;
+#pragma unroll
+		for (int s = 0; s < 6; ++s)
+			c += __popc(v[s]) + __popc(v[s] & d);
+		return c;
+	}
+
+	// =====================================================================================================================
+	__global__ void __launch_bounds__(MESH_THREADS, 2) mesh_count_kernel(const MeshArgs a)
+	{
+		extern __shared__ __align__(128) unsigned char smemRaw[];
+		CountSmem& sm = *reinterpret_cast<CountSmem*>(smemRaw);
+		const int tid = threadIdx.x;
+		const int lane = tid & 31;
+		const int warp = tid >> 5;
+
+		if (tid == 0)
+		{
+			mbar_init(&sm.bar, 1);
+			fence_mbar_init();
+		}
+		__syncthreads();
+
+		uint32_t parity = 0;
+		for (;;)
+		{
+			if (tid == 0)
+				sm.job = atomicAdd(a.jobCounter, 1u);
+			__syncthreads();
+			const uint32_t job = sm.job;
+			if (job >= a.nJobs)
+				break;
+			const uint32_t slot = a.jobSlot[job];
+			const bool hasContent = a.chunkIdx[slot].w != 0;
+			if (!hasContent)
+			{
+				if (tid == 0)
+					a.faceCount[job] = 0;
+				__syncthreads();
+				continue;
+			}
+
+			stage_chunk(a, slot, sm.ids, sm.halo, &sm.bar);
+			mbar_wait(&sm.bar, parity);
+			parity ^= 1;
+			__syncthreads();
+
+			build_masks(a, sm.ids, sm.halo, sm.mT, sm.mE, sm.mD, sm.hT);
+			__syncthreads();
+
+			uint32_t v[2][6];
+			row_visibility(sm.ids, sm.halo, sm.mT, sm.mE, sm.hT, v);
+			uint32_t c = row_faces(v[0], sm.mD[2 * tid]) + row_faces(v[1], sm.mD[2 * tid + 1]);
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				c += __shfl_xor_sync(0xffffffffu, c, o);
+			if (lane == 0)
+				sm.warpSum[warp] = c;
+			__syncthreads();
+			if (tid == 0)
+			{
+				uint32_t total = 0;
+#pragma unroll
+				for (int w = 0; w < MESH_WARPS; ++w)
+					total += sm.warpSum[w];
+				a.faceCount[job] = total;
+			}
+			__syncthreads(); // all reads of the staged data are done before the next chunk's TMA writes
+		}
+	}
+
+	// =====================================================================================================================
+	struct FaceCtx
+	{
+		float tile;
+		F3 gravity; // Chunk::BuildMesh `center` argument; also the deformation centre
+		float radius;
+		bool deformed;
+		bool wantAttr; // normals + uv (render) — collider-only skips them like null SparsePtrs do (Chunk.cpp:33,39)
+	};
+
+	// DeformedChunk::DeformPosition (reference src/CommonLib/DeformedChunk.cpp:139-154)
+	__device__ __forceinline__ F3 deform_position(const FaceCtx& cx, F3 p)
+	{
+		const F3 c = cx.gravity;
+		float dist = fmaxf(fmaxf(fabsf(p.x - c.x), fabsf(p.y - c.y)), fabsf(p.z - c.z));
+		float inner = fmaxf(dist - cx.radius, 0.f);
+		F3 bmin = c - f3(inner, inner, inner);
+		float len = inner * 2.f;
+		F3 bmax = f3(bmin.x + len, bmin.y + len, bmin.z + len);
+		F3 ip = f3(fmaxf(fminf(p.x, bmax.x), bmin.x), fmaxf(fminf(p.y, bmax.y), bmin.y), fmaxf(fminf(p.z, bmax.z), bmin.z));
+		F3 n = normalize(p - ip);
+		return ip + n * fminf(cx.radius, dist);
+	}
+
+	// one voxel corner, code = dX | dY<<1 | dZ<<2 (FlatChunk.cpp:48-54 / DeformedChunk.cpp:115-137)
+	__device__ __forceinline__ F3 voxel_corner(const FaceCtx& cx, int x, int y, int z, unsigned code)
+	{
+		const float s = cx.tile;
+		F3 p;
+		if (!cx.deformed)
+		{
+			float bx = (float(x) - float(CS) * 0.5f) * s;
+			float by = (float(y) - float(CS) * 0.5f) * s;
+			float bz = (float(z) - float(CS) * 0.5f) * s;
+			// Boxf(blockPos.x, blockPos.z, blockPos.y, s, s, s)
+			p = f3((code & 1u) ? bx + s : bx, (code & 2u) ? bz + s : bz, (code & 4u) ? by + s : by);
+		}
+		else
+		{
+			float fx = float(unsigned(x)) * s;
+			float fy = float(unsigned(y)) * s;
+			float fz = float(unsigned(z)) * s;
+			p = f3((code & 1u) ? fx + s : fx, (code & 2u) ? fz + s : fz, (code & 4u) ? fy + s : fy);
+			p = deform_position(cx, p);
+		}
+		return p;
+	}
+
+	// DrawFace (Chunk.cpp:22-102): writes 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}
+	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	{
+		// block centre = mean of the 8 corners, summed in enum order (Chunk.cpp:186-188)
+		F3 sum = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+			sum = sum + voxel_corner(cx, x, y, z, c_cornerSumOrder[i]);
+		const F3 blockCenter = sum / 8.f;
+
+		F3 pos[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			pos[i] = voxel_corner(cx, x, y, z, c_faceCorners[slot][twin ? (i ^ 1) : i]);
+
+		F3 fc = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			fc = fc + pos[i];
+		fc = fc / 4.f;
+
+		F3 normal = f3(0.f, 0.f, 0.f);
+		float u[4] = { 0.f, 0.f, 0.f, 0.f }, v[4] = { 0.f, 0.f, 0.f, 0.f };
+		float slice = 0.f;
+		if (cx.wantAttr)
+		{
+			normal = normalize(fc - blockCenter);
+
+			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
+			const float qw = a.quat[faceUp][0];
+			const F3 qv = f3(a.quat[faceUp][1], a.quat[faceUp][2], a.quat[faceUp][3]);
+			const int texDir = direction_from_normal(quat_rotate(qw, qv, normal));
+			slice = float(__ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir));
+
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				F3 dir = quat_rotate(qw, qv, pos[i] - blockCenter);
+				float mag, uu, vv;
+				if (texDir == D_BACK || texDir == D_FRONT)
+				{
+					mag = 0.5f / fabsf(dir.x);
+					uu = dir.x < 0.f ? -dir.z : dir.z;
+					vv = -dir.y;
+				}
+				else if (texDir == D_DOWN || texDir == D_UP)
+				{
+					mag = 0.5f / fabsf(dir.y);
+					uu = dir.x;
+					vv = dir.y < 0.f ? -dir.z : dir.z;
+				}
+				else
+				{
+					mag = 0.5f / fabsf(dir.z);
+					uu = dir.z < 0.f ? dir.x : -dir.x;
+					vv = -dir.y;
+				}
+				u[i] = uu * mag + 0.5f;
+				v[i] = vv * mag + 0.5f;
+			}
+		}
+
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			out[i * 3 + 0] = make_float4(pos[i].x, pos[i].y, pos[i].z, normal.x);
+			out[i * 3 + 1] = make_float4(normal.y, normal.z, u[i], v[i]);
+			out[i * 3 + 2] = make_float4(slice, 0.f, 0.f, 0.f); // tangent stays zero (never written by Chunk::BuildMesh)
+		}
+	}
+
+	__global__ void __launch_bounds__(MESH_THREADS, 1) mesh_emit_kernel(const MeshArgs a)
+	{
+		extern __shared__ __align__(128) unsigned char smemRaw[];
+		MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smemRaw);
+		const int tid = threadIdx.x;
+		const int lane = tid & 31;
+		const int warp = tid >> 5;
+
+		if (tid == 0)
+		{
+			mbar_init(&sm.bar, 1);
+			fence_mbar_init();
+		}
+		__syncthreads();
+
+		const uint32_t nWork = *a.nWork;
+		uint32_t parity = 0;
+		for (;;)
+		{
+			if (tid == 0)
+				sm.job = atomicAdd(a.jobCounter, 1u);
+			__syncthreads();
+			const uint32_t w = sm.job;
+			if (w >= nWork)
+				break;
+			const uint32_t job = a.worklist[w];
+			const uint32_t slot = a.jobSlot[job];
+			const unsigned long long firstFace = a.firstFace[job];
+
+			// ---- front end: stage + masks + visibility
+			stage_chunk(a, slot, sm.ids, sm.u.front.halo, &sm.bar);
+			mbar_wait(&sm.bar, parity);
+			parity ^= 1;
+			__syncthreads();
+
+			build_masks(a, sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.mD, sm.u.front.hT);
+			__syncthreads();
+
+			uint32_t v[2][6];
+			row_visibility(sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.u.front.hT, v);
+			const uint32_t c0 = row_faces(v[0], sm.mD[2 * tid]);
+			const uint32_t c1 = row_faces(v[1], sm.mD[2 * tid + 1]);
+#pragma unroll
+			for (int s = 0; s < 6; ++s)
+			{
+				sm.V[s][2 * tid] = v[0][s];
+				sm.V[s][2 * tid + 1] = v[1][s];
+			}
+
+			// ---- block-wide exclusive scan of the 1024 row counts (rows 2*tid, 2*tid+1 are adjacent)
+			uint32_t incl = c0 + c1;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o)
+					incl += n;
+			}
+			if (lane == 31)
+				sm.warpSum[warp] = incl;
+			__syncthreads(); // also: every read of the front-end buffers is done -> the staging union may be overwritten
+			if (warp == 0)
+			{
+				uint32_t ws = lane < MESH_WARPS ? sm.warpSum[lane] : 0u;
+				uint32_t wi = ws;
+#pragma unroll
+				for (int o = 1; o < MESH_WARPS; o <<= 1)
+				{
+					uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+					if (lane >= o)
+						wi += n;
+				}
+				if (lane < MESH_WARPS)
+					sm.warpSum[lane] = wi - ws; // exclusive
+				if (lane == MESH_WARPS - 1)
+					sm.total = wi;
+			}
+			__syncthreads();
+			{
+				const uint32_t excl = sm.warpSum[warp] + incl - (c0 + c1);
+				sm.rowOff[2 * tid] = excl;
+				sm.rowOff[2 * tid + 1] = excl + c0;
+				if (tid == MESH_THREADS - 1)
+					sm.rowOff[ROWS] = excl + c0 + c1;
+			}
+			__syncthreads();
+
+			const uint32_t F = sm.total;
+			const bool overflow = firstFace + F > a.arenaFaces;
+			if (overflow && tid == 0)
+				atomicExch(a.overflow, 1u);
+
+			if (!overflow && F > 0)
+			{
+				FaceCtx cx;
+				cx.tile = a.tile;
+				cx.radius = a.deformRadius;
+				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
+				cx.wantAttr = (a.flags & MESH_F_RENDER) != 0;
+				if (a.gravity)
+					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);
+				else
+				{
+					// container centre - GetChunkOffset(indices) (ClientChunkEntities.cpp:160, ChunkContainer.inl:53-56)
+					const int4 ci = a.chunkIdx[slot];
+					cx.gravity = f3(a.center[0] - float(ci.x) * float(CS) * a.tile, a.center[1] - float(ci.y) * float(CS) * a.tile, a.center[2] - float(ci.z) * float(CS) * a.tile);
+				}
+
+				float4* stage = sm.u.stage[warp];
+				uint32_t* desc = sm.desc[warp];
+				const uint32_t nTiles = (F + 31u) >> 5;
+
+				for (uint32_t tile = warp; tile < nTiles; tile += MESH_WARPS)
+				{
+					const uint32_t f0 = tile << 5;
+					const uint32_t nf = min(32u, F - f0);
+
+					// ---- descriptors of faces [f0, f0+nf): walk the rows that hold them, lane = x
+					uint32_t f = f0;
+					while (f < f0 + nf)
+					{
+						// largest row with rowOff[row] <= f (rowOff is non-decreasing; ties end on the non-empty row)
+						uint32_t top = __popc(__ballot_sync(0xffffffffu, sm.rowOff[lane * 32] <= f)) - 1u;
+						uint32_t row = top * 32u + __popc(__ballot_sync(0xffffffffu, sm.rowOff[top * 32u + lane] <= f)) - 1u;
+
+						const uint32_t base = sm.rowOff[row];
+						const uint32_t d = sm.mD[row];
+						const uint32_t lt = (1u << lane) - 1u;
+						uint32_t vs[6];
+						uint32_t p = base;
+#pragma unroll
+						for (int s = 0; s < 6; ++s)
+						{
+							vs[s] = sm.V[s][row];
+							p += __popc(vs[s] & lt) + __popc(vs[s] & d & lt);
+						}
+						const bool twin = (d >> lane) & 1u;
+						const uint32_t blk = row * 32u + lane;
+#pragma unroll
+						for (int s = 0; s < 6; ++s)
+						{
+							if ((vs[s] >> lane) & 1u)
+							{
+								uint32_t q = p - f0; // wraps when p < f0 -> fails the range test
+								if (q < 32u)
+									desc[q] = blk | (uint32_t(s) << 15);
+								++p;
+								if (twin)
+								{
+									q = p - f0;
+									if (q < 32u)
+										desc[q] = blk | (uint32_t(s) << 15) | (1u << 18);
+									++p;
+								}
+							}
+						}
+						f = sm.rowOff[row + 1];
+					}
+					__syncwarp();
+
+					// ---- one face per lane -> staging
+					if (uint32_t(lane) < nf)
+					{
+						const uint32_t de = desc[lane];
+						const uint32_t blk = de & 0x7fffu;
+						draw_face(a, cx, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
+					}
+					__syncwarp();
+
+					// ---- coalesced write-out
+					const unsigned long long face0 = firstFace + f0;
+					if (a.flags & MESH_F_RENDER)
+					{
+						float4* dst = a.vertices + face0 * 12ull;
+						const uint32_t n4 = nf * 12u;
+						for (uint32_t i = lane; i < n4; i += 32u)
+							dst[i] = stage[(i / 12u) * STAGE_FACE_F4 + (i % 12u)];
+					}
+					if (a.flags & MESH_F_COLLIDER)
+					{
+						// positions only: 3 float4 per face gathered from the staged vertices
+						float4* dst = a.collider + face0 * 3ull;
+						const float* sf = reinterpret_cast<const float*>(stage);
+						const uint32_t n4 = nf * 3u;
+						for (uint32_t i = lane; i < n4; i += 32u)
+						{
+							const uint32_t face = i / 3u, j = i % 3u;
+							float e[4];
+#pragma unroll
+							for (int m = 0; m < 4; ++m)
+							{
+								const uint32_t k = j * 4u + m; // float k of the face's 12 position floats
+								e[m] = sf[face * (STAGE_FACE_F4 * 4) + (k / 3u) * 12u + (k % 3u)];
+							}
+							dst[i] = make_float4(e[0], e[1], e[2], e[3]);
+						}
+					}
+					{
+						// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
+						uint2* dst = a.indices + face0 * 3ull;
+						const uint32_t n2 = nf * 3u;
+						for (uint32_t i = lane; i < n2; i += 32u)
+						{
+							const uint32_t face = i / 3u, j = i % 3u;
+							const uint32_t b = (f0 + face) * 4u;
+							dst[i] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
+						}
+					}
+					__syncwarp();
+				}
+			}
+			__syncthreads(); // staging / ids free for the next chunk
+		}
+	}
+
+	// =====================================================================================================================
+	// exclusive scan of face counts -> first face per job, total, and the worklist of jobs that have faces (single CTA)
+	__global__ void __launch_bounds__(1024, 1) mesh_scan_kernel(const uint32_t* __restrict__ faceCount, uint32_t nJobs,
+	                                                            unsigned long long* __restrict__ firstFace, uint32_t* __restrict__ worklist,
+	                                                            uint32_t* __restrict__ nWork, unsigned long long* __restrict__ totalFaces,
+	                                                            unsigned long long faceBase)
+	{
+		__shared__ unsigned long long wsF[32];
+		__shared__ uint32_t wsW[32];
+		__shared__ unsigned long long carryF;
+		__shared__ uint32_t carryW;
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		if (tid == 0)
+		{
+			carryF = faceBase;
+			carryW = 0;
+		}
+		__syncthreads();
+		for (uint32_t base = 0; base < nJobs; base += 1024u)
+		{
+			const uint32_t i = base + tid;
+			const uint32_t c = i < nJobs ? faceCount[i] : 0u;
+			unsigned long long inF = c;
+			uint32_t inW = c ? 1u : 0u;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				unsigned long long nf = __shfl_up_sync(0xffffffffu, inF, o);
+				uint32_t nw = __shfl_up_sync(0xffffffffu, inW, o);
+				if (lane >= o)
+				{
+					inF += nf;
+					inW += nw;
+				}
+			}
+			if (lane == 31)
+			{
+				wsF[warp] = inF;
+				wsW[warp] = inW;
+			}
+			__syncthreads();
+			if (warp == 0)
+			{
+				unsigned long long sf = wsF[lane], xf = sf;
+				uint32_t sw = wsW[lane], xw = sw;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					unsigned long long nf = __shfl_up_sync(0xffffffffu, xf, o);
+					uint32_t nw = __shfl_up_sync(0xffffffffu, xw, o);
+					if (lane >= o)
+					{
+						xf += nf;
+						xw += nw;
+					}
+				}
+				wsF[lane] = xf - sf;
+				wsW[lane] = xw - sw;
+			}
+			__syncthreads();
+			const unsigned long long exF = carryF + wsF[warp] + inF - c;
+			const uint32_t exW = carryW + wsW[warp] + inW - (c ? 1u : 0u);
+			if (i < nJobs)
+			{
+				firstFace[i] = exF;
+				if (c)
+					worklist[exW] = i;
+			}
+			__syncthreads();
+			if (tid == 1023)
+			{
+				carryF = exF + c;
+				carryW = exW + (c ? 1u : 0u);
+			}
+			__syncthreads();
+		}
+		if (tid == 0)
+		{
+			*nWork = carryW;
+			*totalFaces = carryF - faceBase;
+		}
+	}
+
+	// ---- launchers ----
+	size_t mesh_count_smem_bytes() { return sizeof(CountSmem); }
+	size_t mesh_emit_smem_bytes() { return sizeof(MeshSmem); }
+
+	cudaError_t mesh_kernels_init()
+	{
+		cudaError_t e = cudaFuncSetAttribute(mesh_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CountSmem)));
+		if (e != cudaSuccess)
+			return e;
+		return cudaFuncSetAttribute(mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MeshSmem)));
+	}
+
+	void launch_mesh_count(const MeshArgs& a, int grid, cudaStream_t st)
+	{
+		mesh_count_kernel<<<grid, MESH_THREADS, sizeof(CountSmem), st>>>(a);
+	}
+
+	void launch_mesh_scan(const uint32_t* faceCount, uint32_t nJobs, unsigned long long* firstFace, uint32_t* worklist, uint32_t* nWork,
+	                      unsigned long long* totalFaces, unsigned long long faceBase, cudaStream_t st)
+	{
+		mesh_scan_kernel<<<1, 1024, 0, st>>>(faceCount, nJobs, firstFace, worklist, nWork, totalFaces, faceBase);
+	}
+
+	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st)
+	{
+		mesh_emit_kernel<<<grid, MESH_THREADS, sizeof(MeshSmem), st>>>(a);
+	}
+}

@@ -1,0 +1,1355 @@
+// tsom_host.cu — host side of libtsom_b200.so: context / container bookkeeping and the C ABI of include/tsom_b200.h.
+// Everything that computes runs in the sm_100a kernels of mesh_kernels.cu / gen_kernels.cu; there is no CPU fallback.
+#include "../../include/tsom_b200.h"
+#include "tsom_kernels.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <random>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+// halo pointer encoding (mirrors HALO_CONTIG / HALO_ROWS of tsom_device.cuh, which is device-only)
+static inline unsigned long long tsomk_halo_contig() { return 0ull; }
+static inline unsigned long long tsomk_halo_rows() { return 1ull; }
+
+namespace
+{
+	thread_local std::string g_lastError;
+
+	int Fail(int code, const std::string& msg)
+	{
+		g_lastError = msg;
+		return code;
+	}
+
+#define TSOM_CUDA(expr)                                                                                          \
+	do                                                                                                           \
+	{                                                                                                            \
+		cudaError_t _e = (expr);                                                                                 \
+		if (_e != cudaSuccess)                                                                                   \
+			return Fail(TSOM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+	} while (0)
+
+	constexpr int CS = TSOM_CHUNK_SIZE;
+	constexpr size_t NB = TSOM_CHUNK_BLOCKS;
+	constexpr size_t SLAB = 1024;
+
+	// reference include/CommonLib/Direction.hpp:83-90 (world axes)
+	const int kChunkDirOffset[6][3] = { { 0, 0, 1 }, { 0, -1, 0 }, { 0, 0, -1 }, { -1, 0, 0 }, { 1, 0, 0 }, { 0, 1, 0 } };
+
+	struct Key
+	{
+		int32_t x, y, z;
+		bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; }
+		bool operator<(const Key& o) const { return std::tie(x, y, z) < std::tie(o.x, o.y, o.z); }
+	};
+	struct KeyHash
+	{
+		size_t operator()(const Key& k) const
+		{
+			uint64_t h = uint64_t(uint32_t(k.x)) * 0x9E3779B97F4A7C15ull;
+			h ^= uint64_t(uint32_t(k.y)) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+			h ^= uint64_t(uint32_t(k.z)) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+			return size_t(h);
+		}
+	};
+
+	// grow-only device scratch buffer
+	template<typename T> struct DevBuf
+	{
+		T* ptr = nullptr;
+		size_t cap = 0;
+		cudaError_t Ensure(size_t n)
+		{
+			if (n <= cap)
+				return cudaSuccess;
+			size_t want = std::max(n, cap * 2);
+			T* p = nullptr;
+			cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+			if (e != cudaSuccess)
+				return e;
+			if (ptr)
+				cudaFree(ptr);
+			ptr = p;
+			cap = want;
+			return cudaSuccess;
+		}
+		void Free()
+		{
+			if (ptr)
+				cudaFree(ptr);
+			ptr = nullptr;
+			cap = 0;
+		}
+	};
+
+	// ---- product-side restatement of the small third-party pieces the host needs ----
+
+	// siv::PerlinNoise::reseed (v3.0.0): iota then the library's own shuffle driven by std::mt19937{seed}
+	void PerlinPermutation(uint32_t seed, uint8_t out[256])
+	{
+		std::mt19937 urbg{ seed };
+		for (int i = 0; i < 256; ++i)
+			out[i] = uint8_t(i);
+		for (uint64_t i = 1; i < 256; ++i)
+			std::swap(out[i], out[uint64_t(urbg()) % (i + 1)]);
+	}
+
+	// A URBG with std::minstd_rand's range that replays two chosen outputs, so the threshold below is derived from the very
+	// std::generate_canonical the reference's std::bernoulli_distribution uses (libstdc++).
+	struct ReplayEngine
+	{
+		using result_type = uint_fast32_t;
+		static constexpr result_type min() { return 1u; }
+		static constexpr result_type max() { return 2147483646u; }
+		result_type v[2];
+		int i = 0;
+		result_type operator()() { return v[i++ & 1]; }
+	};
+
+	bool BernoulliFromDraws(uint32_t u1, uint32_t u2)
+	{
+		ReplayEngine e{ { u1, u2 } };
+		return std::generate_canonical<double, std::numeric_limits<double>::digits>(e) < 0.9;
+	}
+
+	// Integer form of the decision: true <=> (u2-1, u1-1) < (bStar, aStar) lexicographically.  Verified at start-up.
+	bool DeriveBernoulliThreshold(uint32_t& bStar, uint32_t& aStar)
+	{
+		const uint32_t R = 2147483646u; // outputs u in [1, R], a = u - 1 in [0, R)
+		// smallest b for which not every a is accepted
+		uint32_t lo = 0, hi = R; // invariant: all b < lo fully accepted
+		while (lo < hi)
+		{
+			uint32_t mid = lo + (hi - lo) / 2;
+			if (BernoulliFromDraws(R, mid + 1)) // a = R-1 (largest) still accepted -> every a accepted
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		bStar = lo;
+		if (bStar >= R)
+			return false;
+		// number of accepted a at b = bStar (accepted set is a prefix)
+		uint32_t alo = 0, ahi = R;
+		while (alo < ahi)
+		{
+			uint32_t mid = alo + (ahi - alo) / 2;
+			if (BernoulliFromDraws(mid + 1, bStar + 1))
+				alo = mid + 1;
+			else
+				ahi = mid;
+		}
+		aStar = alo;
+		// the next b must reject everything, otherwise the two-level form would not be exact
+		if (bStar + 1 < R && BernoulliFromDraws(1, bStar + 2))
+			return false;
+		return true;
+	}
+
+	struct F3h
+	{
+		float x, y, z;
+	};
+
+	// Nz::Quaternionf::RotationBetween(from, Up) for an axis-aligned `from` (third-party arithmetic #3)
+	void RotationBetween(F3h from, F3h to, float q[4])
+	{
+		auto dot = [](F3h a, F3h b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+		auto cross = [](F3h a, F3h b) { return F3h{ a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; };
+		float d = dot(from, to);
+		if (d < -0.999999f)
+		{
+			F3h axis = dot(from, F3h{ 1.f, 0.f, 0.f }) < 0.999999f ? cross(F3h{ 1.f, 0.f, 0.f }, from) : cross(F3h{ 0.f, 1.f, 0.f }, from);
+			float n = std::sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+			if (n > 0.f)
+			{
+				float inv = 1.f / n;
+				axis.x *= inv;
+				axis.y *= inv;
+				axis.z *= inv;
+			}
+			float half = 3.14159265358979323846f / 2.f;
+			float s = std::sin(half), c = std::cos(half);
+			q[0] = c;
+			q[1] = axis.x * s;
+			q[2] = axis.y * s;
+			q[3] = axis.z * s;
+		}
+		else if (d > 0.999999f)
+		{
+			q[0] = 1.f;
+			q[1] = q[2] = q[3] = 0.f;
+		}
+		else
+		{
+			float norm = std::sqrt(dot(from, from) * dot(to, to));
+			F3h c = cross(from, to);
+			float w = norm + d;
+			float n = std::sqrt(w * w + c.x * c.x + c.y * c.y + c.z * c.z);
+			float inv = n > 0.f ? 1.f / n : 1.f;
+			q[0] = w * inv;
+			q[1] = c.x * inv;
+			q[2] = c.y * inv;
+			q[3] = c.z * inv;
+		}
+	}
+}
+
+// =====================================================================================================================
+struct tsom_ctx
+{
+	int device = 0;
+	int numSMs = 148;
+	cudaStream_t stream = nullptr;
+	uint64_t launches = 0;
+
+	// block table
+	uint8_t* dFlags = nullptr;
+	uint32_t* dTex = nullptr;
+	uint32_t nTypes = 0;
+
+	// arenas (faces)
+	float4* dVertices = nullptr;
+	uint2* dIndices = nullptr;
+	float4* dCollider = nullptr;
+	uint64_t capVertices = 0, capIndices = 0, capCollider = 0;
+	uint64_t totalFaces = 0;
+
+	// per-call scratch
+	DevBuf<uint32_t> jobSlot, faceCount, worklist;
+	DevBuf<unsigned long long> firstFace;
+	DevBuf<float> gravity;
+	DevBuf<tsomk::EditDev> edits;
+	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
+	uint32_t* hSmall = nullptr; // pinned mirror
+	void* hPinned = nullptr;    // pinned staging for small result read-backs
+	size_t hPinnedBytes = 0;
+
+	float quat[6][4];
+	uint32_t bStar = 0, aStar = 0, aInv = 0;
+
+	cudaError_t EnsurePinned(size_t bytes)
+	{
+		if (bytes <= hPinnedBytes)
+			return cudaSuccess;
+		if (hPinned)
+			cudaFreeHost(hPinned);
+		hPinned = nullptr;
+		hPinnedBytes = 0;
+		cudaError_t e = cudaMallocHost(&hPinned, bytes);
+		if (e == cudaSuccess)
+			hPinnedBytes = bytes;
+		return e;
+	}
+};
+
+struct tsom_container
+{
+	tsom_ctx* ctx = nullptr;
+	uint32_t capacity = 0;
+	float tile = 1.f;
+	float center[3] = { 0.f, 0.f, 0.f };
+
+	uint16_t* dBlocks = nullptr;
+	uint16_t* dXslabs = nullptr;
+	unsigned long long* dHalo = nullptr;
+	int4* dChunkIdx = nullptr;
+	uint8_t* dInvalid = nullptr;
+
+	std::unordered_map<Key, uint32_t, KeyHash> slotOf;
+	std::vector<Key> idxOf;
+	std::vector<uint8_t> exists, hasContent, hostInvalid;
+	std::vector<uint32_t> freeSlots;
+	uint32_t highWater = 0;
+	bool topoDirty = true;
+
+	// remote neighbours (other ranks) and the ghost slabs that mirror their boundary layers
+	struct Remote
+	{
+		int rank;
+		uint32_t slot;
+	};
+	std::unordered_map<Key, Remote, KeyHash> remotes;
+	struct Peer
+	{
+		const uint16_t* blocks = nullptr;
+		const uint16_t* xslabs = nullptr;
+		bool ipc = false;
+	};
+	std::map<int, Peer> peers;
+	DevBuf<uint16_t> ghostSlabs;
+	DevBuf<tsomk::GhostDesc> ghostDescs;
+	uint32_t nGhost = 0;
+
+	// terrain tables of the last generate call
+	DevBuf<int16_t> terrain;
+	uint8_t* dPerm = nullptr;
+	DevBuf<int> slotGrid;
+
+	uint32_t SlotOf(const Key& k) const
+	{
+		auto it = slotOf.find(k);
+		return it == slotOf.end() ? 0xFFFFFFFFu : it->second;
+	}
+};
+
+namespace
+{
+	int AddChunk(tsom_container* c, const Key& k, uint32_t* slotOut)
+	{
+		auto it = c->slotOf.find(k);
+		if (it != c->slotOf.end())
+		{
+			if (slotOut)
+				*slotOut = it->second;
+			return TSOM_OK;
+		}
+		uint32_t slot;
+		if (!c->freeSlots.empty())
+		{
+			slot = c->freeSlots.back();
+			c->freeSlots.pop_back();
+		}
+		else
+		{
+			if (c->highWater >= c->capacity)
+				return Fail(TSOM_ERR_CAPACITY, "container is full");
+			slot = c->highWater++;
+		}
+		c->slotOf.emplace(k, slot);
+		c->idxOf[slot] = k;
+		c->exists[slot] = 1;
+		c->hasContent[slot] = 0;
+		c->hostInvalid[slot] = 0;
+		c->topoDirty = true;
+		if (slotOut)
+			*slotOut = slot;
+		return TSOM_OK;
+	}
+
+	// (re)build the per-chunk index and halo pointer tables and the ghost list, then upload them
+	int SyncTopology(tsom_container* c)
+	{
+		if (!c->topoDirty)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		const uint32_t n = c->highWater;
+		std::vector<int4> idx(n);
+		std::vector<unsigned long long> halo(size_t(n) * 6, 0ull);
+		std::vector<tsomk::GhostDesc> ghosts;
+
+		for (uint32_t s = 0; s < n; ++s)
+		{
+			if (!c->exists[s])
+			{
+				idx[s] = make_int4(0, 0, 0, 0);
+				continue;
+			}
+			const Key k = c->idxOf[s];
+			idx[s] = make_int4(k.x, k.y, k.z, c->hasContent[s] ? 1 : 0);
+			if (!c->hasContent[s])
+				continue;
+			for (int d = 0; d < 6; ++d)
+			{
+				const Key nk{ k.x + kChunkDirOffset[d][0], k.y + kChunkDirOffset[d][1], k.z + kChunkDirOffset[d][2] };
+				// which boundary layer of the neighbour faces us
+				const bool far = (d == TSOM_DOWN || d == TSOM_FRONT || d == TSOM_LEFT); // neighbour's layer 31
+				auto it = c->slotOf.find(nk);
+				if (it != c->slotOf.end())
+				{
+					const uint32_t ns = it->second;
+					if (!c->hasContent[ns])
+						continue; // !HasContent() => face drawn, same as no neighbour (Chunk.cpp:165-166)
+					const uint16_t* nb = c->dBlocks + size_t(ns) * NB;
+					const uint16_t* nx = c->dXslabs + size_t(ns) * 2 * SLAB;
+					unsigned long long e;
+					if (d == TSOM_UP || d == TSOM_DOWN)
+						e = reinterpret_cast<unsigned long long>(nb + (far ? 31 * SLAB : 0)) | tsomk_halo_contig();
+					else if (d == TSOM_BACK || d == TSOM_FRONT)
+						e = reinterpret_cast<unsigned long long>(nb + (far ? 31 * CS : 0)) | tsomk_halo_rows();
+					else
+						e = reinterpret_cast<unsigned long long>(nx + (far ? SLAB : 0)) | tsomk_halo_contig();
+					halo[size_t(s) * 6 + d] = e;
+					continue;
+				}
+				auto rt = c->remotes.find(nk);
+				if (rt != c->remotes.end())
+				{
+					auto pt = c->peers.find(rt->second.rank);
+					if (pt == c->peers.end())
+						return Fail(TSOM_ERR_INVALID, "remote neighbour's rank has no attached peer buffers");
+					const uint16_t* nb = pt->second.blocks + size_t(rt->second.slot) * NB;
+					const uint16_t* nx = pt->second.xslabs + size_t(rt->second.slot) * 2 * SLAB;
+					tsomk::GhostDesc g;
+					g.ghost = uint32_t(ghosts.size());
+					if (d == TSOM_UP || d == TSOM_DOWN)
+					{
+						g.src = nb + (far ? 31 * SLAB : 0);
+						g.contig = 1;
+					}
+					else if (d == TSOM_BACK || d == TSOM_FRONT)
+					{
+						g.src = nb + (far ? 31 * CS : 0);
+						g.contig = 0;
+					}
+					else
+					{
+						g.src = nx + (far ? SLAB : 0);
+						g.contig = 1;
+					}
+					ghosts.push_back(g);
+					halo[size_t(s) * 6 + d] = 1ull; // patched below once the ghost buffer address is known
+				}
+			}
+		}
+
+		c->nGhost = uint32_t(ghosts.size());
+		if (c->nGhost)
+		{
+			TSOM_CUDA(c->ghostSlabs.Ensure(size_t(c->nGhost) * SLAB));
+			TSOM_CUDA(c->ghostDescs.Ensure(c->nGhost));
+			TSOM_CUDA(cudaMemcpyAsync(c->ghostDescs.ptr, ghosts.data(), ghosts.size() * sizeof(tsomk::GhostDesc), cudaMemcpyHostToDevice, ctx->stream));
+			// second pass: ghost order == encounter order above
+			uint32_t g = 0;
+			for (uint32_t s = 0; s < n; ++s)
+				for (int d = 0; d < 6; ++d)
+					if (halo[size_t(s) * 6 + d] == 1ull)
+						halo[size_t(s) * 6 + d] = reinterpret_cast<unsigned long long>(c->ghostSlabs.ptr + size_t(g++) * SLAB) | tsomk_halo_contig();
+		}
+
+		if (n)
+		{
+			TSOM_CUDA(cudaMemcpyAsync(c->dChunkIdx, idx.data(), size_t(n) * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaMemcpyAsync(c->dHalo, halo.data(), halo.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the host vectors die at scope exit
+		}
+		c->topoDirty = false;
+		return TSOM_OK;
+	}
+
+	int EnsureArenas(tsom_ctx* ctx, uint64_t faces, uint32_t flags)
+	{
+		auto grow = [&](auto*& ptr, uint64_t& cap, size_t bytesPerFace) -> int {
+			if (faces <= cap)
+				return TSOM_OK;
+			uint64_t want = std::max<uint64_t>(faces, cap + cap / 4);
+			if (ptr)
+				cudaFree(ptr);
+			ptr = nullptr;
+			cap = 0;
+			void* p = nullptr;
+			cudaError_t e = cudaMalloc(&p, want * bytesPerFace);
+			if (e != cudaSuccess)
+				return Fail(TSOM_ERR_NOMEM, std::string("mesh arena cudaMalloc: ") + cudaGetErrorString(e));
+			ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(p);
+			cap = want;
+			return TSOM_OK;
+		};
+		int rc;
+		if ((rc = grow(ctx->dIndices, ctx->capIndices, TSOM_FACE_INDEX_BYTES)) != TSOM_OK)
+			return rc;
+		if ((flags & TSOM_MESH_RENDER) && (rc = grow(ctx->dVertices, ctx->capVertices, TSOM_FACE_VERTEX_BYTES)) != TSOM_OK)
+			return rc;
+		if ((flags & TSOM_MESH_COLLIDER) && (rc = grow(ctx->dCollider, ctx->capCollider, TSOM_FACE_COLLIDER_BYTES)) != TSOM_OK)
+			return rc;
+		return TSOM_OK;
+	}
+
+	uint64_t ArenaFaces(const tsom_ctx* ctx, uint32_t flags)
+	{
+		uint64_t cap = ctx->capIndices;
+		if (flags & TSOM_MESH_RENDER)
+			cap = std::min(cap, ctx->capVertices);
+		if (flags & TSOM_MESH_COLLIDER)
+			cap = std::min(cap, ctx->capCollider);
+		return cap;
+	}
+}
+
+// =====================================================================================================================
+extern "C"
+{
+	const char* tsom_last_error(void) { return g_lastError.c_str(); }
+	const char* tsom_version(void) { return "tsom_b200 0.1 (sm_100a)"; }
+
+	int tsom_create(int cuda_device, tsom_ctx** out)
+	{
+		if (!out)
+			return Fail(TSOM_ERR_INVALID, "out is null");
+		*out = nullptr;
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0)
+			return Fail(TSOM_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + " (libtsom_b200 has no CPU fallback)");
+		if (cuda_device < 0 || cuda_device >= count)
+			return Fail(TSOM_ERR_INVALID, "cuda_device out of range");
+		TSOM_CUDA(cudaSetDevice(cuda_device));
+		cudaDeviceProp prop;
+		TSOM_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+		if (prop.major < 10)
+			return Fail(TSOM_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; this library ships sm_100a code only");
+
+		auto ctx = std::make_unique<tsom_ctx>();
+		ctx->device = cuda_device;
+		ctx->numSMs = prop.multiProcessorCount;
+		TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		TSOM_CUDA(tsomk::mesh_kernels_init());
+		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
+		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
+		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
+
+		const F3h normals[6] = { { 0.f, 0.f, 1.f }, { 0.f, -1.f, 0.f }, { 0.f, 0.f, -1.f }, { -1.f, 0.f, 0.f }, { 1.f, 0.f, 0.f }, { 0.f, 1.f, 0.f } };
+		for (int d = 0; d < 6; ++d)
+			RotationBetween(normals[d], F3h{ 0.f, 1.f, 0.f }, ctx->quat[d]);
+
+		if (!DeriveBernoulliThreshold(ctx->bStar, ctx->aStar))
+			return Fail(TSOM_ERR_UNSUPPORTED, "std::bernoulli_distribution(0.9) over std::minstd_rand is not a two-level integer threshold on this standard library");
+		{
+			// 48271^-1 mod (2^31 - 1) by Fermat
+			auto mulmod = [](uint64_t a, uint64_t b) { return (a * b) % 2147483647ull; };
+			uint64_t r = 1, b = 48271, ex = 2147483647ull - 2;
+			while (ex)
+			{
+				if (ex & 1)
+					r = mulmod(r, b);
+				b = mulmod(b, b);
+				ex >>= 1;
+			}
+			ctx->aInv = uint32_t(r);
+		}
+		*out = ctx.release();
+		return TSOM_OK;
+	}
+
+	void tsom_destroy(tsom_ctx* ctx)
+	{
+		if (!ctx)
+			return;
+		cudaSetDevice(ctx->device);
+		cudaStreamSynchronize(ctx->stream);
+		cudaFree(ctx->dFlags);
+		cudaFree(ctx->dTex);
+		cudaFree(ctx->dVertices);
+		cudaFree(ctx->dIndices);
+		cudaFree(ctx->dCollider);
+		ctx->jobSlot.Free();
+		ctx->faceCount.Free();
+		ctx->worklist.Free();
+		ctx->firstFace.Free();
+		ctx->gravity.Free();
+		ctx->edits.Free();
+		cudaFree(ctx->dSmall);
+		cudaFreeHost(ctx->hSmall);
+		if (ctx->hPinned)
+			cudaFreeHost(ctx->hPinned);
+		cudaStreamDestroy(ctx->stream);
+		delete ctx;
+	}
+
+	void* tsom_stream(tsom_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+	int tsom_synchronize(tsom_ctx* ctx)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	uint64_t tsom_launch_count(tsom_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+	int tsom_set_block_table(tsom_ctx* ctx, const tsom_block_desc* blocks, uint32_t n)
+	{
+		if (!ctx || !blocks || n == 0 || n > 65535)
+			return Fail(TSOM_ERR_INVALID, "bad block table");
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		std::vector<uint8_t> flags(n);
+		std::vector<uint32_t> tex(size_t(n) * 6);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			flags[i] = uint8_t((blocks[i].has_collisions ? 1u : 0u) | (blocks[i].is_double_sided ? 2u : 0u) | (blocks[i].is_transparent ? 4u : 0u));
+			for (int d = 0; d < 6; ++d)
+				tex[size_t(i) * 6 + d] = blocks[i].tex[d];
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->dFlags);
+		cudaFree(ctx->dTex);
+		ctx->dFlags = nullptr;
+		ctx->dTex = nullptr;
+		TSOM_CUDA(cudaMalloc(&ctx->dFlags, n));
+		TSOM_CUDA(cudaMalloc(&ctx->dTex, size_t(n) * 6 * sizeof(uint32_t)));
+		TSOM_CUDA(cudaMemcpy(ctx->dFlags, flags.data(), n, cudaMemcpyHostToDevice));
+		TSOM_CUDA(cudaMemcpy(ctx->dTex, tex.data(), tex.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		ctx->nTypes = n;
+		return TSOM_OK;
+	}
+
+	int tsom_reserve_faces(tsom_ctx* ctx, uint64_t faces, uint32_t flags)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return EnsureArenas(ctx, faces, flags);
+	}
+
+	// ---------------------------------------------------------------------------------------------------- container
+	int tsom_container_create(tsom_ctx* ctx, uint32_t capacity_chunks, float tile_size, tsom_container** out)
+	{
+		if (!ctx || !out || capacity_chunks == 0)
+			return Fail(TSOM_ERR_INVALID, "bad container arguments");
+		*out = nullptr;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		auto c = std::make_unique<tsom_container>();
+		c->ctx = ctx;
+		c->capacity = capacity_chunks;
+		c->tile = tile_size;
+		cudaError_t e;
+		if ((e = cudaMalloc(&c->dBlocks, size_t(capacity_chunks) * NB * sizeof(uint16_t))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dXslabs, size_t(capacity_chunks) * 2 * SLAB * sizeof(uint16_t))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dHalo, size_t(capacity_chunks) * 6 * sizeof(unsigned long long))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dChunkIdx, size_t(capacity_chunks) * sizeof(int4))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dInvalid, capacity_chunks)) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dPerm, 6 * 256)) != cudaSuccess)
+		{
+			cudaFree(c->dBlocks);
+			cudaFree(c->dXslabs);
+			cudaFree(c->dHalo);
+			cudaFree(c->dChunkIdx);
+			cudaFree(c->dInvalid);
+			cudaFree(c->dPerm);
+			return Fail(TSOM_ERR_NOMEM, std::string("container cudaMalloc: ") + cudaGetErrorString(e));
+		}
+		TSOM_CUDA(cudaMemset(c->dInvalid, 0, capacity_chunks));
+		c->idxOf.resize(capacity_chunks);
+		c->exists.assign(capacity_chunks, 0);
+		c->hasContent.assign(capacity_chunks, 0);
+		c->hostInvalid.assign(capacity_chunks, 0);
+		*out = c.release();
+		return TSOM_OK;
+	}
+
+	void tsom_container_destroy(tsom_container* c)
+	{
+		if (!c)
+			return;
+		cudaSetDevice(c->ctx->device);
+		cudaStreamSynchronize(c->ctx->stream);
+		for (auto& [rank, p] : c->peers)
+		{
+			if (p.ipc)
+			{
+				cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.blocks));
+				cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.xslabs));
+			}
+		}
+		cudaFree(c->dBlocks);
+		cudaFree(c->dXslabs);
+		cudaFree(c->dHalo);
+		cudaFree(c->dChunkIdx);
+		cudaFree(c->dInvalid);
+		cudaFree(c->dPerm);
+		c->ghostSlabs.Free();
+		c->ghostDescs.Free();
+		c->terrain.Free();
+		c->slotGrid.Free();
+		delete c;
+	}
+
+	int tsom_container_add_chunks(tsom_container* c, const int32_t* chunk_indices, uint32_t n)
+	{
+		if (!c || (!chunk_indices && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, nullptr);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		return TSOM_OK;
+	}
+
+	int tsom_container_remove_chunk(tsom_container* c, const int32_t chunk_index[3])
+	{
+		if (!c || !chunk_index)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		Key k{ chunk_index[0], chunk_index[1], chunk_index[2] };
+		auto it = c->slotOf.find(k);
+		if (it == c->slotOf.end())
+			return Fail(TSOM_ERR_INVALID, "unknown chunk");
+		TSOM_CUDA(cudaSetDevice(c->ctx->device));
+		const uint32_t slot = it->second;
+		c->exists[slot] = 0;
+		c->hasContent[slot] = 0;
+		c->hostInvalid[slot] = 0;
+		TSOM_CUDA(cudaMemsetAsync(c->dInvalid + slot, 0, 1, c->ctx->stream));
+		c->freeSlots.push_back(slot);
+		c->slotOf.erase(it);
+		c->topoDirty = true;
+		return TSOM_OK;
+	}
+
+	uint32_t tsom_container_chunk_count(const tsom_container* c) { return c ? uint32_t(c->slotOf.size()) : 0; }
+
+	static int ResetCommon(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const void* src, cudaMemcpyKind kind)
+	{
+		if (!c || !chunk_indices || !src)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		// coalesce runs of consecutive slots into single copies
+		const uint16_t* s = static_cast<const uint16_t*>(src);
+		uint32_t i = 0;
+		while (i < n)
+		{
+			uint32_t j = i + 1;
+			while (j < n && slots[j] == slots[j - 1] + 1)
+				++j;
+			TSOM_CUDA(cudaMemcpyAsync(c->dBlocks + size_t(slots[i]) * NB, s + size_t(i) * NB, size_t(j - i) * NB * sizeof(uint16_t), kind, ctx->stream));
+			i = j;
+		}
+		TSOM_CUDA(ctx->jobSlot.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_build_xslabs(c->dBlocks, c->dXslabs, ctx->jobSlot.ptr, n, ctx->stream);
+		ctx->launches += n ? 1 : 0;
+		TSOM_CUDA(cudaGetLastError());
+		for (uint32_t k = 0; k < n; ++k)
+		{
+			if (!c->hasContent[slots[k]])
+				c->topoDirty = true;
+			c->hasContent[slots[k]] = 1;
+			c->hostInvalid[slots[k]] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // `slots` and possibly pageable `src` must outlive the copies
+		return TSOM_OK;
+	}
+
+	int tsom_chunks_reset(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint16_t* blocks_host)
+	{
+		return ResetCommon(c, chunk_indices, n, blocks_host, cudaMemcpyHostToDevice);
+	}
+
+	int tsom_chunks_reset_device(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const void* blocks_device)
+	{
+		return ResetCommon(c, chunk_indices, n, blocks_device, cudaMemcpyDeviceToDevice);
+	}
+
+	int tsom_chunks_get_content(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint16_t* blocks_host)
+	{
+		if (!c || !chunk_indices || !blocks_host)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_CUDA(cudaSetDevice(c->ctx->device));
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			uint32_t slot = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+			if (slot == 0xFFFFFFFFu || !c->hasContent[slot])
+				return Fail(TSOM_ERR_INVALID, "chunk is unknown or has no content");
+			TSOM_CUDA(cudaMemcpyAsync(blocks_host + size_t(i) * NB, c->dBlocks + size_t(slot) * NB, NB * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->ctx->stream));
+		}
+		TSOM_CUDA(cudaStreamSynchronize(c->ctx->stream));
+		return TSOM_OK;
+	}
+
+	const void* tsom_chunk_device_ptr(tsom_container* c, const int32_t chunk_index[3])
+	{
+		if (!c || !chunk_index)
+			return nullptr;
+		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
+		if (slot == 0xFFFFFFFFu || !c->hasContent[slot])
+			return nullptr;
+		return c->dBlocks + size_t(slot) * NB;
+	}
+
+	int tsom_chunk_slot(tsom_container* c, const int32_t chunk_index[3], uint32_t* slot_out)
+	{
+		if (!c || !chunk_index || !slot_out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
+		if (slot == 0xFFFFFFFFu)
+			return Fail(TSOM_ERR_INVALID, "unknown chunk");
+		*slot_out = slot;
+		return TSOM_OK;
+	}
+
+	// ---------------------------------------------------------------------------------------------------- generation
+	int tsom_planet_generate_chunks(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids, const int32_t* chunk_indices, uint32_t n)
+	{
+		if (!c || !chunk_count || !ids || (!chunk_indices && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+
+		int maxH[3];
+		for (int k = 0; k < 3; ++k)
+			maxH[k] = ((int(chunk_count[k]) + 1) / 2) * CS; // Planet.cpp:176-177
+
+		// bounding box of the requested chunks + the reference's own precondition (Nz::SafeCaster at Planet.cpp:199: depth >= 0)
+		int lo[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, hi[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			const int32_t* ci = chunk_indices + size_t(i) * 3;
+			for (int k = 0; k < 3; ++k)
+			{
+				lo[k] = std::min(lo[k], ci[k]);
+				hi[k] = std::max(hi[k], ci[k]);
+			}
+			// world coordinate ranges: X from cx, Y(up) from cy, Z from cz; depth crosses Y/Z (Planet.cpp:199-203)
+			auto maxAbs = [](int cidx) { int a = cidx * CS - CS / 2, b = a + CS - 1; return std::max(std::abs(a), std::abs(b)); };
+			if (maxAbs(ci[0]) > maxH[0] || maxAbs(ci[2]) > maxH[1] || maxAbs(ci[1]) > maxH[2])
+				return Fail(TSOM_ERR_UNSUPPORTED, "chunk lies outside +-maxHeight: the reference's depth computation asserts (Nz::SafeCaster, Planet.cpp:199)");
+		}
+
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		// generation reads chunkIdx on the device: make sure new chunks are there
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (!c->hasContent[slots[i]])
+				c->topoDirty = true;
+			c->hasContent[slots[i]] = 1;
+			c->hostInvalid[slots[i]] = 0x80u | 0x3Fu;
+		}
+		int rc = SyncTopology(c);
+		if (rc != TSOM_OK)
+			return rc;
+
+		// terrain tables over the bounding box
+		tsomk::TerrainArgs ta{};
+		size_t total = 0;
+		for (int k = 0; k < 3; ++k)
+		{
+			ta.tileOrigin[k] = lo[k];
+			ta.tileCount[k] = hi[k] - lo[k] + 1;
+			ta.maxH[k] = maxH[k];
+		}
+		const size_t tilesX = size_t(ta.tileCount[1]) * ta.tileCount[2], tilesY = size_t(ta.tileCount[0]) * ta.tileCount[2], tilesZ = size_t(ta.tileCount[0]) * ta.tileCount[1];
+		const size_t tiles[6] = { tilesZ, tilesY, tilesZ, tilesX, tilesX, tilesY }; // Direction order: Back Down Front Left Right Up
+		for (int d = 0; d < 6; ++d)
+		{
+			ta.terrainOffset[d] = total;
+			total += tiles[d] * SLAB;
+		}
+		TSOM_CUDA(c->terrain.Ensure(total));
+		ta.terrain = c->terrain.ptr;
+		uint8_t perm[6 * 256];
+		for (int d = 0; d < 6; ++d)
+			PerlinPermutation(seed + unsigned(d), perm + d * 256); // Planet.cpp:179-181
+		TSOM_CUDA(cudaMemcpyAsync(c->dPerm, perm, sizeof(perm), cudaMemcpyHostToDevice, ctx->stream));
+		ta.perm = c->dPerm;
+		tsomk::launch_terrain(ta, ctx->stream);
+		ctx->launches += 6;
+		TSOM_CUDA(cudaGetLastError());
+
+		TSOM_CUDA(ctx->jobSlot.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+		tsomk::GenArgs ga{};
+		ga.blocks = c->dBlocks;
+		ga.xslabs = c->dXslabs;
+		ga.chunkIdx = c->dChunkIdx;
+		ga.jobSlot = ctx->jobSlot.ptr;
+		ga.nJobs = n;
+		ga.seed = seed;
+		for (int k = 0; k < 3; ++k)
+		{
+			ga.maxH[k] = maxH[k];
+			ga.tileOrigin[k] = ta.tileOrigin[k];
+			ga.tileCount[k] = ta.tileCount[k];
+		}
+		ga.terrain = c->terrain.ptr;
+		for (int d = 0; d < 6; ++d)
+			ga.terrainOffset[d] = ta.terrainOffset[d];
+		ga.dirt = ids->dirt;
+		ga.grass = ids->grass;
+		ga.stone = ids->stone;
+		ga.stoneMossy = ids->stone_mossy;
+		ga.snow = ids->snow;
+		ga.bStar = ctx->bStar;
+		ga.aStar = ctx->aStar;
+		ga.aInv = ctx->aInv;
+		tsomk::launch_generate(ga, int(n), ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // blocking like Planet::GenerateChunks (WaitForTasks, Planet.cpp:402)
+		return TSOM_OK;
+	}
+
+	int tsom_planet_generate(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids)
+	{
+		if (!c || !chunk_count || !ids)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		const uint64_t n = uint64_t(chunk_count[0]) * chunk_count[1] * chunk_count[2];
+		if (n == 0 || n > c->capacity)
+			return Fail(TSOM_ERR_CAPACITY, "chunk_count exceeds the container capacity");
+		std::vector<int32_t> idx;
+		idx.reserve(n * 3);
+		// Planet.cpp:387-393: z, y, x loops; indices = (x, y, z) - chunkCount / 2
+		for (int cz = 0; cz < int(chunk_count[2]); ++cz)
+			for (int cy = 0; cy < int(chunk_count[1]); ++cy)
+				for (int cx = 0; cx < int(chunk_count[0]); ++cx)
+				{
+					idx.push_back(cx - int(chunk_count[0] / 2));
+					idx.push_back(cy - int(chunk_count[1] / 2));
+					idx.push_back(cz - int(chunk_count[2] / 2));
+				}
+		return tsom_planet_generate_chunks(c, seed, chunk_count, ids, idx.data(), uint32_t(n));
+	}
+
+	int tsom_planet_generate_platform(tsom_container* c, int up_direction, const int32_t platform_center[3], const tsom_platform_blocks* ids)
+	{
+		if (!c || !platform_center || !ids || up_direction < 0 || up_direction > 5)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		// dense slot grid over the bounding box of existing chunks
+		int lo[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, hi[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
+		for (auto& [k, s] : c->slotOf)
+		{
+			const int v[3] = { k.x, k.y, k.z };
+			for (int a = 0; a < 3; ++a)
+			{
+				lo[a] = std::min(lo[a], v[a]);
+				hi[a] = std::max(hi[a], v[a]);
+			}
+		}
+		if (c->slotOf.empty())
+			return TSOM_OK;
+		tsomk::PlatformArgs pa{};
+		size_t cells = 1;
+		for (int a = 0; a < 3; ++a)
+		{
+			pa.gridOrigin[a] = lo[a];
+			pa.gridDim[a] = hi[a] - lo[a] + 1;
+			cells *= size_t(pa.gridDim[a]);
+		}
+		if (cells > (size_t(1) << 28))
+			return Fail(TSOM_ERR_UNSUPPORTED, "chunk bounding box too large for the platform slot grid");
+		std::vector<int> grid(cells, -1);
+		for (auto& [k, s] : c->slotOf)
+			if (c->hasContent[s])
+				grid[(size_t(k.z - lo[2]) * pa.gridDim[1] + size_t(k.y - lo[1])) * pa.gridDim[0] + size_t(k.x - lo[0])] = int(s);
+		TSOM_CUDA(c->slotGrid.Ensure(cells));
+		TSOM_CUDA(cudaMemcpyAsync(c->slotGrid.ptr, grid.data(), cells * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		pa.blocks = c->dBlocks;
+		pa.xslabs = c->dXslabs;
+		pa.invalidMask = c->dInvalid;
+		pa.slotGrid = c->slotGrid.ptr;
+		pa.upDirection = up_direction;
+		for (int a = 0; a < 3; ++a)
+			pa.center[a] = platform_center[a];
+		pa.copper = ids->copper_block;
+		pa.stoneBricks = ids->stone_bricks;
+		pa.planks = ids->planks;
+		tsomk::launch_platform(pa, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	// ---------------------------------------------------------------------------------------------------- edits / dirty
+	int tsom_apply_edits(tsom_container* c, const tsom_edit* edits, uint32_t n)
+	{
+		if (!c || (!edits && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		TSOM_CUDA(ctx->EnsurePinned(size_t(n) * sizeof(tsomk::EditDev)));
+		auto* staged = static_cast<tsomk::EditDev*>(ctx->hPinned);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			const tsom_edit& e = edits[i];
+			if (e.x >= CS || e.y >= CS || e.z >= CS)
+				return Fail(TSOM_ERR_INVALID, "edit coordinates out of range");
+			uint32_t slot = c->SlotOf(Key{ e.chunk[0], e.chunk[1], e.chunk[2] });
+			if (slot != 0xFFFFFFFFu && !c->hasContent[slot])
+				slot = 0xFFFFFFFFu;
+			staged[i].slot = slot;
+			staged[i].packed = uint32_t(e.x) | (uint32_t(e.y) << 5) | (uint32_t(e.z) << 10) | (uint32_t(e.block) << 16);
+		}
+		TSOM_CUDA(ctx->edits.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->edits.ptr, staged, size_t(n) * sizeof(tsomk::EditDev), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_apply_edits(c->dBlocks, c->dXslabs, c->dInvalid, ctx->edits.ptr, n, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the pinned staging buffer is reused by the next call
+		return TSOM_OK;
+	}
+
+	int tsom_collect_dirty(tsom_container* c, int32_t* chunk_indices_out, uint32_t cap, uint32_t* n_out, int clear)
+	{
+		if (!c || !n_out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		const uint32_t n = c->highWater;
+		std::vector<uint8_t> mask(n, 0);
+		if (n)
+		{
+			TSOM_CUDA(ctx->EnsurePinned(n));
+			TSOM_CUDA(cudaMemcpyAsync(ctx->hPinned, c->dInvalid, n, cudaMemcpyDeviceToHost, ctx->stream));
+			if (clear)
+				TSOM_CUDA(cudaMemsetAsync(c->dInvalid, 0, n, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			std::memcpy(mask.data(), ctx->hPinned, n);
+		}
+		std::vector<Key> dirty;
+		std::vector<uint8_t> seen(n, 0);
+		for (uint32_t s = 0; s < n; ++s)
+		{
+			const uint8_t m = mask[s] | c->hostInvalid[s];
+			if (clear)
+				c->hostInvalid[s] = 0;
+			if (!(m & 0x80u) || !c->exists[s] || !c->hasContent[s])
+				continue;
+			if (!seen[s])
+			{
+				seen[s] = 1;
+				dirty.push_back(c->idxOf[s]);
+			}
+			const Key k = c->idxOf[s];
+			for (int d = 0; d < 6; ++d)
+			{
+				if (!(m & (1u << d)))
+					continue;
+				uint32_t ns = c->SlotOf(Key{ k.x + kChunkDirOffset[d][0], k.y + kChunkDirOffset[d][1], k.z + kChunkDirOffset[d][2] });
+				if (ns == 0xFFFFFFFFu || !c->hasContent[ns] || seen[ns])
+					continue;
+				seen[ns] = 1;
+				dirty.push_back(c->idxOf[ns]);
+			}
+		}
+		std::sort(dirty.begin(), dirty.end());
+		*n_out = uint32_t(dirty.size());
+		if (chunk_indices_out)
+		{
+			for (uint32_t i = 0; i < dirty.size() && i < cap; ++i)
+			{
+				chunk_indices_out[i * 3 + 0] = dirty[i].x;
+				chunk_indices_out[i * 3 + 1] = dirty[i].y;
+				chunk_indices_out[i * 3 + 2] = dirty[i].z;
+			}
+		}
+		return TSOM_OK;
+	}
+
+	// ---------------------------------------------------------------------------------------------------- meshing
+	int tsom_mesh(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, tsom_mesh_view* views_out)
+	{
+		if (!c || !params)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		const uint32_t flags = params->flags;
+		if (!(flags & (TSOM_MESH_RENDER | TSOM_MESH_COLLIDER)))
+			return Fail(TSOM_ERR_INVALID, "flags must request TSOM_MESH_RENDER and/or TSOM_MESH_COLLIDER");
+		if (!ctx->dFlags)
+			return Fail(TSOM_ERR_INVALID, "no block table: call tsom_set_block_table first");
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+
+		std::vector<uint32_t> slots;
+		if (chunk_indices)
+		{
+			slots.resize(n);
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				slots[i] = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+				if (slots[i] == 0xFFFFFFFFu)
+					return Fail(TSOM_ERR_INVALID, "tsom_mesh: unknown chunk");
+			}
+		}
+		else
+		{
+			for (uint32_t s = 0; s < c->highWater; ++s)
+				if (c->exists[s] && c->hasContent[s])
+					slots.push_back(s);
+			if (views_out && n != slots.size())
+				return Fail(TSOM_ERR_INVALID, "tsom_mesh: with chunk_indices == NULL, n must equal the number of chunks with content");
+			n = uint32_t(slots.size());
+		}
+		ctx->totalFaces = 0;
+		if (n == 0)
+			return TSOM_OK;
+
+		int rc = SyncTopology(c);
+		if (rc != TSOM_OK)
+			return rc;
+
+		TSOM_CUDA(ctx->jobSlot.Ensure(n));
+		TSOM_CUDA(ctx->faceCount.Ensure(n));
+		TSOM_CUDA(ctx->worklist.Ensure(n));
+		TSOM_CUDA(ctx->firstFace.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		if (params->gravity_centers)
+		{
+			TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * 3));
+			TSOM_CUDA(cudaMemcpyAsync(ctx->gravity.ptr, params->gravity_centers, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		}
+		TSOM_CUDA(cudaMemsetAsync(ctx->dSmall, 0, 8 * sizeof(uint32_t), ctx->stream));
+		if (ArenaFaces(ctx, flags) == 0 && (rc = EnsureArenas(ctx, 1u << 16, flags)) != TSOM_OK)
+			return rc;
+
+		tsomk::MeshArgs a{};
+		a.blocks = c->dBlocks;
+		a.halo = c->dHalo;
+		a.chunkIdx = c->dChunkIdx;
+		a.jobSlot = ctx->jobSlot.ptr;
+		a.gravity = params->gravity_centers ? ctx->gravity.ptr : nullptr;
+		a.nJobs = n;
+		a.blkFlags = ctx->dFlags;
+		a.blkTex = ctx->dTex;
+		a.nTypes = ctx->nTypes;
+		a.faceCount = ctx->faceCount.ptr;
+		a.firstFace = ctx->firstFace.ptr;
+		a.worklist = ctx->worklist.ptr;
+		a.nWork = ctx->dSmall + 2;
+		a.overflow = ctx->dSmall + 3;
+		a.flags = flags;
+		a.tile = c->tile;
+		a.deformRadius = params->deform_radius;
+		std::memcpy(a.center, c->center, sizeof(a.center));
+		std::memcpy(a.quat, ctx->quat, sizeof(a.quat));
+
+		auto launchEmit = [&]() {
+			a.vertices = ctx->dVertices;
+			a.indices = ctx->dIndices;
+			a.collider = ctx->dCollider;
+			a.arenaFaces = ArenaFaces(ctx, flags);
+			a.jobCounter = ctx->dSmall + 1;
+			tsomk::launch_mesh_emit(a, int(std::min<uint32_t>(n, uint32_t(ctx->numSMs))), ctx->stream);
+			ctx->launches += 1;
+		};
+
+		a.jobCounter = ctx->dSmall + 0;
+		tsomk::launch_mesh_count(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
+		tsomk::launch_mesh_scan(ctx->faceCount.ptr, n, ctx->firstFace.ptr, ctx->worklist.ptr, ctx->dSmall + 2, reinterpret_cast<unsigned long long*>(ctx->dSmall + 4), 0ull, ctx->stream);
+		ctx->launches += 2;
+		launchEmit();
+		TSOM_CUDA(cudaGetLastError());
+
+		// read back totals (+ views)
+		const size_t viewBytes = views_out ? size_t(n) * (sizeof(uint32_t) + sizeof(unsigned long long)) : 0;
+		TSOM_CUDA(ctx->EnsurePinned(std::max<size_t>(viewBytes, 64)));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall, ctx->dSmall, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		auto* hFirst = static_cast<unsigned long long*>(ctx->hPinned);
+		auto* hCount = reinterpret_cast<uint32_t*>(hFirst + n);
+		if (views_out)
+		{
+			TSOM_CUDA(cudaMemcpyAsync(hFirst, ctx->firstFace.ptr, size_t(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+			TSOM_CUDA(cudaMemcpyAsync(hCount, ctx->faceCount.ptr, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+
+		unsigned long long total;
+		std::memcpy(&total, ctx->hSmall + 4, sizeof(total));
+		if (ctx->hSmall[3] != 0)
+		{
+			// arenas were too small: grow to the exact need and emit again (counts and offsets are still valid)
+			if ((rc = EnsureArenas(ctx, total, flags)) != TSOM_OK)
+				return rc;
+			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 1, 0, sizeof(uint32_t), ctx->stream));
+			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, sizeof(uint32_t), ctx->stream));
+			launchEmit();
+			TSOM_CUDA(cudaGetLastError());
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+		ctx->totalFaces = total;
+		if (views_out)
+		{
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				views_out[i].first_face = hFirst[i];
+				views_out[i].face_count = hCount[i];
+				views_out[i].reserved = 0;
+			}
+		}
+		return TSOM_OK;
+	}
+
+	int tsom_mesh_arenas(tsom_ctx* ctx, const void** vertices, const void** indices, const void** collider_positions, uint64_t* total_faces)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		if (vertices)
+			*vertices = ctx->dVertices;
+		if (indices)
+			*indices = ctx->dIndices;
+		if (collider_positions)
+			*collider_positions = ctx->dCollider;
+		if (total_faces)
+			*total_faces = ctx->totalFaces;
+		return TSOM_OK;
+	}
+
+	int tsom_mesh_copy_to_host(tsom_ctx* ctx, uint64_t first_face, uint64_t face_count, void* vertices, uint32_t* indices, float* collider_positions)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		if (first_face + face_count > ctx->totalFaces)
+			return Fail(TSOM_ERR_INVALID, "face range exceeds the last mesh result");
+		if (face_count == 0)
+			return TSOM_OK;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		if (vertices)
+		{
+			if (!ctx->dVertices)
+				return Fail(TSOM_ERR_INVALID, "last tsom_mesh call did not produce render vertices");
+			TSOM_CUDA(cudaMemcpyAsync(vertices, reinterpret_cast<const char*>(ctx->dVertices) + first_face * TSOM_FACE_VERTEX_BYTES, face_count * TSOM_FACE_VERTEX_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		if (indices)
+			TSOM_CUDA(cudaMemcpyAsync(indices, reinterpret_cast<const char*>(ctx->dIndices) + first_face * TSOM_FACE_INDEX_BYTES, face_count * TSOM_FACE_INDEX_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+		if (collider_positions)
+		{
+			if (!ctx->dCollider)
+				return Fail(TSOM_ERR_INVALID, "last tsom_mesh call did not produce collider positions");
+			TSOM_CUDA(cudaMemcpyAsync(collider_positions, reinterpret_cast<const char*>(ctx->dCollider) + first_face * TSOM_FACE_COLLIDER_BYTES, face_count * TSOM_FACE_COLLIDER_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out)
+	{
+		if (!c || !chunk_index || !n_out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		if (!ctx->dFlags)
+			return Fail(TSOM_ERR_INVALID, "no block table");
+		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
+		if (slot == 0xFFFFFFFFu || !c->hasContent[slot])
+			return Fail(TSOM_ERR_INVALID, "chunk is unknown or has no content");
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		const uint32_t maxBoxes = 16384; // a 32^3 checkerboard: every other cell is its own box
+		TSOM_CUDA(ctx->gravity.Ensure(size_t(maxBoxes) * 6));
+		tsomk::launch_box_collider(c->dBlocks + size_t(slot) * NB, ctx->dFlags, ctx->nTypes, ctx->gravity.ptr, maxBoxes, ctx->dSmall + 6, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall + 6, ctx->dSmall + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		const uint32_t nb = ctx->hSmall[6];
+		*n_out = nb;
+		if (boxes_out && nb)
+		{
+			TSOM_CUDA(cudaMemcpy(boxes_out, ctx->gravity.ptr, size_t(std::min(nb, std::min(cap, maxBoxes))) * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+		}
+		return TSOM_OK;
+	}
+
+	// ---------------------------------------------------------------------------------------------------- multi-GPU
+	int tsom_container_add_remote_chunks(tsom_container* c, const int32_t* chunk_indices, const uint32_t* remote_slots, const int32_t* ranks, uint32_t n)
+	{
+		if (!c || !chunk_indices || !remote_slots || !ranks)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			Key k{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] };
+			if (c->slotOf.count(k))
+				return Fail(TSOM_ERR_INVALID, "remote chunk is already a local chunk");
+			c->remotes[k] = tsom_container::Remote{ ranks[i], remote_slots[i] };
+		}
+		c->topoDirty = true;
+		return TSOM_OK;
+	}
+
+	int tsom_ipc_export(tsom_container* c, tsom_ipc_handle* out)
+	{
+		if (!c || !out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+		TSOM_CUDA(cudaSetDevice(c->ctx->device));
+		cudaIpcMemHandle_t h0, h1;
+		TSOM_CUDA(cudaIpcGetMemHandle(&h0, c->dBlocks));
+		TSOM_CUDA(cudaIpcGetMemHandle(&h1, c->dXslabs));
+		std::memset(out, 0, sizeof(*out));
+		std::memcpy(out->bytes, &h0, 64);
+		std::memcpy(out->bytes + 64, &h1, 64);
+		std::memcpy(out->bytes + 128, &c->capacity, 4);
+		return TSOM_OK;
+	}
+
+	int tsom_ipc_attach(tsom_container* c, int rank, const tsom_ipc_handle* handle)
+	{
+		if (!c || !handle)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_CUDA(cudaSetDevice(c->ctx->device));
+		cudaIpcMemHandle_t h0, h1;
+		std::memcpy(&h0, handle->bytes, 64);
+		std::memcpy(&h1, handle->bytes + 64, 64);
+		void *p0 = nullptr, *p1 = nullptr;
+		TSOM_CUDA(cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess));
+		TSOM_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
+		tsom_container::Peer p;
+		p.blocks = static_cast<const uint16_t*>(p0);
+		p.xslabs = static_cast<const uint16_t*>(p1);
+		p.ipc = true;
+		c->peers[rank] = p;
+		c->topoDirty = true;
+		return TSOM_OK;
+	}
+
+	int tsom_peer_attach_local(tsom_container* c, int rank, tsom_container* peer)
+	{
+		if (!c || !peer)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (peer->ctx->device != c->ctx->device)
+		{
+			TSOM_CUDA(cudaSetDevice(c->ctx->device));
+			cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				return Fail(TSOM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+			cudaGetLastError();
+		}
+		tsom_container::Peer p;
+		p.blocks = peer->dBlocks;
+		p.xslabs = peer->dXslabs;
+		p.ipc = false;
+		c->peers[rank] = p;
+		c->topoDirty = true;
+		return TSOM_OK;
+	}
+
+	int tsom_halo_pull(tsom_container* c)
+	{
+		if (!c)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		int rc = SyncTopology(c);
+		if (rc != TSOM_OK)
+			return rc;
+		if (c->nGhost)
+		{
+			tsomk::launch_halo_pull(c->ghostDescs.ptr, c->nGhost, c->ghostSlabs.ptr, ctx->stream);
+			ctx->launches += 1;
+			TSOM_CUDA(cudaGetLastError());
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+}

@@ -1,0 +1,121 @@
+// tsom_kernels.h — host-visible declarations of the sm_100a kernels' argument blocks and launchers.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tsomk
+{
+	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u };
+
+	struct MeshArgs
+	{
+		// container
+		const uint16_t* blocks;          // [capacity][32768]
+		const unsigned long long* halo;  // [capacity][6] encoded slab pointers (0 = no neighbour)
+		const int4* chunkIdx;            // [capacity] (cx, cy, cz, hasContent)
+		// jobs
+		const uint32_t* jobSlot;         // [nJobs]
+		const float* gravity;            // [nJobs][3] or nullptr
+		uint32_t nJobs;
+		// block table
+		const uint8_t* blkFlags;
+		const uint32_t* blkTex;          // [nTypes][6]
+		uint32_t nTypes;
+		// count -> scan -> emit plumbing
+		uint32_t* faceCount;                   // [nJobs]
+		const unsigned long long* firstFace;   // [nJobs]
+		const uint32_t* worklist;              // jobs with faces
+		const uint32_t* nWork;
+		uint32_t* jobCounter;                  // work-stealing ticket, zeroed before each launch
+		// arenas
+		float4* vertices;
+		uint2* indices;
+		float4* collider;
+		unsigned long long arenaFaces;
+		uint32_t* overflow;
+		// parameters
+		uint32_t flags;
+		float tile;
+		float deformRadius;
+		float center[3];  // ChunkContainer::GetCenter()
+		float quat[6][4]; // RotationBetween(s_dirNormals[d], Up) as (w, x, y, z)
+	};
+
+	cudaError_t mesh_kernels_init();
+	size_t mesh_count_smem_bytes();
+	size_t mesh_emit_smem_bytes();
+	void launch_mesh_count(const MeshArgs& a, int grid, cudaStream_t st);
+	void launch_mesh_scan(const uint32_t* faceCount, uint32_t nJobs, unsigned long long* firstFace, uint32_t* worklist, uint32_t* nWork,
+	                      unsigned long long* totalFaces, unsigned long long faceBase, cudaStream_t st);
+	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st);
+
+	// ---- generation ----
+	struct GenArgs
+	{
+		uint16_t* blocks;        // [capacity][32768]
+		uint16_t* xslabs;        // [capacity][2][1024]
+		const int4* chunkIdx;    // [capacity]
+		const uint32_t* jobSlot; // [nJobs]
+		uint32_t nJobs;
+		uint32_t seed;
+		int maxH[3];             // ((chunkCount + 1) / 2) * 32 per axis
+		int tileOrigin[3];       // smallest chunk index covered by the terrain tables, per axis
+		int tileCount[3];        // tiles per axis
+		const int16_t* terrain;  // 6 tables of 32x32 tiles, see gen_kernels.cu
+		size_t terrainOffset[6]; // element offset of each direction's table
+		uint16_t dirt, grass, stone, stoneMossy, snow;
+		uint32_t bStar, aStar;   // integer form of `bernoulli(0.9)` over two minstd draws
+		uint32_t aInv;           // 48271^-1 mod (2^31 - 1)
+	};
+
+	struct TerrainArgs
+	{
+		int16_t* terrain;
+		size_t terrainOffset[6];
+		int tileOrigin[3];
+		int tileCount[3];
+		int maxH[3];
+		const uint8_t* perm; // [6][256] siv::PerlinNoise permutations, reseed(seed + dir)
+	};
+
+	void launch_terrain(const TerrainArgs& a, cudaStream_t st);
+	void launch_generate(const GenArgs& a, int grid, cudaStream_t st);
+
+	// ---- chunk maintenance ----
+	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, const uint32_t* slots, uint32_t n, cudaStream_t st);
+
+	struct EditDev
+	{
+		uint32_t slot; // 0xFFFFFFFF = skip
+		uint32_t packed; // x | y<<5 | z<<10 | block<<16
+	};
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, cudaStream_t st);
+
+	struct PlatformArgs
+	{
+		uint16_t* blocks;
+		uint16_t* xslabs;
+		uint8_t* invalidMask;
+		const int* slotGrid; // dense grid of slots (-1 absent / no content) covering [gridOrigin, gridOrigin + gridDim)
+		int gridOrigin[3];
+		int gridDim[3];
+		int upDirection;
+		int center[3];
+		uint16_t copper, stoneBricks, planks;
+	};
+	void launch_platform(const PlatformArgs& a, cudaStream_t st);
+
+	// FlatChunk greedy box collider; boxes = [cap][6] floats, count = number found (may exceed cap)
+	void launch_box_collider(const uint16_t* chunkBlocks, const uint8_t* blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count, cudaStream_t st);
+
+	// ---- multi-GPU halo pull ----
+	struct GhostDesc
+	{
+		const uint16_t* src; // peer address of the slab's first id
+		uint32_t contig;     // 1 = contiguous 2 KiB, 0 = 32 rows of 64 B at stride 2 KiB
+		uint32_t ghost;      // destination ghost slab index
+	};
+	void launch_halo_pull(const GhostDesc* descs, uint32_t n, uint16_t* ghostSlabs, cudaStream_t st);
+}

@@ -1,0 +1,435 @@
+"""Host-side mirror of the reference's call surface for the chunk pipeline, over the C ABI of libtsom_b200.so.
+
+Names, argument meaning and error behaviour follow the reference classes (method names keep the reference's CamelCase):
+
+  BlockLibrary      include/CommonLib/BlockLibrary.hpp, src/CommonLib/BlockLibrary.cpp
+  ChunkContainer    include/CommonLib/ChunkContainer.hpp/.inl
+  Planet            include/CommonLib/Planet.hpp, src/CommonLib/Planet.cpp
+  Chunk             include/CommonLib/Chunk.hpp, src/CommonLib/Chunk.cpp (FlatChunk / DeformedChunk corner providers)
+  ChunkEntities     src/CommonLib/ChunkEntities.cpp + src/ClientLib/ClientChunkEntities.cpp (per-tick batch of invalidated chunks)
+
+All block data lives in HBM; every compute call runs sm_100a kernels.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+ChunkSize = 32
+ChunkBlockCount = ChunkSize ** 3
+EmptyBlockIndex = 0
+InvalidBlockIndex = 0xFFFF
+
+
+class Direction:
+    """include/CommonLib/Direction.hpp:18-28"""
+    Back, Down, Front, Left, Right, Up = range(6)
+
+
+DirectionMask_All = 0x3F
+
+# Direction.hpp:83-90 (world axes)
+s_chunkDirOffset = np.array([[0, 0, 1], [0, -1, 0], [0, 0, -1], [-1, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.int32)
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _idx(v) -> np.ndarray:
+    a = np.ascontiguousarray(v, dtype=np.int32).reshape(-1, 3)
+    return a
+
+
+# ------------------------------------------------------------------------------------------------ BlockLibrary
+@dataclass
+class BlockInfo:
+    """BlockLibrary::BlockInfo (BlockLibrary.hpp:37-50)"""
+    basePath: str = ""
+    baseBackPath: str = ""
+    baseDownPath: str = ""
+    baseFrontPath: str = ""
+    baseLeftPath: str = ""
+    baseRightPath: str = ""
+    baseSidePath: str = ""
+    baseUpPath: str = ""
+    hasCollisions: bool = True
+    isDoubleSided: bool = False
+    isTransparent: bool = False
+    permeability: float = 0.0
+
+
+@dataclass
+class BlockData:
+    """BlockLibrary::BlockData (BlockLibrary.hpp:52-60)"""
+    name: str
+    texIndices: list = field(default_factory=lambda: [0] * 6)
+    hasCollisions: bool = True
+    isDoubleSided: bool = False
+    isTransparent: bool = False
+    permeability: float = 0.0
+
+
+class BlockLibrary:
+    """The 14 built-in block types and their texture slices (BlockLibrary.cpp:10-143)."""
+
+    def __init__(self, register_defaults: bool = True):
+        self._blocks: list[BlockData] = []
+        self._blockIndices: dict[str, int] = {}
+        self._textureIndices: dict[str, int] = {}
+        if register_defaults:
+            R = self.RegisterBlock
+            R("empty", BlockInfo(hasCollisions=False, isTransparent=True, permeability=1.0))
+            R("debug", BlockInfo(baseBackPath="blocks/debug_back", baseDownPath="blocks/debug_down", baseFrontPath="blocks/debug_front",
+                                 baseLeftPath="blocks/debug_left", baseRightPath="blocks/debug_right", baseUpPath="blocks/debug_up"))
+            R("dirt", BlockInfo(basePath="blocks/dirt", permeability=0.1))
+            R("grass", BlockInfo(basePath="blocks/grass_top", baseDownPath="blocks/dirt", baseSidePath="blocks/grass_side", permeability=0.1))
+            R("hull", BlockInfo(basePath="blocks/smooth_stone"))
+            R("hull2", BlockInfo(basePath="blocks/smooth_stone_slab_side"))
+            R("snow", BlockInfo(basePath="blocks/snow", permeability=0.5))
+            R("stone", BlockInfo(basePath="blocks/cobblestone"))
+            R("stone_mossy", BlockInfo(basePath="blocks/mossy_cobblestone"))
+            R("forcefield", BlockInfo(basePath="blocks/forcefield", hasCollisions=False, isTransparent=True))
+            R("planks", BlockInfo(basePath="blocks/planks"))
+            R("stone_bricks", BlockInfo(basePath="blocks/stone_bricks"))
+            R("copper_block", BlockInfo(basePath="blocks/copper_block"))
+            R("glass", BlockInfo(basePath="blocks/glass", isDoubleSided=True, isTransparent=True))
+
+    def RegisterBlock(self, name: str, info: BlockInfo) -> int:
+        index = len(self._blocks)
+        data = BlockData(name=name, hasCollisions=info.hasCollisions, isDoubleSided=info.isDoubleSided, isTransparent=info.isTransparent, permeability=info.permeability)
+        base = self._RegisterTexture(info.basePath) if info.basePath else 0
+        side = self._RegisterTexture(info.baseSidePath) if info.baseSidePath else base
+        per_dir = [info.baseBackPath, info.baseDownPath, info.baseFrontPath, info.baseLeftPath, info.baseRightPath, info.baseUpPath]
+        for d, path in enumerate(per_dir):
+            if path:
+                data.texIndices[d] = self._RegisterTexture(path)
+            elif d not in (Direction.Up, Direction.Down):
+                data.texIndices[d] = side
+            else:
+                data.texIndices[d] = base
+        assert name not in self._blockIndices
+        self._blocks.append(data)
+        self._blockIndices[name] = index
+        return index
+
+    def _RegisterTexture(self, path: str) -> int:
+        if path in self._textureIndices:
+            return self._textureIndices[path]
+        tex = len(self._textureIndices) + 1  # slice #0 stays empty
+        self._textureIndices[path] = tex
+        return tex
+
+    def GetBlockData(self, blockIndex: int) -> BlockData:
+        return self._blocks[blockIndex]
+
+    def GetBlockIndex(self, blockName: str) -> int:
+        return self._blockIndices.get(blockName, InvalidBlockIndex)
+
+    def __len__(self):
+        return len(self._blocks)
+
+    def to_descs(self):
+        arr = (L.BlockDesc * len(self._blocks))()
+        for i, b in enumerate(self._blocks):
+            for d in range(6):
+                arr[i].tex[d] = b.texIndices[d]
+            arr[i].has_collisions = int(b.hasCollisions)
+            arr[i].is_double_sided = int(b.isDoubleSided)
+            arr[i].is_transparent = int(b.isTransparent)
+        return arr
+
+
+# ------------------------------------------------------------------------------------------------ device context
+class Context:
+    """One per process and GPU (tsom_ctx): stream, device block table, mesh arenas."""
+
+    def __init__(self, device: int = 0, blockLibrary: Optional[BlockLibrary] = None):
+        self._h = C.c_void_p()
+        L.check(L.lib().tsom_create(device, C.byref(self._h)))
+        self.device = device
+        self.blockLibrary = blockLibrary or BlockLibrary()
+        descs = self.blockLibrary.to_descs()
+        L.check(L.lib().tsom_set_block_table(self._h, descs, len(descs)))
+
+    def close(self):
+        if self._h:
+            L.lib().tsom_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(L.lib().tsom_stream(self._h) or 0)
+
+    def synchronize(self):
+        L.check(L.lib().tsom_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(L.lib().tsom_launch_count(self._h))
+
+    def reserve_faces(self, faces: int, render=True, collider=False):
+        L.check(L.lib().tsom_reserve_faces(self._h, int(faces), (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0)))
+
+    def arenas(self):
+        v, i, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        L.check(L.lib().tsom_mesh_arenas(self._h, C.byref(v), C.byref(i), C.byref(c), C.byref(n)))
+        return v.value, i.value, c.value, int(n.value)
+
+
+@dataclass
+class ChunkMesh:
+    """What ClientChunkEntities::BuildMesh / DeformedChunk::BuildCollider hand to Nazara, as host arrays."""
+    vertices: Optional[np.ndarray]            # [4F, 12] float32: position, normal, uvw, tangent (48 B stride)
+    indices: np.ndarray                       # [6F] uint32, chunk-relative
+    collider_positions: Optional[np.ndarray]  # [4F, 3] float32
+
+    @property
+    def face_count(self) -> int:
+        return len(self.indices) // 6
+
+    @property
+    def position(self):
+        return self.vertices[:, 0:3]
+
+    @property
+    def normal(self):
+        return self.vertices[:, 3:6]
+
+    @property
+    def uvw(self):
+        return self.vertices[:, 6:9]
+
+    @property
+    def tangent(self):
+        return self.vertices[:, 9:12]
+
+
+class MeshBatch:
+    """Result of one batched tsom_mesh call: per-chunk views into the device arenas."""
+
+    def __init__(self, ctx: Context, indices: np.ndarray, views, flags: int):
+        self.ctx, self.chunk_indices, self._views, self.flags = ctx, indices, views, flags
+        self.face_counts = np.array([v.face_count for v in views], dtype=np.uint32)
+        self.first_faces = np.array([v.first_face for v in views], dtype=np.uint64)
+
+    @property
+    def total_faces(self) -> int:
+        return int(self.face_counts.sum())
+
+    def __len__(self):
+        return len(self._views)
+
+    def chunk(self, i: int) -> Optional[ChunkMesh]:
+        """Host copy of chunk i's mesh; None when it has no face (the reference returns a null mesh, ClientChunkEntities.cpp:161-162)."""
+        f = int(self.face_counts[i])
+        if f == 0:
+            return None
+        first = int(self.first_faces[i])
+        verts = np.empty((4 * f, 12), np.float32) if self.flags & L.MESH_RENDER else None
+        coll = np.empty((4 * f, 3), np.float32) if self.flags & L.MESH_COLLIDER else None
+        ind = np.empty(6 * f, np.uint32)
+        L.check(L.lib().tsom_mesh_copy_to_host(self.ctx._h, first, f, None if verts is None else verts.ctypes.data_as(C.c_void_p), _p(ind, C.c_uint32),
+                                               None if coll is None else _p(coll, C.c_float)))
+        return ChunkMesh(verts, ind, coll)
+
+
+# ------------------------------------------------------------------------------------------------ ChunkContainer / Planet
+class ChunkContainer:
+    """ChunkContainer (ChunkContainer.hpp): a set of 32^3 chunks resident in HBM, addressed by world-axis chunk indices."""
+
+    ChunkSize = ChunkSize
+
+    def __init__(self, ctx: Context, capacity: int, tileSize: float = 1.0):
+        self.ctx = ctx
+        self.capacity = capacity
+        self._tileSize = float(tileSize)
+        self._h = C.c_void_p()
+        L.check(L.lib().tsom_container_create(ctx._h, capacity, self._tileSize, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            L.lib().tsom_container_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- index math (ChunkContainer.inl:14-56) — host integer helpers
+    @staticmethod
+    def GetBlockIndices(chunkIndices, indices):
+        cx, cy, cz = (int(v) for v in chunkIndices)
+        x, y, z = (int(v) for v in indices)
+        h = ChunkSize // 2
+        return (cx * ChunkSize + x - h, cy * ChunkSize + z - h, cz * ChunkSize + y - h)
+
+    @staticmethod
+    def GetChunkIndicesByBlockIndices(indices):
+        def trunc_div(a, b):  # C++ integer division truncates toward zero
+            q = abs(a) // b
+            return -q if a < 0 else q
+
+        adj = [int(v) + ChunkSize // 2 for v in indices]
+        chunk = [trunc_div(a - ChunkSize + 1 if a < 0 else a, ChunkSize) for a in adj]
+        local = [a - c * ChunkSize for a, c in zip(adj, chunk)]
+        local = [l + ChunkSize if l < 0 else l for l in local]
+        return tuple(chunk), (local[0], local[2], local[1])
+
+    def GetChunkOffset(self, indices):
+        return tuple(np.float32(np.float32(np.float32(i) * np.float32(ChunkSize)) * np.float32(self._tileSize)) for i in indices)
+
+    def GetTileSize(self) -> float:
+        return self._tileSize
+
+    def GetCenter(self):
+        return (0.0, 0.0, 0.0)
+
+    def GetChunkCount(self) -> int:
+        return int(L.lib().tsom_container_chunk_count(self._h))
+
+    # ---- chunk set
+    def AddChunk(self, indices, blocks: Optional[np.ndarray] = None):
+        """Planet::AddChunk (Planet.cpp:28-68); `blocks` plays the initCallback."""
+        idx = _idx(indices)
+        if blocks is None:
+            L.check(L.lib().tsom_container_add_chunks(self._h, _p(idx, C.c_int32), len(idx)))
+        else:
+            self.ResetChunks(idx, blocks)
+
+    def RemoveChunk(self, indices):
+        idx = _idx(indices)
+        L.check(L.lib().tsom_container_remove_chunk(self._h, _p(idx, C.c_int32)))
+
+    def ResetChunks(self, indices, blocks):
+        """Chunk::Reset(F) for a batch: F copies 32768 ids per chunk from host memory (or a device pointer given as int)."""
+        idx = _idx(indices)
+        if isinstance(blocks, int):
+            L.check(L.lib().tsom_chunks_reset_device(self._h, _p(idx, C.c_int32), len(idx), C.c_void_p(blocks)))
+            return
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(len(idx), ChunkBlockCount)
+        L.check(L.lib().tsom_chunks_reset(self._h, _p(idx, C.c_int32), len(idx), _p(b, C.c_uint16)))
+
+    def GetContent(self, indices) -> np.ndarray:
+        """Chunk::GetContent for a batch -> [n, 32768] uint16."""
+        idx = _idx(indices)
+        out = np.empty((len(idx), ChunkBlockCount), np.uint16)
+        L.check(L.lib().tsom_chunks_get_content(self._h, _p(idx, C.c_int32), len(idx), _p(out, C.c_uint16)))
+        return out
+
+    # ---- edits
+    def UpdateBlocks(self, edits: np.ndarray):
+        """n x Chunk::UpdateBlock, in order; `edits` is [n, 7] int: cx, cy, cz, x, y, z, block."""
+        e = np.ascontiguousarray(edits, dtype=np.int64).reshape(-1, 7)
+        arr = (L.Edit * len(e))()
+        raw = np.zeros(len(e), dtype=np.dtype([("chunk", np.int32, 3), ("x", np.uint8), ("y", np.uint8), ("z", np.uint8), ("r", np.uint8), ("block", np.uint16), ("r2", np.uint16)]))
+        raw["chunk"] = e[:, 0:3]
+        raw["x"], raw["y"], raw["z"], raw["block"] = e[:, 3], e[:, 4], e[:, 5], e[:, 6]
+        C.memmove(arr, raw.ctypes.data, raw.nbytes)
+        L.check(L.lib().tsom_apply_edits(self._h, arr, len(e)))
+
+    def UpdateBlock(self, chunkIndices, indices, newBlock: int):
+        self.UpdateBlocks(np.array([[*chunkIndices, *indices, newBlock]]))
+
+    def CollectInvalidated(self, clear: bool = True) -> np.ndarray:
+        """The chunks ChunkEntities::Update would rebuild this tick, sorted by (x, y, z) -> [n, 3] int32."""
+        n = C.c_uint32()
+        cap = max(self.GetChunkCount(), 1)
+        out = np.zeros((cap, 3), np.int32)
+        L.check(L.lib().tsom_collect_dirty(self._h, _p(out, C.c_int32), cap, C.byref(n), int(clear)))
+        return out[: n.value].copy()
+
+    # ---- meshing
+    def BuildMeshes(self, indices=None, render: bool = True, collider: bool = False, deformed: bool = False, deformRadius: float = 0.0,
+                    gravityCenters: Optional[np.ndarray] = None, views: bool = True) -> MeshBatch:
+        """Chunk::BuildMesh for a whole batch in one call (one count + scan + emit kernel sequence)."""
+        flags = (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0) | (L.MESH_DEFORMED if deformed else 0)
+        params = L.MeshParams(flags, float(deformRadius), None)
+        g = None
+        if gravityCenters is not None:
+            g = np.ascontiguousarray(gravityCenters, dtype=np.float32).reshape(-1, 3)
+            params.gravity_centers = _p(g, C.c_float)
+        if indices is None:
+            raise ValueError("indices is required (use list_chunks() for all)")
+        idx = _idx(indices)
+        v = (L.MeshView * len(idx))() if views else None
+        L.check(L.lib().tsom_mesh(self._h, _p(idx, C.c_int32), len(idx), C.byref(params), v))
+        return MeshBatch(self.ctx, idx, v if views else [], flags)
+
+    def BuildBoxCollider(self, indices) -> np.ndarray:
+        """FlatChunk::BuildCollider boxes -> [n, 6] float32 (pos.xyz, size.xyz) in block units."""
+        idx = _idx(indices)
+        out = np.zeros((16384, 6), np.float32)
+        n = C.c_uint32()
+        L.check(L.lib().tsom_box_collider(self._h, _p(idx, C.c_int32), _p(out, C.c_float), len(out), C.byref(n)))
+        return out[: n.value].copy()
+
+
+class Planet(ChunkContainer):
+    """Planet (Planet.hpp / Planet.cpp): a ChunkContainer of FlatChunks with generation."""
+
+    def __init__(self, ctx: Context, tileSize: float = 1.0, cornerRadius: float = 16.0, gravity: float = 9.81, capacity: int = 125):
+        super().__init__(ctx, capacity, tileSize)
+        self._cornerRadius, self._gravity = cornerRadius, gravity
+
+    def GetCornerRadius(self) -> float:
+        return self._cornerRadius
+
+    def GetGravity(self) -> float:
+        return self._gravity
+
+    def _gen_ids(self, lib: BlockLibrary):
+        return L.GenBlocks(*(lib.GetBlockIndex(n) for n in ("dirt", "grass", "stone", "stone_mossy", "snow")))
+
+    def GenerateChunks(self, blockLibrary: BlockLibrary, seed: int, chunkCount: Sequence[int]):
+        """Planet::GenerateChunks (Planet.cpp:385-403); the TaskScheduler argument has no counterpart (the GPU is the scheduler)."""
+        cc = np.ascontiguousarray(chunkCount, dtype=np.uint32)
+        ids = self._gen_ids(blockLibrary)
+        L.check(L.lib().tsom_planet_generate(self._h, seed & 0xFFFFFFFF, _p(cc, C.c_uint32), C.byref(ids)))
+
+    def GenerateChunk(self, blockLibrary: BlockLibrary, indices, seed: int, chunkCount: Sequence[int]):
+        """Planet::GenerateChunk (Planet.cpp:160-383) on one or more chunks."""
+        cc = np.ascontiguousarray(chunkCount, dtype=np.uint32)
+        idx = _idx(indices)
+        ids = self._gen_ids(blockLibrary)
+        L.check(L.lib().tsom_planet_generate_chunks(self._h, seed & 0xFFFFFFFF, _p(cc, C.c_uint32), C.byref(ids), _p(idx, C.c_int32), len(idx)))
+
+    def GeneratePlatform(self, blockLibrary: BlockLibrary, upDirection: int, platformCenter: Sequence[int]):
+        """Planet::GeneratePlatform (Planet.cpp:405-512)."""
+        ids = L.PlatformBlocks(*(blockLibrary.GetBlockIndex(n) for n in ("copper_block", "stone_bricks", "planks")))
+        ctr = np.ascontiguousarray(platformCenter, dtype=np.int32)
+        L.check(L.lib().tsom_planet_generate_platform(self._h, int(upDirection), _p(ctr, C.c_int32), C.byref(ids)))
+
+    @staticmethod
+    def chunk_grid(chunkCount: Sequence[int]) -> np.ndarray:
+        """Chunk indices in GenerateChunks order (z, y, x loops; (x,y,z) - chunkCount/2) -> [n, 3] int32."""
+        nx, ny, nz = (int(v) for v in chunkCount)
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        return np.stack([x.ravel() - nx // 2, y.ravel() - ny // 2, z.ravel() - nz // 2], axis=1).astype(np.int32)
+
+
+class ChunkEntities:
+    """Per-tick glue (ChunkEntities::Update, ClientChunkEntities::ProcessChunkUpdate): rebuild every invalidated chunk and the
+    masked neighbours in ONE batched GPU call instead of one TaskScheduler task per chunk."""
+
+    def __init__(self, chunkContainer: ChunkContainer, render: bool = True, collider: bool = True):
+        self.container, self.render, self.collider = chunkContainer, render, collider
+
+    def Update(self) -> Optional[MeshBatch]:
+        dirty = self.container.CollectInvalidated(clear=True)
+        if len(dirty) == 0:
+            return None
+        return self.container.BuildMeshes(dirty, render=self.render, collider=self.collider)
