@@ -123,6 +123,18 @@ int tsom_synchronize(tsom_ctx* ctx);
 int tsom_set_block_table(tsom_ctx* ctx, const tsom_block_desc* blocks, uint32_t n);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t tsom_launch_count(tsom_ctx* ctx);
+/* device-side durations (CUDA events on the context's stream) of the kernels of the most recent generate / mesh call */
+enum tsom_timing
+{
+	TSOM_TIMING_TERRAIN_MS = 0,   /* 6 x terrain_kernel */
+	TSOM_TIMING_GENERATE_MS = 1,  /* generate_kernel */
+	TSOM_TIMING_MESH_COUNT_MS = 2,
+	TSOM_TIMING_MESH_SCAN_MS = 3,
+	TSOM_TIMING_MESH_EMIT_MS = 4,
+	TSOM_TIMING_MESH_REEMIT = 5,  /* 1.0 when the arenas had to grow and emit ran twice (the emit time is then of the first, aborted run) */
+	TSOM_TIMING_COUNT = 6
+};
+int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n);
 /* pre-size the mesh arenas (faces); they also grow on demand */
 int tsom_reserve_faces(tsom_ctx* ctx, uint64_t faces, uint32_t flags);
 

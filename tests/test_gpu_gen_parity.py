@@ -36,7 +36,7 @@ def _assert_blocks_equal(gp, op, grid):
             raise AssertionError(f"chunk {tuple(idx)}: {len(bad)} ids differ, first at local {(k % 32, (k // 32) % 32, k // 1024)}: gpu {got[i][k]} oracle {want[k]}")
 
 
-@pytest.mark.parametrize("seed,count", [(42, (5, 5, 5)), (42, (3, 3, 3)), (7, (1, 1, 1)), (123456789, (3, 5, 1)), (0xFFFFFFFE, (7, 3, 5))])
+@pytest.mark.parametrize("seed,count", [(42, (5, 5, 5)), (42, (3, 3, 3)), (7, (1, 1, 1)), (123456789, (3, 5, 5)), (0xFFFFFFFE, (7, 3, 3))])
 def test_generate_chunks_bit_exact(ctx, seed, count):
     gp, op = _planets(ctx, seed, count)
     _assert_blocks_equal(gp, op, T.Planet.chunk_grid(count))
@@ -67,6 +67,16 @@ def test_even_chunk_count_is_rejected(ctx):
     assert e.value.code == 3
     _, ok = O.generate_chunk(42, (4, 4, 4), (-2, 0, 0))
     assert not ok
+
+
+def test_crossed_axes_reject_unequal_y_z(ctx):
+    """depth crosses Y and Z (Planet.cpp:199-203), so chunkCount.y != chunkCount.z leaves blocks beyond maxHeight: refused on
+    both sides."""
+    gp = T.Planet(ctx, capacity=15)
+    with pytest.raises(T.TsomError) as e:
+        gp.GenerateChunks(ctx.blockLibrary, 1, (3, 5, 1))
+    assert e.value.code == 3
+    assert not O.Planet().generate(1, (3, 5, 1))
 
 
 def test_regen_single_chunk(ctx):

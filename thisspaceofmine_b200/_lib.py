@@ -63,6 +63,7 @@ SYMBOLS = {
     "tsom_set_block_table": (C.c_int, [_vp, C.POINTER(BlockDesc), C.c_uint32]),
     "tsom_launch_count": (C.c_uint64, [_vp]),
     "tsom_reserve_faces": (C.c_int, [_vp, C.c_uint64, C.c_uint32]),
+    "tsom_get_timings": (C.c_int, [_vp, _f32p, C.c_uint32]),
     "tsom_container_create": (C.c_int, [_vp, C.c_uint32, C.c_float, C.POINTER(_vp)]),
     "tsom_container_destroy": (None, [_vp]),
     "tsom_container_add_chunks": (C.c_int, [_vp, _i32p, C.c_uint32]),

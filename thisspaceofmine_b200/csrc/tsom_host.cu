@@ -239,6 +239,10 @@ struct tsom_ctx
 	float quat[6][4];
 	uint32_t bStar = 0, aStar = 0, aInv = 0;
 
+	// device-side timing of the last calls (CUDA events on `stream`)
+	cudaEvent_t ev[6] = {};
+	float timings[TSOM_TIMING_COUNT] = {};
+
 	cudaError_t EnsurePinned(size_t bytes)
 	{
 		if (bytes <= hPinnedBytes)
@@ -508,6 +512,8 @@ extern "C"
 		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
+		for (auto& e : ctx->ev)
+			TSOM_CUDA(cudaEventCreate(&e));
 
 		const F3h normals[6] = { { 0.f, 0.f, 1.f }, { 0.f, -1.f, 0.f }, { 0.f, 0.f, -1.f }, { -1.f, 0.f, 0.f }, { 1.f, 0.f, 0.f }, { 0.f, 1.f, 0.f } };
 		for (int d = 0; d < 6; ++d)
@@ -550,6 +556,9 @@ extern "C"
 		ctx->gravity.Free();
 		ctx->edits.Free();
 		cudaFree(ctx->dSmall);
+		for (auto& e : ctx->ev)
+			if (e)
+				cudaEventDestroy(e);
 		cudaFreeHost(ctx->hSmall);
 		if (ctx->hPinned)
 			cudaFreeHost(ctx->hPinned);
@@ -568,6 +577,15 @@ extern "C"
 	}
 
 	uint64_t tsom_launch_count(tsom_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+	int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n)
+	{
+		if (!ctx || !out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		for (uint32_t i = 0; i < n && i < TSOM_TIMING_COUNT; ++i)
+			out[i] = ctx->timings[i];
+		return TSOM_OK;
+	}
 
 	int tsom_set_block_table(tsom_ctx* ctx, const tsom_block_desc* blocks, uint32_t n)
 	{
@@ -861,9 +879,11 @@ extern "C"
 			PerlinPermutation(seed + unsigned(d), perm + d * 256); // Planet.cpp:179-181
 		TSOM_CUDA(cudaMemcpyAsync(c->dPerm, perm, sizeof(perm), cudaMemcpyHostToDevice, ctx->stream));
 		ta.perm = c->dPerm;
+		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 		tsomk::launch_terrain(ta, ctx->stream);
 		ctx->launches += 6;
 		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -895,7 +915,10 @@ extern "C"
 		tsomk::launch_generate(ga, int(n), ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // blocking like Planet::GenerateChunks (WaitForTasks, Planet.cpp:402)
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_TERRAIN_MS], ctx->ev[0], ctx->ev[1]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[1], ctx->ev[2]);
 		return TSOM_OK;
 	}
 
@@ -1147,10 +1170,14 @@ extern "C"
 		};
 
 		a.jobCounter = ctx->dSmall + 0;
+		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 		tsomk::launch_mesh_count(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
+		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 		tsomk::launch_mesh_scan(ctx->faceCount.ptr, n, ctx->firstFace.ptr, ctx->worklist.ptr, ctx->dSmall + 2, reinterpret_cast<unsigned long long*>(ctx->dSmall + 4), 0ull, ctx->stream);
+		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
 		ctx->launches += 2;
 		launchEmit();
+		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
 		TSOM_CUDA(cudaGetLastError());
 
 		// read back totals (+ views)
@@ -1166,10 +1193,16 @@ extern "C"
 		}
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_COUNT_MS], ctx->ev[0], ctx->ev[1]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_SCAN_MS], ctx->ev[1], ctx->ev[2]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_EMIT_MS], ctx->ev[2], ctx->ev[3]);
+		ctx->timings[TSOM_TIMING_MESH_REEMIT] = 0.f;
+
 		unsigned long long total;
 		std::memcpy(&total, ctx->hSmall + 4, sizeof(total));
 		if (ctx->hSmall[3] != 0)
 		{
+			ctx->timings[TSOM_TIMING_MESH_REEMIT] = 1.f;
 			// arenas were too small: grow to the exact need and emit again (counts and offsets are still valid)
 			if ((rc = EnsureArenas(ctx, total, flags)) != TSOM_OK)
 				return rc;
