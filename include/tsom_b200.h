@@ -50,7 +50,8 @@ enum
 {
 	TSOM_MESH_RENDER = 1,   /* 48-byte vertices + indices: ClientChunkEntities::BuildMesh (src/ClientLib/ClientChunkEntities.cpp:141-176) */
 	TSOM_MESH_COLLIDER = 2, /* positions only + the same indices: DeformedChunk::BuildCollider (src/CommonLib/DeformedChunk.cpp:15-36) */
-	TSOM_MESH_DEFORMED = 4  /* corner provider DeformedChunk::ComputeVoxelCorners (DeformedChunk.cpp:115-154) instead of FlatChunk (FlatChunk.cpp:48-54) */
+	TSOM_MESH_DEFORMED = 4, /* corner provider DeformedChunk::ComputeVoxelCorners (DeformedChunk.cpp:115-154) instead of FlatChunk (FlatChunk.cpp:48-54) */
+	TSOM_MESH_GENERIC_MATH = 8 /* diagnostics: evaluate DrawFace's float math per face even where the exact table-driven flat path applies */
 };
 
 typedef struct tsom_ctx tsom_ctx;             /* one per process and GPU: stream, block table, mesh arenas */

@@ -108,6 +108,24 @@ def test_tile_size_and_custom_gravity(ctx):
     _compare_all(gc, op, [(1, -2, 3)], gravityCenters=g)
 
 
+@pytest.mark.parametrize("tile", [1.0, 0.5, 4.0, 0.3])
+def test_table_path_is_bit_identical_to_generic_math(ctx, tile):
+    """Power-of-two block sizes take the table-driven flat path; it must reproduce the per-face float math bit for bit
+    (0.3 is not a power of two: both calls run the generic math)."""
+    rng = np.random.default_rng(17)
+    chunks = {(-3, 2, 1): random_chunk(rng, 0.5, ids=(1, 3, 7, 13)), (0, -4, 0): random_chunk(rng, 0.2, ids=(1, 3))}
+    gc, op = _pair(ctx, chunks, tile=tile)
+    idx = list(chunks)
+    fast = gc.BuildMeshes(idx)
+    meshes_fast = [fast.chunk(i) for i in range(len(idx))]
+    gen = gc.BuildMeshes(idx, genericMath=True)
+    for i, k in enumerate(idx):
+        g = gen.chunk(i)
+        assert np.array_equal(meshes_fast[i].vertices.view(np.uint32), g.vertices.view(np.uint32)), f"tile {tile} chunk {k}"
+        assert np.array_equal(meshes_fast[i].indices, g.indices)
+        assert_mesh_equal(g, op.mesh(k), f"tile {tile} chunk {k}")
+
+
 def test_collider_reuses_face_list(ctx):
     """DeformedChunk::BuildCollider path: positions only + the same indices, from the same compacted face list."""
     rng = np.random.default_rng(11)

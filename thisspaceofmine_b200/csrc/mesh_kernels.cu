@@ -55,6 +55,7 @@ namespace tsomk
 		uint32_t job;
 		uint32_t total;
 		alignas(8) uint64_t bar;
+		alignas(16) FaceTable table;
 		// phase 1-2 only; the emit kernel reuses this area as the face staging buffer
 		union
 		{
@@ -361,68 +362,81 @@ namespace tsomk
 		return p;
 	}
 
-	// DrawFace (Chunk.cpp:22-102): writes 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}
-	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	// geometry of one face: block centre (mean of the 8 corners, summed in enum order, Chunk.cpp:186-188), the 4 quad corners
+	// and their mean (Chunk.cpp:30)
+	__device__ __forceinline__ void face_geometry(const FaceCtx& cx, int x, int y, int z, int slot, bool twin, F3& blockCenter, F3 pos[4], F3& fc)
 	{
-		// block centre = mean of the 8 corners, summed in enum order (Chunk.cpp:186-188)
 		F3 sum = f3(0.f, 0.f, 0.f);
 #pragma unroll
 		for (int i = 0; i < 8; ++i)
 			sum = sum + voxel_corner(cx, x, y, z, c_cornerSumOrder[i]);
-		const F3 blockCenter = sum / 8.f;
-
-		F3 pos[4];
+		blockCenter = sum / 8.f;
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 			pos[i] = voxel_corner(cx, x, y, z, c_faceCorners[slot][twin ? (i ^ 1) : i]);
-
-		F3 fc = f3(0.f, 0.f, 0.f);
+		fc = f3(0.f, 0.f, 0.f);
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 			fc = fc + pos[i];
 		fc = fc / 4.f;
+	}
+
+	// normal + texture direction + per-vertex uv of one face for a given faceUp (DrawFace, Chunk.cpp:31-92)
+	__device__ __forceinline__ void face_attrs(const float (*quat)[4], int faceUp, const F3& blockCenter, const F3 pos[4], const F3& fc, F3& normal, int& texDir, float u[4], float v[4])
+	{
+		normal = normalize(fc - blockCenter);
+		const float qw = quat[faceUp][0];
+		const F3 qv = f3(quat[faceUp][1], quat[faceUp][2], quat[faceUp][3]);
+		texDir = direction_from_normal(quat_rotate(qw, qv, normal));
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			F3 dir = quat_rotate(qw, qv, pos[i] - blockCenter);
+			float mag, uu, vv;
+			if (texDir == D_BACK || texDir == D_FRONT)
+			{
+				mag = 0.5f / fabsf(dir.x);
+				uu = dir.x < 0.f ? -dir.z : dir.z;
+				vv = -dir.y;
+			}
+			else if (texDir == D_DOWN || texDir == D_UP)
+			{
+				mag = 0.5f / fabsf(dir.y);
+				uu = dir.x;
+				vv = dir.y < 0.f ? -dir.z : dir.z;
+			}
+			else
+			{
+				mag = 0.5f / fabsf(dir.z);
+				uu = dir.z < 0.f ? dir.x : -dir.x;
+				vv = -dir.y;
+			}
+			u[i] = uu * mag + 0.5f;
+			v[i] = vv * mag + 0.5f;
+		}
+	}
+
+	__device__ __forceinline__ unsigned tex_slice(const MeshArgs& a, unsigned id, int texDir)
+	{
+		return __ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir);
+	}
+
+	// DrawFace (Chunk.cpp:22-102), generic arithmetic: writes 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}
+	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	{
+		F3 blockCenter, pos[4], fc;
+		face_geometry(cx, x, y, z, slot, twin, blockCenter, pos, fc);
 
 		F3 normal = f3(0.f, 0.f, 0.f);
 		float u[4] = { 0.f, 0.f, 0.f, 0.f }, v[4] = { 0.f, 0.f, 0.f, 0.f };
 		float slice = 0.f;
 		if (cx.wantAttr)
 		{
-			normal = normalize(fc - blockCenter);
-
 			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
-			const float qw = a.quat[faceUp][0];
-			const F3 qv = f3(a.quat[faceUp][1], a.quat[faceUp][2], a.quat[faceUp][3]);
-			const int texDir = direction_from_normal(quat_rotate(qw, qv, normal));
-			slice = float(__ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir));
-
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				F3 dir = quat_rotate(qw, qv, pos[i] - blockCenter);
-				float mag, uu, vv;
-				if (texDir == D_BACK || texDir == D_FRONT)
-				{
-					mag = 0.5f / fabsf(dir.x);
-					uu = dir.x < 0.f ? -dir.z : dir.z;
-					vv = -dir.y;
-				}
-				else if (texDir == D_DOWN || texDir == D_UP)
-				{
-					mag = 0.5f / fabsf(dir.y);
-					uu = dir.x;
-					vv = dir.y < 0.f ? -dir.z : dir.z;
-				}
-				else
-				{
-					mag = 0.5f / fabsf(dir.z);
-					uu = dir.z < 0.f ? dir.x : -dir.x;
-					vv = -dir.y;
-				}
-				u[i] = uu * mag + 0.5f;
-				v[i] = vv * mag + 0.5f;
-			}
+			int texDir;
+			face_attrs(a.quat, faceUp, blockCenter, pos, fc, normal, texDir, u, v);
+			slice = float(tex_slice(a, id, texDir));
 		}
-
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 		{
@@ -430,6 +444,81 @@ namespace tsomk
 			out[i * 3 + 1] = make_float4(normal.y, normal.z, u[i], v[i]);
 			out[i * 3 + 2] = make_float4(slice, 0.f, 0.f, 0.f); // tangent stays zero (never written by Chunk::BuildMesh)
 		}
+	}
+
+	// ---- table-driven flat path ----
+	// For a FlatChunk whose block size is a power of two every intermediate of DrawFace is exact in fp32, so the normal, the
+	// texture direction and the four uv pairs of a face depend only on (faceUp, slot, twin) — not on the block.  They are
+	// evaluated once by face_table_kernel with the generic arithmetic above (so both paths are bit-identical) and then looked up.
+	__global__ void face_table_kernel(FaceTable* table, float tile, MeshArgs a)
+	{
+		const int t = threadIdx.x;
+		if (t >= 72)
+			return;
+		const int faceUp = t / 12, slot = (t >> 1) % 6;
+		const bool twin = t & 1;
+		FaceCtx cx;
+		cx.tile = tile;
+		cx.gravity = f3(0.f, 0.f, 0.f);
+		cx.radius = 0.f;
+		cx.deformed = false;
+		cx.wantAttr = true;
+		F3 blockCenter, pos[4], fc, normal;
+		face_geometry(cx, 0, 0, 0, slot, twin, blockCenter, pos, fc);
+		int texDir;
+		float u[4], v[4];
+		face_attrs(a.quat, faceUp, blockCenter, pos, fc, normal, texDir, u, v);
+		table->uv[faceUp][slot][twin][0] = make_float4(u[0], v[0], u[1], v[1]);
+		table->uv[faceUp][slot][twin][1] = make_float4(u[2], v[2], u[3], v[3]);
+		table->texDir[faceUp][slot] = uint32_t(texDir);
+		if (faceUp == 0 && !twin)
+			table->normal[slot] = make_float4(normal.x, normal.y, normal.z, 0.f);
+	}
+
+	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st) { face_table_kernel<<<1, 96, 0, st>>>(table, tile, a); }
+
+	__device__ __forceinline__ void draw_face_flat(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	{
+		const float s = cx.tile;
+		// Boxf(blockPos.x, blockPos.z, blockPos.y, s, s, s) with blockPos = (indices - size / 2) * s (FlatChunk.cpp:50-53)
+		const float ox = (float(x) - float(CS) * 0.5f) * s;
+		const float oy = (float(z) - float(CS) * 0.5f) * s;
+		const float oz = (float(y) - float(CS) * 0.5f) * s;
+		const float ex = ox + s, ey = oy + s, ez = oz + s;
+		F3 pos[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const unsigned code = c_faceCorners[slot][twin ? (i ^ 1) : i];
+			pos[i] = f3((code & 1u) ? ex : ox, (code & 2u) ? ey : oy, (code & 4u) ? ez : oz);
+		}
+		float4 uv0 = make_float4(0.f, 0.f, 0.f, 0.f), uv1 = uv0, n = uv0;
+		float slice = 0.f;
+		if (cx.wantAttr)
+		{
+			F3 fc = f3(0.f, 0.f, 0.f);
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				fc = fc + pos[i];
+			fc = fc / 4.f;
+			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
+			uv0 = tb.uv[faceUp][slot][twin][0];
+			uv1 = tb.uv[faceUp][slot][twin][1];
+			n = tb.normal[slot];
+			slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
+		}
+		out[0] = make_float4(pos[0].x, pos[0].y, pos[0].z, n.x);
+		out[1] = make_float4(n.y, n.z, uv0.x, uv0.y);
+		out[2] = make_float4(slice, 0.f, 0.f, 0.f);
+		out[3] = make_float4(pos[1].x, pos[1].y, pos[1].z, n.x);
+		out[4] = make_float4(n.y, n.z, uv0.z, uv0.w);
+		out[5] = make_float4(slice, 0.f, 0.f, 0.f);
+		out[6] = make_float4(pos[2].x, pos[2].y, pos[2].z, n.x);
+		out[7] = make_float4(n.y, n.z, uv1.x, uv1.y);
+		out[8] = make_float4(slice, 0.f, 0.f, 0.f);
+		out[9] = make_float4(pos[3].x, pos[3].y, pos[3].z, n.x);
+		out[10] = make_float4(n.y, n.z, uv1.z, uv1.w);
+		out[11] = make_float4(slice, 0.f, 0.f, 0.f);
 	}
 
 	__global__ void __launch_bounds__(MESH_THREADS, 1) mesh_emit_kernel(const MeshArgs a)
@@ -446,6 +535,31 @@ namespace tsomk
 			fence_mbar_init();
 		}
 		__syncthreads();
+
+		const bool fastFlat = a.faceTable != nullptr;
+		if (fastFlat)
+		{
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(a.faceTable);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.table);
+			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += MESH_THREADS)
+				dst[i] = src[i];
+		}
+		// write-out constants of this lane (a tile is 32 faces = 384 float4 of vertices, 96 uint2 of indices)
+		uint32_t stageOff[12];
+#pragma unroll
+		for (int k = 0; k < 12; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
+		}
+		uint2 idxPat[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			const uint32_t b = (i / 3u) * 4u, j = i % 3u;
+			idxPat[k] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
+		}
 
 		const uint32_t nWork = *a.nWork;
 		uint32_t parity = 0;
@@ -597,7 +711,10 @@ namespace tsomk
 					{
 						const uint32_t de = desc[lane];
 						const uint32_t blk = de & 0x7fffu;
-						draw_face(a, cx, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
+						if (fastFlat)
+							draw_face_flat(a, cx, sm.table, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
+						else
+							draw_face(a, cx, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
 					}
 					__syncwarp();
 
@@ -605,10 +722,21 @@ namespace tsomk
 					const unsigned long long face0 = firstFace + f0;
 					if (a.flags & MESH_F_RENDER)
 					{
-						float4* dst = a.vertices + face0 * 12ull;
-						const uint32_t n4 = nf * 12u;
-						for (uint32_t i = lane; i < n4; i += 32u)
-							dst[i] = stage[(i / 12u) * STAGE_FACE_F4 + (i % 12u)];
+						float4* dst = a.vertices + face0 * 12ull + lane;
+						if (nf == 32u)
+						{
+#pragma unroll
+							for (int k = 0; k < 12; ++k)
+								dst[32 * k] = stage[stageOff[k]];
+						}
+						else
+						{
+							const uint32_t n4 = nf * 12u;
+#pragma unroll
+							for (int k = 0; k < 12; ++k)
+								if (uint32_t(lane) + 32u * k < n4)
+									dst[32 * k] = stage[stageOff[k]];
+						}
 					}
 					if (a.flags & MESH_F_COLLIDER)
 					{
@@ -631,14 +759,13 @@ namespace tsomk
 					}
 					{
 						// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
-						uint2* dst = a.indices + face0 * 3ull;
+						uint2* dst = a.indices + face0 * 3ull + lane;
+						const uint32_t base = f0 * 4u;
 						const uint32_t n2 = nf * 3u;
-						for (uint32_t i = lane; i < n2; i += 32u)
-						{
-							const uint32_t face = i / 3u, j = i % 3u;
-							const uint32_t b = (f0 + face) * 4u;
-							dst[i] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
-						}
+#pragma unroll
+						for (int k = 0; k < 3; ++k)
+							if (nf == 32u || uint32_t(lane) + 32u * k < n2)
+								dst[32 * k] = make_uint2(idxPat[k].x + base, idxPat[k].y + base);
 					}
 					__syncwarp();
 				}

@@ -239,6 +239,10 @@ struct tsom_ctx
 	float quat[6][4];
 	uint32_t bStar = 0, aStar = 0, aInv = 0;
 
+	// flat fast path: face attribute table for block size `faceTableTile`
+	tsomk::FaceTable* dFaceTable = nullptr;
+	float faceTableTile = 0.f;
+
 	// device-side timing of the last calls (CUDA events on `stream`)
 	cudaEvent_t ev[6] = {};
 	float timings[TSOM_TIMING_COUNT] = {};
@@ -514,6 +518,7 @@ extern "C"
 		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
 		for (auto& e : ctx->ev)
 			TSOM_CUDA(cudaEventCreate(&e));
+		TSOM_CUDA(cudaMalloc(&ctx->dFaceTable, sizeof(tsomk::FaceTable)));
 
 		const F3h normals[6] = { { 0.f, 0.f, 1.f }, { 0.f, -1.f, 0.f }, { 0.f, 0.f, -1.f }, { -1.f, 0.f, 0.f }, { 1.f, 0.f, 0.f }, { 0.f, 1.f, 0.f } };
 		for (int d = 0; d < 6; ++d)
@@ -556,6 +561,7 @@ extern "C"
 		ctx->gravity.Free();
 		ctx->edits.Free();
 		cudaFree(ctx->dSmall);
+		cudaFree(ctx->dFaceTable);
 		for (auto& e : ctx->ev)
 			if (e)
 				cudaEventDestroy(e);
@@ -1158,6 +1164,21 @@ extern "C"
 		a.deformRadius = params->deform_radius;
 		std::memcpy(a.center, c->center, sizeof(a.center));
 		std::memcpy(a.quat, ctx->quat, sizeof(a.quat));
+
+		// table-driven path: FlatChunk corners and a power-of-two block size make every DrawFace intermediate exact
+		int expo = 0;
+		const bool pow2Tile = c->tile > 0.f && std::isfinite(c->tile) && std::frexp(c->tile, &expo) == 0.5f && expo > -100 && expo < 100;
+		a.faceTable = nullptr;
+		if (!(flags & (TSOM_MESH_DEFORMED | TSOM_MESH_GENERIC_MATH)) && pow2Tile)
+		{
+			if (ctx->faceTableTile != c->tile)
+			{
+				tsomk::launch_face_table(ctx->dFaceTable, c->tile, a, ctx->stream);
+				ctx->launches += 1;
+				ctx->faceTableTile = c->tile;
+			}
+			a.faceTable = ctx->dFaceTable;
+		}
 
 		auto launchEmit = [&]() {
 			a.vertices = ctx->dVertices;

@@ -7,7 +7,15 @@
 
 namespace tsomk
 {
-	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u };
+	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u, MESH_F_GENERIC = 8u };
+
+	// per-(faceUp, slot, twin) face attributes of a FlatChunk with a power-of-two block size (see mesh_kernels.cu)
+	struct FaceTable
+	{
+		float4 uv[6][6][2][2]; // (u0,v0,u1,v1), (u2,v2,u3,v3)
+		float4 normal[6];      // per emission slot
+		uint32_t texDir[6][6]; // [faceUp][slot]
+	};
 
 	struct MeshArgs
 	{
@@ -41,7 +49,10 @@ namespace tsomk
 		float deformRadius;
 		float center[3];  // ChunkContainer::GetCenter()
 		float quat[6][4]; // RotationBetween(s_dirNormals[d], Up) as (w, x, y, z)
+		const FaceTable* faceTable; // non-null: table-driven flat path
 	};
+
+	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st);
 
 	cudaError_t mesh_kernels_init();
 	size_t mesh_count_smem_bytes();
