@@ -15,6 +15,8 @@
 #include "tsom_kernels.h"
 #include "tsom_device.cuh"
 
+#include <climits>
+
 namespace tsomk
 {
 	// ------------------------------------------------------------------------------------------------ siv::PerlinNoise v3.0.0
@@ -119,7 +121,41 @@ namespace tsomk
 		const double cap = double(half);
 		if (cap < t)
 			t = cap;
-		a.terrain[a.terrainOffset[dir] + size_t(tile) * SLAB + j * CS + i] = int16_t(int(round(t)));
+		const int td = int(round(t));
+		a.terrain[a.terrainOffset[dir] + size_t(tile) * SLAB + j * CS + i] = int16_t(td);
+
+		// per-tile range: lets generate_kernel skip a pass for a whole chunk without touching the tile
+		__shared__ int redMin[32], redMax[32];
+		int mn = td, mx = td;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+			mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			redMin[threadIdx.x >> 5] = mn;
+			redMax[threadIdx.x >> 5] = mx;
+		}
+		__syncthreads();
+		if (threadIdx.x < 32)
+		{
+			mn = redMin[threadIdx.x];
+			mx = redMax[threadIdx.x];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+				mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+			}
+			if (threadIdx.x == 0)
+			{
+				const size_t t2 = (a.terrainOffset[dir] / SLAB + size_t(tile)) * 2;
+				a.tileRange[t2] = int16_t(mn);
+				a.tileRange[t2 + 1] = int16_t(mx);
+			}
+		}
 	}
 
 	void launch_terrain(const TerrainArgs& a, cudaStream_t st)
@@ -168,7 +204,13 @@ namespace tsomk
 		uint32_t powX[CS], powY[CS], powZ[CS];
 	};
 
-	__global__ void __launch_bounds__(GEN_THREADS) generate_kernel(const GenArgs a)
+	// ids of 8 consecutive blocks of one row segment
+	struct Ids8
+	{
+		unsigned v[8];
+	};
+
+	__global__ void __launch_bounds__(GEN_THREADS, 3) generate_kernel(const GenArgs a)
 	{
 		__shared__ GenSmem sm;
 		const int tid = threadIdx.x;
@@ -182,15 +224,17 @@ namespace tsomk
 		const int wx0 = ci.x * CS - CS / 2; // + local x
 		const int wy0 = ci.y * CS - CS / 2; // + local z (up)
 		const int wz0 = ci.z * CS - CS / 2; // + local y
+		const int Hx = a.maxH[0], Hy = a.maxH[1], Hz = a.maxH[2];
 
 		// ---- terrain passes: column start heights (Planet.cpp:241-248 and the five twins)
 		// pass order in sm.start: 0 +X(Right) 1 -X(Left) 2 +Y(Up) 3 -Y(Down) 4 +Z(Back) 5 -Z(Front)
+		bool act[6];
 		{
 			const int passDir[6] = { D_RIGHT, D_LEFT, D_UP, D_DOWN, D_BACK, D_FRONT };
 			const int blockDepth[6] = {
-				a.maxH[0] - wx0 + 1, a.maxH[0] + (wx0 + CS - 1) + 1,
-				a.maxH[1] - wy0 + 1, a.maxH[1] + (wy0 + CS - 1) + 1,
-				a.maxH[2] - wz0 + 1, a.maxH[2] + (wz0 + CS - 1) + 1,
+				Hx - wx0 + 1, Hx + (wx0 + CS - 1) + 1,
+				Hy - wy0 + 1, Hy + (wy0 + CS - 1) + 1,
+				Hz - wz0 + 1, Hz + (wz0 + CS - 1) + 1,
 			};
 			const int tx = ci.x - a.tileOrigin[0], ty = ci.y - a.tileOrigin[1], tz = ci.z - a.tileOrigin[2];
 			const size_t tileIdx[6] = {
@@ -201,21 +245,32 @@ namespace tsomk
 #pragma unroll
 			for (int p = 0; p < 6; ++p)
 			{
-				const int16_t* tile = a.terrain + a.terrainOffset[passDir[p]] + tileIdx[p] * SLAB;
+				const size_t tileNo = a.terrainOffset[passDir[p]] / SLAB + tileIdx[p];
+				const int tdMin = a.tileRange[tileNo * 2], tdMax = a.tileRange[tileNo * 2 + 1];
 				const int bd = blockDepth[p];
-				for (int c = tid; c < SLAB; c += GEN_THREADS)
+				// some column has blockDepth >= terrainDepth and start = blockDepth - terrainDepth < 32 ?
+				act[p] = (bd >= tdMin) && (bd - tdMax < CS);
+				if (act[p])
 				{
-					const int td = tile[c];
-					int s = 32;
-					if (bd >= td && bd - td < CS)
-						s = bd - td;
-					sm.start[p][c] = uint8_t(s);
+					const int16_t* tile = a.terrain + tileNo * SLAB;
+#pragma unroll
+					for (int k = 0; k < SLAB / GEN_THREADS; ++k)
+					{
+						const int c = tid + k * GEN_THREADS;
+						const int td = tile[c];
+						int st = 32;
+						if (bd >= td && bd - td < CS)
+							st = bd - td;
+						sm.start[p][c] = uint8_t(st);
+					}
 				}
 			}
 		}
+		const bool actX = act[0] | act[1], actY = act[2] | act[3], actZ = act[4] | act[5];
+		const bool anyAct = actX | actY | actZ;
 
 		// ---- RNG: the blocks that draw (depth - 30 > 18, Planet.cpp:218-219) form a box in local coordinates
-		const int Lx = a.maxH[0] - 49, Ly = a.maxH[1] - 49, Lz = a.maxH[2] - 49; // |wx| <= Lx, |wz| <= Ly, |wy| <= Lz (y/z crossed, :199-203)
+		const int Lx = Hx - 49, Ly = Hy - 49, Lz = Hz - 49; // |wx| <= Lx, |wz| <= Ly, |wy| <= Lz (y/z crossed, :199-203)
 		const int ax0 = max(0, -Lx - wx0), ax1 = min(CS - 1, Lx - wx0);
 		const int ay0 = max(0, -Ly - wz0), ay1 = min(CS - 1, Ly - wz0); // local y <-> world Z
 		const int az0 = max(0, -Lz - wy0), az1 = min(CS - 1, Lz - wy0); // local z <-> world Y
@@ -239,82 +294,116 @@ namespace tsomk
 		uint16_t* out = a.blocks + size_t(slot) * NB;
 		uint16_t* xs = a.xslabs + size_t(slot) * 2 * SLAB;
 
+		// ---- per-thread constants: this thread always produces x in [8*xq, 8*xq+8) of rows with local y = `y`
 		const int xq = tid & 3;
 		const int y = (tid >> 2) & 31;
+		const int xb = xq * 8;
 		const int wz = wz0 + y;
 		const int absWz = abs(wz);
+		const int dYZ_y = Hy - absWz; // the maxHeight.y - |blockPos.z| term
+
+		int dX[8];
+		uint32_t px[8];
+		int dXmin = INT_MAX;
+		unsigned shaft = 0u;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			const int x = xb + j, wx = wx0 + x;
+			dX[j] = Hx - abs(wx);
+			dXmin = min(dXmin, dX[j]);
+			px[j] = (anyDraw && x >= ax0 && x <= ax1) ? sm.powX[x - ax0] : 0u;
+			if (abs(wx) <= 2 && absWz <= 2)
+				shaft |= 1u << j;
+		}
+		// Y passes run along local z: the kept z interval of this thread's 8 columns never changes
+		int zLo[8], zHi[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			zHi[j] = act[2] ? int(sm.start[2][y * CS + xb + j]) : 32;
+			zLo[j] = CS - 1 - (act[3] ? int(sm.start[3][y * CS + xb + j]) : 32);
+		}
+		const bool rowYDraws = anyDraw && y >= ay0 && y <= ay1;
+		const uint32_t rowMulY = rowYDraws ? mulmod31(base2, sm.powY[y - ay0]) : 0u;
 
 #pragma unroll 1
 		for (int it = 0; it < CS / 2; ++it)
 		{
 			const int z = 2 * it + (tid >> 7);
 			const int wy = wy0 + z;
-			const int mYZ = min(a.maxH[1] - absWz, a.maxH[2] - abs(wy));
+			const int mYZ = min(dYZ_y, Hz - abs(wy));
+			const int col = z * CS + y;
 
-			const bool rowDraws = anyDraw && y >= ay0 && y <= ay1 && z >= az0 && z <= az1;
-			uint32_t rowMul = 0u;
-			if (rowDraws)
-				rowMul = mulmod31(mulmod31(base2, sm.powY[y - ay0]), sm.powZ[z - az0]);
-
-			const int col = z * CS + y;  // X passes: [local z][local y]
-			const int sXp = sm.start[0][col], sXm = sm.start[1][col];
-
-			uint32_t packed[4];
-#pragma unroll
-			for (int j = 0; j < 8; ++j)
+			unsigned id[8];
+			if (mYZ < 30)
 			{
-				const int x = xq * 8 + j;
-				const int wx = wx0 + x;
-				const int depth = min(a.maxH[0] - abs(wx), mYZ);
-
-				unsigned id;
-				if (depth < 30)
-					id = 0u;
-				else
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					id[j] = 0u;
+			}
+			else
+			{
+				// bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
+				const bool rowDraws = rowYDraws && z >= az0 && z <= az1;
+				const uint32_t rowMul = rowDraws ? mulmod31(rowMulY, sm.powZ[z - az0]) : 0u;
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
 				{
-					const int d = depth - 30;
-					if (d <= 6)
-						id = a.snow;
-					else if (d <= 18)
-						id = a.dirt;
-					else
+					const int depth = min(dX[j], mYZ);
+					unsigned v;
+					if (depth >= 49)
 					{
-						// draw n of the chunk: u1 = x_{2n+1}, u2 = x_{2n+2}; bernoulli(0.9) == (u2-1, u1-1) lexicographically below (bStar, aStar)
-						const uint32_t u2 = mulmod31(rowMul, sm.powX[x - ax0]);
-						bool stone = (u2 - 1u) < a.bStar;
-						if ((u2 - 1u) == a.bStar)
-						{
-							const uint32_t u1 = mulmod31(u2, a.aInv);
-							stone = (u1 - 1u) < a.aStar;
-						}
-						id = stone ? a.stone : a.stoneMossy;
+						const uint32_t u2 = mulmod31(rowMul, px[j]);
+						bool stone = u2 <= a.bStar;
+						if (u2 == a.bStar + 1u)
+							stone = (mulmod31(u2, a.aInv) - 1u) < a.aStar;
+						v = stone ? a.stone : a.stoneMossy;
 					}
-					if (abs(wx) <= 2 && absWz <= 2)
-						id = 0u; // central shaft, after the draw (Planet.cpp:221-222)
+					else
+						v = depth < 30 ? 0u : (depth <= 36 ? a.snow : a.dirt);
+					id[j] = v;
+				}
+				if (shaft)
+				{
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+						if ((shaft >> j) & 1u)
+							id[j] = 0u; // central shaft, after the draw (Planet.cpp:221-222)
 				}
 
-				// terrain carve: height along each pass's axis
-				const int sYp = sm.start[2][y * CS + x], sYm = sm.start[3][y * CS + x]; // Y passes: [local y][local x], along local z
-				const int sZp = sm.start[4][z * CS + x], sZm = sm.start[5][z * CS + x]; // Z passes: [local z][local x], along local y
-				const int hXp = x, hXm = CS - 1 - x, hYp = z, hYm = CS - 1 - z, hZp = y, hZm = CS - 1 - y;
-				const bool above = (hXp > sXp) | (hXm > sXm) | (hYp > sYp) | (hYm > sYm) | (hZp > sZp) | (hZm > sZm);
-				const bool at = (hXp == sXp) | (hXm == sXm) | (hYp == sYp) | (hYm == sYm) | (hZp == sZp) | (hZm == sZm);
-				if (above)
-					id = 0u;
-				else if (at && id == a.dirt)
-					id = a.grass;
-
-				if (j & 1)
-					packed[j >> 1] |= id << 16;
-				else
-					packed[j >> 1] = id;
-
-				if (x == 0)
-					xs[col] = uint16_t(id);
-				if (x == CS - 1)
-					xs[SLAB + col] = uint16_t(id);
+				if (anyAct)
+				{
+					// "Empty above any column start, grass if dirt at a column start" (Planet.cpp:250-254 and twins)
+					const int sXp = act[0] ? int(sm.start[0][col]) : 32;
+					const int xLo = CS - 1 - (act[1] ? int(sm.start[1][col]) : 32);
+					uint2 zp = make_uint2(0x20202020u, 0x20202020u), zm = zp;
+					if (act[4])
+						zp = *reinterpret_cast<const uint2*>(&sm.start[4][z * CS + xb]);
+					if (act[5])
+						zm = *reinterpret_cast<const uint2*>(&sm.start[5][z * CS + xb]);
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+					{
+						const int x = xb + j;
+						const int sZp = int(((j < 4 ? zp.x : zp.y) >> (8 * (j & 3))) & 0xffu);
+						const int yLo = CS - 1 - int(((j < 4 ? zm.x : zm.y) >> (8 * (j & 3))) & 0xffu);
+						const bool above = (x > sXp) | (x < xLo) | (z > zHi[j]) | (z < zLo[j]) | (y > sZp) | (y < yLo);
+						const bool at = (x == sXp) | (x == xLo) | (z == zHi[j]) | (z == zLo[j]) | (y == sZp) | (y == yLo);
+						if (above)
+							id[j] = 0u;
+						else if (at && id[j] == a.dirt)
+							id[j] = a.grass;
+					}
+				}
 			}
-			*reinterpret_cast<uint4*>(out + (size_t(z) * CS + y) * CS + xq * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+
+			*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) =
+				make_uint4(id[0] | (id[1] << 16), id[2] | (id[3] << 16), id[4] | (id[5] << 16), id[6] | (id[7] << 16));
+			if (xq == 0)
+				xs[col] = uint16_t(id[0]);
+			if (xq == 3)
+				xs[SLAB + col] = uint16_t(id[7]);
 		}
 	}
 

@@ -20,6 +20,7 @@ namespace tsomk
 	constexpr int MESH_THREADS = 512;
 	constexpr int MESH_WARPS = MESH_THREADS / 32;
 	constexpr int ROWS = CS * CS; // 1024 x-rows per chunk
+	constexpr int FLAG_LUT = 256; // block types below this id are looked up in shared memory, the rest in global memory
 
 	// staging: one face = 12 float4 (4 vertices x 48 B) padded to 13 so lane-strided 16-byte stores are conflict free
 	constexpr int STAGE_FACE_F4 = 13;
@@ -56,6 +57,7 @@ namespace tsomk
 		uint32_t total;
 		alignas(8) uint64_t bar;
 		alignas(16) FaceTable table;
+		uint8_t flagLut[FLAG_LUT];
 		// phase 1-2 only; the emit kernel reuses this area as the face staging buffer
 		union
 		{
@@ -81,11 +83,20 @@ namespace tsomk
 		uint32_t warpSum[MESH_WARPS + 1];
 		uint32_t job;
 		alignas(8) uint64_t bar;
+		uint8_t flagLut[FLAG_LUT];
 	};
 
-	__device__ __forceinline__ unsigned block_flags(const MeshArgs& a, unsigned id)
+	__device__ __forceinline__ unsigned block_flags(const MeshArgs& a, const uint8_t* lut, unsigned id)
 	{
+		if (id < FLAG_LUT)
+			return lut[id];
 		return __ldg(a.blkFlags + (id < a.nTypes ? id : a.nTypes - 1));
+	}
+
+	__device__ __forceinline__ void load_flag_lut(const MeshArgs& a, uint8_t* lut)
+	{
+		for (int i = threadIdx.x; i < FLAG_LUT; i += MESH_THREADS)
+			lut[i] = a.blkFlags[uint32_t(i) < a.nTypes ? i : a.nTypes - 1];
 	}
 
 	// ---- stage one chunk: 64 KiB of ids + six 2 KiB halo slabs, by TMA bulk copies completing on one mbarrier ----
@@ -141,34 +152,62 @@ namespace tsomk
 	}
 
 	// ---- phase 1: per-row bit masks via warp ballots (lane = x) ----
-	__device__ __forceinline__ void build_masks(const MeshArgs& a, const uint16_t* ids, const uint16_t (*halo)[SLAB],
+	__device__ __forceinline__ void build_masks(const MeshArgs& a, const uint8_t* lut, const uint16_t* ids, const uint16_t (*halo)[SLAB],
 	                                            uint32_t* mT, uint32_t* mE, uint32_t* mD, uint32_t (*hT)[CS])
 	{
 		const int lane = threadIdx.x & 31;
 		const int warp = threadIdx.x >> 5;
 
-		for (int r = warp; r < ROWS; r += MESH_WARPS)
+		// own rows: 64 per warp, 8 at a time so the shared-memory loads of a batch overlap
+#pragma unroll 1
+		for (int r0 = warp * (ROWS / MESH_WARPS); r0 < (warp + 1) * (ROWS / MESH_WARPS); r0 += 8)
 		{
-			unsigned id = ids[r * CS + lane];
-			unsigned f = block_flags(a, id);
-			uint32_t t = __ballot_sync(0xffffffffu, (f & BF_TRANSPARENT) != 0);
-			uint32_t e = __ballot_sync(0xffffffffu, id != 0);
-			uint32_t d = __ballot_sync(0xffffffffu, (f & BF_DOUBLE_SIDED) != 0);
-			if (lane == 0)
+			unsigned id[8], f[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				id[k] = ids[(r0 + k) * CS + lane];
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				f[k] = block_flags(a, lut, id[k]);
+			uint32_t t = 0, e = 0, d = 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
 			{
-				mT[r] = t;
-				mE[r] = e;
-				mD[r] = d;
+				const uint32_t bt = __ballot_sync(0xffffffffu, (f[k] & BF_TRANSPARENT) != 0);
+				const uint32_t be = __ballot_sync(0xffffffffu, id[k] != 0);
+				const uint32_t bd = __ballot_sync(0xffffffffu, (f[k] & BF_DOUBLE_SIDED) != 0);
+				if (lane == k)
+				{
+					t = bt;
+					e = be;
+					d = bd;
+				}
+			}
+			if (lane < 8)
+			{
+				mT[r0 + lane] = t;
+				mE[r0 + lane] = e;
+				mD[r0 + lane] = d;
 			}
 		}
-		// halo slabs: 6 x 32 rows
-		for (int r = warp; r < 6 * CS; r += MESH_WARPS)
+		// halo slabs: 6 x 32 rows = 12 per warp
+#pragma unroll 1
+		for (int r0 = warp * (6 * CS / MESH_WARPS); r0 < (warp + 1) * (6 * CS / MESH_WARPS); r0 += 4)
 		{
-			int d = r >> 5, j = r & 31;
-			unsigned id = halo[d][j * CS + lane];
-			uint32_t t = __ballot_sync(0xffffffffu, (block_flags(a, id) & BF_TRANSPARENT) != 0);
-			if (lane == 0)
-				hT[d][j] = t;
+			unsigned id[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				id[k] = halo[(r0 + k) >> 5][((r0 + k) & 31) * CS + lane];
+			uint32_t t = 0;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+			{
+				const uint32_t bt = __ballot_sync(0xffffffffu, (block_flags(a, lut, id[k]) & BF_TRANSPARENT) != 0);
+				if (lane == k)
+					t = bt;
+			}
+			if (lane < 4)
+				hT[(r0 + lane) >> 5][(r0 + lane) & 31] = t;
 		}
 	}
 
@@ -264,6 +303,7 @@ namespace tsomk
 			mbar_init(&sm.bar, 1);
 			fence_mbar_init();
 		}
+		load_flag_lut(a, sm.flagLut);
 		__syncthreads();
 
 		uint32_t parity = 0;
@@ -290,7 +330,7 @@ namespace tsomk
 			parity ^= 1;
 			__syncthreads();
 
-			build_masks(a, sm.ids, sm.halo, sm.mT, sm.mE, sm.mD, sm.hT);
+			build_masks(a, sm.flagLut, sm.ids, sm.halo, sm.mT, sm.mE, sm.mD, sm.hT);
 			__syncthreads();
 
 			uint32_t v[2][6];
@@ -534,6 +574,7 @@ namespace tsomk
 			mbar_init(&sm.bar, 1);
 			fence_mbar_init();
 		}
+		load_flag_lut(a, sm.flagLut);
 		__syncthreads();
 
 		const bool fastFlat = a.faceTable != nullptr;
@@ -581,7 +622,7 @@ namespace tsomk
 			parity ^= 1;
 			__syncthreads();
 
-			build_masks(a, sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.mD, sm.u.front.hT);
+			build_masks(a, sm.flagLut, sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.mD, sm.u.front.hT);
 			__syncthreads();
 
 			uint32_t v[2][6];

@@ -301,7 +301,7 @@ struct tsom_container
 	uint32_t nGhost = 0;
 
 	// terrain tables of the last generate call
-	DevBuf<int16_t> terrain;
+	DevBuf<int16_t> terrain, tileRange;
 	uint8_t* dPerm = nullptr;
 	DevBuf<int> slotGrid;
 
@@ -687,6 +687,7 @@ extern "C"
 		c->ghostSlabs.Free();
 		c->ghostDescs.Free();
 		c->terrain.Free();
+		c->tileRange.Free();
 		c->slotGrid.Free();
 		delete c;
 	}
@@ -879,7 +880,9 @@ extern "C"
 			total += tiles[d] * SLAB;
 		}
 		TSOM_CUDA(c->terrain.Ensure(total));
+		TSOM_CUDA(c->tileRange.Ensure(total / SLAB * 2));
 		ta.terrain = c->terrain.ptr;
+		ta.tileRange = c->tileRange.ptr;
 		uint8_t perm[6 * 256];
 		for (int d = 0; d < 6; ++d)
 			PerlinPermutation(seed + unsigned(d), perm + d * 256); // Planet.cpp:179-181
@@ -908,6 +911,7 @@ extern "C"
 			ga.tileCount[k] = ta.tileCount[k];
 		}
 		ga.terrain = c->terrain.ptr;
+		ga.tileRange = c->tileRange.ptr;
 		for (int d = 0; d < 6; ++d)
 			ga.terrainOffset[d] = ta.terrainOffset[d];
 		ga.dirt = ids->dirt;

@@ -75,6 +75,7 @@ namespace tsomk
 		int tileOrigin[3];       // smallest chunk index covered by the terrain tables, per axis
 		int tileCount[3];        // tiles per axis
 		const int16_t* terrain;  // 6 tables of 32x32 tiles, see gen_kernels.cu
+		const int16_t* tileRange; // (min, max) terrainDepth per tile, indexed by global tile number
 		size_t terrainOffset[6]; // element offset of each direction's table
 		uint16_t dirt, grass, stone, stoneMossy, snow;
 		uint32_t bStar, aStar;   // integer form of `bernoulli(0.9)` over two minstd draws
@@ -84,6 +85,7 @@ namespace tsomk
 	struct TerrainArgs
 	{
 		int16_t* terrain;
+		int16_t* tileRange;
 		size_t terrainOffset[6];
 		int tileOrigin[3];
 		int tileCount[3];
