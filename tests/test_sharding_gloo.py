@@ -1,0 +1,168 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of thisspaceofmine_b200.sharding.
+
+Each rank generates its chunk range with the oracle, fetches ONLY the boundary slabs ShardPlan says it needs from the other rank
+(the CPU stand-in for tsom_halo_pull's P2P copy), meshes its range and must reproduce the single-process golden fixture
+(tests/golden/planet_7_3x3x3.npz): mesh(N ranks) == mesh(1 rank)."""
+import os
+import socket
+import sys
+import zlib
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from thisspaceofmine_b200.sharding import CHUNK_DIR_OFFSET, ShardPlan, chunk_grid, partition  # noqa: E402
+
+
+def test_partition_is_contiguous_and_balanced():
+    for n, w in [(125, 1), (125, 2), (125, 8), (27, 4), (3, 8), (103823, 8)]:
+        r = partition(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [e - s for s, e in r]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_chunk_grid_is_generatechunks_order():
+    g = chunk_grid((5, 5, 5))
+    assert g[0].tolist() == [-2, -2, -2] and g[1].tolist() == [-1, -2, -2] and g[5].tolist() == [-2, -1, -2] and g[25].tolist() == [-2, -2, -1]
+    plan = ShardPlan((5, 3, 7), 3)
+    assert np.array_equal(plan.linear_id(plan.grid), np.arange(plan.n))
+    assert plan.linear_id([[3, 0, 0], [0, 2, 0], [0, 0, -4]]).tolist() == [-1, -1, -1]
+
+
+def test_remote_neighbours_are_symmetric_and_face_adjacent_only():
+    plan = ShardPlan((5, 5, 5), 4)
+    rem = [plan.remote_neighbours(r) for r in range(4)]
+    for r in range(4):
+        mine = set(map(tuple, plan.local(r).tolist()))
+        for peer, lids in rem[r].items():
+            assert peer != r and np.all(plan.owner[lids] == peer)
+            for idx in plan.grid[lids]:
+                assert any(tuple((idx - CHUNK_DIR_OFFSET[d]).tolist()) in mine for d in range(6))
+            # symmetry: if I need chunks from peer, peer needs chunks from me
+            assert r in rem[peer]
+    # z-major ranges: with 5 z-layers over 4 ranks most cuts cross Back/Front only; halo volume is bounded by 2 layers per cut + ragged rows
+    assert plan.halo_bytes(0) <= (25 + 10) * 2048 * 2
+    # slots: position inside the owner's range
+    s, e = plan.ranges[2]
+    assert plan.slot_of(np.arange(s, e)).tolist() == list(range(e - s))
+    assert ShardPlan((3, 3, 3), 1).remote_neighbours(0) == {}
+
+
+def _crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+
+
+def _facing_layer(blocks, d):
+    """The layer of a neighbour chunk (towards direction d from me) that faces me, as a full ghost chunk (zeros elsewhere)."""
+    b = blocks.reshape(32, 32, 32)  # [z(up), y(world Z), x]
+    g = np.zeros_like(b)
+    # Direction order Back(+Z: local y+1), Down(local z-1), Front(local y-1), Left(x-1), Right(x+1), Up(local z+1)
+    if d == 0:
+        g[:, 0, :] = b[:, 0, :]
+    elif d == 1:
+        g[31, :, :] = b[31, :, :]
+    elif d == 2:
+        g[:, 31, :] = b[:, 31, :]
+    elif d == 3:
+        g[:, :, 31] = b[:, :, 31]
+    elif d == 4:
+        g[:, :, 0] = b[:, :, 0]
+    else:
+        g[0, :, :] = b[0, :, :]
+    return g.reshape(-1)
+
+
+def _worker(rank, world, port, result_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.load(os.path.join(GOLDEN, "planet_7_3x3x3.npz"))
+        count = tuple(int(v) for v in g["count"])
+        seed = int(g["seed"])
+        plan = ShardPlan(count, world)
+        s, e = plan.ranges[rank]
+        mine = plan.local(rank)
+        blocks = {}
+        for idx in mine:
+            b, ok = O.generate_chunk(seed, count, idx)
+            assert ok
+            blocks[tuple(idx.tolist())] = b
+
+        # "halo pull": publish which (linear id, direction) slabs I need, owners answer with exactly those slabs
+        need = []  # (owner, linear id of the neighbour, direction from my chunk)
+        for idx in mine:
+            for d in range(6):
+                lid = int(plan.linear_id(idx + CHUNK_DIR_OFFSET[d])[0])
+                if lid >= 0 and plan.owner[lid] != rank:
+                    need.append((int(plan.owner[lid]), lid, d))
+        # the plan's remote list must cover exactly the owners/chunks found by the brute-force walk
+        rem = plan.remote_neighbours(rank)
+        assert {(o, l) for o, l, _ in need} == {(p, int(l)) for p, ls in rem.items() for l in ls}
+        all_need = [None] * world
+        dist.all_gather_object(all_need, need)
+        answers = []
+        for r in range(world):
+            answers.append([(lid, d, _facing_layer(blocks[tuple(plan.grid[lid].tolist())], d)) for o, lid, d in all_need[r] if o == rank])
+        got = [None] * world
+        dist.all_gather_object(got, answers)  # got[p][rank] = slabs rank p owns that I asked for
+        assert sum(len(got[p][rank]) for p in range(world)) * 2048 == plan.halo_bytes(rank)
+
+        planet = O.Planet(1.0, 16.0)
+        for k, b in blocks.items():
+            planet.add_chunk(k, b)
+        ghosts = {}
+        for p in range(world):
+            for lid, d, layer in got[p][rank]:
+                k = tuple(plan.grid[lid].tolist())
+                ghosts[k] = layer if k not in ghosts else np.maximum(ghosts[k], layer)  # a ghost can face two of my chunks
+        for k, b in ghosts.items():
+            planet.add_chunk(k, b)
+
+        faces, icrc = [], []
+        for idx in mine:
+            m = planet.mesh(idx)
+            faces.append(0 if m is None else m.face_count)
+            icrc.append(0 if m is None else _crc(m.indices))
+        ok = np.array_equal(np.array(faces, np.uint32), g["face_count"][s:e]) and np.array_equal(np.array(icrc, np.uint32), g["index_crc"][s:e])
+        bok = all(_crc(blocks[tuple(idx.tolist())]) == g["block_crc"][s + i] for i, idx in enumerate(mine))
+        result_q.put((rank, bool(ok), bool(bok), int(sum(faces))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_planet_matches_single_process_golden():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [0, 1]
+    assert all(r[1] for r in res), "sharded meshes differ from the single-process golden"
+    assert all(r[2] for r in res), "sharded block ids differ from the single-process golden"
+    g = np.load(os.path.join(GOLDEN, "planet_7_3x3x3.npz"))
+    assert sum(r[3] for r in res) == int(g["face_count"].sum())

@@ -1,0 +1,160 @@
+"""Whole-planet sharding across GPUs: one process per GPU, chunks split by linear chunk id, halo slabs pulled over NVLink P2P.
+
+Chunks are independent given the boundary layers of their six face-adjacent neighbours (reference src/CommonLib/Chunk.cpp:104-172),
+so a planet is cut into contiguous ranges of the linear chunk id ``i = (z * ny + y) * nx + x`` — the order Planet::GenerateChunks
+walks (reference src/CommonLib/Planet.cpp:387-393).  Each rank generates and meshes its own range; between the two phases it copies
+the 2 KiB facing slab of every neighbour chunk owned by another rank straight out of that rank's HBM (cudaIpc mapping + a copy
+kernel, ``tsom_halo_pull``).  There is no collective on the data path; ``torch.distributed`` only carries the 136-byte IPC handles
+once and the barriers that order "peer finished writing" before "I read".
+
+``ShardPlan`` is pure integer host logic (tested on CPU with gloo, world_size 2); ``ShardedPlanet`` drives the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# Direction.hpp:83-90 (world axes): Back, Down, Front, Left, Right, Up
+CHUNK_DIR_OFFSET = np.array([[0, 0, 1], [0, -1, 0], [0, 0, -1], [-1, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.int32)
+
+
+def chunk_grid(chunkCount: Sequence[int]) -> np.ndarray:
+    """Chunk indices in GenerateChunks order (z, y, x loops; (x,y,z) - chunkCount/2, Planet.cpp:387-393) -> [n, 3] int32."""
+    nx, ny, nz = (int(v) for v in chunkCount)
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    return np.stack([x.ravel() - nx // 2, y.ravel() - ny // 2, z.ravel() - nz // 2], axis=1).astype(np.int32)
+
+
+def partition(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced ranges [start, end) of the linear chunk id; the first n % world ranks get one extra chunk."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    base, extra = divmod(n, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+class ShardPlan:
+    """Who owns which chunk, and which neighbour chunks each rank must mirror."""
+
+    def __init__(self, chunkCount: Sequence[int], world: int):
+        self.chunkCount = tuple(int(v) for v in chunkCount)
+        self.world = int(world)
+        self.grid = chunk_grid(self.chunkCount)
+        self.n = len(self.grid)
+        self.ranges = partition(self.n, self.world)
+        self.owner = np.empty(self.n, np.int32)
+        for r, (s, e) in enumerate(self.ranges):
+            self.owner[s:e] = r
+
+    def linear_id(self, idx) -> np.ndarray:
+        """Linear chunk id of chunk indices [k, 3]; -1 outside the planet."""
+        a = np.asarray(idx, np.int64).reshape(-1, 3)
+        nx, ny, nz = self.chunkCount
+        x, y, z = a[:, 0] + nx // 2, a[:, 1] + ny // 2, a[:, 2] + nz // 2
+        ok = (x >= 0) & (x < nx) & (y >= 0) & (y < ny) & (z >= 0) & (z < nz)
+        return np.where(ok, (z * ny + y) * nx + x, -1)
+
+    def local(self, rank: int) -> np.ndarray:
+        s, e = self.ranges[rank]
+        return self.grid[s:e]
+
+    def slot_of(self, linear: np.ndarray) -> np.ndarray:
+        """Slot of a chunk inside its owner's container: chunks are added in range order into an empty container."""
+        starts = np.array([s for s, _ in self.ranges], np.int64)
+        return (np.asarray(linear, np.int64) - starts[self.owner[linear]]).astype(np.uint32)
+
+    def remote_neighbours(self, rank: int) -> Dict[int, np.ndarray]:
+        """peer rank -> sorted unique linear ids of the chunks it owns that are face-adjacent to a chunk of `rank`."""
+        mine = self.local(rank)
+        out: Dict[int, set] = {}
+        for d in range(6):
+            lid = self.linear_id(mine + CHUNK_DIR_OFFSET[d])
+            lid = lid[lid >= 0]
+            own = self.owner[lid]
+            for peer in np.unique(own):
+                if peer != rank:
+                    out.setdefault(int(peer), set()).update(int(v) for v in lid[own == peer])
+        return {p: np.array(sorted(v), np.int64) for p, v in sorted(out.items())}
+
+    def halo_bytes(self, rank: int) -> int:
+        """Bytes `rank` pulls per exchange: one 2 KiB slab per (local chunk, direction) whose neighbour is remote."""
+        mine = self.local(rank)
+        total = 0
+        for d in range(6):
+            lid = self.linear_id(mine + CHUNK_DIR_OFFSET[d])
+            lid = lid[lid >= 0]
+            total += int((self.owner[lid] != rank).sum()) * 2048
+        return total
+
+
+class ShardedPlanet:
+    """One rank's share of a Planet (Planet::GenerateChunks + Chunk::BuildMesh over the rank's chunk range)."""
+
+    def __init__(self, ctx, chunkCount: Sequence[int], rank: int, world: int, tileSize: float = 1.0, group=None):
+        from .host import Planet
+
+        self.ctx, self.rank, self.world, self.group = ctx, int(rank), int(world), group
+        self.plan = ShardPlan(chunkCount, world)
+        self.local_grid = np.ascontiguousarray(self.plan.local(rank))
+        self.planet = Planet(ctx, tileSize, capacity=max(len(self.local_grid), 1))
+        self._connected = False
+
+    def close(self):
+        self.planet.close()
+
+    # ---- phase 1: generation (no communication)
+    def GenerateChunks(self, blockLibrary, seed: int):
+        if len(self.local_grid):
+            self.planet.GenerateChunk(blockLibrary, self.local_grid, seed, self.plan.chunkCount)
+
+    # ---- phase 1.5: halo exchange over P2P
+    def _dist(self):
+        import torch.distributed as dist
+
+        return dist
+
+    def ConnectPeers(self):
+        """Once per planet: swap IPC handles of the block stores, map the peers, declare the remote neighbour chunks."""
+        from . import _lib as L
+
+        if self._connected or self.world == 1:
+            self._connected = True
+            return
+        dist = self._dist()
+        h = L.IpcHandle()
+        L.check(L.lib().tsom_ipc_export(self.planet._h, C.byref(h)))
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(h.bytes), group=self.group)
+        rem = self.plan.remote_neighbours(self.rank)
+        for peer, lids in rem.items():
+            ph = L.IpcHandle()
+            C.memmove(ph.bytes, handles[peer], len(handles[peer]))
+            L.check(L.lib().tsom_ipc_attach(self.planet._h, peer, C.byref(ph)))
+            idx = np.ascontiguousarray(self.plan.grid[lids])
+            slots = np.ascontiguousarray(self.plan.slot_of(lids))
+            ranks = np.full(len(lids), peer, np.int32)
+            L.check(L.lib().tsom_container_add_remote_chunks(self.planet._h, idx.ctypes.data_as(C.POINTER(C.c_int32)), slots.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                             ranks.ctypes.data_as(C.POINTER(C.c_int32)), len(lids)))
+        self._connected = True
+
+    def PullHalos(self):
+        """Barrier (every peer finished writing its blocks) -> copy the remote boundary slabs into the local ghost slabs."""
+        from . import _lib as L
+
+        if self.world == 1:
+            return
+        self.ConnectPeers()
+        self.ctx.synchronize()
+        self._dist().barrier(group=self.group)
+        L.check(L.lib().tsom_halo_pull(self.planet._h))
+
+    # ---- phase 2: meshing (no communication)
+    def BuildMeshes(self, **kw):
+        return self.planet.BuildMeshes(self.local_grid, **kw)
