@@ -461,29 +461,52 @@ namespace tsomk
 		return __ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir);
 	}
 
-	// DrawFace (Chunk.cpp:22-102), generic arithmetic: writes 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}
-	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	// one face held in registers: 4 positions, the shared normal, 4 uv pairs and the texture slice
+	struct FaceOut
 	{
-		F3 blockCenter, pos[4], fc;
-		face_geometry(cx, x, y, z, slot, twin, blockCenter, pos, fc);
+		F3 pos[4];
+		F3 n;
+		float u[4], v[4];
+		float slice;
+	};
 
-		F3 normal = f3(0.f, 0.f, 0.f);
-		float u[4] = { 0.f, 0.f, 0.f, 0.f }, v[4] = { 0.f, 0.f, 0.f, 0.f };
-		float slice = 0.f;
+	// 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}; the tangent slot stays zero (never written by Chunk::BuildMesh)
+	__device__ __forceinline__ void store_face(float4* out, const FaceOut& f)
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			out[i * 3 + 0] = make_float4(f.pos[i].x, f.pos[i].y, f.pos[i].z, f.n.x);
+			out[i * 3 + 1] = make_float4(f.n.y, f.n.z, f.u[i], f.v[i]);
+			out[i * 3 + 2] = make_float4(f.slice, 0.f, 0.f, 0.f);
+		}
+	}
+
+	// DrawFace (Chunk.cpp:22-102), generic arithmetic
+	__device__ __forceinline__ void draw_face_r(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, FaceOut& o)
+	{
+		F3 blockCenter, fc;
+		face_geometry(cx, x, y, z, slot, twin, blockCenter, o.pos, fc);
+
+		o.n = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			o.u[i] = o.v[i] = 0.f;
+		o.slice = 0.f;
 		if (cx.wantAttr)
 		{
 			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
 			int texDir;
-			face_attrs(a.quat, faceUp, blockCenter, pos, fc, normal, texDir, u, v);
-			slice = float(tex_slice(a, id, texDir));
+			face_attrs(a.quat, faceUp, blockCenter, o.pos, fc, o.n, texDir, o.u, o.v);
+			o.slice = float(tex_slice(a, id, texDir));
 		}
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-		{
-			out[i * 3 + 0] = make_float4(pos[i].x, pos[i].y, pos[i].z, normal.x);
-			out[i * 3 + 1] = make_float4(normal.y, normal.z, u[i], v[i]);
-			out[i * 3 + 2] = make_float4(slice, 0.f, 0.f, 0.f); // tangent stays zero (never written by Chunk::BuildMesh)
-		}
+	}
+
+	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	{
+		FaceOut o;
+		draw_face_r(a, cx, x, y, z, slot, twin, id, o);
+		store_face(out, o);
 	}
 
 	// ---- table-driven flat path ----
@@ -517,7 +540,7 @@ namespace tsomk
 
 	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st) { face_table_kernel<<<1, 96, 0, st>>>(table, tile, a); }
 
-	__device__ __forceinline__ void draw_face_flat(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	__device__ __forceinline__ void draw_face_flat_r(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, FaceOut& o)
 	{
 		const float s = cx.tile;
 		// Boxf(blockPos.x, blockPos.z, blockPos.y, s, s, s) with blockPos = (indices - size / 2) * s (FlatChunk.cpp:50-53)
@@ -525,40 +548,39 @@ namespace tsomk
 		const float oy = (float(z) - float(CS) * 0.5f) * s;
 		const float oz = (float(y) - float(CS) * 0.5f) * s;
 		const float ex = ox + s, ey = oy + s, ez = oz + s;
-		F3 pos[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 		{
 			const unsigned code = c_faceCorners[slot][twin ? (i ^ 1) : i];
-			pos[i] = f3((code & 1u) ? ex : ox, (code & 2u) ? ey : oy, (code & 4u) ? ez : oz);
+			o.pos[i] = f3((code & 1u) ? ex : ox, (code & 2u) ? ey : oy, (code & 4u) ? ez : oz);
 		}
 		float4 uv0 = make_float4(0.f, 0.f, 0.f, 0.f), uv1 = uv0, n = uv0;
-		float slice = 0.f;
+		o.slice = 0.f;
 		if (cx.wantAttr)
 		{
 			F3 fc = f3(0.f, 0.f, 0.f);
 #pragma unroll
 			for (int i = 0; i < 4; ++i)
-				fc = fc + pos[i];
+				fc = fc + o.pos[i];
 			fc = fc / 4.f;
 			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
 			n = tb.normal[slot];
-			slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
+			o.slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
 		}
-		out[0] = make_float4(pos[0].x, pos[0].y, pos[0].z, n.x);
-		out[1] = make_float4(n.y, n.z, uv0.x, uv0.y);
-		out[2] = make_float4(slice, 0.f, 0.f, 0.f);
-		out[3] = make_float4(pos[1].x, pos[1].y, pos[1].z, n.x);
-		out[4] = make_float4(n.y, n.z, uv0.z, uv0.w);
-		out[5] = make_float4(slice, 0.f, 0.f, 0.f);
-		out[6] = make_float4(pos[2].x, pos[2].y, pos[2].z, n.x);
-		out[7] = make_float4(n.y, n.z, uv1.x, uv1.y);
-		out[8] = make_float4(slice, 0.f, 0.f, 0.f);
-		out[9] = make_float4(pos[3].x, pos[3].y, pos[3].z, n.x);
-		out[10] = make_float4(n.y, n.z, uv1.z, uv1.w);
-		out[11] = make_float4(slice, 0.f, 0.f, 0.f);
+		o.n = f3(n.x, n.y, n.z);
+		o.u[0] = uv0.x; o.v[0] = uv0.y;
+		o.u[1] = uv0.z; o.v[1] = uv0.w;
+		o.u[2] = uv1.x; o.v[2] = uv1.y;
+		o.u[3] = uv1.z; o.v[3] = uv1.w;
+	}
+
+	__device__ __forceinline__ void draw_face_flat(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
+	{
+		FaceOut o;
+		draw_face_flat_r(a, cx, tb, x, y, z, slot, twin, id, o);
+		store_face(out, o);
 	}
 
 	__global__ void __launch_bounds__(MESH_THREADS, 1) mesh_emit_kernel(const MeshArgs a)
@@ -816,6 +838,540 @@ namespace tsomk
 	}
 
 	// =====================================================================================================================
+	// mesh_fused_kernel — the whole of Chunk::BuildMesh for a batch of chunks in ONE pass over the ids.
+	//
+	//   * 256 threads, 2 CTAs per SM (113 KB of shared memory each): while one CTA streams faces out, the other stages and
+	//     classifies its next chunk, so the front end hides behind the HBM writes instead of serialising with them.
+	//   * ids arrive by TMA bulk copies (4 x 16 KiB on one mbarrier); the six halo slabs are read straight from global memory
+	//     (16-byte loads) while the TMA is in flight, and only their 32x32 transparency bits are kept.
+	//   * row masks: each thread classifies 8 ids per 16-byte shared-memory load through a packed flag table
+	//     (transparent | non-empty << 8 | double-sided << 16), with a one-lookup shortcut when the 8 ids are equal.
+	//   * the per-chunk face count is chained across chunks by a decoupled look-back over `status` (job order == ticket order),
+	//     so every chunk learns its first face in the arena without a separate count kernel; `firstFace`/`faceCount` are
+	//     identical to an exclusive scan in job order.  If the arena is too small the kernel only counts; the host grows the
+	//     arena to the exact total and runs it again.
+	//   * faces are enumerated from a compact list of the rows that have faces (`ne`): a warp takes a window of 128 consecutive
+	//     faces, finds the first row by a two-level ballot search, and lanes walk one row each, writing 16-bit face descriptors
+	//     in the reference's emission order.  Faces are then built one per lane in registers and streamed out through a
+	//     16-face staging tile with fully coalesced 16-byte stores.
+	constexpr int FUSED_THREADS = 256;
+	constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+	constexpr int WIN = 128;        // faces per descriptor window
+	constexpr int HALF_FACES = 16;  // faces per staging round
+	constexpr int LUTN = 128;       // block types below this id are classified from shared memory
+	constexpr uint32_t NE_OFF_MASK = 0x7FFFFu; // ne[k] = first face of the row (19 bits; a chunk has at most 393,216 faces) | row << 19
+	constexpr int NE_ROW_SHIFT = 19;
+
+	struct FusedSmem
+	{
+		uint16_t ids[NB];                 // 65536 B, TMA destination
+		uint32_t mT[ROWS], mE[ROWS], mD[ROWS];
+		uint32_t ne[ROWS + 4];            // compact list of rows with faces, + sentinel ne[K] = F
+		uint32_t hT[6][CS];               // transparency bits of the six halo slabs (Left/Right: bit = y, row = z)
+		float4 stage[FUSED_WARPS][HALF_FACES * STAGE_FACE_F4];
+		uint16_t desc[FUSED_WARPS][WIN];  // x | slot << 5 | twin << 8 | (compact row - first compact row of the window) << 9
+		uint32_t lut32[LUTN];
+		alignas(16) FaceTable table;
+		uint32_t warpSum[FUSED_WARPS];
+		uint32_t job;
+		unsigned long long firstFace;
+		alignas(8) uint64_t bar;
+	};
+	static_assert(sizeof(FusedSmem) <= 113 * 1024, "two CTAs of mesh_fused_kernel must fit one SM");
+
+	__device__ __forceinline__ uint32_t pack_flags(unsigned f, unsigned id)
+	{
+		return ((f & BF_TRANSPARENT) ? 1u : 0u) | (id != 0u ? 0x100u : 0u) | ((f & BF_DOUBLE_SIDED) ? 0x10000u : 0u);
+	}
+
+	__device__ __forceinline__ uint32_t flags32(const MeshArgs& a, const uint32_t* lut, unsigned id)
+	{
+		if (id < LUTN)
+			return lut[id];
+		return pack_flags(__ldg(a.blkFlags + (id < a.nTypes ? id : a.nTypes - 1)), id);
+	}
+
+	// 8 ids -> t8 | e8 << 8 | d8 << 16 (bit j of each byte = id j)
+	__device__ __forceinline__ uint32_t flags8(const MeshArgs& a, const uint32_t* lut, uint4 w)
+	{
+		if (w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu))
+			return flags32(a, lut, w.x & 0xffffu) * 0xFFu;
+		const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+		uint32_t acc = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+		{
+			acc |= flags32(a, lut, ws[j] & 0xffffu) << (2 * j);
+			acc |= flags32(a, lut, ws[j] >> 16) << (2 * j + 1);
+		}
+		return acc;
+	}
+
+	// transparency bits of the six facing slabs, read from global memory; an absent neighbour reads as a slab of Empty
+	__device__ __forceinline__ void build_halo_masks(const MeshArgs& a, const uint32_t* lut, uint32_t slot, uint32_t (*hT)[CS])
+	{
+		const int tid = threadIdx.x;
+		const unsigned long long* hp = a.halo + size_t(slot) * 6;
+		const uint32_t emptyT = (lut[0] & 1u) ? 0xFFu : 0u;
+#pragma unroll
+		for (int j = 0; j < 6 * (SLAB / 8) / FUSED_THREADS; ++j)
+		{
+			const int u = tid + j * FUSED_THREADS;
+			const int d = u >> 7, q = u & 127, row = q >> 2, seg = q & 3;
+			const unsigned long long e = hp[d];
+			uint32_t t8 = emptyT;
+			if (e != 0ull)
+			{
+				const uint16_t* src = reinterpret_cast<const uint16_t*>(e & ~HALO_KIND_MASK);
+				const size_t rowStride = (e & HALO_KIND_MASK) == HALO_ROWS ? SLAB : CS;
+				const uint4 w = *reinterpret_cast<const uint4*>(src + size_t(row) * rowStride + seg * 8);
+				t8 = flags8(a, lut, w) & 0xFFu;
+			}
+			uint32_t t = t8 << (seg * 8);
+			t |= __shfl_xor_sync(0xffffffffu, t, 1);
+			t |= __shfl_xor_sync(0xffffffffu, t, 2);
+			if (seg == 0)
+				hT[d][row] = t;
+		}
+	}
+
+	// row masks of the staged chunk: warp w owns rows [128w, 128w + 128), 8 rows per step, 4 lanes per row
+	__device__ __forceinline__ void build_masks_fused(const MeshArgs& a, FusedSmem& sm)
+	{
+		const int lane = threadIdx.x & 31;
+		const int warp = threadIdx.x >> 5;
+		const int seg = lane & 3;
+#pragma unroll 4
+		for (int it = 0; it < ROWS / FUSED_WARPS / 8; ++it)
+		{
+			const int row = warp * (ROWS / FUSED_WARPS) + it * 8 + (lane >> 2);
+			const uint4 w = *reinterpret_cast<const uint4*>(&sm.ids[row * CS + seg * 8]);
+			const uint32_t acc = flags8(a, sm.lut32, w);
+			uint32_t t = (acc & 0xFFu) << (seg * 8);
+			uint32_t e = ((acc >> 8) & 0xFFu) << (seg * 8);
+			uint32_t d = ((acc >> 16) & 0xFFu) << (seg * 8);
+			t |= __shfl_xor_sync(0xffffffffu, t, 1);
+			e |= __shfl_xor_sync(0xffffffffu, e, 1);
+			d |= __shfl_xor_sync(0xffffffffu, d, 1);
+			t |= __shfl_xor_sync(0xffffffffu, t, 2);
+			e |= __shfl_xor_sync(0xffffffffu, e, 2);
+			d |= __shfl_xor_sync(0xffffffffu, d, 2);
+			if (seg == 0)
+				sm.mT[row] = t;
+			else if (seg == 1)
+				sm.mE[row] = e;
+			else if (seg == 2)
+				sm.mD[row] = d;
+		}
+	}
+
+	// id of a block of the facing slab, from global memory (rare path only)
+	__device__ __forceinline__ unsigned halo_id(const MeshArgs& a, uint32_t slot, int d, int slow, int fast)
+	{
+		const unsigned long long e = a.halo[size_t(slot) * 6 + d];
+		if (e == 0ull)
+			return 0u;
+		const uint16_t* src = reinterpret_cast<const uint16_t*>(e & ~HALO_KIND_MASK);
+		const size_t rowStride = (e & HALO_KIND_MASK) == HALO_ROWS ? SLAB : CS;
+		return src[size_t(slow) * rowStride + fast];
+	}
+
+	// visibility masks of row r in emission-slot order; returns the row's double-sided mask.  Thread-local (no warp collectives).
+	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const FusedSmem& sm, uint32_t slot, int r, uint32_t v[6])
+	{
+		const int z = r >> 5, y = r & 31;
+		const uint32_t t = sm.mT[r], e = sm.mE[r];
+		const uint32_t tUp = z < CS - 1 ? sm.mT[r + CS] : sm.hT[D_UP][y];
+		const uint32_t tDown = z > 0 ? sm.mT[r - CS] : sm.hT[D_DOWN][y];
+		const uint32_t tFront = y > 0 ? sm.mT[r - 1] : sm.hT[D_FRONT][z];
+		const uint32_t tBack = y < CS - 1 ? sm.mT[r + 1] : sm.hT[D_BACK][z];
+		const uint32_t tLeft = (t << 1) | ((sm.hT[D_LEFT][z] >> y) & 1u);
+		const uint32_t tRight = (t >> 1) | (((sm.hT[D_RIGHT][z] >> y) & 1u) << 31);
+		v[0] = e & tUp;
+		v[1] = e & tDown;
+		v[2] = e & tFront;
+		v[3] = e & tBack;
+		v[4] = e & tLeft;
+		v[5] = e & tRight;
+
+		// transparent non-empty blocks (glass, forcefield): no face towards a neighbour of the same type (Chunk.cpp:192-194)
+		uint32_t need = e & t;
+		while (need)
+		{
+			const int x = __ffs(need) - 1;
+			need &= need - 1;
+			const uint32_t bit = 1u << x;
+			const unsigned self = sm.ids[r * CS + x];
+			if (v[0] & bit)
+				if ((z < CS - 1 ? sm.ids[(r + CS) * CS + x] : halo_id(a, slot, D_UP, y, x)) == self)
+					v[0] &= ~bit;
+			if (v[1] & bit)
+				if ((z > 0 ? sm.ids[(r - CS) * CS + x] : halo_id(a, slot, D_DOWN, y, x)) == self)
+					v[1] &= ~bit;
+			if (v[2] & bit)
+				if ((y > 0 ? sm.ids[(r - 1) * CS + x] : halo_id(a, slot, D_FRONT, z, x)) == self)
+					v[2] &= ~bit;
+			if (v[3] & bit)
+				if ((y < CS - 1 ? sm.ids[(r + 1) * CS + x] : halo_id(a, slot, D_BACK, z, x)) == self)
+					v[3] &= ~bit;
+			if (v[4] & bit)
+				if ((x > 0 ? sm.ids[r * CS + x - 1] : halo_id(a, slot, D_LEFT, z, y)) == self)
+					v[4] &= ~bit;
+			if (v[5] & bit)
+				if ((x < CS - 1 ? sm.ids[r * CS + x + 1] : halo_id(a, slot, D_RIGHT, z, y)) == self)
+					v[5] &= ~bit;
+		}
+		return sm.mD[r];
+	}
+
+	__global__ void __launch_bounds__(FUSED_THREADS, 2) mesh_fused_kernel(const MeshArgs a)
+	{
+		extern __shared__ __align__(128) unsigned char smemRaw[];
+		FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smemRaw);
+		const int tid = threadIdx.x;
+		const int lane = tid & 31;
+		const int warp = tid >> 5;
+		constexpr uint32_t FULL = 0xffffffffu;
+
+		if (tid == 0)
+		{
+			mbar_init(&sm.bar, 1);
+			fence_mbar_init();
+		}
+		for (int i = tid; i < LUTN; i += FUSED_THREADS)
+			sm.lut32[i] = pack_flags(a.blkFlags[uint32_t(i) < a.nTypes ? i : a.nTypes - 1], unsigned(i));
+		const bool fastFlat = a.faceTable != nullptr;
+		if (fastFlat)
+		{
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(a.faceTable);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.table);
+			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += FUSED_THREADS)
+				dst[i] = src[i];
+		}
+		// write-out constants of this lane: a staging round is 16 faces = 192 float4; an index tile is 32 faces = 96 uint2
+		uint32_t stageOff[6];
+#pragma unroll
+		for (int k = 0; k < 6; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
+		}
+		uint2 idxPat[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			const uint32_t b = (i / 3u) * 4u, j = i % 3u;
+			idxPat[k] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
+		}
+		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
+		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
+		__syncthreads();
+
+		uint32_t parity = 0;
+		for (;;)
+		{
+			if (tid == 0)
+				sm.job = atomicAdd(a.jobCounter, 1u);
+			__syncthreads(); // also: every read of the previous chunk's shared state is done
+			const uint32_t job = sm.job;
+			if (job >= a.nJobs)
+				break;
+			const uint32_t slot = a.jobSlot[job];
+			const bool hasContent = a.chunkIdx[slot].w != 0;
+
+			uint32_t F = 0, K = 0;
+			if (hasContent)
+			{
+				// ---- stage the ids (TMA) and classify the halo slabs meanwhile
+				if (tid == 0)
+				{
+					fence_proxy_async(); // the generic reads of the previous chunk (ordered by the barrier above) precede the async writes
+					mbar_arrive_expect_tx(&sm.bar, NB * 2);
+					const uint16_t* src = a.blocks + size_t(slot) * NB;
+#pragma unroll
+					for (int p = 0; p < 4; ++p)
+						tma_load_1d(sm.ids + p * (NB / 4), src + p * (NB / 4), NB / 2, &sm.bar);
+				}
+				build_halo_masks(a, sm.lut32, slot, sm.hT);
+				mbar_wait(&sm.bar, parity);
+				parity ^= 1;
+
+				build_masks_fused(a, sm);
+				__syncthreads();
+
+				// ---- faces per row (thread t owns rows 4t .. 4t+3) and one packed scan: faces | rows-with-faces << 20
+				uint32_t c[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					uint32_t v[6];
+					const uint32_t d = row_vis(a, sm, slot, 4 * tid + j, v);
+					c[j] = row_faces(v, d);
+				}
+				const uint32_t mine = (c[0] + c[1] + c[2] + c[3]) | (uint32_t((c[0] != 0) + (c[1] != 0) + (c[2] != 0) + (c[3] != 0)) << 20);
+				uint32_t incl = mine;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t n = __shfl_up_sync(FULL, incl, o);
+					if (lane >= o)
+						incl += n;
+				}
+				if (lane == 31)
+					sm.warpSum[warp] = incl;
+				__syncthreads();
+				uint32_t wbase = 0, total = 0;
+#pragma unroll
+				for (int w = 0; w < FUSED_WARPS; ++w)
+				{
+					const uint32_t ws = sm.warpSum[w];
+					if (w < warp)
+						wbase += ws;
+					total += ws;
+				}
+				F = total & 0xFFFFFu;
+				K = total >> 20;
+				const uint32_t excl = wbase + incl - mine;
+				uint32_t off = excl & 0xFFFFFu, k = excl >> 20;
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					if (c[j])
+						sm.ne[k++] = off | (uint32_t(4 * tid + j) << NE_ROW_SHIFT);
+					off += c[j];
+				}
+				if (tid == 0)
+					sm.ne[K] = F;
+			}
+
+			// ---- chain the chunk into the arena: decoupled look-back over the jobs before this one
+			if (warp == 0)
+			{
+				constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL = (1ull << 62) - 1ull;
+				volatile unsigned long long* st = a.status;
+				unsigned long long excl = 0ull;
+				if (job == 0u)
+				{
+					if (lane == 0)
+						st[0] = FLAG_INC | F;
+				}
+				else
+				{
+					if (lane == 0)
+						st[job] = FLAG_AGG | F;
+					long long base = (long long)job - 1;
+					for (;;)
+					{
+						const long long i = base - lane;
+						unsigned long long s;
+						uint32_t incMask, notReady;
+						do
+						{
+							s = i >= 0 ? st[i] : FLAG_INC; // before job 0: inclusive prefix 0
+							const unsigned fl = unsigned(s >> 62);
+							incMask = __ballot_sync(FULL, fl == 2u);
+							notReady = __ballot_sync(FULL, fl == 0u);
+							if (incMask)
+								notReady &= (2u << (__ffs(incMask) - 1)) - 1u; // only the lanes up to the first inclusive prefix matter
+						} while (notReady);
+						const int firstInc = incMask ? __ffs(incMask) - 1 : 31;
+						unsigned long long val = lane <= firstInc ? (s & VAL) : 0ull;
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1)
+							val += __shfl_xor_sync(FULL, val, o);
+						excl += val;
+						if (incMask)
+							break;
+						base -= 32;
+					}
+					if (lane == 0)
+						st[job] = FLAG_INC | (excl + F);
+				}
+				if (lane == 0)
+				{
+					sm.firstFace = excl;
+					a.faceCount[job] = F;
+					a.firstFaceOut[job] = excl;
+					if (job == a.nJobs - 1u)
+						*a.totalFacesOut = excl + F;
+				}
+			}
+			__syncthreads();
+
+			const unsigned long long firstFace = sm.firstFace;
+			const bool overflow = firstFace + F > a.arenaFaces;
+			if (overflow && F > 0 && tid == 0)
+				atomicExch(a.overflow, 1u);
+
+			if (!overflow && F > 0)
+			{
+				FaceCtx cx;
+				cx.tile = a.tile;
+				cx.radius = a.deformRadius;
+				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
+				cx.wantAttr = wantRender;
+				if (a.gravity)
+					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);
+				else
+				{
+					// container centre - GetChunkOffset(indices) (ClientChunkEntities.cpp:160, ChunkContainer.inl:53-56)
+					const int4 ci = a.chunkIdx[slot];
+					cx.gravity = f3(a.center[0] - float(ci.x) * float(CS) * a.tile, a.center[1] - float(ci.y) * float(CS) * a.tile, a.center[2] - float(ci.z) * float(CS) * a.tile);
+				}
+
+				float4* stage = sm.stage[warp];
+				uint16_t* desc = sm.desc[warp];
+				const uint32_t nWin = (F + WIN - 1u) / WIN;
+
+				for (uint32_t win = warp; win < nWin; win += FUSED_WARPS)
+				{
+					const uint32_t w0 = win * WIN;
+					const uint32_t nw = min(uint32_t(WIN), F - w0);
+
+					// ---- first compact row of the window: largest k with ne[k].off <= w0 (offsets increase strictly)
+					uint32_t kA;
+					{
+						const uint32_t i1 = uint32_t(lane) * 32u;
+						const uint32_t top = __popc(__ballot_sync(FULL, i1 < K && (sm.ne[i1] & NE_OFF_MASK) <= w0)) - 1u;
+						const uint32_t i2 = top * 32u + lane;
+						kA = top * 32u + __popc(__ballot_sync(FULL, i2 < K && (sm.ne[i2] & NE_OFF_MASK) <= w0)) - 1u;
+					}
+
+					// ---- descriptors: one row per lane, faces in the reference's order (x, then Up/Down/Front/Back/Left/Right, twin)
+					for (uint32_t k0 = kA;; k0 += 32u)
+					{
+						const uint32_t k = k0 + lane;
+						if (k < K)
+						{
+							const uint32_t en = sm.ne[k];
+							uint32_t p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
+							if (int(p) < int(nw))
+							{
+								uint32_t v[6];
+								const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
+								const uint32_t base = (k - kA) << 9;
+								uint32_t any = v[0] | v[1] | v[2] | v[3] | v[4] | v[5];
+								while (any && int(p) < int(nw))
+								{
+									const uint32_t x = uint32_t(__ffs(any) - 1);
+									any &= any - 1u;
+									const uint32_t bit = 1u << x;
+									const bool tw = (d & bit) != 0u;
+#pragma unroll
+									for (uint32_t s = 0; s < 6; ++s)
+									{
+										if (v[s] & bit)
+										{
+											if (p < nw)
+												desc[p] = uint16_t(base | x | (s << 5));
+											++p;
+											if (tw)
+											{
+												if (p < nw)
+													desc[p] = uint16_t(base | x | (s << 5) | 0x100u);
+												++p;
+											}
+										}
+									}
+								}
+							}
+						}
+						const uint32_t nx = k0 + 32u;
+						if (nx >= K || (sm.ne[nx] & NE_OFF_MASK) >= w0 + nw)
+							break;
+					}
+					__syncwarp();
+
+					// ---- build one face per lane, stream out through the 16-face staging tile
+					const uint32_t nTiles = (nw + 31u) >> 5;
+					for (uint32_t tt = 0; tt < nTiles; ++tt)
+					{
+						const uint32_t f = tt * 32u + lane;
+						const uint32_t nf = min(32u, nw - tt * 32u);
+						const bool valid = f < nw;
+						FaceOut fo;
+						if (valid)
+						{
+							const uint32_t de = desc[f];
+							const uint32_t row = sm.ne[kA + (de >> 9)] >> NE_ROW_SHIFT;
+							const int x = int(de & 31u), y = int(row & 31u), z = int(row >> 5);
+							const int s = int((de >> 5) & 7u);
+							const bool twin = ((de >> 8) & 1u) != 0u;
+							const unsigned id = sm.ids[row * CS + x];
+							if (fastFlat)
+								draw_face_flat_r(a, cx, sm.table, x, y, z, s, twin, id, fo);
+							else
+								draw_face_r(a, cx, x, y, z, s, twin, id, fo);
+						}
+						const unsigned long long face0 = firstFace + w0 + tt * 32u;
+#pragma unroll
+						for (uint32_t h = 0; h < 2; ++h)
+						{
+							if (nf <= h * HALF_FACES)
+								break;
+							const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
+							if (valid && (uint32_t(lane) >> 4) == h)
+								store_face(stage + (lane & 15) * STAGE_FACE_F4, fo);
+							__syncwarp();
+							const unsigned long long faceH = face0 + h * HALF_FACES;
+							if (wantRender)
+							{
+								float4* dst = a.vertices + faceH * 12ull + lane;
+								if (nh == HALF_FACES)
+								{
+#pragma unroll
+									for (int k = 0; k < 6; ++k)
+										dst[32 * k] = stage[stageOff[k]];
+								}
+								else
+								{
+									const uint32_t n4 = nh * 12u;
+#pragma unroll
+									for (int k = 0; k < 6; ++k)
+										if (uint32_t(lane) + 32u * k < n4)
+											dst[32 * k] = stage[stageOff[k]];
+								}
+							}
+							if (wantCollider)
+							{
+								// positions only: 3 float4 per face gathered from the staged vertices
+								float4* dst = a.collider + faceH * 3ull;
+								const float* sf = reinterpret_cast<const float*>(stage);
+								const uint32_t n4 = nh * 3u;
+								for (uint32_t i = lane; i < n4; i += 32u)
+								{
+									const uint32_t face = i / 3u, j = i % 3u;
+									float e[4];
+#pragma unroll
+									for (int m = 0; m < 4; ++m)
+									{
+										const uint32_t q = j * 4u + m; // float q of the face's 12 position floats
+										e[m] = sf[face * (STAGE_FACE_F4 * 4) + (q / 3u) * 12u + (q % 3u)];
+									}
+									dst[i] = make_float4(e[0], e[1], e[2], e[3]);
+								}
+							}
+							__syncwarp();
+						}
+						{
+							// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
+							uint2* dst = a.indices + face0 * 3ull + lane;
+							const uint32_t base = (w0 + tt * 32u) * 4u;
+							const uint32_t n2 = nf * 3u;
+#pragma unroll
+							for (int k = 0; k < 3; ++k)
+								if (nf == 32u || uint32_t(lane) + 32u * k < n2)
+									dst[32 * k] = make_uint2(idxPat[k].x + base, idxPat[k].y + base);
+						}
+					}
+					__syncwarp(); // the descriptors are consumed before the next window overwrites them
+				}
+			}
+		}
+	}
+
+	// =====================================================================================================================
 	// exclusive scan of face counts -> first face per job, total, and the worklist of jobs that have faces (single CTA)
 	__global__ void __launch_bounds__(1024, 1) mesh_scan_kernel(const uint32_t* __restrict__ faceCount, uint32_t nJobs,
 	                                                            unsigned long long* __restrict__ firstFace, uint32_t* __restrict__ worklist,
@@ -901,13 +1457,20 @@ namespace tsomk
 	// ---- launchers ----
 	size_t mesh_count_smem_bytes() { return sizeof(CountSmem); }
 	size_t mesh_emit_smem_bytes() { return sizeof(MeshSmem); }
+	size_t mesh_fused_smem_bytes() { return sizeof(FusedSmem); }
 
 	cudaError_t mesh_kernels_init()
 	{
 		cudaError_t e = cudaFuncSetAttribute(mesh_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CountSmem)));
 		if (e != cudaSuccess)
 			return e;
-		return cudaFuncSetAttribute(mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MeshSmem)));
+		e = cudaFuncSetAttribute(mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MeshSmem)));
+		if (e != cudaSuccess)
+			return e;
+		e = cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)));
+		if (e != cudaSuccess)
+			return e;
+		return cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 	}
 
 	void launch_mesh_count(const MeshArgs& a, int grid, cudaStream_t st)
@@ -924,5 +1487,10 @@ namespace tsomk
 	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st)
 	{
 		mesh_emit_kernel<<<grid, MESH_THREADS, sizeof(MeshSmem), st>>>(a);
+	}
+
+	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st)
+	{
+		mesh_fused_kernel<<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
 	}
 }

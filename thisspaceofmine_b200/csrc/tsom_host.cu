@@ -7,6 +7,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -228,7 +229,8 @@ struct tsom_ctx
 
 	// per-call scratch
 	DevBuf<uint32_t> jobSlot, faceCount, worklist;
-	DevBuf<unsigned long long> firstFace;
+	DevBuf<unsigned long long> firstFace, status;
+	bool legacyMesh = false; // TSOM_MESH_LEGACY=1: count -> scan -> emit (kept for A/B measurements)
 	DevBuf<float> gravity;
 	DevBuf<tsomk::EditDev> edits;
 	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
@@ -513,6 +515,8 @@ extern "C"
 		ctx->numSMs = prop.multiProcessorCount;
 		TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		TSOM_CUDA(tsomk::mesh_kernels_init());
+		if (const char* env = std::getenv("TSOM_MESH_LEGACY"))
+			ctx->legacyMesh = env[0] == '1';
 		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
@@ -558,6 +562,7 @@ extern "C"
 		ctx->faceCount.Free();
 		ctx->worklist.Free();
 		ctx->firstFace.Free();
+		ctx->status.Free();
 		ctx->gravity.Free();
 		ctx->edits.Free();
 		cudaFree(ctx->dSmall);
@@ -1194,15 +1199,45 @@ extern "C"
 			ctx->launches += 1;
 		};
 
-		a.jobCounter = ctx->dSmall + 0;
-		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-		tsomk::launch_mesh_count(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
-		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-		tsomk::launch_mesh_scan(ctx->faceCount.ptr, n, ctx->firstFace.ptr, ctx->worklist.ptr, ctx->dSmall + 2, reinterpret_cast<unsigned long long*>(ctx->dSmall + 4), 0ull, ctx->stream);
-		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-		ctx->launches += 2;
-		launchEmit();
-		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+		auto launchFused = [&]() -> cudaError_t {
+			a.vertices = ctx->dVertices;
+			a.indices = ctx->dIndices;
+			a.collider = ctx->dCollider;
+			a.arenaFaces = ArenaFaces(ctx, flags);
+			a.jobCounter = ctx->dSmall + 1;
+			a.status = ctx->status.ptr;
+			a.firstFaceOut = ctx->firstFace.ptr;
+			a.totalFacesOut = reinterpret_cast<unsigned long long*>(ctx->dSmall + 4);
+			cudaError_t e = cudaMemsetAsync(ctx->status.ptr, 0, size_t(n) * sizeof(unsigned long long), ctx->stream);
+			if (e != cudaSuccess)
+				return e;
+			tsomk::launch_mesh_fused(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
+			ctx->launches += 1;
+			return cudaSuccess;
+		};
+
+		if (ctx->legacyMesh)
+		{
+			a.jobCounter = ctx->dSmall + 0;
+			TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+			tsomk::launch_mesh_count(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
+			TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+			tsomk::launch_mesh_scan(ctx->faceCount.ptr, n, ctx->firstFace.ptr, ctx->worklist.ptr, ctx->dSmall + 2, reinterpret_cast<unsigned long long*>(ctx->dSmall + 4), 0ull, ctx->stream);
+			TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+			ctx->launches += 2;
+			launchEmit();
+			TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+		}
+		else
+		{
+			// single pass: the count and the scan live inside mesh_fused_kernel (their timing slots read 0)
+			TSOM_CUDA(ctx->status.Ensure(n));
+			TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+			TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+			TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+			TSOM_CUDA(launchFused());
+			TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+		}
 		TSOM_CUDA(cudaGetLastError());
 
 		// read back totals (+ views)
@@ -1233,7 +1268,10 @@ extern "C"
 				return rc;
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 1, 0, sizeof(uint32_t), ctx->stream));
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, sizeof(uint32_t), ctx->stream));
-			launchEmit();
+			if (ctx->legacyMesh)
+				launchEmit();
+			else
+				TSOM_CUDA(launchFused());
 			TSOM_CUDA(cudaGetLastError());
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		}

@@ -37,6 +37,10 @@ namespace tsomk
 		const uint32_t* worklist;              // jobs with faces
 		const uint32_t* nWork;
 		uint32_t* jobCounter;                  // work-stealing ticket, zeroed before each launch
+		// single-pass path (mesh_fused_kernel): chained scan over the jobs by decoupled look-back
+		unsigned long long* status;            // [nJobs] (flag << 62) | faces, zeroed before each launch
+		unsigned long long* firstFaceOut;      // [nJobs]
+		unsigned long long* totalFacesOut;     // inclusive prefix of the last job
 		// arenas
 		float4* vertices;
 		uint2* indices;
@@ -61,6 +65,8 @@ namespace tsomk
 	void launch_mesh_scan(const uint32_t* faceCount, uint32_t nJobs, unsigned long long* firstFace, uint32_t* worklist, uint32_t* nWork,
 	                      unsigned long long* totalFaces, unsigned long long faceBase, cudaStream_t st);
 	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st);
+	size_t mesh_fused_smem_bytes();
+	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st);
 
 	// ---- generation ----
 	struct GenArgs
