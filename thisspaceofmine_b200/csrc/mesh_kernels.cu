@@ -874,6 +874,7 @@ namespace tsomk
 		alignas(16) FaceTable table;
 		uint32_t warpSum[FUSED_WARPS];
 		uint32_t job;
+		uint32_t ffSeq;                   // == job + 1 once firstFace of the current job is known
 		unsigned long long firstFace;
 		alignas(8) uint64_t bar;
 	};
@@ -891,11 +892,9 @@ namespace tsomk
 		return pack_flags(__ldg(a.blkFlags + (id < a.nTypes ? id : a.nTypes - 1)), id);
 	}
 
-	// 8 ids -> t8 | e8 << 8 | d8 << 16 (bit j of each byte = id j)
-	__device__ __forceinline__ uint32_t flags8(const MeshArgs& a, const uint32_t* lut, uint4 w)
+	// 8 ids -> t8 | e8 << 8 | d8 << 16 (bit j of each byte = id j); out of line: only taken when an id is >= LUTN
+	__device__ __noinline__ uint32_t flags8_slow(const MeshArgs& a, const uint32_t* lut, uint4 w)
 	{
-		if (w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu))
-			return flags32(a, lut, w.x & 0xffffu) * 0xFFu;
 		const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
 		uint32_t acc = 0;
 #pragma unroll
@@ -903,6 +902,23 @@ namespace tsomk
 		{
 			acc |= flags32(a, lut, ws[j] & 0xffffu) << (2 * j);
 			acc |= flags32(a, lut, ws[j] >> 16) << (2 * j + 1);
+		}
+		return acc;
+	}
+
+	__device__ __forceinline__ uint32_t flags8(const MeshArgs& a, const uint32_t* lut, uint4 w)
+	{
+		if (((w.x | w.y | w.z | w.w) & ~(uint32_t(LUTN - 1) * 0x10001u)) != 0u)
+			return flags8_slow(a, lut, w);
+		if (w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu))
+			return lut[w.x & 0xffffu] * 0xFFu;
+		const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+		uint32_t acc = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+		{
+			acc |= lut[ws[j] & 0xffffu] << (2 * j);
+			acc |= lut[ws[j] >> 16] << (2 * j + 1);
 		}
 		return acc;
 	}
@@ -1068,12 +1084,15 @@ namespace tsomk
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
 		__syncthreads();
 
+		if (tid == 0)
+		{
+			sm.ffSeq = 0u;
+			sm.job = atomicAdd(a.jobCounter, 1u);
+		}
 		uint32_t parity = 0;
 		for (;;)
 		{
-			if (tid == 0)
-				sm.job = atomicAdd(a.jobCounter, 1u);
-			__syncthreads(); // also: every read of the previous chunk's shared state is done
+			__syncthreads(); // the ticket is visible; every read of the previous chunk's shared state is done
 			const uint32_t job = sm.job;
 			if (job >= a.nJobs)
 				break;
@@ -1145,7 +1164,12 @@ namespace tsomk
 					sm.ne[K] = F;
 			}
 
-			// ---- chain the chunk into the arena: decoupled look-back over the jobs before this one
+			__syncthreads(); // ne[] is complete; sm.job has been read by everyone
+
+			// ---- chain the chunk into the arena: decoupled look-back over the jobs before this one (warp 0; the other warps
+			// already build their first descriptor window and pick firstFace up when they are about to store)
+			unsigned long long firstFace = 0ull;
+			bool haveFirst = false;
 			if (warp == 0)
 			{
 				constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL = (1ull << 62) - 1ull;
@@ -1191,20 +1215,20 @@ namespace tsomk
 				if (lane == 0)
 				{
 					sm.firstFace = excl;
+					__threadfence_block();
+					*reinterpret_cast<volatile uint32_t*>(&sm.ffSeq) = job + 1u;
 					a.faceCount[job] = F;
 					a.firstFaceOut[job] = excl;
 					if (job == a.nJobs - 1u)
 						*a.totalFacesOut = excl + F;
+					if (F > 0 && excl + F > a.arenaFaces)
+						atomicExch(a.overflow, 1u);
 				}
+				firstFace = excl;
+				haveFirst = true;
 			}
-			__syncthreads();
 
-			const unsigned long long firstFace = sm.firstFace;
-			const bool overflow = firstFace + F > a.arenaFaces;
-			if (overflow && F > 0 && tid == 0)
-				atomicExch(a.overflow, 1u);
-
-			if (!overflow && F > 0)
+			if (F > 0)
 			{
 				FaceCtx cx;
 				cx.tile = a.tile;
@@ -1229,59 +1253,78 @@ namespace tsomk
 					const uint32_t w0 = win * WIN;
 					const uint32_t nw = min(uint32_t(WIN), F - w0);
 
-					// ---- first compact row of the window: largest k with ne[k].off <= w0 (offsets increase strictly)
-					uint32_t kA;
+					// ---- compact rows [kA, kB] of the window: largest k with ne[k].off <= first / last face (offsets increase strictly)
+					uint32_t kA, kB;
 					{
+						const uint32_t wLast = w0 + nw - 1u;
 						const uint32_t i1 = uint32_t(lane) * 32u;
-						const uint32_t top = __popc(__ballot_sync(FULL, i1 < K && (sm.ne[i1] & NE_OFF_MASK) <= w0)) - 1u;
-						const uint32_t i2 = top * 32u + lane;
-						kA = top * 32u + __popc(__ballot_sync(FULL, i2 < K && (sm.ne[i2] & NE_OFF_MASK) <= w0)) - 1u;
+						const uint32_t o1 = i1 < K ? (sm.ne[i1] & NE_OFF_MASK) : 0xFFFFFFFFu;
+						const uint32_t topA = __popc(__ballot_sync(FULL, o1 <= w0)) - 1u;
+						const uint32_t topB = __popc(__ballot_sync(FULL, o1 <= wLast)) - 1u;
+						const uint32_t iA = topA * 32u + lane, iB = topB * 32u + lane;
+						const uint32_t oA = iA < K ? (sm.ne[iA] & NE_OFF_MASK) : 0xFFFFFFFFu;
+						const uint32_t oB = iB < K ? (sm.ne[iB] & NE_OFF_MASK) : 0xFFFFFFFFu;
+						kA = topA * 32u + __popc(__ballot_sync(FULL, oA <= w0)) - 1u;
+						kB = topB * 32u + __popc(__ballot_sync(FULL, oB <= wLast)) - 1u;
 					}
 
-					// ---- descriptors: one row per lane, faces in the reference's order (x, then Up/Down/Front/Back/Left/Right, twin)
-					for (uint32_t k0 = kA;; k0 += 32u)
+					// ---- descriptors, faces in the reference's order (x, then Up/Down/Front/Back/Left/Right, twin).  A window of R
+					// rows is walked by 32 lanes: S = 32 / R (power of two) lanes share a row, each taking 32 / S consecutive blocks.
+					const uint32_t R = kB - kA + 1u;
+					const uint32_t lgS = R > 16u ? 0u : (R > 8u ? 1u : (R > 4u ? 2u : (R > 2u ? 3u : (R > 1u ? 4u : 5u))));
+					const uint32_t x0 = (uint32_t(lane) & ((1u << lgS) - 1u)) << (5u - lgS);
+					const uint32_t segMask = lgS == 0u ? 0xFFFFFFFFu : (((1u << (32u >> lgS)) - 1u) << x0);
+					const uint32_t below = (1u << x0) - 1u;
+					for (uint32_t k0 = kA; k0 <= kB; k0 += 32u >> lgS)
 					{
-						const uint32_t k = k0 + lane;
-						if (k < K)
+						const uint32_t k = k0 + (uint32_t(lane) >> lgS);
+						if (k <= kB)
 						{
 							const uint32_t en = sm.ne[k];
+							uint32_t v[6];
+							const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
 							uint32_t p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
-							if (int(p) < int(nw))
-							{
-								uint32_t v[6];
-								const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
-								const uint32_t base = (k - kA) << 9;
-								uint32_t any = v[0] | v[1] | v[2] | v[3] | v[4] | v[5];
-								while (any && int(p) < int(nw))
-								{
-									const uint32_t x = uint32_t(__ffs(any) - 1);
-									any &= any - 1u;
-									const uint32_t bit = 1u << x;
-									const bool tw = (d & bit) != 0u;
 #pragma unroll
-									for (uint32_t s = 0; s < 6; ++s)
+							for (int s = 0; s < 6; ++s)
+								p += __popc(v[s] & below) + __popc(v[s] & d & below);
+							const uint32_t base = (k - kA) << 9;
+							uint32_t any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+							while (any && int(p) < int(nw))
+							{
+								const uint32_t x = uint32_t(__ffs(any) - 1);
+								any &= any - 1u;
+								const uint32_t bit = 1u << x;
+								const bool tw = (d & bit) != 0u;
+#pragma unroll
+								for (uint32_t s = 0; s < 6; ++s)
+								{
+									if (v[s] & bit)
 									{
-										if (v[s] & bit)
+										if (p < nw)
+											desc[p] = uint16_t(base | x | (s << 5));
+										++p;
+										if (tw)
 										{
 											if (p < nw)
-												desc[p] = uint16_t(base | x | (s << 5));
+												desc[p] = uint16_t(base | x | (s << 5) | 0x100u);
 											++p;
-											if (tw)
-											{
-												if (p < nw)
-													desc[p] = uint16_t(base | x | (s << 5) | 0x100u);
-												++p;
-											}
 										}
 									}
 								}
 							}
 						}
-						const uint32_t nx = k0 + 32u;
-						if (nx >= K || (sm.ne[nx] & NE_OFF_MASK) >= w0 + nw)
-							break;
 					}
 					__syncwarp();
+
+					if (!haveFirst)
+					{
+						while (*reinterpret_cast<volatile uint32_t*>(&sm.ffSeq) != job + 1u) {}
+						__threadfence_block();
+						firstFace = *reinterpret_cast<volatile unsigned long long*>(&sm.firstFace);
+						haveFirst = true;
+					}
+					if (firstFace + F > a.arenaFaces)
+						break; // arena too small: this launch only counts (the host grows the arena and runs the kernel again)
 
 					// ---- build one face per lane, stream out through the 16-face staging tile
 					const uint32_t nTiles = (nw + 31u) >> 5;
@@ -1368,6 +1411,11 @@ namespace tsomk
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}
+			// next ticket: only once every warp is done with this chunk.  (Not earlier: a ticket held during an emission would
+			// stall the look-back of every later job until this CTA gets to its front end.)
+			__syncthreads();
+			if (tid == 0)
+				sm.job = atomicAdd(a.jobCounter, 1u);
 		}
 	}
 
