@@ -3,11 +3,12 @@
 
 Metric (BASELINE.json): 32^3 chunks meshed / s.  Workload at every N: BASELINE config 2 — a synthetic batch of 4096 independent
 32^3 chunks per GPU with random solid/air fill (p = 0.5 stone, counter-based hash, seed 1234), mesh-only, render attributes
-(48-byte vertices + u32 indices).  "step" = one pass of Chunk::BuildMesh over the whole batch (count + scan + emit kernels).
+(48-byte vertices + u32 indices).  "step" = one pass of Chunk::BuildMesh over the whole batch (one mesh_fused_kernel launch: classify, count, chain, emit).
 
   value      : chunks/s with the block ids already resident in HBM (device time, CUDA events on the library's stream)
   e2e        : the same through the C ABI with HOST buffers: H2D of the ids + meshing + D2H of vertices and indices, per step
-  roofline   : the dominant kernel (mesh_emit_kernel): algorithmic bytes / its own CUDA-event duration vs the measured HBM peak
+  roofline   : the dominant kernel (mesh_fused_kernel): algorithmic bytes / its own CUDA-event duration vs the measured HBM peak;
+               `traffic` = DRAM bytes of that launch from the committed ncu capture (profiles/r01/traffic.json), same chunk count
   cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's Chunk::BuildMesh, kind "port" — the reference
                itself cannot be built here) on all host cores, on a bounded sample of the same workload
 
@@ -49,6 +50,16 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def ncu_traffic(chunks):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one mesh_fused_kernel launch of this workload, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    try:
+        t = json.load(open(p))
+        return t["dram_bytes"] if int(t["chunks"]) == int(chunks) else None
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------- workload (device side, torch plumbing)
@@ -310,8 +321,8 @@ def run_b200(args):
                     "note": "tsom_chunks_reset (pinned host ids) + tsom_mesh + tsom_mesh_copy_to_host (pinned host vertices+indices), 256-chunk sub-batches"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mesh_emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": emit, "traffic": None},
+            "roofline": {"bound": "hbm", "kernel": "mesh_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": emit, "traffic": ncu_traffic(n)},
             "kernels_ms": {"mesh_count": sum(count_ms) / len(count_ms), "mesh_scan": sum(scan_ms) / len(scan_ms), "mesh_emit": emit},
         }
         if not args.no_cpu and world == 1:
