@@ -9,8 +9,9 @@ Metric (BASELINE.json): 32^3 chunks meshed / s.  Workload at every N: BASELINE c
   e2e        : the same through the C ABI with HOST buffers: H2D of the ids + meshing + D2H of vertices and indices, per step
   roofline   : the dominant kernel (mesh_fused_kernel): algorithmic bytes / its own CUDA-event duration vs the measured HBM peak;
                `traffic` = DRAM bytes of that launch from the committed ncu capture (profiles/r01/traffic.json), same chunk count
-  cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's Chunk::BuildMesh, kind "port" — the reference
-               itself cannot be built here) on all host cores, on a bounded sample of the same workload
+  cpu_baseline / --impl reference : the reference's own Chunk::BuildMesh (oracle/_ref: its sources compiled over the third-party
+               stand-ins of oracle/ref_shim, kind "reference"; the oracle port, kind "port", only if that library is missing)
+               on all host cores, on a bounded sample of the same workload
 
 N > 1 (torchrun): chunks are independent, so each rank meshes its own 4096-chunk batch (weak scaling, no data-path collective);
 time = max over ranks, value = N * 4096 / time.
@@ -142,9 +143,27 @@ def cpu_sample(n_chunks, first_chunk=0):
     return np.stack([hash_fill(SEED, first_chunk + i, FILL_P, STONE) for i in range(n_chunks)])
 
 
-def cpu_mesh_rate(target_seconds):
-    """Oracle Chunk::BuildMesh (render attributes) over a bounded sample of the benchmark workload, all host threads."""
+def cpu_arm():
+    """(module-like front-end, kind): the reference's own sources (oracle/_ref, "reference") when built, else the oracle port."""
     import oracle as O
+
+    if O.reference_available():
+        try:
+            return O.reference(), "reference"
+        except Exception:
+            pass
+    return O, "port"
+
+
+CPU_KIND_NOTE = {
+    "reference": "the reference's own Chunk::BuildMesh (src/CommonLib/Chunk.cpp + FlatChunk.cpp compiled from its sources over the oracle/ref_shim third-party stand-ins)",
+    "port": "oracle port of Chunk::BuildMesh",
+}
+
+
+def cpu_mesh_rate(target_seconds):
+    """The reference's Chunk::BuildMesh (render attributes) over a bounded sample of the benchmark workload, all host threads."""
+    O, kind = cpu_arm()
 
     threads = host_threads()
     probe = cpu_sample(max(2 * threads, 8))
@@ -154,14 +173,14 @@ def cpu_mesh_rate(target_seconds):
     n = max(threads, (n // threads) * threads)
     blocks = cpu_sample(n)
     t, faces = O.bench_mesh_isolated(blocks, threads)
-    return dict(value=n / t, seconds=t, chunks=n, faces=faces, threads=threads)
+    return dict(value=n / t, seconds=t, chunks=n, faces=faces, threads=threads, kind=kind)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    """--impl reference: the reference's CPU implementation (its own sources via oracle/_ref, else the oracle port) on the host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import oracle as O
+    O, kind = cpu_arm()
 
     threads = host_threads()
     probe = cpu_sample(max(2 * threads, 8))
@@ -180,12 +199,12 @@ def run_reference(args):
         times.append(t)
     ms = 1000.0 * sum(times) / len(times)
     value = n / (ms / 1000.0)
-    sample = f"first {n} of the {CHUNKS_PER_GPU} hash-filled chunks (seed {SEED}, p={FILL_P}), {faces} faces, Chunk::BuildMesh with normals+uv per step"
+    sample = f"first {n} of the {CHUNKS_PER_GPU} hash-filled chunks (seed {SEED}, p={FILL_P}), {faces} faces, {CPU_KIND_NOTE[kind]} with normals+uv, one task per chunk"
     print(json.dumps({
         "impl": "reference", "metric": "chunks_meshed_per_sec", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16+f32", "data": "synthetic",
         "config": {"workload": "config[1]: 4096 independent 32^3 chunks, random solid/air fill p=0.5 (stone), mesh-only, render attributes", "chunks_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -327,8 +346,8 @@ def run_b200(args):
         }
         if not args.no_cpu and world == 1:
             c = cpu_mesh_rate(args.cpu_seconds)
-            out["cpu_baseline"] = {"value": c["value"], "unit": "chunks/s", "cores": c["threads"], "kind": "port",
-                                   "sample": f"first {c['chunks']} of the 4096 chunks ({c['faces']} faces) in {c['seconds']:.1f} s, oracle Chunk::BuildMesh with normals+uv, one task per chunk"}
+            out["cpu_baseline"] = {"value": c["value"], "unit": "chunks/s", "cores": c["threads"], "kind": c["kind"],
+                                   "sample": f"first {c['chunks']} of the 4096 chunks ({c['faces']} faces) in {c['seconds']:.1f} s, {CPU_KIND_NOTE[c['kind']]} with normals+uv, one task per chunk"}
         if args.planet and world == 1:
             try:
                 out["planet"] = planet_bench(T, ctx, args.planet)

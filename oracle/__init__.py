@@ -1,9 +1,19 @@
 """oracle — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 ctypes front-end of ``libtsom_oracle.so`` (``oracle/capi.cpp`` over ``oracle/tsom_oracle.hpp``), the CPU restatement of
-ThisSpaceOfMine's chunk generation / meshing / collider / edit rules.  Parity status: *unpinned* for gen / mesh / collider
-(the reference ships no golden vectors for them and cannot be compiled here); the reference's only KATs
-(``tests/UnitTests/Common/ChunkTests.cpp:17-43``) are checked in ``tests/test_oracle_kat.py``.
+ThisSpaceOfMine's chunk generation / meshing / collider / edit rules.
+
+Two backends share this front-end (same C entry points, ``orc_*``):
+
+* the default one, ``libtsom_oracle.so`` — the restatement ("port"), travels everywhere;
+* ``reference()`` — ``oracle/_ref/libtsom_ref.so``: the reference's OWN ``Chunk.cpp / FlatChunk.cpp / DeformedChunk.cpp / Planet.cpp /
+  BlockLibrary.cpp`` compiled unmodified from ``/root/reference`` against the stand-in third-party headers of ``oracle/ref_shim``
+  (built by ``oracle/ref_shim/Makefile`` wherever ``/root/reference`` exists; the prebuilt ``.so`` travels to the GPU box).
+
+Parity status: the restatement's structure is pinned against the reference's real code by ``tests/test_reference_vs_oracle.py``;
+what stays *unpinned* is the third-party arithmetic that both the shim and the oracle restate (Nazara ``Box`` corner naming,
+``Quaternion::RotationBetween``, ``siv::PerlinNoise``), for which the reference ships no test.  The reference's only KATs
+(``tests/UnitTests/Common/ChunkTests.cpp:17-43``) are checked in ``tests/test_oracle_kat.py`` against both backends.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this.
 """
@@ -33,52 +43,89 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+_REF_SO = os.path.join(_HERE, "_ref", "libtsom_ref.so")
+_REF_DIR = os.path.join(_HERE, "ref_shim")
+
+
+def build_reference() -> str | None:
+    """(Re)build oracle/_ref/libtsom_ref.so from the reference's sources when /root/reference is present; else keep the prebuilt one."""
+    subprocess.check_call(["make", "-C", _REF_DIR], stdout=subprocess.DEVNULL)
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def _bind(path: str, full: bool):
+    L = C.CDLL(path)
+    i32p, u32p, u16p, f32p, u8p = (C.POINTER(t) for t in (C.c_int32, C.c_uint32, C.c_uint16, C.c_float, C.c_uint8))
+    L.orc_get_block_indices.argtypes = [i32p, u32p, i32p]
+    L.orc_get_chunk_indices_by_block_indices.argtypes = [i32p, i32p, u32p]
+    L.orc_direction_from_normal.argtypes = [f32p]
+    L.orc_blocklib_count.restype = C.c_uint32
+    L.orc_blocklib_get.argtypes = [C.c_uint32, u32p, u8p, C.c_char_p]
+    L.orc_blocklib_index.argtypes = [C.c_char_p]
+    if full:  # probes of the restatement's internals; the reference build has no such entry points
+        L.orc_perlin_perm.argtypes = [C.c_uint32, u8p]
+        L.orc_perlin_octave01.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_int]
+        L.orc_perlin_octave01.restype = C.c_double
+        L.orc_bernoulli_draws.argtypes = [C.c_uint32, C.c_uint32, u8p]
+    L.orc_generate_chunk.argtypes = [C.c_uint32, u32p, i32p, u16p]
+    L.orc_planet_create.argtypes = [C.c_float, C.c_float]
+    L.orc_planet_create.restype = C.c_void_p
+    L.orc_planet_destroy.argtypes = [C.c_void_p]
+    L.orc_planet_add_chunk.argtypes = [C.c_void_p, i32p, u16p]
+    L.orc_planet_reset_chunk.argtypes = [C.c_void_p, i32p, u16p]
+    L.orc_planet_generate.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_int]
+    L.orc_planet_generate_platform.argtypes = [C.c_void_p, C.c_int, i32p]
+    L.orc_planet_get_blocks.argtypes = [C.c_void_p, i32p, u16p]
+    L.orc_planet_update_block.argtypes = [C.c_void_p, i32p, u32p, C.c_uint16]
+    L.orc_planet_apply_edits.argtypes = [C.c_void_p, i32p, C.c_uint32]
+    L.orc_planet_clear_invalidated.argtypes = [C.c_void_p]
+    L.orc_planet_collect_dirty.argtypes = [C.c_void_p, i32p, C.c_uint32]
+    L.orc_planet_collect_dirty.restype = C.c_uint32
+    L.orc_mesh_build.argtypes = [C.c_void_p, i32p, C.c_int, f32p, f32p, C.c_float, C.c_int, C.c_int]
+    L.orc_mesh_build.restype = C.c_void_p
+    L.orc_mesh_face_count.argtypes = [C.c_void_p]
+    L.orc_mesh_face_count.restype = C.c_uint32
+    L.orc_mesh_copy.argtypes = [C.c_void_p, f32p, f32p, f32p, u32p]
+    L.orc_mesh_free.argtypes = [C.c_void_p]
+    L.orc_box_collider.argtypes = [C.c_void_p, i32p, f32p, C.c_uint32]
+    L.orc_box_collider.restype = C.c_uint32
+    L.orc_bench_mesh_isolated.argtypes = [u16p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    L.orc_bench_mesh_isolated.restype = C.c_double
+    L.orc_bench_planet.argtypes = [C.c_uint32, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), u32p]
+    return L
+
+
 _lib = None
+_ref_lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
-        i32p, u32p, u16p, f32p, u8p = (C.POINTER(t) for t in (C.c_int32, C.c_uint32, C.c_uint16, C.c_float, C.c_uint8))
-        L.orc_get_block_indices.argtypes = [i32p, u32p, i32p]
-        L.orc_get_chunk_indices_by_block_indices.argtypes = [i32p, i32p, u32p]
-        L.orc_direction_from_normal.argtypes = [f32p]
-        L.orc_blocklib_count.restype = C.c_uint32
-        L.orc_blocklib_get.argtypes = [C.c_uint32, u32p, u8p, C.c_char_p]
-        L.orc_blocklib_index.argtypes = [C.c_char_p]
-        L.orc_perlin_perm.argtypes = [C.c_uint32, u8p]
-        L.orc_perlin_octave01.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_int]
-        L.orc_perlin_octave01.restype = C.c_double
-        L.orc_bernoulli_draws.argtypes = [C.c_uint32, C.c_uint32, u8p]
-        L.orc_generate_chunk.argtypes = [C.c_uint32, u32p, i32p, u16p]
-        L.orc_planet_create.argtypes = [C.c_float, C.c_float]
-        L.orc_planet_create.restype = C.c_void_p
-        L.orc_planet_destroy.argtypes = [C.c_void_p]
-        L.orc_planet_add_chunk.argtypes = [C.c_void_p, i32p, u16p]
-        L.orc_planet_reset_chunk.argtypes = [C.c_void_p, i32p, u16p]
-        L.orc_planet_generate.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_int]
-        L.orc_planet_generate_platform.argtypes = [C.c_void_p, C.c_int, i32p]
-        L.orc_planet_get_blocks.argtypes = [C.c_void_p, i32p, u16p]
-        L.orc_planet_update_block.argtypes = [C.c_void_p, i32p, u32p, C.c_uint16]
-        L.orc_planet_apply_edits.argtypes = [C.c_void_p, i32p, C.c_uint32]
-        L.orc_planet_clear_invalidated.argtypes = [C.c_void_p]
-        L.orc_planet_collect_dirty.argtypes = [C.c_void_p, i32p, C.c_uint32]
-        L.orc_planet_collect_dirty.restype = C.c_uint32
-        L.orc_mesh_build.argtypes = [C.c_void_p, i32p, C.c_int, f32p, f32p, C.c_float, C.c_int, C.c_int]
-        L.orc_mesh_build.restype = C.c_void_p
-        L.orc_mesh_face_count.argtypes = [C.c_void_p]
-        L.orc_mesh_face_count.restype = C.c_uint32
-        L.orc_mesh_copy.argtypes = [C.c_void_p, f32p, f32p, f32p, u32p]
-        L.orc_mesh_free.argtypes = [C.c_void_p]
-        L.orc_box_collider.argtypes = [C.c_void_p, i32p, f32p, C.c_uint32]
-        L.orc_box_collider.restype = C.c_uint32
-        L.orc_bench_mesh_isolated.argtypes = [u16p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
-        L.orc_bench_mesh_isolated.restype = C.c_double
-        L.orc_bench_planet.argtypes = [C.c_uint32, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), u32p]
-        _lib = L
+        _lib = _bind(_SO, full=True)
     return _lib
+
+
+def reference_available() -> bool:
+    """True when oracle/_ref/libtsom_ref.so exists (prebuilt) or can be built here (/root/reference present)."""
+    if os.path.exists(_REF_SO):
+        return True
+    try:
+        return build_reference() is not None
+    except Exception:
+        return False
+
+
+def ref_lib():
+    global _ref_lib
+    if _ref_lib is None:
+        if os.path.isdir("/root/reference"):
+            build_reference()  # make: no-op when up to date
+        if not os.path.exists(_REF_SO):
+            raise RuntimeError("oracle/_ref/libtsom_ref.so is not built (needs /root/reference; see oracle/ref_shim/Makefile)")
+        _ref_lib = _bind(_REF_SO, full=False)
+    return _ref_lib
 
 
 def _p(a, t):
@@ -94,60 +141,60 @@ def _u3(v):
 
 
 # ---------------------------------------------------------------- index math / tables
-def get_block_indices(chunk, local):
+def get_block_indices(chunk, local, L=None):
     out = np.zeros(3, np.int32)
-    lib().orc_get_block_indices(_p(_i3(chunk), C.c_int32), _p(_u3(local), C.c_uint32), _p(out, C.c_int32))
+    (L or lib()).orc_get_block_indices(_p(_i3(chunk), C.c_int32), _p(_u3(local), C.c_uint32), _p(out, C.c_int32))
     return tuple(int(v) for v in out)
 
 
-def get_chunk_indices_by_block_indices(block):
+def get_chunk_indices_by_block_indices(block, L=None):
     c = np.zeros(3, np.int32)
     l = np.zeros(3, np.uint32)
-    lib().orc_get_chunk_indices_by_block_indices(_p(_i3(block), C.c_int32), _p(c, C.c_int32), _p(l, C.c_uint32))
+    (L or lib()).orc_get_chunk_indices_by_block_indices(_p(_i3(block), C.c_int32), _p(c, C.c_int32), _p(l, C.c_uint32))
     return tuple(int(v) for v in c), tuple(int(v) for v in l)
 
 
-def direction_from_normal(n):
+def direction_from_normal(n, L=None):
     a = np.ascontiguousarray(n, dtype=np.float32)
-    return int(lib().orc_direction_from_normal(_p(a, C.c_float)))
+    return int((L or lib()).orc_direction_from_normal(_p(a, C.c_float)))
 
 
-def block_library():
+def block_library(L=None):
     """[(name, tex[6], hasCollisions, isDoubleSided, isTransparent)] in BlockIndex order (BlockLibrary.cpp:10-83)."""
     res = []
-    for i in range(lib().orc_blocklib_count()):
+    for i in range((L or lib()).orc_blocklib_count()):
         tex = np.zeros(6, np.uint32)
         fl = np.zeros(3, np.uint8)
         name = C.create_string_buffer(64)
-        lib().orc_blocklib_get(i, _p(tex, C.c_uint32), _p(fl, C.c_uint8), name)
+        (L or lib()).orc_blocklib_get(i, _p(tex, C.c_uint32), _p(fl, C.c_uint8), name)
         res.append((name.value.decode(), tex.copy(), bool(fl[0]), bool(fl[1]), bool(fl[2])))
     return res
 
 
 def block_index(name: str) -> int:
-    return int(lib().orc_blocklib_index(name.encode()))
+    return int((L or lib()).orc_blocklib_index(name.encode()))
 
 
 def perlin_perm(seed: int) -> np.ndarray:
     out = np.zeros(256, np.uint8)
-    lib().orc_perlin_perm(seed & 0xFFFFFFFF, _p(out, C.c_uint8))
+    (L or lib()).orc_perlin_perm(seed & 0xFFFFFFFF, _p(out, C.c_uint8))
     return out
 
 
 def perlin_octave01(seed: int, x: float, y: float, octaves: int = 4) -> float:
-    return float(lib().orc_perlin_octave01(seed & 0xFFFFFFFF, x, y, octaves))
+    return float((L or lib()).orc_perlin_octave01(seed & 0xFFFFFFFF, x, y, octaves))
 
 
 def bernoulli_draws(seed: int, n: int) -> np.ndarray:
     out = np.zeros(n, np.uint8)
-    lib().orc_bernoulli_draws(seed & 0xFFFFFFFF, n, _p(out, C.c_uint8))
+    (L or lib()).orc_bernoulli_draws(seed & 0xFFFFFFFF, n, _p(out, C.c_uint8))
     return out
 
 
-def generate_chunk(seed, chunk_count, chunk_idx):
+def generate_chunk(seed, chunk_count, chunk_idx, L=None):
     """Planet::GenerateChunk for one chunk -> (blocks u16[32768], ok)."""
     out = np.zeros(NBLK, np.uint16)
-    rc = lib().orc_generate_chunk(seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), _p(_i3(chunk_idx), C.c_int32), _p(out, C.c_uint16))
+    rc = (L or lib()).orc_generate_chunk(seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), _p(_i3(chunk_idx), C.c_int32), _p(out, C.c_uint16))
     return out, rc == 0
 
 
@@ -176,82 +223,100 @@ class Mesh:
 class Planet:
     """Handle on an oracle Planet (ChunkContainer of FlatChunks, Planet.cpp)."""
 
-    def __init__(self, tile: float = 1.0, corner_radius: float = 16.0):
-        self._h = C.c_void_p(lib().orc_planet_create(tile, corner_radius))
+    def __init__(self, tile: float = 1.0, corner_radius: float = 16.0, L=None):
+        self._L = L or lib()
+        self._h = C.c_void_p(self._L.orc_planet_create(tile, corner_radius))
         self.tile = tile
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_planet_destroy(self._h)
+            self._L.orc_planet_destroy(self._h)
             self._h = None
 
     def add_chunk(self, idx, blocks=None):
         b = None if blocks is None else _p(np.ascontiguousarray(blocks, dtype=np.uint16), C.c_uint16)
-        return lib().orc_planet_add_chunk(self._h, _p(_i3(idx), C.c_int32), b)
+        return self._L.orc_planet_add_chunk(self._h, _p(_i3(idx), C.c_int32), b)
 
     def reset_chunk(self, idx, blocks):
-        return lib().orc_planet_reset_chunk(self._h, _p(_i3(idx), C.c_int32), _p(np.ascontiguousarray(blocks, dtype=np.uint16), C.c_uint16))
+        return self._L.orc_planet_reset_chunk(self._h, _p(_i3(idx), C.c_int32), _p(np.ascontiguousarray(blocks, dtype=np.uint16), C.c_uint16))
 
     def generate(self, seed, chunk_count, nthreads=1) -> bool:
-        return lib().orc_planet_generate(self._h, seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), nthreads) == 0
+        return self._L.orc_planet_generate(self._h, seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), nthreads) == 0
 
     def generate_platform(self, direction, center):
-        lib().orc_planet_generate_platform(self._h, int(direction), _p(_i3(center), C.c_int32))
+        self._L.orc_planet_generate_platform(self._h, int(direction), _p(_i3(center), C.c_int32))
 
     def get_blocks(self, idx):
         out = np.zeros(NBLK, np.uint16)
-        rc = lib().orc_planet_get_blocks(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_uint16))
+        rc = self._L.orc_planet_get_blocks(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_uint16))
         return out if rc == 0 else None
 
     def update_block(self, idx, local, block_id):
-        return lib().orc_planet_update_block(self._h, _p(_i3(idx), C.c_int32), _p(_u3(local), C.c_uint32), int(block_id))
+        return self._L.orc_planet_update_block(self._h, _p(_i3(idx), C.c_int32), _p(_u3(local), C.c_uint32), int(block_id))
 
     def apply_edits(self, edits):
         e = np.ascontiguousarray(edits, dtype=np.int32).reshape(-1, 7)
-        lib().orc_planet_apply_edits(self._h, _p(e, C.c_int32), len(e))
+        self._L.orc_planet_apply_edits(self._h, _p(e, C.c_int32), len(e))
 
     def clear_invalidated(self):
-        lib().orc_planet_clear_invalidated(self._h)
+        self._L.orc_planet_clear_invalidated(self._h)
 
     def collect_dirty(self, cap=1 << 20):
         out = np.zeros((cap, 3), np.int32)
-        n = lib().orc_planet_collect_dirty(self._h, _p(out, C.c_int32), cap)
+        n = self._L.orc_planet_collect_dirty(self._h, _p(out, C.c_int32), cap)
         return out[:n].copy()
 
     def mesh(self, idx, deformed=False, gravity_center=None, deform_center=None, deform_radius=0.0, normal=True, uv=True):
         g = None if gravity_center is None else _p(np.ascontiguousarray(gravity_center, dtype=np.float32), C.c_float)
         d = None if deform_center is None else _p(np.ascontiguousarray(deform_center, dtype=np.float32), C.c_float)
-        h = lib().orc_mesh_build(self._h, _p(_i3(idx), C.c_int32), int(deformed), g, d, float(deform_radius), int(normal), int(uv))
+        h = self._L.orc_mesh_build(self._h, _p(_i3(idx), C.c_int32), int(deformed), g, d, float(deform_radius), int(normal), int(uv))
         if not h:
             return None
         h = C.c_void_p(h)
-        f = lib().orc_mesh_face_count(h)
+        f = self._L.orc_mesh_face_count(h)
         pos = np.zeros((4 * f, 3), np.float32)
         nor = np.zeros((4 * f, 3), np.float32) if normal else None
         uvw = np.zeros((4 * f, 3), np.float32) if uv else None
         ind = np.zeros(6 * f, np.uint32)
-        lib().orc_mesh_copy(h, _p(pos, C.c_float), None if nor is None else _p(nor, C.c_float), None if uvw is None else _p(uvw, C.c_float), _p(ind, C.c_uint32))
-        lib().orc_mesh_free(h)
+        self._L.orc_mesh_copy(h, _p(pos, C.c_float), None if nor is None else _p(nor, C.c_float), None if uvw is None else _p(uvw, C.c_float), _p(ind, C.c_uint32))
+        self._L.orc_mesh_free(h)
         return Mesh(pos, nor, uvw, ind)
 
     def box_collider(self, idx, cap=32768):
         out = np.zeros((cap, 6), np.float32)
-        n = lib().orc_box_collider(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_float), cap)
+        n = self._L.orc_box_collider(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_float), cap)
         return out[:n].copy()
 
 
-def bench_mesh_isolated(blocks: np.ndarray, nthreads: int):
+def bench_mesh_isolated(blocks: np.ndarray, nthreads: int, L=None):
     """Time Chunk::BuildMesh (render attributes) over n isolated chunks -> (seconds, faces)."""
     b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1, NBLK)
     faces = C.c_uint64(0)
-    t = lib().orc_bench_mesh_isolated(_p(b, C.c_uint16), len(b), nthreads, C.byref(faces))
+    t = (L or lib()).orc_bench_mesh_isolated(_p(b, C.c_uint16), len(b), nthreads, C.byref(faces))
     return float(t), int(faces.value)
 
 
-def bench_planet(seed, chunk_count, nthreads, stride=1):
+def bench_planet(seed, chunk_count, nthreads, stride=1, L=None):
     """Generate a planet and mesh every stride-th chunk -> dict(gen_s, mesh_s, faces, meshed, ok)."""
     times = (C.c_double * 2)()
     faces = C.c_uint64(0)
     meshed = C.c_uint32(0)
-    rc = lib().orc_bench_planet(seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), nthreads, stride, times, C.byref(faces), C.byref(meshed))
+    rc = (L or lib()).orc_bench_planet(seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), nthreads, stride, times, C.byref(faces), C.byref(meshed))
     return dict(gen_s=times[0], mesh_s=times[1], faces=int(faces.value), meshed=int(meshed.value), ok=rc == 0)
+
+
+class _Reference:
+    """The same front-end bound to oracle/_ref/libtsom_ref.so — the reference's own sources (see the module docstring)."""
+
+    def __getattr__(self, name):
+        target = globals()[name]
+        if name == "Planet":
+            return lambda *a, **k: Planet(*a, L=ref_lib(), **k)
+        if callable(target):
+            return lambda *a, **k: target(*a, L=ref_lib(), **k)
+        return target
+
+
+def reference() -> _Reference:
+    ref_lib()
+    return _Reference()

@@ -1,5 +1,5 @@
-"""The reference's only known-answer vectors — tests/UnitTests/Common/ChunkTests.cpp:17-43 — checked against the CPU oracle
-and against the host mirror (thisspaceofmine_b200.ChunkContainer).  They pin ChunkContainer::GetBlockIndices
+"""The reference's only known-answer vectors — tests/UnitTests/Common/ChunkTests.cpp:17-43 — checked against the CPU oracle,
+the reference's own ChunkContainer (oracle/_ref) and the host mirror (thisspaceofmine_b200.ChunkContainer).  They pin ChunkContainer::GetBlockIndices
 (ChunkContainer.inl:14-17) and GetChunkIndicesByBlockIndices (ChunkContainer.inl:19-42)."""
 import pytest
 
@@ -31,8 +31,16 @@ ROUND_TRIP_KAT = [
     ((3, 42, -2), (ChunkSize - 1, ChunkSize - 1, ChunkSize - 1)),
 ]
 
+def _ref(name):
+    def call(*a):
+        return getattr(O.reference(), name)(*a)
+    return call
+
+
 IMPLS = [
     pytest.param((O.get_block_indices, O.get_chunk_indices_by_block_indices), id="oracle"),
+    pytest.param((_ref("get_block_indices"), _ref("get_chunk_indices_by_block_indices")), id="reference-sources",
+                 marks=pytest.mark.skipif(not O.reference_available(), reason="oracle/_ref not built")),
     pytest.param((ChunkContainer.GetBlockIndices, ChunkContainer.GetChunkIndicesByBlockIndices), id="host-mirror"),
 ]
 
