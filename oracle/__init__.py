@@ -171,21 +171,21 @@ def block_library(L=None):
     return res
 
 
-def block_index(name: str) -> int:
+def block_index(name: str, L=None) -> int:
     return int((L or lib()).orc_blocklib_index(name.encode()))
 
 
-def perlin_perm(seed: int) -> np.ndarray:
+def perlin_perm(seed: int, L=None) -> np.ndarray:
     out = np.zeros(256, np.uint8)
     (L or lib()).orc_perlin_perm(seed & 0xFFFFFFFF, _p(out, C.c_uint8))
     return out
 
 
-def perlin_octave01(seed: int, x: float, y: float, octaves: int = 4) -> float:
+def perlin_octave01(seed: int, x: float, y: float, octaves: int = 4, L=None) -> float:
     return float((L or lib()).orc_perlin_octave01(seed & 0xFFFFFFFF, x, y, octaves))
 
 
-def bernoulli_draws(seed: int, n: int) -> np.ndarray:
+def bernoulli_draws(seed: int, n: int, L=None) -> np.ndarray:
     out = np.zeros(n, np.uint8)
     (L or lib()).orc_bernoulli_draws(seed & 0xFFFFFFFF, n, _p(out, C.c_uint8))
     return out
