@@ -98,7 +98,7 @@ static void TestGpu()
 	BlockLibrary lib;
 	Device device(lib, 0);
 	const Vector3ui chunkCount(3, 3, 3);
-	Planet planet(device, 1.f, 16.f, 9.81f, 27);
+	Planet planet(device, 1.f, 16.f, 9.81f, 28);
 	TestBlockPositions(&planet);
 
 	planet.GenerateChunks(lib, 42, chunkCount);
@@ -183,7 +183,14 @@ static void TestGpu()
 		for (unsigned int i = 0; i < TSOM_CHUNK_BLOCKS; ++i)
 			blocks[i] = lib.GetBlockIndex("stone");
 	});
-	(void)solid;
+	auto boxes = solid.BuildBoxCollider();
+	CHECK(boxes.size() == 1);
+	if (boxes.size() == 1)
+	{
+		CHECK(boxes[0].position == Vector3f(-16.f, -16.f, -16.f));
+		CHECK(boxes[0].size == Vector3f(32.f, 32.f, 32.f));
+	}
+	CHECK(planet.GetChunkCount() == 28);
 	std::printf("adapter GPU pass: %llu faces over %zu chunks\n", (unsigned long long)faces, grid.size());
 }
 
