@@ -129,10 +129,10 @@ enum tsom_timing
 {
 	TSOM_TIMING_TERRAIN_MS = 0,   /* 6 x terrain_kernel */
 	TSOM_TIMING_GENERATE_MS = 1,  /* generate_kernel */
-	TSOM_TIMING_MESH_COUNT_MS = 2,
+	TSOM_TIMING_MESH_COUNT_MS = 2, /* 0 on the single-pass path (count and scan live inside mesh_fused_kernel) */
 	TSOM_TIMING_MESH_SCAN_MS = 3,
-	TSOM_TIMING_MESH_EMIT_MS = 4,
-	TSOM_TIMING_MESH_REEMIT = 5,  /* 1.0 when the arenas had to grow and emit ran twice (the emit time is then of the first, aborted run) */
+	TSOM_TIMING_MESH_EMIT_MS = 4,  /* mesh_fused_kernel: classify + count + chain + emit */
+	TSOM_TIMING_MESH_REEMIT = 5,  /* 1.0 when the arenas had to grow and the kernel ran twice (the time is then of the first, count-only run) */
 	TSOM_TIMING_COUNT = 6
 };
 int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n);
