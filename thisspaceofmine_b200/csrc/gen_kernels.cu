@@ -202,7 +202,34 @@ namespace tsomk
 	{
 		uint8_t start[6][SLAB]; // per pass and column: start height (32 = pass does not touch the column)
 		uint32_t powX[CS], powY[CS], powZ[CS];
+		uint32_t above[ROWS_PER_CHUNK]; // per x-row (z, y): bit x = emptied by some pass (above a column start)
+		uint32_t at[ROWS_PER_CHUNK];    // per x-row: bit x = sits on a column start (dirt -> grass)
 	};
+
+	// 32x32 bit-matrix transpose across a warp: lane i holds row i; afterwards lane j holds column j (bit i = old M[i][j])
+	__device__ __forceinline__ uint32_t warp_transpose32(uint32_t v)
+	{
+		const int lane = threadIdx.x & 31;
+#pragma unroll
+		for (int k = 16; k >= 1; k >>= 1)
+		{
+			const uint32_t lowMask = k == 16 ? 0x0000FFFFu : (k == 8 ? 0x00FF00FFu : (k == 4 ? 0x0F0F0F0Fu : (k == 2 ? 0x33333333u : 0x55555555u)));
+			const uint32_t other = __shfl_xor_sync(0xffffffffu, v, k);
+			if (lane & k)
+				v = (v & ~lowMask) | ((other >> k) & lowMask);
+			else
+				v = (v & lowMask) | ((other << k) & ~lowMask);
+		}
+		return v;
+	}
+
+	// column of 32 cells along an axis with kept interval [lo, hi]: bits above (i > hi or i < lo) and at (i == hi or i == lo);
+	// hi = 32 / lo = -1 mean "pass does not touch the column"
+	__device__ __forceinline__ void column_masks(int hi, int lo, uint32_t& above, uint32_t& at)
+	{
+		above = (hi >= 31 ? 0u : ~((2u << hi) - 1u)) | (lo <= 0 ? 0u : ((1u << lo) - 1u));
+		at = (hi < 32 ? (1u << hi) : 0u) | (lo >= 0 ? (1u << lo) : 0u);
+	}
 
 	// ids of 8 consecutive blocks of one row segment
 	struct Ids8
@@ -285,6 +312,55 @@ namespace tsomk
 		}
 		__syncthreads();
 
+		// ---- the six passes as two bit masks per x-row: "Empty above any column start, grass if dirt at a column start"
+		// (Planet.cpp:250-254 and twins).  X passes start per row; Y / Z passes start per (y, x) / (z, x) column: a lane builds its
+		// column's 32-bit mask along the axis and a warp transpose turns 32 columns into 32 row masks.
+		if (anyAct)
+		{
+			const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+			for (int k = 0; k < ROWS_PER_CHUNK / GEN_THREADS; ++k)
+			{
+				const int row = tid + k * GEN_THREADS;
+				uint32_t ab = 0u, at = 0u;
+				if (actX)
+					column_masks(act[0] ? int(sm.start[0][row]) : 32, CS - 1 - (act[1] ? int(sm.start[1][row]) : 32), ab, at);
+				sm.above[row] = ab;
+				sm.at[row] = at;
+			}
+			__syncthreads();
+			if (actY)
+			{
+				// columns (y, x) along local z; warp owns y = 4 * warp .. 4 * warp + 3, lane = x -> after the transpose lane = z
+#pragma unroll 1
+				for (int y = 4 * warp; y < 4 * warp + 4; ++y)
+				{
+					uint32_t ab, at;
+					column_masks(act[2] ? int(sm.start[2][y * CS + lane]) : 32, CS - 1 - (act[3] ? int(sm.start[3][y * CS + lane]) : 32), ab, at);
+					ab = warp_transpose32(ab);
+					at = warp_transpose32(at);
+					sm.above[lane * CS + y] |= ab;
+					sm.at[lane * CS + y] |= at;
+				}
+				__syncthreads();
+			}
+			if (actZ)
+			{
+				// columns (z, x) along local y; warp owns z = 4 * warp .. 4 * warp + 3, lane = x -> after the transpose lane = y
+#pragma unroll 1
+				for (int z = 4 * warp; z < 4 * warp + 4; ++z)
+				{
+					uint32_t ab, at;
+					column_masks(act[4] ? int(sm.start[4][z * CS + lane]) : 32, CS - 1 - (act[5] ? int(sm.start[5][z * CS + lane]) : 32), ab, at);
+					ab = warp_transpose32(ab);
+					at = warp_transpose32(at);
+					sm.above[z * CS + lane] |= ab;
+					sm.at[z * CS + lane] |= at;
+				}
+				__syncthreads();
+			}
+		}
+
 		uint32_t chunkSeed = a.seed + uint32_t(ci.x) + uint32_t(ci.y) + uint32_t(ci.z);
 		uint32_t x0 = chunkSeed % LCG_M; // std::linear_congruential_engine::seed: 0 -> 1
 		if (x0 == 0u)
@@ -304,7 +380,7 @@ namespace tsomk
 
 		int dX[8];
 		uint32_t px[8];
-		int dXmin = INT_MAX;
+		int dXmin = INT_MAX, dXmax = INT_MIN;
 		unsigned shaft = 0u;
 #pragma unroll
 		for (int j = 0; j < 8; ++j)
@@ -312,20 +388,18 @@ namespace tsomk
 			const int x = xb + j, wx = wx0 + x;
 			dX[j] = Hx - abs(wx);
 			dXmin = min(dXmin, dX[j]);
+			dXmax = max(dXmax, dX[j]);
 			px[j] = (anyDraw && x >= ax0 && x <= ax1) ? sm.powX[x - ax0] : 0u;
 			if (abs(wx) <= 2 && absWz <= 2)
 				shaft |= 1u << j;
 		}
-		// Y passes run along local z: the kept z interval of this thread's 8 columns never changes
-		int zLo[8], zHi[8];
-#pragma unroll
-		for (int j = 0; j < 8; ++j)
-		{
-			zHi[j] = act[2] ? int(sm.start[2][y * CS + xb + j]) : 32;
-			zLo[j] = CS - 1 - (act[3] ? int(sm.start[3][y * CS + xb + j]) : 32);
-		}
 		const bool rowYDraws = anyDraw && y >= ay0 && y <= ay1;
 		const uint32_t rowMulY = rowYDraws ? mulmod31(base2, sm.powY[y - ay0]) : 0u;
+		const uint32_t stoneId = a.stone, mossyId = a.stoneMossy, dirtId = a.dirt, grassId = a.grass, snowId = a.snow;
+		const uint32_t bStar = a.bStar;
+
+		// depth class: 0 Empty (< 30), 1 snow (<= 36), 2 dirt (<= 48), 3 stone / stone_mossy by draw (Planet.cpp:205-219)
+		auto depthClass = [](int d) { return (d >= 30) + (d >= 37) + (d >= 49); };
 
 #pragma unroll 1
 		for (int it = 0; it < CS / 2; ++it)
@@ -335,8 +409,15 @@ namespace tsomk
 			const int mYZ = min(dYZ_y, Hz - abs(wy));
 			const int col = z * CS + y;
 
+			uint32_t ab8 = 0u, at8 = 0u;
+			if (anyAct)
+			{
+				ab8 = (sm.above[col] >> xb) & 0xFFu;
+				at8 = (sm.at[col] >> xb) & 0xFFu & ~ab8;
+			}
+
 			unsigned id[8];
-			if (mYZ < 30)
+			if (mYZ < 30 || ab8 == 0xFFu)
 			{
 #pragma unroll
 				for (int j = 0; j < 8; ++j)
@@ -344,56 +425,61 @@ namespace tsomk
 			}
 			else
 			{
-				// bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
-				const bool rowDraws = rowYDraws && z >= az0 && z <= az1;
-				const uint32_t rowMul = rowDraws ? mulmod31(rowMulY, sm.powZ[z - az0]) : 0u;
-#pragma unroll
-				for (int j = 0; j < 8; ++j)
+				const int cMin = depthClass(min(dXmin, mYZ)), cMax = depthClass(min(dXmax, mYZ));
+				if (cMin == 3)
 				{
-					const int depth = min(dX[j], mYZ);
-					unsigned v;
-					if (depth >= 49)
+					// all eight blocks draw: bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
+					const uint32_t rowMul = mulmod31(rowMulY, sm.powZ[z - az0]);
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
 					{
 						const uint32_t u2 = mulmod31(rowMul, px[j]);
-						bool stone = u2 <= a.bStar;
-						if (u2 == a.bStar + 1u)
+						bool stone = u2 <= bStar;
+						if (u2 == bStar + 1u)
 							stone = (mulmod31(u2, a.aInv) - 1u) < a.aStar;
-						v = stone ? a.stone : a.stoneMossy;
+						id[j] = stone ? stoneId : mossyId;
 					}
-					else
-						v = depth < 30 ? 0u : (depth <= 36 ? a.snow : a.dirt);
-					id[j] = v;
 				}
-				if (shaft)
+				else if (cMin == cMax)
 				{
+					const unsigned v = cMin == 0 ? 0u : (cMin == 1 ? snowId : dirtId);
 #pragma unroll
 					for (int j = 0; j < 8; ++j)
-						if ((shaft >> j) & 1u)
-							id[j] = 0u; // central shaft, after the draw (Planet.cpp:221-222)
+						id[j] = v;
 				}
-
-				if (anyAct)
+				else
 				{
-					// "Empty above any column start, grass if dirt at a column start" (Planet.cpp:250-254 and twins)
-					const int sXp = act[0] ? int(sm.start[0][col]) : 32;
-					const int xLo = CS - 1 - (act[1] ? int(sm.start[1][col]) : 32);
-					uint2 zp = make_uint2(0x20202020u, 0x20202020u), zm = zp;
-					if (act[4])
-						zp = *reinterpret_cast<const uint2*>(&sm.start[4][z * CS + xb]);
-					if (act[5])
-						zm = *reinterpret_cast<const uint2*>(&sm.start[5][z * CS + xb]);
+					const bool rowDraws = rowYDraws && z >= az0 && z <= az1;
+					const uint32_t rowMul = rowDraws ? mulmod31(rowMulY, sm.powZ[z - az0]) : 0u;
 #pragma unroll
 					for (int j = 0; j < 8; ++j)
 					{
-						const int x = xb + j;
-						const int sZp = int(((j < 4 ? zp.x : zp.y) >> (8 * (j & 3))) & 0xffu);
-						const int yLo = CS - 1 - int(((j < 4 ? zm.x : zm.y) >> (8 * (j & 3))) & 0xffu);
-						const bool above = (x > sXp) | (x < xLo) | (z > zHi[j]) | (z < zLo[j]) | (y > sZp) | (y < yLo);
-						const bool at = (x == sXp) | (x == xLo) | (z == zHi[j]) | (z == zLo[j]) | (y == sZp) | (y == yLo);
-						if (above)
+						const int depth = min(dX[j], mYZ);
+						unsigned v;
+						if (depth >= 49)
+						{
+							const uint32_t u2 = mulmod31(rowMul, px[j]);
+							bool stone = u2 <= bStar;
+							if (u2 == bStar + 1u)
+								stone = (mulmod31(u2, a.aInv) - 1u) < a.aStar;
+							v = stone ? stoneId : mossyId;
+						}
+						else
+							v = depth < 30 ? 0u : (depth <= 36 ? snowId : dirtId);
+						id[j] = v;
+					}
+				}
+				// central shaft (after the draw, Planet.cpp:221-222), then the terrain passes
+				const uint32_t kill = shaft | ab8;
+				if (kill | at8)
+				{
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+					{
+						if ((kill >> j) & 1u)
 							id[j] = 0u;
-						else if (at && id[j] == a.dirt)
-							id[j] = a.grass;
+						else if (((at8 >> j) & 1u) && id[j] == dirtId)
+							id[j] = grassId;
 					}
 				}
 			}
