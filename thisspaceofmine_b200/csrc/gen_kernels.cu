@@ -237,7 +237,7 @@ namespace tsomk
 		unsigned v[8];
 	};
 
-	__global__ void __launch_bounds__(GEN_THREADS, 3) generate_kernel(const GenArgs a)
+	__global__ void __launch_bounds__(GEN_THREADS, 4) generate_kernel(const GenArgs a)
 	{
 		__shared__ GenSmem sm;
 		const int tid = threadIdx.x;
@@ -430,14 +430,21 @@ namespace tsomk
 				{
 					// all eight blocks draw: bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
 					const uint32_t rowMul = mulmod31(rowMulY, sm.powZ[z - az0]);
+					uint32_t u2[8];
+					bool tie = false;
 #pragma unroll
 					for (int j = 0; j < 8; ++j)
 					{
-						const uint32_t u2 = mulmod31(rowMul, px[j]);
-						bool stone = u2 <= bStar;
-						if (u2 == bStar + 1u)
-							stone = (mulmod31(u2, a.aInv) - 1u) < a.aStar;
-						id[j] = stone ? stoneId : mossyId;
+						u2[j] = mulmod31(rowMul, px[j]);
+						tie |= u2[j] == bStar + 1u;
+						id[j] = u2[j] <= bStar ? stoneId : mossyId;
+					}
+					if (tie) // u2 - 1 == bStar: the first draw decides (about once in 2^31 draws)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+							if (u2[j] == bStar + 1u)
+								id[j] = (mulmod31(u2[j], a.aInv) - 1u) < a.aStar ? stoneId : mossyId;
 					}
 				}
 				else if (cMin == cMax)
@@ -469,27 +476,37 @@ namespace tsomk
 						id[j] = v;
 					}
 				}
-				// central shaft (after the draw, Planet.cpp:221-222), then the terrain passes
-				const uint32_t kill = shaft | ab8;
-				if (kill | at8)
-				{
+			}
+
+			// pack, then the central shaft (after the draw, Planet.cpp:221-222) and the terrain passes on the packed words
+			uint32_t w[4];
 #pragma unroll
-					for (int j = 0; j < 8; ++j)
-					{
-						if ((kill >> j) & 1u)
-							id[j] = 0u;
-						else if (((at8 >> j) & 1u) && id[j] == dirtId)
-							id[j] = grassId;
-					}
+			for (int k = 0; k < 4; ++k)
+				w[k] = id[2 * k] | (id[2 * k + 1] << 16);
+			const uint32_t kill = shaft | ab8;
+			if (kill)
+			{
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					w[k] &= ~((((kill >> (2 * k)) & 1u) * 0xFFFFu) | (((kill >> (2 * k + 1)) & 1u) * 0xFFFF0000u));
+			}
+			if (at8)
+			{
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+				{
+					if (((at8 >> (2 * k)) & 1u) && (w[k] & 0xFFFFu) == dirtId)
+						w[k] = (w[k] & 0xFFFF0000u) | grassId;
+					if (((at8 >> (2 * k + 1)) & 1u) && (w[k] >> 16) == dirtId)
+						w[k] = (w[k] & 0xFFFFu) | (grassId << 16);
 				}
 			}
 
-			*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) =
-				make_uint4(id[0] | (id[1] << 16), id[2] | (id[3] << 16), id[4] | (id[5] << 16), id[6] | (id[7] << 16));
+			*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) = make_uint4(w[0], w[1], w[2], w[3]);
 			if (xq == 0)
-				xs[col] = uint16_t(id[0]);
+				xs[col] = uint16_t(w[0] & 0xFFFFu);
 			if (xq == 3)
-				xs[SLAB + col] = uint16_t(id[7]);
+				xs[SLAB + col] = uint16_t(w[3] >> 16);
 		}
 	}
 
