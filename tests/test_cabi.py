@@ -103,3 +103,15 @@ def test_null_handles_are_rejected_not_dereferenced():
     n = C.c_uint32()
     idx = np.zeros(3, np.int32)
     assert lib.tsom_collect_dirty(None, idx.ctypes.data_as(C.POINTER(C.c_int32)), 1, C.byref(n), 0) != L.OK
+
+
+def test_numpy_record_layouts_match_the_ctypes_mirror():
+    """host.py passes numpy record arrays straight through the C ABI (no per-element Python work): same sizes and offsets."""
+    from thisspaceofmine_b200.host import EDIT_DTYPE, VIEW_DTYPE
+
+    assert EDIT_DTYPE.itemsize == C.sizeof(L.Edit)
+    assert VIEW_DTYPE.itemsize == C.sizeof(L.MeshView)
+    for name, _ in L.Edit._fields_:
+        assert EDIT_DTYPE.fields[name][1] == getattr(L.Edit, name).offset, name
+    for name, _ in L.MeshView._fields_:
+        assert VIEW_DTYPE.fields[name][1] == getattr(L.MeshView, name).offset, name

@@ -539,8 +539,7 @@ namespace tsomk
 	}
 
 	// ------------------------------------------------------------------------------------------------ edits
-	// Chunk::UpdateBlock (Chunk.cpp:348-366) + the neighbour-mask rule of Planet.cpp:39-58.  Edits must land in order (a later
-	// edit of the same block wins): every thread scans the whole list and applies only the edits of the chunk slots it owns.
+	// Chunk::UpdateBlock (Chunk.cpp:348-366) + the neighbour-mask rule of Planet.cpp:39-58, single-writer form (platform script)
 	__device__ __forceinline__ void device_update_block(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint32_t slot, int x, int y, int z, uint16_t id)
 	{
 		blocks[size_t(slot) * NB + (z * CS + y) * CS + x] = id;
@@ -566,34 +565,93 @@ namespace tsomk
 		invalidMask[slot] |= uint8_t(mask);
 	}
 
+	// Batched edits: one thread per edit.  Only the order of edits to the SAME block matters (the later one wins), so a first
+	// kernel records, per edited block, the index of its last edit in an open-addressing hash table (64-bit CAS on the key,
+	// atomicMax on the value) and a second kernel lets exactly that edit write.  The neighbour masks are ORed atomically.
 	constexpr int EDIT_THREADS = 256;
-	constexpr int EDIT_CTAS = 16;
 
-	__global__ void __launch_bounds__(EDIT_THREADS) apply_edits_kernel(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* __restrict__ edits, uint32_t n)
+	__device__ __forceinline__ uint32_t edit_hash(unsigned long long k)
 	{
-		__shared__ EditDev tile[1024];
-		const uint32_t g = blockIdx.x * EDIT_THREADS + threadIdx.x;
-		const uint32_t G = gridDim.x * EDIT_THREADS;
-		for (uint32_t base = 0; base < n; base += 1024u)
+		k ^= k >> 33;
+		k *= 0xff51afd7ed558ccdull;
+		k ^= k >> 33;
+		return uint32_t(k);
+	}
+
+	__global__ void __launch_bounds__(EDIT_THREADS) edit_claim_kernel(const EditDev* __restrict__ edits, uint32_t n, unsigned long long* keys, uint32_t* vals, uint32_t capMask)
+	{
+		const uint32_t i = blockIdx.x * EDIT_THREADS + threadIdx.x;
+		if (i >= n)
+			return;
+		const EditDev e = edits[i];
+		if (e.slot == 0xFFFFFFFFu)
+			return;
+		const unsigned long long key = (static_cast<unsigned long long>(e.slot) << 15) | (e.packed & 0x7FFFu);
+		uint32_t h = edit_hash(key) & capMask;
+		for (;;)
 		{
-			const uint32_t m = min(1024u, n - base);
-			for (uint32_t i = threadIdx.x; i < m; i += EDIT_THREADS)
-				tile[i] = edits[base + i];
-			__syncthreads();
-			for (uint32_t i = 0; i < m; ++i)
+			const unsigned long long prev = atomicCAS(&keys[h], ~0ull, key);
+			if (prev == ~0ull || prev == key)
 			{
-				const EditDev e = tile[i];
-				if (e.slot != 0xFFFFFFFFu && e.slot % G == g)
-					device_update_block(blocks, xslabs, invalidMask, e.slot, int(e.packed & 31u), int((e.packed >> 5) & 31u), int((e.packed >> 10) & 31u), uint16_t(e.packed >> 16));
+				atomicMax(&vals[h], i);
+				return;
 			}
-			__syncthreads();
+			h = (h + 1u) & capMask;
 		}
 	}
 
-	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, cudaStream_t st)
+	__global__ void __launch_bounds__(EDIT_THREADS) edit_apply_kernel(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* __restrict__ edits, uint32_t n,
+	                                                                  const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t capMask)
 	{
-		if (n)
-			apply_edits_kernel<<<EDIT_CTAS, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, edits, n);
+		const uint32_t i = blockIdx.x * EDIT_THREADS + threadIdx.x;
+		if (i >= n)
+			return;
+		const EditDev e = edits[i];
+		if (e.slot == 0xFFFFFFFFu)
+			return;
+		const unsigned long long key = (static_cast<unsigned long long>(e.slot) << 15) | (e.packed & 0x7FFFu);
+		uint32_t h = edit_hash(key) & capMask;
+		while (keys[h] != key)
+			h = (h + 1u) & capMask;
+
+		const int x = int(e.packed & 31u), y = int((e.packed >> 5) & 31u), z = int((e.packed >> 10) & 31u);
+		const uint16_t id = uint16_t(e.packed >> 16);
+		const bool last = vals[h] == i;
+		if (last)
+			blocks[size_t(e.slot) * NB + (z * CS + y) * CS + x] = id;
+		unsigned mask = 0x80u; // bit 7: "is in m_invalidatedChunks" (a mask of 0 still invalidates the chunk itself)
+		if (x == 0)
+		{
+			if (last)
+				xslabs[size_t(e.slot) * 2 * SLAB + z * CS + y] = id;
+			mask |= 1u << D_LEFT;
+		}
+		else if (x == CS - 1)
+		{
+			if (last)
+				xslabs[size_t(e.slot) * 2 * SLAB + SLAB + z * CS + y] = id;
+			mask |= 1u << D_RIGHT;
+		}
+		if (y == 0)
+			mask |= 1u << D_FRONT;
+		else if (y == CS - 1)
+			mask |= 1u << D_BACK;
+		if (z == 0)
+			mask |= 1u << D_DOWN;
+		else if (z == CS - 1)
+			mask |= 1u << D_UP;
+		// every edit raises its mask, overwritten or not (each UpdateBlock call fires OnBlockUpdated, Chunk.cpp:365)
+		atomicOr(reinterpret_cast<unsigned int*>(invalidMask) + (e.slot >> 2), mask << (8u * (e.slot & 3u)));
+	}
+
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
+	                        uint32_t cap, cudaStream_t st)
+	{
+		if (!n)
+			return;
+		const int grid = int((n + EDIT_THREADS - 1) / EDIT_THREADS);
+		edit_claim_kernel<<<grid, EDIT_THREADS, 0, st>>>(edits, n, keys, vals, cap - 1u);
+		edit_apply_kernel<<<grid, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, edits, n, keys, vals, cap - 1u);
 	}
 
 	// ------------------------------------------------------------------------------------------------ Planet::GeneratePlatform

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -233,6 +234,8 @@ struct tsom_ctx
 	bool legacyMesh = false; // TSOM_MESH_LEGACY=1: count -> scan -> emit (kept for A/B measurements)
 	DevBuf<float> gravity;
 	DevBuf<tsomk::EditDev> edits;
+	DevBuf<unsigned long long> editKeys; // open-addressing table of the edited blocks of one tsom_apply_edits call
+	DevBuf<uint32_t> editVals;           // ... -> index of the last edit that names the block
 	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
 	uint32_t* hSmall = nullptr; // pinned mirror
 	void* hPinned = nullptr;    // pinned staging for small result read-backs
@@ -307,8 +310,56 @@ struct tsom_container
 	uint8_t* dPerm = nullptr;
 	DevBuf<int> slotGrid;
 
+	// dense chunk-index -> slot grid over the bounding box of the existing chunks (O(1) lookups for per-tick batches: edits,
+	// dirty sets, mesh jobs); rebuilt lazily after the set of chunks changed, skipped for very sparse containers
+	mutable std::vector<uint32_t> hostGrid;
+	mutable int32_t gridOrigin[3] = { 0, 0, 0 }, gridDim[3] = { 0, 0, 0 };
+	mutable bool hostGridValid = false, hostGridUsable = false;
+
+	void EnsureHostGrid() const
+	{
+		if (hostGridValid)
+			return;
+		hostGridValid = true;
+		hostGridUsable = false;
+		hostGrid.clear();
+		if (slotOf.empty())
+			return;
+		int32_t lo[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, hi[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
+		for (auto& kv : slotOf)
+		{
+			const int32_t v[3] = { kv.first.x, kv.first.y, kv.first.z };
+			for (int a = 0; a < 3; ++a)
+			{
+				lo[a] = std::min(lo[a], v[a]);
+				hi[a] = std::max(hi[a], v[a]);
+			}
+		}
+		double cells = 1.0;
+		for (int a = 0; a < 3; ++a)
+		{
+			gridOrigin[a] = lo[a];
+			gridDim[a] = hi[a] - lo[a] + 1;
+			cells *= double(gridDim[a]);
+		}
+		if (cells > std::max(65536.0, 16.0 * double(slotOf.size())))
+			return;
+		hostGrid.assign(size_t(cells), 0xFFFFFFFFu);
+		for (auto& kv : slotOf)
+			hostGrid[(size_t(kv.first.z - lo[2]) * gridDim[1] + size_t(kv.first.y - lo[1])) * gridDim[0] + size_t(kv.first.x - lo[0])] = kv.second;
+		hostGridUsable = true;
+	}
+
 	uint32_t SlotOf(const Key& k) const
 	{
+		EnsureHostGrid();
+		if (hostGridUsable)
+		{
+			const int64_t gx = int64_t(k.x) - gridOrigin[0], gy = int64_t(k.y) - gridOrigin[1], gz = int64_t(k.z) - gridOrigin[2];
+			if (gx < 0 || gy < 0 || gz < 0 || gx >= gridDim[0] || gy >= gridDim[1] || gz >= gridDim[2])
+				return 0xFFFFFFFFu;
+			return hostGrid[(size_t(gz) * gridDim[1] + size_t(gy)) * gridDim[0] + size_t(gx)];
+		}
 		auto it = slotOf.find(k);
 		return it == slotOf.end() ? 0xFFFFFFFFu : it->second;
 	}
@@ -338,6 +389,7 @@ namespace
 			slot = c->highWater++;
 		}
 		c->slotOf.emplace(k, slot);
+		c->hostGridValid = false;
 		c->idxOf[slot] = k;
 		c->exists[slot] = 1;
 		c->hasContent[slot] = 0;
@@ -453,7 +505,7 @@ namespace
 		auto grow = [&](auto*& ptr, uint64_t& cap, size_t bytesPerFace) -> int {
 			if (faces <= cap)
 				return TSOM_OK;
-			uint64_t want = std::max<uint64_t>(faces, cap + cap / 4);
+			uint64_t want = std::max<uint64_t>(faces, cap + cap / 2);
 			if (ptr)
 				cudaFree(ptr);
 			ptr = nullptr;
@@ -563,6 +615,8 @@ extern "C"
 		ctx->worklist.Free();
 		ctx->firstFace.Free();
 		ctx->status.Free();
+		ctx->editKeys.Free();
+		ctx->editVals.Free();
 		ctx->gravity.Free();
 		ctx->edits.Free();
 		cudaFree(ctx->dSmall);
@@ -726,6 +780,7 @@ extern "C"
 		TSOM_CUDA(cudaMemsetAsync(c->dInvalid + slot, 0, 1, c->ctx->stream));
 		c->freeSlots.push_back(slot);
 		c->slotOf.erase(it);
+		c->hostGridValid = false;
 		c->topoDirty = true;
 		return TSOM_OK;
 	}
@@ -1034,8 +1089,16 @@ extern "C"
 		}
 		TSOM_CUDA(ctx->edits.Ensure(n));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->edits.ptr, staged, size_t(n) * sizeof(tsomk::EditDev), cudaMemcpyHostToDevice, ctx->stream));
-		tsomk::launch_apply_edits(c->dBlocks, c->dXslabs, c->dInvalid, ctx->edits.ptr, n, ctx->stream);
-		ctx->launches += 1;
+		// last-writer-wins per block: a hash table of the edited blocks (capacity >= 2n, power of two) records the last edit index
+		uint32_t cap = 1024;
+		while (cap < 2u * n)
+			cap <<= 1;
+		TSOM_CUDA(ctx->editKeys.Ensure(cap));
+		TSOM_CUDA(ctx->editVals.Ensure(cap));
+		TSOM_CUDA(cudaMemsetAsync(ctx->editKeys.ptr, 0xFF, size_t(cap) * sizeof(unsigned long long), ctx->stream));
+		TSOM_CUDA(cudaMemsetAsync(ctx->editVals.ptr, 0, size_t(cap) * sizeof(uint32_t), ctx->stream));
+		tsomk::launch_apply_edits(c->dBlocks, c->dXslabs, c->dInvalid, ctx->edits.ptr, n, ctx->editKeys.ptr, ctx->editVals.ptr, cap, ctx->stream);
+		ctx->launches += 2;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the pinned staging buffer is reused by the next call
 		return TSOM_OK;

@@ -110,7 +110,9 @@ namespace tsomk
 		uint32_t slot; // 0xFFFFFFFF = skip
 		uint32_t packed; // x | y<<5 | z<<10 | block<<16
 	};
-	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, cudaStream_t st);
+	// keys / vals: open-addressing table (capacity `cap`, a power of two >= 2n; keys preset to ~0, vals to 0)
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
+	                        uint32_t cap, cudaStream_t st);
 
 	struct PlatformArgs
 	{

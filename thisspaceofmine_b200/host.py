@@ -41,6 +41,20 @@ def _p(a: np.ndarray, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+# numpy mirrors of tsom_edit / tsom_mesh_view (include/tsom_b200.h), so batches cross the C ABI without per-element Python work
+EDIT_DTYPE = np.dtype([("chunk", np.int32, 3), ("x", np.uint8), ("y", np.uint8), ("z", np.uint8), ("reserved", np.uint8), ("block", np.uint16), ("reserved2", np.uint16)])
+VIEW_DTYPE = np.dtype([("first_face", np.uint64), ("face_count", np.uint32), ("reserved", np.uint32)])
+
+
+def pack_edits(edits) -> np.ndarray:
+    """[n, 7] ints (cx, cy, cz, x, y, z, block) -> tsom_edit records."""
+    e = np.ascontiguousarray(edits, dtype=np.int64).reshape(-1, 7)
+    raw = np.zeros(len(e), EDIT_DTYPE)
+    raw["chunk"] = e[:, 0:3]
+    raw["x"], raw["y"], raw["z"], raw["block"] = e[:, 3], e[:, 4], e[:, 5], e[:, 6]
+    return raw
+
+
 def _idx(v) -> np.ndarray:
     a = np.ascontiguousarray(v, dtype=np.int32).reshape(-1, 3)
     return a
@@ -226,16 +240,21 @@ class MeshBatch:
     """Result of one batched tsom_mesh call: per-chunk views into the device arenas."""
 
     def __init__(self, ctx: Context, indices: np.ndarray, views, flags: int):
+        """`views`: numpy structured array laid out like tsom_mesh_view (VIEW_DTYPE), or None when the caller skipped them."""
         self.ctx, self.chunk_indices, self._views, self.flags = ctx, indices, views, flags
-        self.face_counts = np.array([v.face_count for v in views], dtype=np.uint32)
-        self.first_faces = np.array([v.first_face for v in views], dtype=np.uint64)
+        if views is None:
+            self.face_counts = np.zeros(0, np.uint32)
+            self.first_faces = np.zeros(0, np.uint64)
+        else:
+            self.face_counts = views["face_count"]
+            self.first_faces = views["first_face"]
 
     @property
     def total_faces(self) -> int:
         return int(self.face_counts.sum())
 
     def __len__(self):
-        return len(self._views)
+        return len(self.chunk_indices)
 
     def chunk(self, i: int) -> Optional[ChunkMesh]:
         """Host copy of chunk i's mesh; None when it has no face (the reference returns a null mesh, ClientChunkEntities.cpp:161-162)."""
@@ -339,13 +358,11 @@ class ChunkContainer:
     # ---- edits
     def UpdateBlocks(self, edits: np.ndarray):
         """n x Chunk::UpdateBlock, in order; `edits` is [n, 7] int: cx, cy, cz, x, y, z, block."""
-        e = np.ascontiguousarray(edits, dtype=np.int64).reshape(-1, 7)
-        arr = (L.Edit * len(e))()
-        raw = np.zeros(len(e), dtype=np.dtype([("chunk", np.int32, 3), ("x", np.uint8), ("y", np.uint8), ("z", np.uint8), ("r", np.uint8), ("block", np.uint16), ("r2", np.uint16)]))
-        raw["chunk"] = e[:, 0:3]
-        raw["x"], raw["y"], raw["z"], raw["block"] = e[:, 3], e[:, 4], e[:, 5], e[:, 6]
-        C.memmove(arr, raw.ctypes.data, raw.nbytes)
-        L.check(L.lib().tsom_apply_edits(self._h, arr, len(e)))
+        if isinstance(edits, np.ndarray) and edits.dtype == EDIT_DTYPE:
+            raw = np.ascontiguousarray(edits)  # already in the wire form of tsom_edit (see pack_edits)
+        else:
+            raw = pack_edits(edits)
+        L.check(L.lib().tsom_apply_edits(self._h, C.cast(raw.ctypes.data, C.POINTER(L.Edit)), len(raw)))
 
     def UpdateBlock(self, chunkIndices, indices, newBlock: int):
         self.UpdateBlocks(np.array([[*chunkIndices, *indices, newBlock]]))
@@ -371,9 +388,9 @@ class ChunkContainer:
         if indices is None:
             raise ValueError("indices is required (use list_chunks() for all)")
         idx = _idx(indices)
-        v = (L.MeshView * len(idx))() if views else None
-        L.check(L.lib().tsom_mesh(self._h, _p(idx, C.c_int32), len(idx), C.byref(params), v))
-        return MeshBatch(self.ctx, idx, v if views else [], flags)
+        v = np.zeros(len(idx), VIEW_DTYPE) if views else None
+        L.check(L.lib().tsom_mesh(self._h, _p(idx, C.c_int32), len(idx), C.byref(params), None if v is None else C.cast(v.ctypes.data, C.POINTER(L.MeshView))))
+        return MeshBatch(self.ctx, idx, v, flags)
 
     def BuildBoxCollider(self, indices) -> np.ndarray:
         """FlatChunk::BuildCollider boxes -> [n, 6] float32 (pos.xyz, size.xyz) in block units."""
