@@ -223,6 +223,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
@@ -353,6 +355,16 @@ def run_b200(args):
                 out["planet"] = planet_bench(T, ctx, args.planet)
             except Exception as e:  # secondary measurement: never lose the headline line
                 out["planet"] = {"error": str(e)}
+    if args.planet and world > 1:
+        # BASELINE configs 3 / 5: ONE planet sharded by chunk index over the ranks (strong scaling), halo slabs over NVLink P2P
+        try:
+            cont.close()
+            sharded = {f"{e}^3": planet_sharded_bench(T, ctx, e, rank, world, dist, torch, device) for e in sorted({args.planet, 47})}
+        except Exception as e:
+            sharded = {"error": str(e)}
+        if rank == 0:
+            out["planet"] = sharded
+    if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -390,6 +402,47 @@ def planet_bench(T, ctx, count):
                gen_gbs=n * 65536 / (g / 1e3) / 1e9, gen_frac=n * 65536 / (g / 1e3) / 1e9 / peak,
                mesh_gbs=mesh_bytes / ((c + s + e) / 1e3) / 1e9, mesh_frac=mesh_bytes / ((c + s + e) / 1e3) / 1e9 / peak)
     planet.close()
+    return res
+
+
+def planet_sharded_bench(T, ctx, count, rank, world, dist, torch, device):
+    """One count^3 planet over `world` GPUs: each rank generates its chunk range, pulls the facing slabs of remote neighbours
+    over P2P (tsom_halo_pull, no NCCL on the data path) and meshes its range.  Time = max over ranks of the wall clock around
+    generate + halo pull + mesh (device work synchronised on both sides); value = count^3 / time."""
+    from thisspaceofmine_b200.sharding import ShardedPlanet
+
+    cc = (count, count, count)
+    sp = ShardedPlanet(ctx, cc, rank, world)
+    lib = ctx.blockLibrary
+    res = {"chunk_count": list(cc), "chunks": count ** 3, "n_gpus": world, "scaling": "strong", "halo_bytes_rank0": sp.plan.halo_bytes(0)}
+    variants = [("flat_render", dict(render=True)), ("deformed_render_collider", dict(render=True, collider=True, deformed=True, deformRadius=16.0))]
+    for name, kw in variants:
+        times, gen_ms, mesh_ms, faces = [], [], [], 0
+        for it in range(4):
+            ctx.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            sp.GenerateChunks(lib, 42)
+            t = ctx.timings()
+            sp.PullHalos()
+            batch = sp.BuildMeshes(views=(it == 0), **kw)
+            ctx.synchronize()
+            dt = time.perf_counter() - t0
+            t2 = ctx.timings()
+            if it == 0:
+                faces = int(batch.total_faces)
+                continue  # the first pass sizes the arenas
+            tt = torch.tensor([dt, t["terrain_ms"] + t["generate_ms"], t2["mesh_emit_ms"]], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            times.append(float(tt[0]))
+            gen_ms.append(float(tt[1]))
+            mesh_ms.append(float(tt[2]))
+        ft = torch.tensor([faces], device=device, dtype=torch.int64)
+        dist.all_reduce(ft)
+        sec = sum(times) / len(times)
+        res[name] = {"faces": int(ft.item()), "step_ms": sec * 1e3, "gen_kernels_ms_max": sum(gen_ms) / len(gen_ms), "mesh_kernel_ms_max": sum(mesh_ms) / len(mesh_ms),
+                     "gen_plus_mesh_chunks_per_s": count ** 3 / sec}
+    sp.close()
     return res
 
 
