@@ -42,7 +42,7 @@ namespace tsomk
 
 	// order in which the 8 corners are summed for the block centre (enum order of Nz::BoxCorner as listed at
 	// DeformedChunk.cpp:123-130 under the §8.1 mapping)
-	__constant__ unsigned char c_cornerSumOrder[8] = { 0b100, 0b101, 0b000, 0b001, 0b110, 0b111, 0b010, 0b011 };
+	// (= codes 0b100, 0b101, 0b000, 0b001, 0b110, 0b111, 0b010, 0b011; spelled out in face_geometry)
 
 	struct MeshSmem
 	{
@@ -403,17 +403,38 @@ namespace tsomk
 	}
 
 	// geometry of one face: block centre (mean of the 8 corners, summed in enum order, Chunk.cpp:186-188), the 4 quad corners
-	// and their mean (Chunk.cpp:30)
+	// and their mean (Chunk.cpp:30).  The 8 corners are evaluated once (the deformed ones cost a normalisation each) and the quad
+	// corners are picked from them by their 3-bit codes.
 	__device__ __forceinline__ void face_geometry(const FaceCtx& cx, int x, int y, int z, int slot, bool twin, F3& blockCenter, F3 pos[4], F3& fc)
 	{
-		F3 sum = f3(0.f, 0.f, 0.f);
+		F3 c[8]; // indexed by corner code dX | dY << 1 | dZ << 2
 #pragma unroll
-		for (int i = 0; i < 8; ++i)
-			sum = sum + voxel_corner(cx, x, y, z, c_cornerSumOrder[i]);
+		for (int code = 0; code < 8; ++code)
+			c[code] = voxel_corner(cx, x, y, z, unsigned(code));
+		// enum order of Nz::BoxCorner (c_cornerSumOrder): 0b100, 0b101, 0b000, 0b001, 0b110, 0b111, 0b010, 0b011
+		F3 sum = f3(0.f, 0.f, 0.f);
+		sum = sum + c[4];
+		sum = sum + c[5];
+		sum = sum + c[0];
+		sum = sum + c[1];
+		sum = sum + c[6];
+		sum = sum + c[7];
+		sum = sum + c[2];
+		sum = sum + c[3];
 		blockCenter = sum / 8.f;
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
-			pos[i] = voxel_corner(cx, x, y, z, c_faceCorners[slot][twin ? (i ^ 1) : i]);
+		{
+			const unsigned code = c_faceCorners[slot][twin ? (i ^ 1) : i];
+			const bool b0 = (code & 1u) != 0u, b1 = (code & 2u) != 0u, b2 = (code & 4u) != 0u;
+			auto pick = [&](float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+				const float lo = b1 ? (b0 ? v3 : v2) : (b0 ? v1 : v0);
+				const float hi = b1 ? (b0 ? v7 : v6) : (b0 ? v5 : v4);
+				return b2 ? hi : lo;
+			};
+			pos[i] = f3(pick(c[0].x, c[1].x, c[2].x, c[3].x, c[4].x, c[5].x, c[6].x, c[7].x), pick(c[0].y, c[1].y, c[2].y, c[3].y, c[4].y, c[5].y, c[6].y, c[7].y),
+			            pick(c[0].z, c[1].z, c[2].z, c[3].z, c[4].z, c[5].z, c[6].z, c[7].z));
+		}
 		fc = f3(0.f, 0.f, 0.f);
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
