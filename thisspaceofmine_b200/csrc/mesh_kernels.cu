@@ -894,7 +894,8 @@ namespace tsomk
 		uint32_t lut32[LUTN];
 		alignas(16) FaceTable table;
 		uint32_t warpSum[FUSED_WARPS];
-		uint32_t job;
+		uint32_t job, slot, hasContent;   // the ticket and what it names (written by the lane that took the ticket)
+		uint32_t warpsDone;               // warps that have finished the current chunk; the last one takes the next ticket
 		uint32_t ffSeq;                   // == job + 1 once firstFace of the current job is known
 		unsigned long long firstFace;
 		alignas(8) uint64_t bar;
@@ -927,12 +928,16 @@ namespace tsomk
 		return acc;
 	}
 
+	// Called convergently by all 32 lanes.  The one-lookup shortcut for 8 equal ids is taken only when it holds for the whole
+	// warp (planet interiors and sky): in a mixed warp both sides of a per-lane branch would run back to back.
 	__device__ __forceinline__ uint32_t flags8(const MeshArgs& a, const uint32_t* lut, uint4 w)
 	{
-		if (((w.x | w.y | w.z | w.w) & ~(uint32_t(LUTN - 1) * 0x10001u)) != 0u)
-			return flags8_slow(a, lut, w);
-		if (w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu))
+		const bool big = ((w.x | w.y | w.z | w.w) & ~(uint32_t(LUTN - 1) * 0x10001u)) != 0u; // some id >= LUTN
+		const bool uniform = !big && w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu);
+		if (__all_sync(0xffffffffu, uniform))
 			return lut[w.x & 0xffffu] * 0xFFu;
+		if (big)
+			return flags8_slow(a, lut, w);
 		const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
 		uint32_t acc = 0;
 #pragma unroll
@@ -1061,6 +1066,21 @@ namespace tsomk
 		return sm.mD[r];
 	}
 
+	// one lane: take the next job and look up what it names (two dependent global loads paid once, before the CTA barrier)
+	__device__ __forceinline__ void take_ticket(const MeshArgs& a, FusedSmem& sm)
+	{
+		const uint32_t j = atomicAdd(a.jobCounter, 1u);
+		uint32_t slot = 0u, has = 0u;
+		if (j < a.nJobs)
+		{
+			slot = a.jobSlot[j];
+			has = a.chunkIdx[slot].w != 0 ? 1u : 0u;
+		}
+		sm.slot = slot;
+		sm.hasContent = has;
+		sm.job = j;
+	}
+
 	__global__ void __launch_bounds__(FUSED_THREADS, 2) mesh_fused_kernel(const MeshArgs a)
 	{
 		extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -1108,7 +1128,8 @@ namespace tsomk
 		if (tid == 0)
 		{
 			sm.ffSeq = 0u;
-			sm.job = atomicAdd(a.jobCounter, 1u);
+			sm.warpsDone = 0u;
+			take_ticket(a, sm);
 		}
 		uint32_t parity = 0;
 		for (;;)
@@ -1117,8 +1138,8 @@ namespace tsomk
 			const uint32_t job = sm.job;
 			if (job >= a.nJobs)
 				break;
-			const uint32_t slot = a.jobSlot[job];
-			const bool hasContent = a.chunkIdx[slot].w != 0;
+			const uint32_t slot = sm.slot;
+			const bool hasContent = sm.hasContent != 0u;
 
 			uint32_t F = 0, K = 0;
 			if (hasContent)
@@ -1432,11 +1453,18 @@ namespace tsomk
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}
-			// next ticket: only once every warp is done with this chunk.  (Not earlier: a ticket held during an emission would
-			// stall the look-back of every later job until this CTA gets to its front end.)
-			__syncthreads();
-			if (tid == 0)
-				sm.job = atomicAdd(a.jobCounter, 1u);
+			// next ticket: taken by the LAST warp to finish this chunk, so no extra CTA barrier is needed — and not earlier: a
+			// ticket held during an emission delays this job's aggregate and with it the look-back of every later job (measured).
+			__syncwarp();
+			if (lane == 0)
+			{
+				__threadfence_block();
+				if (atomicAdd(&sm.warpsDone, 1u) == FUSED_WARPS - 1)
+				{
+					sm.warpsDone = 0u;
+					take_ticket(a, sm);
+				}
+			}
 		}
 	}
 
