@@ -168,3 +168,56 @@ def test_unknown_chunk_is_an_error(ctx):
     gc, _ = _pair(ctx, {(0, 0, 0): np.zeros(NBLK, np.uint16)})
     with pytest.raises(T.TsomError):
         gc.BuildMeshes([(9, 9, 9)])
+
+
+def test_hidden_faces_appear_after_edits_resets_and_removals(ctx):
+    """3x3x3 solid stone chunks (the centre has no face at all) and an all-Empty chunk far away; then an edit, a reset and a
+    removal that each uncover hidden faces.  Guards any per-chunk shortcut ("this chunk cannot have a face") against going stale."""
+    stone = np.full(NBLK, 7, np.uint16)
+    chunks = {(x, y, z): stone.copy() for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)}
+    chunks[(5, 5, 5)] = np.zeros(NBLK, np.uint16)
+    gc, op = _pair(ctx, chunks)
+    all_idx = list(chunks)
+
+    def check():
+        present = [i for i in all_idx if i in chunks]
+        f, _ = _compare_all(gc, op, present)
+        return f
+
+    f0 = check()
+    assert check() == f0  # meshing twice gives the same result
+    centre = all_idx.index((0, 0, 0))
+    assert gc.BuildMeshes(all_idx).face_counts[centre] == 0
+
+    # 1. break a block of a neighbour where it touches the centre: the centre chunk gains exactly one face
+    gc.UpdateBlock((1, 0, 0), (0, 5, 5), 0)
+    op.update_block((1, 0, 0), (0, 5, 5), 0)
+    check()
+    assert gc.BuildMeshes(all_idx).face_counts[centre] == 1
+
+    # 2. place a block in the all-Empty chunk
+    gc.UpdateBlock((5, 5, 5), (3, 3, 3), 13)
+    op.update_block((5, 5, 5), (3, 3, 3), 13)
+    check()
+    assert gc.BuildMeshes([(5, 5, 5)]).face_counts[0] == 12  # glass: double-sided
+
+    # 3. reset a neighbour to glass (transparent): the centre's whole Down side becomes visible
+    glass = np.full(NBLK, 13, np.uint16)
+    gc.ResetChunks([(0, -1, 0)], glass[None, :])
+    op.reset_chunk((0, -1, 0), glass)
+    chunks[(0, -1, 0)] = glass
+    check()
+    assert gc.BuildMeshes(all_idx).face_counts[centre] == 1 + 32 * 32
+
+    # 4. remove a neighbour: no neighbour chunk => faces drawn (Chunk.cpp:165-166)
+    gc.RemoveChunk((0, 0, 1))
+    del chunks[(0, 0, 1)]
+    op2 = O.Planet()
+    for idx in chunks:
+        op2.add_chunk(idx, op.get_blocks(idx))
+    op = op2
+    present = [i for i in all_idx if i in chunks]
+    batch = gc.BuildMeshes(present)
+    for i, idx in enumerate(present):
+        assert_mesh_equal(batch.chunk(i), op.mesh(idx), what=f"after removal {idx}")
+    assert batch.face_counts[present.index((0, 0, 0))] == 1 + 2 * 32 * 32
