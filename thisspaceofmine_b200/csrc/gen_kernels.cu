@@ -799,7 +799,6 @@ namespace tsomk
 			return;
 
 		uint32_t nBoxes = 0;
-		auto bit = [&](int x, int y, int z) { return (mask[z * CS + y] >> x) & 1u; };
 		for (int z = 0; z < CS; ++z)
 		{
 			for (int y = 0; y < CS; ++y)

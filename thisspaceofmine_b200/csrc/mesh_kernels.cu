@@ -1,15 +1,9 @@
 // mesh_kernels.cu — face-culled chunk meshing on sm_100a (replaces Chunk::BuildMesh, reference src/CommonLib/Chunk.cpp:20-250).
 //
-// Two kernels share one staging / visibility front end:
-//   mesh_count_kernel : per chunk, stage ids + 6 halo slabs into shared memory with TMA bulk copies (cp.async.bulk + mbarrier),
-//                       build per-row bit masks with warp ballots, derive the 6 visibility masks per row, sum faces.
-//   mesh_emit_kernel  : same front end, then a block-wide prefix scan over the 1024 rows gives every face its ordinal in the
-//                       reference's emission order (z, y, x, Up/Down/Front/Back/Left/Right + double-sided twin); warps take
-//                       tiles of 32 consecutive faces, compute them one face per lane, transpose through shared memory and
-//                       stream them out with fully coalesced 16-byte stores (vertices 48 B x 4, indices u32 x 6,
-//                       collider positions 12 B x 4 from the same face list).
+// One kernel, mesh_fused_kernel (see its header comment below): stage the ids by TMA, classify, count, chain the chunk into
+// the arena by decoupled look-back, enumerate the faces in the reference's order and stream them out with coalesced stores.
 // A face is drawn iff self != Empty and (neighbour chunk absent, or neighbour id != self and neighbour is transparent)
-// (Chunk.cpp:190-201).  An absent neighbour chunk is staged as a slab of Empty ids, which is equivalent.
+// (Chunk.cpp:190-201).  An absent neighbour chunk reads as a slab of Empty ids, which is equivalent.
 //
 // Compiled with -fmad=false: the float math reproduces the reference's operation order without FMA contraction.
 #include "tsom_kernels.h"
@@ -17,14 +11,10 @@
 
 namespace tsomk
 {
-	constexpr int MESH_THREADS = 512;
-	constexpr int MESH_WARPS = MESH_THREADS / 32;
 	constexpr int ROWS = CS * CS; // 1024 x-rows per chunk
-	constexpr int FLAG_LUT = 256; // block types below this id are looked up in shared memory, the rest in global memory
 
 	// staging: one face = 12 float4 (4 vertices x 48 B) padded to 13 so lane-strided 16-byte stores are conflict free
 	constexpr int STAGE_FACE_F4 = 13;
-	constexpr int STAGE_WARP_BYTES = 32 * STAGE_FACE_F4 * 16; // 6656
 
 	// emission order of the reference (Chunk.cpp:200-246) as Direction values
 	__constant__ int c_slotDir[6] = { D_UP, D_DOWN, D_FRONT, D_BACK, D_LEFT, D_RIGHT };
@@ -44,242 +34,6 @@ namespace tsomk
 	// DeformedChunk.cpp:123-130 under the §8.1 mapping)
 	// (= codes 0b100, 0b101, 0b000, 0b001, 0b110, 0b111, 0b010, 0b011; spelled out in face_geometry)
 
-	struct MeshSmem
-	{
-		// persistent for the whole chunk
-		uint16_t ids[NB];          // 65536 B, TMA destination
-		uint32_t mD[ROWS];         // double-sided mask per row
-		uint32_t V[6][ROWS];       // visibility mask per emission slot and row
-		uint32_t rowOff[ROWS + 4]; // exclusive prefix of faces per row (+ total at [ROWS])
-		uint32_t desc[MESH_WARPS][32];
-		uint32_t warpSum[MESH_WARPS + 1];
-		uint32_t job;
-		uint32_t total;
-		alignas(8) uint64_t bar;
-		alignas(16) FaceTable table;
-		uint8_t flagLut[FLAG_LUT];
-		// phase 1-2 only; the emit kernel reuses this area as the face staging buffer
-		union
-		{
-			struct
-			{
-				uint16_t halo[6][SLAB]; // Direction order
-				uint32_t mT[ROWS];      // transparent mask per row
-				uint32_t mE[ROWS];      // non-empty mask per row
-				uint32_t hT[6][CS];     // transparent masks of the halo slabs (Left/Right: bit = y, row = z)
-			} front;
-			float4 stage[MESH_WARPS][32 * STAGE_FACE_F4];
-		} u;
-	};
-
-	struct CountSmem
-	{
-		uint16_t ids[NB];
-		uint16_t halo[6][SLAB];
-		uint32_t mT[ROWS];
-		uint32_t mE[ROWS];
-		uint32_t mD[ROWS];
-		uint32_t hT[6][CS];
-		uint32_t warpSum[MESH_WARPS + 1];
-		uint32_t job;
-		alignas(8) uint64_t bar;
-		uint8_t flagLut[FLAG_LUT];
-	};
-
-	__device__ __forceinline__ unsigned block_flags(const MeshArgs& a, const uint8_t* lut, unsigned id)
-	{
-		if (id < FLAG_LUT)
-			return lut[id];
-		return __ldg(a.blkFlags + (id < a.nTypes ? id : a.nTypes - 1));
-	}
-
-	__device__ __forceinline__ void load_flag_lut(const MeshArgs& a, uint8_t* lut)
-	{
-		for (int i = threadIdx.x; i < FLAG_LUT; i += MESH_THREADS)
-			lut[i] = a.blkFlags[uint32_t(i) < a.nTypes ? i : a.nTypes - 1];
-	}
-
-	// ---- stage one chunk: 64 KiB of ids + six 2 KiB halo slabs, by TMA bulk copies completing on one mbarrier ----
-	__device__ __forceinline__ void stage_chunk(const MeshArgs& a, uint32_t slot, uint16_t* ids, uint16_t (*halo)[SLAB], uint64_t* bar)
-	{
-		const int tid = threadIdx.x;
-		const int lane = tid & 31;
-		const int warp = tid >> 5;
-		const unsigned long long* hp = a.halo + size_t(slot) * 6;
-
-		if (warp == 0)
-		{
-			uint32_t bytes = NB * 2;
-#pragma unroll
-			for (int d = 0; d < 6; ++d)
-				bytes += (hp[d] != 0ull) ? SLAB * 2 : 0;
-
-			fence_proxy_async(); // earlier generic reads of these buffers (previous chunk) happen-before the async writes
-			if (lane == 0)
-			{
-				mbar_arrive_expect_tx(bar, bytes);
-				// the chunk itself, in 4 pieces so several copy engines' worth of requests are in flight
-				const uint16_t* src = a.blocks + size_t(slot) * NB;
-#pragma unroll
-				for (int p = 0; p < 4; ++p)
-					tma_load_1d(ids + p * (NB / 4), src + p * (NB / 4), NB / 2, bar);
-			}
-			__syncwarp();
-#pragma unroll
-			for (int d = 0; d < 6; ++d)
-			{
-				unsigned long long e = hp[d];
-				if (e == 0ull)
-					continue;
-				const uint16_t* src = reinterpret_cast<const uint16_t*>(e & ~HALO_KIND_MASK);
-				if ((e & HALO_KIND_MASK) == HALO_ROWS)
-					tma_load_1d(&halo[d][lane * CS], src + size_t(lane) * SLAB, CS * 2, bar); // 32 rows of 64 B, stride 2 KiB
-				else if (lane == 0)
-					tma_load_1d(&halo[d][0], src, SLAB * 2, bar);
-			}
-		}
-		// absent neighbours read as Empty (generic stores; visible after the block barrier that follows the mbarrier wait)
-#pragma unroll
-		for (int d = 0; d < 6; ++d)
-		{
-			if (hp[d] == 0ull)
-			{
-				uint32_t* z = reinterpret_cast<uint32_t*>(&halo[d][0]);
-				for (int i = tid; i < SLAB / 2; i += MESH_THREADS)
-					z[i] = 0u;
-			}
-		}
-	}
-
-	// ---- phase 1: per-row bit masks via warp ballots (lane = x) ----
-	__device__ __forceinline__ void build_masks(const MeshArgs& a, const uint8_t* lut, const uint16_t* ids, const uint16_t (*halo)[SLAB],
-	                                            uint32_t* mT, uint32_t* mE, uint32_t* mD, uint32_t (*hT)[CS])
-	{
-		const int lane = threadIdx.x & 31;
-		const int warp = threadIdx.x >> 5;
-
-		// own rows: 64 per warp, 8 at a time so the shared-memory loads of a batch overlap
-#pragma unroll 1
-		for (int r0 = warp * (ROWS / MESH_WARPS); r0 < (warp + 1) * (ROWS / MESH_WARPS); r0 += 8)
-		{
-			unsigned id[8], f[8];
-#pragma unroll
-			for (int k = 0; k < 8; ++k)
-				id[k] = ids[(r0 + k) * CS + lane];
-#pragma unroll
-			for (int k = 0; k < 8; ++k)
-				f[k] = block_flags(a, lut, id[k]);
-			uint32_t t = 0, e = 0, d = 0;
-#pragma unroll
-			for (int k = 0; k < 8; ++k)
-			{
-				const uint32_t bt = __ballot_sync(0xffffffffu, (f[k] & BF_TRANSPARENT) != 0);
-				const uint32_t be = __ballot_sync(0xffffffffu, id[k] != 0);
-				const uint32_t bd = __ballot_sync(0xffffffffu, (f[k] & BF_DOUBLE_SIDED) != 0);
-				if (lane == k)
-				{
-					t = bt;
-					e = be;
-					d = bd;
-				}
-			}
-			if (lane < 8)
-			{
-				mT[r0 + lane] = t;
-				mE[r0 + lane] = e;
-				mD[r0 + lane] = d;
-			}
-		}
-		// halo slabs: 6 x 32 rows = 12 per warp
-#pragma unroll 1
-		for (int r0 = warp * (6 * CS / MESH_WARPS); r0 < (warp + 1) * (6 * CS / MESH_WARPS); r0 += 4)
-		{
-			unsigned id[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k)
-				id[k] = halo[(r0 + k) >> 5][((r0 + k) & 31) * CS + lane];
-			uint32_t t = 0;
-#pragma unroll
-			for (int k = 0; k < 4; ++k)
-			{
-				const uint32_t bt = __ballot_sync(0xffffffffu, (block_flags(a, lut, id[k]) & BF_TRANSPARENT) != 0);
-				if (lane == k)
-					t = bt;
-			}
-			if (lane < 4)
-				hT[(r0 + lane) >> 5][(r0 + lane) & 31] = t;
-		}
-	}
-
-	// neighbour id of block (x,y,z) towards emission slot s, staged halo included
-	__device__ __forceinline__ unsigned neighbour_id(const uint16_t* ids, const uint16_t (*halo)[SLAB], int x, int y, int z, int s)
-	{
-		switch (s)
-		{
-			case 0: return z < CS - 1 ? ids[((z + 1) * CS + y) * CS + x] : halo[D_UP][y * CS + x];
-			case 1: return z > 0 ? ids[((z - 1) * CS + y) * CS + x] : halo[D_DOWN][y * CS + x];
-			case 2: return y > 0 ? ids[(z * CS + y - 1) * CS + x] : halo[D_FRONT][z * CS + x];
-			case 3: return y < CS - 1 ? ids[(z * CS + y + 1) * CS + x] : halo[D_BACK][z * CS + x];
-			case 4: return x > 0 ? ids[(z * CS + y) * CS + x - 1] : halo[D_LEFT][z * CS + y];
-			default: return x < CS - 1 ? ids[(z * CS + y) * CS + x + 1] : halo[D_RIGHT][z * CS + y];
-		}
-	}
-
-	// ---- phase 2: visibility masks of the two rows owned by this thread (rows 2*tid, 2*tid+1), in emission-slot order ----
-	// Returns the face count of both rows; v[j][s] receives the masks.
-	__device__ __forceinline__ void row_visibility(const uint16_t* ids, const uint16_t (*halo)[SLAB], const uint32_t* mT, const uint32_t* mE,
-	                                               const uint32_t (*hT)[CS], uint32_t v[2][6])
-	{
-		const int tid = threadIdx.x;
-		const int lane = tid & 31;
-		uint32_t need[2];
-
-#pragma unroll
-		for (int j = 0; j < 2; ++j)
-		{
-			const int r = 2 * tid + j;
-			const int z = r >> 5, y = r & 31;
-			const uint32_t t = mT[r], e = mE[r];
-
-			uint32_t tUp = z < CS - 1 ? mT[r + CS] : hT[D_UP][y];
-			uint32_t tDown = z > 0 ? mT[r - CS] : hT[D_DOWN][y];
-			uint32_t tFront = y > 0 ? mT[r - 1] : hT[D_FRONT][z];
-			uint32_t tBack = y < CS - 1 ? mT[r + 1] : hT[D_BACK][z];
-			uint32_t tLeft = (t << 1) | ((hT[D_LEFT][z] >> y) & 1u);
-			uint32_t tRight = (t >> 1) | (((hT[D_RIGHT][z] >> y) & 1u) << 31);
-
-			v[j][0] = e & tUp;
-			v[j][1] = e & tDown;
-			v[j][2] = e & tFront;
-			v[j][3] = e & tBack;
-			v[j][4] = e & tLeft;
-			v[j][5] = e & tRight;
-			need[j] = e & t; // transparent non-empty blocks: "same type" suppression needs the ids (Chunk.cpp:192-194)
-		}
-
-		// rare path: rows holding transparent non-empty blocks compare ids, one row per step, lane = x
-#pragma unroll
-		for (int j = 0; j < 2; ++j)
-		{
-			uint32_t flagged = __ballot_sync(0xffffffffu, need[j] != 0);
-			while (flagged)
-			{
-				const int b = __ffs(flagged) - 1;
-				flagged &= flagged - 1;
-				const int r = 2 * ((tid & ~31) + b) + j;
-				const int z = r >> 5, y = r & 31;
-				const unsigned self = ids[r * CS + lane];
-#pragma unroll
-				for (int s = 0; s < 6; ++s)
-				{
-					uint32_t same = __ballot_sync(0xffffffffu, neighbour_id(ids, halo, lane, y, z, s) == self);
-					if (lane == b)
-						v[j][s] &= ~same;
-				}
-			}
-		}
-	}
-
 	__device__ __forceinline__ uint32_t row_faces(const uint32_t v[6], uint32_t d)
 	{
 		uint32_t c = 0;
@@ -287,71 +41,6 @@ namespace tsomk
 		for (int s = 0; s < 6; ++s)
 			c += __popc(v[s]) + __popc(v[s] & d);
 		return c;
-	}
-
-	// =====================================================================================================================
-	__global__ void __launch_bounds__(MESH_THREADS, 2) mesh_count_kernel(const MeshArgs a)
-	{
-		extern __shared__ __align__(128) unsigned char smemRaw[];
-		CountSmem& sm = *reinterpret_cast<CountSmem*>(smemRaw);
-		const int tid = threadIdx.x;
-		const int lane = tid & 31;
-		const int warp = tid >> 5;
-
-		if (tid == 0)
-		{
-			mbar_init(&sm.bar, 1);
-			fence_mbar_init();
-		}
-		load_flag_lut(a, sm.flagLut);
-		__syncthreads();
-
-		uint32_t parity = 0;
-		for (;;)
-		{
-			if (tid == 0)
-				sm.job = atomicAdd(a.jobCounter, 1u);
-			__syncthreads();
-			const uint32_t job = sm.job;
-			if (job >= a.nJobs)
-				break;
-			const uint32_t slot = a.jobSlot[job];
-			const bool hasContent = a.chunkIdx[slot].w != 0;
-			if (!hasContent)
-			{
-				if (tid == 0)
-					a.faceCount[job] = 0;
-				__syncthreads();
-				continue;
-			}
-
-			stage_chunk(a, slot, sm.ids, sm.halo, &sm.bar);
-			mbar_wait(&sm.bar, parity);
-			parity ^= 1;
-			__syncthreads();
-
-			build_masks(a, sm.flagLut, sm.ids, sm.halo, sm.mT, sm.mE, sm.mD, sm.hT);
-			__syncthreads();
-
-			uint32_t v[2][6];
-			row_visibility(sm.ids, sm.halo, sm.mT, sm.mE, sm.hT, v);
-			uint32_t c = row_faces(v[0], sm.mD[2 * tid]) + row_faces(v[1], sm.mD[2 * tid + 1]);
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				c += __shfl_xor_sync(0xffffffffu, c, o);
-			if (lane == 0)
-				sm.warpSum[warp] = c;
-			__syncthreads();
-			if (tid == 0)
-			{
-				uint32_t total = 0;
-#pragma unroll
-				for (int w = 0; w < MESH_WARPS; ++w)
-					total += sm.warpSum[w];
-				a.faceCount[job] = total;
-			}
-			__syncthreads(); // all reads of the staged data are done before the next chunk's TMA writes
-		}
 	}
 
 	// =====================================================================================================================
@@ -523,13 +212,6 @@ namespace tsomk
 		}
 	}
 
-	__device__ __forceinline__ void draw_face(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
-	{
-		FaceOut o;
-		draw_face_r(a, cx, x, y, z, slot, twin, id, o);
-		store_face(out, o);
-	}
-
 	// ---- table-driven flat path ----
 	// For a FlatChunk whose block size is a power of two every intermediate of DrawFace is exact in fp32, so the normal, the
 	// texture direction and the four uv pairs of a face depend only on (faceUp, slot, twin) — not on the block.  They are
@@ -595,267 +277,6 @@ namespace tsomk
 		o.u[1] = uv0.z; o.v[1] = uv0.w;
 		o.u[2] = uv1.x; o.v[2] = uv1.y;
 		o.u[3] = uv1.z; o.v[3] = uv1.w;
-	}
-
-	__device__ __forceinline__ void draw_face_flat(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, float4* out)
-	{
-		FaceOut o;
-		draw_face_flat_r(a, cx, tb, x, y, z, slot, twin, id, o);
-		store_face(out, o);
-	}
-
-	__global__ void __launch_bounds__(MESH_THREADS, 1) mesh_emit_kernel(const MeshArgs a)
-	{
-		extern __shared__ __align__(128) unsigned char smemRaw[];
-		MeshSmem& sm = *reinterpret_cast<MeshSmem*>(smemRaw);
-		const int tid = threadIdx.x;
-		const int lane = tid & 31;
-		const int warp = tid >> 5;
-
-		if (tid == 0)
-		{
-			mbar_init(&sm.bar, 1);
-			fence_mbar_init();
-		}
-		load_flag_lut(a, sm.flagLut);
-		__syncthreads();
-
-		const bool fastFlat = a.faceTable != nullptr;
-		if (fastFlat)
-		{
-			const uint32_t* src = reinterpret_cast<const uint32_t*>(a.faceTable);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.table);
-			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += MESH_THREADS)
-				dst[i] = src[i];
-		}
-		// write-out constants of this lane (a tile is 32 faces = 384 float4 of vertices, 96 uint2 of indices)
-		uint32_t stageOff[12];
-#pragma unroll
-		for (int k = 0; k < 12; ++k)
-		{
-			const uint32_t i = uint32_t(lane) + 32u * k;
-			stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
-		}
-		uint2 idxPat[3];
-#pragma unroll
-		for (int k = 0; k < 3; ++k)
-		{
-			const uint32_t i = uint32_t(lane) + 32u * k;
-			const uint32_t b = (i / 3u) * 4u, j = i % 3u;
-			idxPat[k] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
-		}
-
-		const uint32_t nWork = *a.nWork;
-		uint32_t parity = 0;
-		for (;;)
-		{
-			if (tid == 0)
-				sm.job = atomicAdd(a.jobCounter, 1u);
-			__syncthreads();
-			const uint32_t w = sm.job;
-			if (w >= nWork)
-				break;
-			const uint32_t job = a.worklist[w];
-			const uint32_t slot = a.jobSlot[job];
-			const unsigned long long firstFace = a.firstFace[job];
-
-			// ---- front end: stage + masks + visibility
-			stage_chunk(a, slot, sm.ids, sm.u.front.halo, &sm.bar);
-			mbar_wait(&sm.bar, parity);
-			parity ^= 1;
-			__syncthreads();
-
-			build_masks(a, sm.flagLut, sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.mD, sm.u.front.hT);
-			__syncthreads();
-
-			uint32_t v[2][6];
-			row_visibility(sm.ids, sm.u.front.halo, sm.u.front.mT, sm.u.front.mE, sm.u.front.hT, v);
-			const uint32_t c0 = row_faces(v[0], sm.mD[2 * tid]);
-			const uint32_t c1 = row_faces(v[1], sm.mD[2 * tid + 1]);
-#pragma unroll
-			for (int s = 0; s < 6; ++s)
-			{
-				sm.V[s][2 * tid] = v[0][s];
-				sm.V[s][2 * tid + 1] = v[1][s];
-			}
-
-			// ---- block-wide exclusive scan of the 1024 row counts (rows 2*tid, 2*tid+1 are adjacent)
-			uint32_t incl = c0 + c1;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o)
-					incl += n;
-			}
-			if (lane == 31)
-				sm.warpSum[warp] = incl;
-			__syncthreads(); // also: every read of the front-end buffers is done -> the staging union may be overwritten
-			if (warp == 0)
-			{
-				uint32_t ws = lane < MESH_WARPS ? sm.warpSum[lane] : 0u;
-				uint32_t wi = ws;
-#pragma unroll
-				for (int o = 1; o < MESH_WARPS; o <<= 1)
-				{
-					uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-					if (lane >= o)
-						wi += n;
-				}
-				if (lane < MESH_WARPS)
-					sm.warpSum[lane] = wi - ws; // exclusive
-				if (lane == MESH_WARPS - 1)
-					sm.total = wi;
-			}
-			__syncthreads();
-			{
-				const uint32_t excl = sm.warpSum[warp] + incl - (c0 + c1);
-				sm.rowOff[2 * tid] = excl;
-				sm.rowOff[2 * tid + 1] = excl + c0;
-				if (tid == MESH_THREADS - 1)
-					sm.rowOff[ROWS] = excl + c0 + c1;
-			}
-			__syncthreads();
-
-			const uint32_t F = sm.total;
-			const bool overflow = firstFace + F > a.arenaFaces;
-			if (overflow && tid == 0)
-				atomicExch(a.overflow, 1u);
-
-			if (!overflow && F > 0)
-			{
-				FaceCtx cx;
-				cx.tile = a.tile;
-				cx.radius = a.deformRadius;
-				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
-				cx.wantAttr = (a.flags & MESH_F_RENDER) != 0;
-				if (a.gravity)
-					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);
-				else
-				{
-					// container centre - GetChunkOffset(indices) (ClientChunkEntities.cpp:160, ChunkContainer.inl:53-56)
-					const int4 ci = a.chunkIdx[slot];
-					cx.gravity = f3(a.center[0] - float(ci.x) * float(CS) * a.tile, a.center[1] - float(ci.y) * float(CS) * a.tile, a.center[2] - float(ci.z) * float(CS) * a.tile);
-				}
-
-				float4* stage = sm.u.stage[warp];
-				uint32_t* desc = sm.desc[warp];
-				const uint32_t nTiles = (F + 31u) >> 5;
-
-				for (uint32_t tile = warp; tile < nTiles; tile += MESH_WARPS)
-				{
-					const uint32_t f0 = tile << 5;
-					const uint32_t nf = min(32u, F - f0);
-
-					// ---- descriptors of faces [f0, f0+nf): walk the rows that hold them, lane = x
-					uint32_t f = f0;
-					while (f < f0 + nf)
-					{
-						// largest row with rowOff[row] <= f (rowOff is non-decreasing; ties end on the non-empty row)
-						uint32_t top = __popc(__ballot_sync(0xffffffffu, sm.rowOff[lane * 32] <= f)) - 1u;
-						uint32_t row = top * 32u + __popc(__ballot_sync(0xffffffffu, sm.rowOff[top * 32u + lane] <= f)) - 1u;
-
-						const uint32_t base = sm.rowOff[row];
-						const uint32_t d = sm.mD[row];
-						const uint32_t lt = (1u << lane) - 1u;
-						uint32_t vs[6];
-						uint32_t p = base;
-#pragma unroll
-						for (int s = 0; s < 6; ++s)
-						{
-							vs[s] = sm.V[s][row];
-							p += __popc(vs[s] & lt) + __popc(vs[s] & d & lt);
-						}
-						const bool twin = (d >> lane) & 1u;
-						const uint32_t blk = row * 32u + lane;
-#pragma unroll
-						for (int s = 0; s < 6; ++s)
-						{
-							if ((vs[s] >> lane) & 1u)
-							{
-								uint32_t q = p - f0; // wraps when p < f0 -> fails the range test
-								if (q < 32u)
-									desc[q] = blk | (uint32_t(s) << 15);
-								++p;
-								if (twin)
-								{
-									q = p - f0;
-									if (q < 32u)
-										desc[q] = blk | (uint32_t(s) << 15) | (1u << 18);
-									++p;
-								}
-							}
-						}
-						f = sm.rowOff[row + 1];
-					}
-					__syncwarp();
-
-					// ---- one face per lane -> staging
-					if (uint32_t(lane) < nf)
-					{
-						const uint32_t de = desc[lane];
-						const uint32_t blk = de & 0x7fffu;
-						if (fastFlat)
-							draw_face_flat(a, cx, sm.table, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
-						else
-							draw_face(a, cx, int(blk & 31u), int((blk >> 5) & 31u), int(blk >> 10), int((de >> 15) & 7u), ((de >> 18) & 1u) != 0, sm.ids[blk], stage + lane * STAGE_FACE_F4);
-					}
-					__syncwarp();
-
-					// ---- coalesced write-out
-					const unsigned long long face0 = firstFace + f0;
-					if (a.flags & MESH_F_RENDER)
-					{
-						float4* dst = a.vertices + face0 * 12ull + lane;
-						if (nf == 32u)
-						{
-#pragma unroll
-							for (int k = 0; k < 12; ++k)
-								dst[32 * k] = stage[stageOff[k]];
-						}
-						else
-						{
-							const uint32_t n4 = nf * 12u;
-#pragma unroll
-							for (int k = 0; k < 12; ++k)
-								if (uint32_t(lane) + 32u * k < n4)
-									dst[32 * k] = stage[stageOff[k]];
-						}
-					}
-					if (a.flags & MESH_F_COLLIDER)
-					{
-						// positions only: 3 float4 per face gathered from the staged vertices
-						float4* dst = a.collider + face0 * 3ull;
-						const float* sf = reinterpret_cast<const float*>(stage);
-						const uint32_t n4 = nf * 3u;
-						for (uint32_t i = lane; i < n4; i += 32u)
-						{
-							const uint32_t face = i / 3u, j = i % 3u;
-							float e[4];
-#pragma unroll
-							for (int m = 0; m < 4; ++m)
-							{
-								const uint32_t k = j * 4u + m; // float k of the face's 12 position floats
-								e[m] = sf[face * (STAGE_FACE_F4 * 4) + (k / 3u) * 12u + (k % 3u)];
-							}
-							dst[i] = make_float4(e[0], e[1], e[2], e[3]);
-						}
-					}
-					{
-						// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
-						uint2* dst = a.indices + face0 * 3ull + lane;
-						const uint32_t base = f0 * 4u;
-						const uint32_t n2 = nf * 3u;
-#pragma unroll
-						for (int k = 0; k < 3; ++k)
-							if (nf == 32u || uint32_t(lane) + 32u * k < n2)
-								dst[32 * k] = make_uint2(idxPat[k].x + base, idxPat[k].y + base);
-					}
-					__syncwarp();
-				}
-			}
-			__syncthreads(); // staging / ids free for the next chunk
-		}
 	}
 
 	// =====================================================================================================================
@@ -1468,122 +889,15 @@ namespace tsomk
 		}
 	}
 
-	// =====================================================================================================================
-	// exclusive scan of face counts -> first face per job, total, and the worklist of jobs that have faces (single CTA)
-	__global__ void __launch_bounds__(1024, 1) mesh_scan_kernel(const uint32_t* __restrict__ faceCount, uint32_t nJobs,
-	                                                            unsigned long long* __restrict__ firstFace, uint32_t* __restrict__ worklist,
-	                                                            uint32_t* __restrict__ nWork, unsigned long long* __restrict__ totalFaces,
-	                                                            unsigned long long faceBase)
-	{
-		__shared__ unsigned long long wsF[32];
-		__shared__ uint32_t wsW[32];
-		__shared__ unsigned long long carryF;
-		__shared__ uint32_t carryW;
-		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-		if (tid == 0)
-		{
-			carryF = faceBase;
-			carryW = 0;
-		}
-		__syncthreads();
-		for (uint32_t base = 0; base < nJobs; base += 1024u)
-		{
-			const uint32_t i = base + tid;
-			const uint32_t c = i < nJobs ? faceCount[i] : 0u;
-			unsigned long long inF = c;
-			uint32_t inW = c ? 1u : 0u;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				unsigned long long nf = __shfl_up_sync(0xffffffffu, inF, o);
-				uint32_t nw = __shfl_up_sync(0xffffffffu, inW, o);
-				if (lane >= o)
-				{
-					inF += nf;
-					inW += nw;
-				}
-			}
-			if (lane == 31)
-			{
-				wsF[warp] = inF;
-				wsW[warp] = inW;
-			}
-			__syncthreads();
-			if (warp == 0)
-			{
-				unsigned long long sf = wsF[lane], xf = sf;
-				uint32_t sw = wsW[lane], xw = sw;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1)
-				{
-					unsigned long long nf = __shfl_up_sync(0xffffffffu, xf, o);
-					uint32_t nw = __shfl_up_sync(0xffffffffu, xw, o);
-					if (lane >= o)
-					{
-						xf += nf;
-						xw += nw;
-					}
-				}
-				wsF[lane] = xf - sf;
-				wsW[lane] = xw - sw;
-			}
-			__syncthreads();
-			const unsigned long long exF = carryF + wsF[warp] + inF - c;
-			const uint32_t exW = carryW + wsW[warp] + inW - (c ? 1u : 0u);
-			if (i < nJobs)
-			{
-				firstFace[i] = exF;
-				if (c)
-					worklist[exW] = i;
-			}
-			__syncthreads();
-			if (tid == 1023)
-			{
-				carryF = exF + c;
-				carryW = exW + (c ? 1u : 0u);
-			}
-			__syncthreads();
-		}
-		if (tid == 0)
-		{
-			*nWork = carryW;
-			*totalFaces = carryF - faceBase;
-		}
-	}
-
 	// ---- launchers ----
-	size_t mesh_count_smem_bytes() { return sizeof(CountSmem); }
-	size_t mesh_emit_smem_bytes() { return sizeof(MeshSmem); }
 	size_t mesh_fused_smem_bytes() { return sizeof(FusedSmem); }
 
 	cudaError_t mesh_kernels_init()
 	{
-		cudaError_t e = cudaFuncSetAttribute(mesh_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(CountSmem)));
-		if (e != cudaSuccess)
-			return e;
-		e = cudaFuncSetAttribute(mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MeshSmem)));
-		if (e != cudaSuccess)
-			return e;
-		e = cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)));
+		cudaError_t e = cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)));
 		if (e != cudaSuccess)
 			return e;
 		return cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-	}
-
-	void launch_mesh_count(const MeshArgs& a, int grid, cudaStream_t st)
-	{
-		mesh_count_kernel<<<grid, MESH_THREADS, sizeof(CountSmem), st>>>(a);
-	}
-
-	void launch_mesh_scan(const uint32_t* faceCount, uint32_t nJobs, unsigned long long* firstFace, uint32_t* worklist, uint32_t* nWork,
-	                      unsigned long long* totalFaces, unsigned long long faceBase, cudaStream_t st)
-	{
-		mesh_scan_kernel<<<1, 1024, 0, st>>>(faceCount, nJobs, firstFace, worklist, nWork, totalFaces, faceBase);
-	}
-
-	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st)
-	{
-		mesh_emit_kernel<<<grid, MESH_THREADS, sizeof(MeshSmem), st>>>(a);
 	}
 
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st)

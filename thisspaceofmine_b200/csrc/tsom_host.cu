@@ -229,9 +229,8 @@ struct tsom_ctx
 	uint64_t totalFaces = 0;
 
 	// per-call scratch
-	DevBuf<uint32_t> jobSlot, faceCount, worklist;
+	DevBuf<uint32_t> jobSlot, faceCount;
 	DevBuf<unsigned long long> firstFace, status;
-	bool legacyMesh = false; // TSOM_MESH_LEGACY=1: count -> scan -> emit (kept for A/B measurements)
 	DevBuf<float> gravity;
 	DevBuf<tsomk::EditDev> edits;
 	DevBuf<unsigned long long> editKeys; // open-addressing table of the edited blocks of one tsom_apply_edits call
@@ -567,8 +566,6 @@ extern "C"
 		ctx->numSMs = prop.multiProcessorCount;
 		TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		TSOM_CUDA(tsomk::mesh_kernels_init());
-		if (const char* env = std::getenv("TSOM_MESH_LEGACY"))
-			ctx->legacyMesh = env[0] == '1';
 		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
@@ -612,7 +609,6 @@ extern "C"
 		cudaFree(ctx->dCollider);
 		ctx->jobSlot.Free();
 		ctx->faceCount.Free();
-		ctx->worklist.Free();
 		ctx->firstFace.Free();
 		ctx->status.Free();
 		ctx->editKeys.Free();
@@ -1204,7 +1200,6 @@ extern "C"
 
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(ctx->faceCount.Ensure(n));
-		TSOM_CUDA(ctx->worklist.Ensure(n));
 		TSOM_CUDA(ctx->firstFace.Ensure(n));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		if (params->gravity_centers)
@@ -1227,9 +1222,6 @@ extern "C"
 		a.blkTex = ctx->dTex;
 		a.nTypes = ctx->nTypes;
 		a.faceCount = ctx->faceCount.ptr;
-		a.firstFace = ctx->firstFace.ptr;
-		a.worklist = ctx->worklist.ptr;
-		a.nWork = ctx->dSmall + 2;
 		a.overflow = ctx->dSmall + 3;
 		a.flags = flags;
 		a.tile = c->tile;
@@ -1252,16 +1244,6 @@ extern "C"
 			a.faceTable = ctx->dFaceTable;
 		}
 
-		auto launchEmit = [&]() {
-			a.vertices = ctx->dVertices;
-			a.indices = ctx->dIndices;
-			a.collider = ctx->dCollider;
-			a.arenaFaces = ArenaFaces(ctx, flags);
-			a.jobCounter = ctx->dSmall + 1;
-			tsomk::launch_mesh_emit(a, int(std::min<uint32_t>(n, uint32_t(ctx->numSMs))), ctx->stream);
-			ctx->launches += 1;
-		};
-
 		auto launchFused = [&]() -> cudaError_t {
 			a.vertices = ctx->dVertices;
 			a.indices = ctx->dIndices;
@@ -1279,28 +1261,13 @@ extern "C"
 			return cudaSuccess;
 		};
 
-		if (ctx->legacyMesh)
-		{
-			a.jobCounter = ctx->dSmall + 0;
-			TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-			tsomk::launch_mesh_count(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
-			TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-			tsomk::launch_mesh_scan(ctx->faceCount.ptr, n, ctx->firstFace.ptr, ctx->worklist.ptr, ctx->dSmall + 2, reinterpret_cast<unsigned long long*>(ctx->dSmall + 4), 0ull, ctx->stream);
-			TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-			ctx->launches += 2;
-			launchEmit();
-			TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-		}
-		else
-		{
-			// single pass: the count and the scan live inside mesh_fused_kernel (their timing slots read 0)
-			TSOM_CUDA(ctx->status.Ensure(n));
-			TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-			TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-			TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-			TSOM_CUDA(launchFused());
-			TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-		}
+		// single pass: the count and the scan live inside mesh_fused_kernel (their timing slots read 0)
+		TSOM_CUDA(ctx->status.Ensure(n));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+		TSOM_CUDA(launchFused());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
 		TSOM_CUDA(cudaGetLastError());
 
 		// read back totals (+ views)
@@ -1331,10 +1298,7 @@ extern "C"
 				return rc;
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 1, 0, sizeof(uint32_t), ctx->stream));
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, sizeof(uint32_t), ctx->stream));
-			if (ctx->legacyMesh)
-				launchEmit();
-			else
-				TSOM_CUDA(launchFused());
+			TSOM_CUDA(launchFused());
 			TSOM_CUDA(cudaGetLastError());
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		}

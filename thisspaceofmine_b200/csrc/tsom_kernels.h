@@ -31,13 +31,9 @@ namespace tsomk
 		const uint8_t* blkFlags;
 		const uint32_t* blkTex;          // [nTypes][6]
 		uint32_t nTypes;
-		// count -> scan -> emit plumbing
+		// results per job + the chained scan over the jobs (decoupled look-back)
 		uint32_t* faceCount;                   // [nJobs]
-		const unsigned long long* firstFace;   // [nJobs]
-		const uint32_t* worklist;              // jobs with faces
-		const uint32_t* nWork;
 		uint32_t* jobCounter;                  // work-stealing ticket, zeroed before each launch
-		// single-pass path (mesh_fused_kernel): chained scan over the jobs by decoupled look-back
 		unsigned long long* status;            // [nJobs] (flag << 62) | faces, zeroed before each launch
 		unsigned long long* firstFaceOut;      // [nJobs]
 		unsigned long long* totalFacesOut;     // inclusive prefix of the last job
@@ -59,12 +55,6 @@ namespace tsomk
 	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st);
 
 	cudaError_t mesh_kernels_init();
-	size_t mesh_count_smem_bytes();
-	size_t mesh_emit_smem_bytes();
-	void launch_mesh_count(const MeshArgs& a, int grid, cudaStream_t st);
-	void launch_mesh_scan(const uint32_t* faceCount, uint32_t nJobs, unsigned long long* firstFace, uint32_t* worklist, uint32_t* nWork,
-	                      unsigned long long* totalFaces, unsigned long long faceBase, cudaStream_t st);
-	void launch_mesh_emit(const MeshArgs& a, int grid, cudaStream_t st);
 	size_t mesh_fused_smem_bytes();
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st);
 
