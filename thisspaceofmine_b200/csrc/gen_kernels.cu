@@ -850,7 +850,6 @@ namespace tsomk
 					}
 					++nBoxes;
 					x = endX + 1;
-					(void)bit;
 				}
 			}
 		}
