@@ -349,47 +349,55 @@ namespace tsomk
 		return acc;
 	}
 
-	// Called convergently by all 32 lanes.  The one-lookup shortcut for 8 equal ids is taken only when it holds for the whole
-	// warp (planet interiors and sky): in a mixed warp both sides of a per-lane branch would run back to back.
-	__device__ __forceinline__ uint32_t flags8(const MeshArgs& a, const uint32_t* lut, uint4 w)
+	// branch-free classification of 8 ids that are all < LUTN (callers mask; ids >= LUTN are fixed up separately):
+	// the three flag bits of an entry sit 8 bits apart, so the 8 shifted entries add up without carries
+	__device__ __forceinline__ uint32_t flags8_fast(const uint32_t* lut, uint4 w)
 	{
-		const bool big = ((w.x | w.y | w.z | w.w) & ~(uint32_t(LUTN - 1) * 0x10001u)) != 0u; // some id >= LUTN
-		const bool uniform = !big && w.x == w.y && w.x == w.z && w.x == w.w && (w.x >> 16) == (w.x & 0xffffu);
-		if (__all_sync(0xffffffffu, uniform))
-			return lut[w.x & 0xffffu] * 0xFFu;
-		if (big)
-			return flags8_slow(a, lut, w);
 		const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
 		uint32_t acc = 0;
 #pragma unroll
 		for (int j = 0; j < 4; ++j)
 		{
-			acc |= lut[ws[j] & 0xffffu] << (2 * j);
-			acc |= lut[ws[j] >> 16] << (2 * j + 1);
+			acc += lut[ws[j] & uint32_t(LUTN - 1)] << (2 * j);
+			acc += lut[(ws[j] >> 16) & uint32_t(LUTN - 1)] << (2 * j + 1);
 		}
 		return acc;
 	}
 
-	// transparency bits of the six facing slabs, read from global memory; an absent neighbour reads as a slab of Empty
-	__device__ __forceinline__ void build_halo_masks(const MeshArgs& a, const uint32_t* lut, uint32_t slot, uint32_t (*hT)[CS])
+	__device__ __forceinline__ bool has_big_id(uint4 w) { return ((w.x | w.y | w.z | w.w) & ~(uint32_t(LUTN - 1) * 0x10001u)) != 0u; }
+
+	// transparency bits of the six facing slabs, read from global memory; an absent neighbour reads as a slab of Empty.
+	// All loads of a thread are issued before any is used (no branch or vote in between), so their latencies overlap.
+	template<int NT>
+	__device__ __forceinline__ void build_halo_masks(const MeshArgs& a, const uint32_t* lut, uint32_t slot, uint32_t (*hT)[CS], int tid)
 	{
-		const int tid = threadIdx.x;
+		constexpr int N = 6 * (SLAB / 8) / NT;
 		const unsigned long long* hp = a.halo + size_t(slot) * 6;
 		const uint32_t emptyT = (lut[0] & 1u) ? 0xFFu : 0u;
+		unsigned long long e[N];
+		uint4 w[N];
 #pragma unroll
-		for (int j = 0; j < 6 * (SLAB / 8) / FUSED_THREADS; ++j)
+		for (int j = 0; j < N; ++j)
+			e[j] = hp[(tid + j * NT) >> 7];
+#pragma unroll
+		for (int j = 0; j < N; ++j)
 		{
-			const int u = tid + j * FUSED_THREADS;
+			const int q = (tid + j * NT) & 127, row = q >> 2, seg = q & 3;
+			// an absent neighbour loads from the chunk's own ids instead (any valid address; the result is discarded)
+			const uint16_t* src = e[j] != 0ull ? reinterpret_cast<const uint16_t*>(e[j] & ~HALO_KIND_MASK) : a.blocks + size_t(slot) * NB;
+			const size_t rowStride = (e[j] & HALO_KIND_MASK) == HALO_ROWS ? SLAB : CS;
+			w[j] = *reinterpret_cast<const uint4*>(src + size_t(row) * rowStride + seg * 8);
+		}
+#pragma unroll
+		for (int j = 0; j < N; ++j)
+		{
+			const int u = tid + j * NT;
 			const int d = u >> 7, q = u & 127, row = q >> 2, seg = q & 3;
-			const unsigned long long e = hp[d];
-			uint32_t t8 = emptyT;
-			if (e != 0ull)
-			{
-				const uint16_t* src = reinterpret_cast<const uint16_t*>(e & ~HALO_KIND_MASK);
-				const size_t rowStride = (e & HALO_KIND_MASK) == HALO_ROWS ? SLAB : CS;
-				const uint4 w = *reinterpret_cast<const uint4*>(src + size_t(row) * rowStride + seg * 8);
-				t8 = flags8(a, lut, w) & 0xFFu;
-			}
+			uint32_t t8 = flags8_fast(lut, w[j]) & 0xFFu;
+			if (has_big_id(w[j]))
+				t8 = flags8_slow(a, lut, w[j]) & 0xFFu;
+			if (e[j] == 0ull)
+				t8 = emptyT;
 			uint32_t t = t8 << (seg * 8);
 			t |= __shfl_xor_sync(0xffffffffu, t, 1);
 			t |= __shfl_xor_sync(0xffffffffu, t, 2);
@@ -398,33 +406,54 @@ namespace tsomk
 		}
 	}
 
-	// row masks of the staged chunk: warp w owns rows [128w, 128w + 128), 8 rows per step, 4 lanes per row
-	__device__ __forceinline__ void build_masks_fused(const MeshArgs& a, FusedSmem& sm)
+	// row masks of the staged chunk, one x-row (32 ids = four 16-byte loads) per thread and step: no shuffles, 32 independent
+	// table lookups in flight per thread.  Lane i of a quarter-warp starts with 16-byte segment (i >> 1) & 3 of its row and rotates
+	// from there, which makes the 64-byte-strided 16-byte loads bank-conflict free.  Block ids beyond the in-shared-memory table
+	// (never seen with the reference's 14 block types) are fixed up by a second, slow pass.
+	template<int NT, class B>
+	__device__ __forceinline__ void build_masks_fused(const MeshArgs& a, const uint32_t* lut, B& sm, int tid)
 	{
-		const int lane = threadIdx.x & 31;
-		const int warp = threadIdx.x >> 5;
-		const int seg = lane & 3;
-#pragma unroll 4
-		for (int it = 0; it < ROWS / FUSED_WARPS / 8; ++it)
+		const int rot = (tid >> 1) & 3;
+		bool big = false;
+#pragma unroll 2
+		for (int k = 0; k < ROWS / NT; ++k)
 		{
-			const int row = warp * (ROWS / FUSED_WARPS) + it * 8 + (lane >> 2);
-			const uint4 w = *reinterpret_cast<const uint4*>(&sm.ids[row * CS + seg * 8]);
-			const uint32_t acc = flags8(a, sm.lut32, w);
-			uint32_t t = (acc & 0xFFu) << (seg * 8);
-			uint32_t e = ((acc >> 8) & 0xFFu) << (seg * 8);
-			uint32_t d = ((acc >> 16) & 0xFFu) << (seg * 8);
-			t |= __shfl_xor_sync(0xffffffffu, t, 1);
-			e |= __shfl_xor_sync(0xffffffffu, e, 1);
-			d |= __shfl_xor_sync(0xffffffffu, d, 1);
-			t |= __shfl_xor_sync(0xffffffffu, t, 2);
-			e |= __shfl_xor_sync(0xffffffffu, e, 2);
-			d |= __shfl_xor_sync(0xffffffffu, d, 2);
-			if (seg == 0)
+			const int row = k * NT + tid;
+			uint32_t t = 0, e = 0, d = 0;
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+			{
+				const int seg = (j + rot) & 3;
+				const uint4 w = *reinterpret_cast<const uint4*>(&sm.ids[row * CS + seg * 8]);
+				big |= has_big_id(w);
+				const uint32_t acc = flags8_fast(lut, w);
+				t |= (acc & 0xFFu) << (seg * 8);
+				e |= ((acc >> 8) & 0xFFu) << (seg * 8);
+				d |= ((acc >> 16) & 0xFFu) << (seg * 8);
+			}
+			sm.mT[row] = t;
+			sm.mE[row] = e;
+			sm.mD[row] = d;
+		}
+		if (__any_sync(0xffffffffu, big))
+		{
+#pragma unroll 1
+			for (int k = 0; k < ROWS / NT; ++k)
+			{
+				const int row = k * NT + tid;
+				uint32_t t = 0, e = 0, d = 0;
+				for (int seg = 0; seg < 4; ++seg)
+				{
+					const uint4 w = *reinterpret_cast<const uint4*>(&sm.ids[row * CS + seg * 8]);
+					const uint32_t acc = flags8_slow(a, lut, w);
+					t |= (acc & 0xFFu) << (seg * 8);
+					e |= ((acc >> 8) & 0xFFu) << (seg * 8);
+					d |= ((acc >> 16) & 0xFFu) << (seg * 8);
+				}
 				sm.mT[row] = t;
-			else if (seg == 1)
 				sm.mE[row] = e;
-			else if (seg == 2)
 				sm.mD[row] = d;
+			}
 		}
 	}
 
@@ -440,7 +469,8 @@ namespace tsomk
 	}
 
 	// visibility masks of row r in emission-slot order; returns the row's double-sided mask.  Thread-local (no warp collectives).
-	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const FusedSmem& sm, uint32_t slot, int r, uint32_t v[6])
+	template<class B>
+	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const B& sm, uint32_t slot, int r, uint32_t v[6])
 	{
 		const int z = r >> 5, y = r & 31;
 		const uint32_t t = sm.mT[r], e = sm.mE[r];
@@ -487,6 +517,266 @@ namespace tsomk
 		return sm.mD[r];
 	}
 
+	// per-lane write-out constants: a staging round is 16 faces = 192 float4; an index tile is 32 faces = 96 uint2
+	struct LaneConst
+	{
+		uint32_t stageOff[6];
+		uint2 idxPat[3];
+	};
+
+	__device__ __forceinline__ LaneConst lane_constants(int lane)
+	{
+		LaneConst lc;
+#pragma unroll
+		for (int k = 0; k < 6; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			lc.stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
+		}
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			const uint32_t i = uint32_t(lane) + 32u * k;
+			const uint32_t b = (i / 3u) * 4u, j = i % 3u;
+			lc.idxPat[k] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
+		}
+		return lc;
+	}
+
+	// Descriptors of window `win` (faces [128 win, 128 win + 128) of the chunk held by `sm`), written by one warp; returns the
+	// first compact row of the window (the descriptors count rows from it).
+	template<class B>
+	__device__ __forceinline__ uint32_t expand_window(const MeshArgs& a, const B& sm, uint32_t slot, uint32_t F, uint32_t K, uint32_t win, uint16_t* desc, int lane)
+	{
+		constexpr uint32_t FULL = 0xffffffffu;
+		const uint32_t w0 = win * WIN;
+		const uint32_t nw = min(uint32_t(WIN), F - w0);
+
+		// ---- compact rows [kA, kB] of the window: largest k with ne[k].off <= first / last face (offsets increase strictly)
+		uint32_t kA, kB;
+		{
+			const uint32_t wLast = w0 + nw - 1u;
+			const uint32_t i1 = uint32_t(lane) * 32u;
+			const uint32_t o1 = i1 < K ? (sm.ne[i1] & NE_OFF_MASK) : 0xFFFFFFFFu;
+			const uint32_t topA = __popc(__ballot_sync(FULL, o1 <= w0)) - 1u;
+			const uint32_t topB = __popc(__ballot_sync(FULL, o1 <= wLast)) - 1u;
+			const uint32_t iA = topA * 32u + lane, iB = topB * 32u + lane;
+			const uint32_t oA = iA < K ? (sm.ne[iA] & NE_OFF_MASK) : 0xFFFFFFFFu;
+			const uint32_t oB = iB < K ? (sm.ne[iB] & NE_OFF_MASK) : 0xFFFFFFFFu;
+			kA = topA * 32u + __popc(__ballot_sync(FULL, oA <= w0)) - 1u;
+			kB = topB * 32u + __popc(__ballot_sync(FULL, oB <= wLast)) - 1u;
+		}
+
+		// ---- descriptors, faces in the reference's order (x, then Up/Down/Front/Back/Left/Right, twin).  A window of R
+		// rows is walked by 32 lanes: S = 32 / R (power of two) lanes share a row, each taking 32 / S consecutive blocks.
+		const uint32_t R = kB - kA + 1u;
+		const uint32_t lgS = R > 16u ? 0u : (R > 8u ? 1u : (R > 4u ? 2u : (R > 2u ? 3u : (R > 1u ? 4u : 5u))));
+		const uint32_t x0 = (uint32_t(lane) & ((1u << lgS) - 1u)) << (5u - lgS);
+		const uint32_t segMask = lgS == 0u ? 0xFFFFFFFFu : (((1u << (32u >> lgS)) - 1u) << x0);
+		const uint32_t below = (1u << x0) - 1u;
+		for (uint32_t k0 = kA; k0 <= kB; k0 += 32u >> lgS)
+		{
+			const uint32_t k = k0 + (uint32_t(lane) >> lgS);
+			if (k <= kB)
+			{
+				const uint32_t en = sm.ne[k];
+				uint32_t v[6];
+				const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
+				uint32_t p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
+#pragma unroll
+				for (int s = 0; s < 6; ++s)
+					p += __popc(v[s] & below) + __popc(v[s] & d & below);
+				const uint32_t base = (k - kA) << 9;
+				uint32_t any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+				while (any && int(p) < int(nw))
+				{
+					const uint32_t x = uint32_t(__ffs(any) - 1);
+					any &= any - 1u;
+					const uint32_t bit = 1u << x;
+					const bool tw = (d & bit) != 0u;
+#pragma unroll
+					for (uint32_t s = 0; s < 6; ++s)
+					{
+						if (v[s] & bit)
+						{
+							if (p < nw)
+								desc[p] = uint16_t(base | x | (s << 5));
+							++p;
+							if (tw)
+							{
+								if (p < nw)
+									desc[p] = uint16_t(base | x | (s << 5) | 0x100u);
+								++p;
+							}
+						}
+					}
+				}
+			}
+		}
+		__syncwarp();
+
+		return kA;
+	}
+
+	// Build the faces of window `win` from their descriptors, one per lane, and stream them out through the warp's 16-face
+	// staging tile with coalesced 16-byte stores (vertices, collider positions, indices).
+	template<class B>
+	__device__ __forceinline__ void store_window(const MeshArgs& a, const B& sm, const FaceTable& table, bool fastFlat, const FaceCtx& cx, uint32_t F, uint32_t win, uint32_t kA,
+	                                             const uint16_t* desc, float4* stage, unsigned long long firstFace, const LaneConst& lc, bool wantRender, bool wantCollider, int lane)
+	{
+		const uint32_t w0 = win * WIN;
+		const uint32_t nw = min(uint32_t(WIN), F - w0);
+		// ---- build one face per lane, stream out through the 16-face staging tile
+		const uint32_t nTiles = (nw + 31u) >> 5;
+		for (uint32_t tt = 0; tt < nTiles; ++tt)
+		{
+			const uint32_t f = tt * 32u + lane;
+			const uint32_t nf = min(32u, nw - tt * 32u);
+			const bool valid = f < nw;
+			FaceOut fo;
+			if (valid)
+			{
+				const uint32_t de = desc[f];
+				const uint32_t row = sm.ne[kA + (de >> 9)] >> NE_ROW_SHIFT;
+				const int x = int(de & 31u), y = int(row & 31u), z = int(row >> 5);
+				const int s = int((de >> 5) & 7u);
+				const bool twin = ((de >> 8) & 1u) != 0u;
+				const unsigned id = sm.ids[row * CS + x];
+				if (fastFlat)
+					draw_face_flat_r(a, cx, table, x, y, z, s, twin, id, fo);
+				else
+					draw_face_r(a, cx, x, y, z, s, twin, id, fo);
+			}
+			const unsigned long long face0 = firstFace + w0 + tt * 32u;
+#pragma unroll
+			for (uint32_t h = 0; h < 2; ++h)
+			{
+				if (nf <= h * HALF_FACES)
+					break;
+				const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
+				if (valid && (uint32_t(lane) >> 4) == h)
+					store_face(stage + (lane & 15) * STAGE_FACE_F4, fo);
+				__syncwarp();
+				const unsigned long long faceH = face0 + h * HALF_FACES;
+				if (wantRender)
+				{
+					float4* dst = a.vertices + faceH * 12ull + lane;
+					if (nh == HALF_FACES)
+					{
+#pragma unroll
+						for (int k = 0; k < 6; ++k)
+							dst[32 * k] = stage[lc.stageOff[k]];
+					}
+					else
+					{
+						const uint32_t n4 = nh * 12u;
+#pragma unroll
+						for (int k = 0; k < 6; ++k)
+							if (uint32_t(lane) + 32u * k < n4)
+								dst[32 * k] = stage[lc.stageOff[k]];
+					}
+				}
+				if (wantCollider)
+				{
+					// positions only: 3 float4 per face gathered from the staged vertices
+					float4* dst = a.collider + faceH * 3ull;
+					const float* sf = reinterpret_cast<const float*>(stage);
+					const uint32_t n4 = nh * 3u;
+					for (uint32_t i = lane; i < n4; i += 32u)
+					{
+						const uint32_t face = i / 3u, j = i % 3u;
+						float e[4];
+#pragma unroll
+						for (int m = 0; m < 4; ++m)
+						{
+							const uint32_t q = j * 4u + m; // float q of the face's 12 position floats
+							e[m] = sf[face * (STAGE_FACE_F4 * 4) + (q / 3u) * 12u + (q % 3u)];
+						}
+						dst[i] = make_float4(e[0], e[1], e[2], e[3]);
+					}
+				}
+				__syncwarp();
+			}
+			{
+				// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
+				uint2* dst = a.indices + face0 * 3ull + lane;
+				const uint32_t base = (w0 + tt * 32u) * 4u;
+				const uint32_t n2 = nf * 3u;
+#pragma unroll
+				for (int k = 0; k < 3; ++k)
+					if (nf == 32u || uint32_t(lane) + 32u * k < n2)
+						dst[32 * k] = make_uint2(lc.idxPat[k].x + base, lc.idxPat[k].y + base);
+			}
+		}
+	}
+
+	// Decoupled look-back over the jobs before `job` (one warp): publish this job's face count, add up the counts of the
+	// predecessors back to the nearest one whose inclusive prefix is known, publish the own inclusive prefix, return the
+	// exclusive one.  Each step inspects 32 * LBK predecessors with independent loads (one L2 round trip); position
+	// p = lane * LBK + k counts backwards from job - 1.  Measured on the 31^3 planet: LBK = 1 is best (2 the same, 8 is 25 % slower
+	// in the count-only pass) — the cost is waiting for the nearest predecessors to publish, not the distance walked.
+	template<int LBK>
+	__device__ __forceinline__ unsigned long long chain_lookback(unsigned long long* status, uint32_t job, uint32_t F, int lane)
+	{
+		constexpr uint32_t FULL = 0xffffffffu;
+		constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL = (1ull << 62) - 1ull;
+		volatile unsigned long long* st = status;
+		unsigned long long excl = 0ull;
+		if (job == 0u)
+		{
+			if (lane == 0)
+				st[0] = FLAG_INC | F;
+			return 0ull;
+		}
+		if (lane == 0)
+			st[job] = FLAG_AGG | F;
+		long long base = (long long)job - 1;
+		for (;;)
+		{
+			unsigned long long s[LBK];
+			uint32_t pInc; // position of the nearest inclusive prefix in this window, 32 * LBK if none
+			bool retry;
+			do
+			{
+#pragma unroll
+				for (int k = 0; k < LBK; ++k)
+				{
+					const long long i = base - (long long)lane * LBK - k;
+					s[k] = i >= 0 ? st[i] : FLAG_INC; // before job 0: inclusive prefix 0
+				}
+				pInc = 32u * LBK;
+				uint32_t pWait = 32u * LBK; // position of the nearest entry that is not published yet
+#pragma unroll
+				for (int k = 0; k < LBK; ++k)
+				{
+					const unsigned fl = unsigned(s[k] >> 62);
+					const uint32_t inc = __ballot_sync(FULL, fl == 2u);
+					const uint32_t wait = __ballot_sync(FULL, fl == 0u);
+					if (inc)
+						pInc = min(pInc, uint32_t(__ffs(inc) - 1) * LBK + k);
+					if (wait)
+						pWait = min(pWait, uint32_t(__ffs(wait) - 1) * LBK + k);
+				}
+				retry = pWait < pInc || (pInc == 32u * LBK && pWait < 32u * LBK);
+			} while (retry);
+			unsigned long long val = 0ull;
+#pragma unroll
+			for (int k = 0; k < LBK; ++k)
+				if (uint32_t(lane) * LBK + k <= pInc)
+					val += s[k] & VAL;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				val += __shfl_xor_sync(FULL, val, o);
+			excl += val;
+			if (pInc < 32u * LBK)
+				break;
+			base -= 32 * LBK;
+		}
+		if (lane == 0)
+			st[job] = FLAG_INC | (excl + F);
+		return excl;
+	}
+
 	// one lane: take the next job and look up what it names (two dependent global loads paid once, before the CTA barrier)
 	__device__ __forceinline__ void take_ticket(const MeshArgs& a, FusedSmem& sm)
 	{
@@ -526,22 +816,7 @@ namespace tsomk
 			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += FUSED_THREADS)
 				dst[i] = src[i];
 		}
-		// write-out constants of this lane: a staging round is 16 faces = 192 float4; an index tile is 32 faces = 96 uint2
-		uint32_t stageOff[6];
-#pragma unroll
-		for (int k = 0; k < 6; ++k)
-		{
-			const uint32_t i = uint32_t(lane) + 32u * k;
-			stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
-		}
-		uint2 idxPat[3];
-#pragma unroll
-		for (int k = 0; k < 3; ++k)
-		{
-			const uint32_t i = uint32_t(lane) + 32u * k;
-			const uint32_t b = (i / 3u) * 4u, j = i % 3u;
-			idxPat[k] = j == 0 ? make_uint2(b, b + 2u) : (j == 1 ? make_uint2(b + 1u, b + 1u) : make_uint2(b + 2u, b + 3u));
-		}
+		const LaneConst lc = lane_constants(lane);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
 		__syncthreads();
@@ -575,11 +850,11 @@ namespace tsomk
 					for (int p = 0; p < 4; ++p)
 						tma_load_1d(sm.ids + p * (NB / 4), src + p * (NB / 4), NB / 2, &sm.bar);
 				}
-				build_halo_masks(a, sm.lut32, slot, sm.hT);
+				build_halo_masks<FUSED_THREADS>(a, sm.lut32, slot, sm.hT, tid);
 				mbar_wait(&sm.bar, parity);
 				parity ^= 1;
 
-				build_masks_fused(a, sm);
+				build_masks_fused<FUSED_THREADS>(a, sm.lut32, sm, tid);
 				__syncthreads();
 
 				// ---- faces per row (thread t owns rows 4t .. 4t+3) and one packed scan: faces | rows-with-faces << 20
@@ -635,46 +910,7 @@ namespace tsomk
 			bool haveFirst = false;
 			if (warp == 0)
 			{
-				constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL = (1ull << 62) - 1ull;
-				volatile unsigned long long* st = a.status;
-				unsigned long long excl = 0ull;
-				if (job == 0u)
-				{
-					if (lane == 0)
-						st[0] = FLAG_INC | F;
-				}
-				else
-				{
-					if (lane == 0)
-						st[job] = FLAG_AGG | F;
-					long long base = (long long)job - 1;
-					for (;;)
-					{
-						const long long i = base - lane;
-						unsigned long long s;
-						uint32_t incMask, notReady;
-						do
-						{
-							s = i >= 0 ? st[i] : FLAG_INC; // before job 0: inclusive prefix 0
-							const unsigned fl = unsigned(s >> 62);
-							incMask = __ballot_sync(FULL, fl == 2u);
-							notReady = __ballot_sync(FULL, fl == 0u);
-							if (incMask)
-								notReady &= (2u << (__ffs(incMask) - 1)) - 1u; // only the lanes up to the first inclusive prefix matter
-						} while (notReady);
-						const int firstInc = incMask ? __ffs(incMask) - 1 : 31;
-						unsigned long long val = lane <= firstInc ? (s & VAL) : 0ull;
-#pragma unroll
-						for (int o = 16; o > 0; o >>= 1)
-							val += __shfl_xor_sync(FULL, val, o);
-						excl += val;
-						if (incMask)
-							break;
-						base -= 32;
-					}
-					if (lane == 0)
-						st[job] = FLAG_INC | (excl + F);
-				}
+				const unsigned long long excl = chain_lookback<1>(a.status, job, F, lane);
 				if (lane == 0)
 				{
 					sm.firstFace = excl;
@@ -713,70 +949,7 @@ namespace tsomk
 
 				for (uint32_t win = warp; win < nWin; win += FUSED_WARPS)
 				{
-					const uint32_t w0 = win * WIN;
-					const uint32_t nw = min(uint32_t(WIN), F - w0);
-
-					// ---- compact rows [kA, kB] of the window: largest k with ne[k].off <= first / last face (offsets increase strictly)
-					uint32_t kA, kB;
-					{
-						const uint32_t wLast = w0 + nw - 1u;
-						const uint32_t i1 = uint32_t(lane) * 32u;
-						const uint32_t o1 = i1 < K ? (sm.ne[i1] & NE_OFF_MASK) : 0xFFFFFFFFu;
-						const uint32_t topA = __popc(__ballot_sync(FULL, o1 <= w0)) - 1u;
-						const uint32_t topB = __popc(__ballot_sync(FULL, o1 <= wLast)) - 1u;
-						const uint32_t iA = topA * 32u + lane, iB = topB * 32u + lane;
-						const uint32_t oA = iA < K ? (sm.ne[iA] & NE_OFF_MASK) : 0xFFFFFFFFu;
-						const uint32_t oB = iB < K ? (sm.ne[iB] & NE_OFF_MASK) : 0xFFFFFFFFu;
-						kA = topA * 32u + __popc(__ballot_sync(FULL, oA <= w0)) - 1u;
-						kB = topB * 32u + __popc(__ballot_sync(FULL, oB <= wLast)) - 1u;
-					}
-
-					// ---- descriptors, faces in the reference's order (x, then Up/Down/Front/Back/Left/Right, twin).  A window of R
-					// rows is walked by 32 lanes: S = 32 / R (power of two) lanes share a row, each taking 32 / S consecutive blocks.
-					const uint32_t R = kB - kA + 1u;
-					const uint32_t lgS = R > 16u ? 0u : (R > 8u ? 1u : (R > 4u ? 2u : (R > 2u ? 3u : (R > 1u ? 4u : 5u))));
-					const uint32_t x0 = (uint32_t(lane) & ((1u << lgS) - 1u)) << (5u - lgS);
-					const uint32_t segMask = lgS == 0u ? 0xFFFFFFFFu : (((1u << (32u >> lgS)) - 1u) << x0);
-					const uint32_t below = (1u << x0) - 1u;
-					for (uint32_t k0 = kA; k0 <= kB; k0 += 32u >> lgS)
-					{
-						const uint32_t k = k0 + (uint32_t(lane) >> lgS);
-						if (k <= kB)
-						{
-							const uint32_t en = sm.ne[k];
-							uint32_t v[6];
-							const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
-							uint32_t p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
-#pragma unroll
-							for (int s = 0; s < 6; ++s)
-								p += __popc(v[s] & below) + __popc(v[s] & d & below);
-							const uint32_t base = (k - kA) << 9;
-							uint32_t any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
-							while (any && int(p) < int(nw))
-							{
-								const uint32_t x = uint32_t(__ffs(any) - 1);
-								any &= any - 1u;
-								const uint32_t bit = 1u << x;
-								const bool tw = (d & bit) != 0u;
-#pragma unroll
-								for (uint32_t s = 0; s < 6; ++s)
-								{
-									if (v[s] & bit)
-									{
-										if (p < nw)
-											desc[p] = uint16_t(base | x | (s << 5));
-										++p;
-										if (tw)
-										{
-											if (p < nw)
-												desc[p] = uint16_t(base | x | (s << 5) | 0x100u);
-											++p;
-										}
-									}
-								}
-							}
-						}
-					}
+					const uint32_t kA = expand_window(a, sm, slot, F, K, win, desc, lane);
 					__syncwarp();
 
 					if (!haveFirst)
@@ -789,88 +962,7 @@ namespace tsomk
 					if (firstFace + F > a.arenaFaces)
 						break; // arena too small: this launch only counts (the host grows the arena and runs the kernel again)
 
-					// ---- build one face per lane, stream out through the 16-face staging tile
-					const uint32_t nTiles = (nw + 31u) >> 5;
-					for (uint32_t tt = 0; tt < nTiles; ++tt)
-					{
-						const uint32_t f = tt * 32u + lane;
-						const uint32_t nf = min(32u, nw - tt * 32u);
-						const bool valid = f < nw;
-						FaceOut fo;
-						if (valid)
-						{
-							const uint32_t de = desc[f];
-							const uint32_t row = sm.ne[kA + (de >> 9)] >> NE_ROW_SHIFT;
-							const int x = int(de & 31u), y = int(row & 31u), z = int(row >> 5);
-							const int s = int((de >> 5) & 7u);
-							const bool twin = ((de >> 8) & 1u) != 0u;
-							const unsigned id = sm.ids[row * CS + x];
-							if (fastFlat)
-								draw_face_flat_r(a, cx, sm.table, x, y, z, s, twin, id, fo);
-							else
-								draw_face_r(a, cx, x, y, z, s, twin, id, fo);
-						}
-						const unsigned long long face0 = firstFace + w0 + tt * 32u;
-#pragma unroll
-						for (uint32_t h = 0; h < 2; ++h)
-						{
-							if (nf <= h * HALF_FACES)
-								break;
-							const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
-							if (valid && (uint32_t(lane) >> 4) == h)
-								store_face(stage + (lane & 15) * STAGE_FACE_F4, fo);
-							__syncwarp();
-							const unsigned long long faceH = face0 + h * HALF_FACES;
-							if (wantRender)
-							{
-								float4* dst = a.vertices + faceH * 12ull + lane;
-								if (nh == HALF_FACES)
-								{
-#pragma unroll
-									for (int k = 0; k < 6; ++k)
-										dst[32 * k] = stage[stageOff[k]];
-								}
-								else
-								{
-									const uint32_t n4 = nh * 12u;
-#pragma unroll
-									for (int k = 0; k < 6; ++k)
-										if (uint32_t(lane) + 32u * k < n4)
-											dst[32 * k] = stage[stageOff[k]];
-								}
-							}
-							if (wantCollider)
-							{
-								// positions only: 3 float4 per face gathered from the staged vertices
-								float4* dst = a.collider + faceH * 3ull;
-								const float* sf = reinterpret_cast<const float*>(stage);
-								const uint32_t n4 = nh * 3u;
-								for (uint32_t i = lane; i < n4; i += 32u)
-								{
-									const uint32_t face = i / 3u, j = i % 3u;
-									float e[4];
-#pragma unroll
-									for (int m = 0; m < 4; ++m)
-									{
-										const uint32_t q = j * 4u + m; // float q of the face's 12 position floats
-										e[m] = sf[face * (STAGE_FACE_F4 * 4) + (q / 3u) * 12u + (q % 3u)];
-									}
-									dst[i] = make_float4(e[0], e[1], e[2], e[3]);
-								}
-							}
-							__syncwarp();
-						}
-						{
-							// indices are a pure function of the chunk-relative face ordinal (Chunk.cpp:95-101): k*4 + {0,2,1,1,2,3}
-							uint2* dst = a.indices + face0 * 3ull + lane;
-							const uint32_t base = (w0 + tt * 32u) * 4u;
-							const uint32_t n2 = nf * 3u;
-#pragma unroll
-							for (int k = 0; k < 3; ++k)
-								if (nf == 32u || uint32_t(lane) + 32u * k < n2)
-									dst[32 * k] = make_uint2(idxPat[k].x + base, idxPat[k].y + base);
-						}
-					}
+					store_window(a, sm, sm.table, fastFlat, cx, F, win, kA, desc, stage, firstFace, lc, wantRender, wantCollider, lane);
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}

@@ -44,6 +44,17 @@ namespace tsomk
 		             : "memory");
 	}
 
+	__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+	{
+		asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+	}
+
+	// named barrier over a subset of the CTA's warps (id 1..15; `threads` must be a multiple of 32)
+	__device__ __forceinline__ void named_bar_sync(int id, int threads)
+	{
+		asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+	}
+
 	__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 	{
 		uint32_t ok;
