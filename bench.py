@@ -130,11 +130,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
+try:
+    ORIGINAL_AFFINITY = os.sched_getaffinity(0)
+except Exception:
+    ORIGINAL_AFFINITY = None
+
+
 def host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    """All host threads this process may use (the affinity it was started with, not the per-GPU NUMA binding of the GPU arm)."""
+    if ORIGINAL_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, ORIGINAL_AFFINITY)
+        except Exception:
+            pass
+        return len(ORIGINAL_AFFINITY)
+    return os.cpu_count() or 1
 
 
 def cpu_sample(n_chunks, first_chunk=0):
@@ -210,6 +220,24 @@ def run_reference(args):
     }))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned host buffer is allocated (first touch then
+    places the e2e staging buffers on the GPU's NUMA node; without it the 45 GB/step D2H of 8 ranks crosses the socket link)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass  # best effort: the measurement is still valid, only possibly NUMA-remote
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -229,6 +257,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    bind_to_gpu_numa_node(local)
 
     n = args.chunks
     ctx = T.Context(local)
