@@ -62,6 +62,7 @@ def _bind(path: str, full: bool):
     L.orc_blocklib_count.restype = C.c_uint32
     L.orc_blocklib_get.argtypes = [C.c_uint32, u32p, u8p, C.c_char_p]
     L.orc_blocklib_index.argtypes = [C.c_char_p]
+    L.orc_blocklib_register.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
     if full:  # probes of the restatement's internals; the reference build has no such entry points
         L.orc_perlin_perm.argtypes = [C.c_uint32, u8p]
         L.orc_perlin_octave01.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_int]
@@ -169,6 +170,11 @@ def block_library(L=None):
         (L or lib()).orc_blocklib_get(i, _p(tex, C.c_uint32), _p(fl, C.c_uint8), name)
         res.append((name.value.decode(), tex.copy(), bool(fl[0]), bool(fl[1]), bool(fl[2])))
     return res
+
+
+def register_block(name, basePath="", sidePath="", upPath="", hasCollisions=True, isDoubleSided=False, isTransparent=False, L=None) -> int:
+    """BlockLibrary::RegisterBlock on the backend's process-wide library (appends; use a fresh process for such tests)."""
+    return int((L or lib()).orc_blocklib_register(name.encode(), basePath.encode(), sidePath.encode(), upPath.encode(), int(hasCollisions), int(isDoubleSided), int(isTransparent)))
 
 
 def block_index(name: str, L=None) -> int:

@@ -11,11 +11,12 @@ using namespace orc;
 
 namespace
 {
-	const BlockLibrary& Lib()
+	BlockLibrary& MutableLib()
 	{
 		static BlockLibrary lib;
 		return lib;
 	}
+	const BlockLibrary& Lib() { return MutableLib(); }
 
 	struct PlanetHandle
 	{
@@ -87,6 +88,20 @@ extern "C"
 	}
 
 	int orc_blocklib_index(const char* name) { return Lib().GetBlockIndex(name); }
+
+	// BlockLibrary::RegisterBlock (BlockLibrary.cpp:85-131) on the process-wide library: appends one block type (tests of large
+	// block tables run in their own process).  Empty strings mean "not given".
+	int orc_blocklib_register(const char* name, const char* basePath, const char* sidePath, const char* upPath, int hasCollisions, int isDoubleSided, int isTransparent)
+	{
+		BlockInfo info;
+		info.basePath = basePath;
+		info.baseSidePath = sidePath;
+		info.baseUpPath = upPath;
+		info.hasCollisions = hasCollisions != 0;
+		info.isDoubleSided = isDoubleSided != 0;
+		info.isTransparent = isTransparent != 0;
+		return MutableLib().RegisterBlock(name, info);
+	}
 
 	// ---- perlin / rng probes
 	void orc_perlin_perm(std::uint32_t seed, std::uint8_t out[256])

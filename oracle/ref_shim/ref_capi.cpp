@@ -27,11 +27,14 @@ namespace
 {
 	constexpr std::size_t ChunkBlockCount = 32 * 32 * 32;
 
-	const BlockLibrary& Lib()
+	std::uint32_t g_registered = 0; // blocks added through orc_blocklib_register
+
+	BlockLibrary& MutableLib()
 	{
 		static BlockLibrary lib;
 		return lib;
 	}
+	const BlockLibrary& Lib() { return MutableLib(); }
 
 	struct Key
 	{
@@ -126,7 +129,7 @@ extern "C"
 		for (const char* nm : names)
 			if (Lib().GetBlockIndex(nm) != InvalidBlockIndex)
 				++n;
-		return n;
+		return n + g_registered;
 	}
 
 	void orc_blocklib_get(std::uint32_t idx, std::uint32_t tex[6], std::uint8_t flags[3], char name[64])
@@ -140,6 +143,21 @@ extern "C"
 	}
 
 	int orc_blocklib_index(const char* name) { return Lib().GetBlockIndex(name); }
+
+	// BlockLibrary::RegisterBlock (BlockLibrary.cpp:85-131) on the process-wide library: appends one block type (tests of large
+	// block tables run in their own process).  Empty strings mean "not given".
+	int orc_blocklib_register(const char* name, const char* basePath, const char* sidePath, const char* upPath, int hasCollisions, int isDoubleSided, int isTransparent)
+	{
+		BlockLibrary::BlockInfo info;
+		info.basePath = basePath;
+		info.baseSidePath = sidePath;
+		info.baseUpPath = upPath;
+		info.hasCollisions = hasCollisions != 0;
+		info.isDoubleSided = isDoubleSided != 0;
+		info.isTransparent = isTransparent != 0;
+		++g_registered;
+		return MutableLib().RegisterBlock(name, std::move(info));
+	}
 
 	int orc_generate_chunk(std::uint32_t seed, const std::uint32_t count[3], const std::int32_t chunk[3], std::uint16_t* out)
 	{
