@@ -178,6 +178,21 @@ static void TestGpu()
 	CHECK(after[victim] == EmptyBlockIndex);
 	CHECK(planet.CollectInvalidatedChunks().empty());
 
+	// save format: serialize -> deserialize into another chunk -> same ids; a corrupted version is rejected like the reference does
+	{
+		auto bytes = chunk.Serialize(lib);
+		CHECK(bytes.size() > 18 + 32768 - 1);
+		CHECK(bytes[3] == 1 && bytes[7] == 32);
+		Chunk copy = planet.AddChunk(lib, ChunkIndices(10, 10, 10));
+		copy.Deserialize(lib, bytes.data(), bytes.size());
+		CHECK(copy.GetContent() == after);
+		planet.RemoveChunk(ChunkIndices(10, 10, 10));
+		bytes[3] = 2;
+		bool threw = false;
+		try { chunk.Deserialize(lib, bytes.data(), bytes.size()); } catch (const std::runtime_error& e) { threw = std::string(e.what()) == "incompatible chunk version"; }
+		CHECK(threw);
+	}
+
 	// greedy box collider of a full chunk: one box covering everything
 	Chunk solid = planet.AddChunk(lib, ChunkIndices(10, 10, 10), [&](BlockIndex* blocks) {
 		for (unsigned int i = 0; i < TSOM_CHUNK_BLOCKS; ++i)

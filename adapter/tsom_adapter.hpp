@@ -21,6 +21,7 @@
 
 #include "../include/tsom_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -302,6 +303,12 @@ namespace tsom_b200
 
 			// Chunk::UpdateBlock (Chunk.cpp:348-366); batching many edits per tick: ChunkContainer::UpdateBlocks
 			void UpdateBlock(const Vector3ui& indices, BlockIndex cellType);
+
+			// Chunk::Serialize / Deserialize (Chunk.cpp:252-346), the `<x>_<y>_<z>.chunk` save format: header composed / parsed
+			// here (big-endian integers, UInt32-prefixed names — Nazara ByteStream conventions), palette + payload on the device.
+			// Deserialize throws std::runtime_error with the reference's messages.
+			std::vector<std::uint8_t> Serialize(const BlockLibrary& blockLibrary) const;
+			void Deserialize(const BlockLibrary& blockLibrary, const std::uint8_t* data, std::size_t size);
 
 			static unsigned int GetBlockLocalIndex(const Vector3ui& i) { return 32u * (32u * i.z + i.y) + i.x; } // Chunk.inl:25-28
 
@@ -591,6 +598,61 @@ namespace tsom_b200
 		std::vector<BlockIndex> blocks(TSOM_CHUNK_BLOCKS, EmptyBlockIndex);
 		func(blocks.data());
 		Check(tsom_chunks_reset(m_owner->Handle(), &m_indices.x, 1, blocks.data()), "tsom_chunks_reset");
+	}
+
+	inline std::vector<std::uint8_t> Chunk::Serialize(const BlockLibrary& blockLibrary) const
+	{
+		const std::uint32_t stride = std::uint32_t(blockLibrary.GetBlockCount());
+		std::vector<std::uint16_t> palette(stride);
+		std::vector<std::uint8_t> payload(TSOM_CHUNK_BLOCKS * 2);
+		std::uint32_t count = 0;
+		Check(tsom_chunks_palettize(m_owner->Handle(), &m_indices.x, 1, palette.data(), stride, &count, payload.data(), 1), "tsom_chunks_palettize");
+		std::vector<std::uint8_t> out;
+		auto put32 = [&](std::uint32_t v) { for (int s = 24; s >= 0; s -= 8) out.push_back(std::uint8_t(v >> s)); };
+		put32(1); // Constants::ChunkBinaryVersion (InternalConstants.hpp:24)
+		put32(TSOM_CHUNK_SIZE); put32(TSOM_CHUNK_SIZE); put32(TSOM_CHUNK_SIZE);
+		out.push_back(std::uint8_t(count >> 8));
+		out.push_back(std::uint8_t(count));
+		for (std::uint32_t i = 0; i < count; ++i)
+		{
+			const std::string& name = blockLibrary.GetBlockData(palette[i]).name;
+			put32(std::uint32_t(name.size()));
+			out.insert(out.end(), name.begin(), name.end());
+		}
+		out.insert(out.end(), payload.begin(), payload.begin() + TSOM_CHUNK_BLOCKS * (count > 8 ? 2 : 1));
+		return out;
+	}
+
+	inline void Chunk::Deserialize(const BlockLibrary& blockLibrary, const std::uint8_t* data, std::size_t size)
+	{
+		std::size_t cur = 0;
+		auto need = [&](std::size_t k) { if (cur + k > size) throw std::runtime_error("ByteStream: read past end"); };
+		auto get32 = [&]() { need(4); std::uint32_t v = std::uint32_t(data[cur]) << 24 | std::uint32_t(data[cur + 1]) << 16 | std::uint32_t(data[cur + 2]) << 8 | data[cur + 3]; cur += 4; return v; };
+		if (get32() != 1)
+			throw std::runtime_error("incompatible chunk version");
+		const std::uint32_t sx = get32(), sy = get32(), sz = get32();
+		if (sx != TSOM_CHUNK_SIZE || sy != TSOM_CHUNK_SIZE || sz != TSOM_CHUNK_SIZE)
+			throw std::runtime_error("incompatible chunk size");
+		need(2);
+		const std::uint32_t count = std::uint32_t(data[cur]) << 8 | data[cur + 1];
+		cur += 2;
+		std::vector<std::uint16_t> palette(std::max<std::uint32_t>(count, 1));
+		for (std::uint32_t i = 0; i < count; ++i)
+		{
+			const std::uint32_t len = get32();
+			need(len);
+			std::string name(reinterpret_cast<const char*>(data + cur), len);
+			cur += len;
+			const BlockIndex idx = blockLibrary.GetBlockIndex(name);
+			if (idx == InvalidBlockIndex)
+				throw std::runtime_error("unknown block " + name);
+			palette[i] = idx;
+		}
+		const std::size_t bytes = std::size_t(TSOM_CHUNK_BLOCKS) * (count > 8 ? 2 : 1);
+		need(bytes);
+		std::vector<std::uint8_t> payload(TSOM_CHUNK_BLOCKS * 2, 0);
+		std::memcpy(payload.data(), data + cur, bytes);
+		Check(tsom_chunks_reset_palettized(m_owner->Handle(), &m_indices.x, 1, palette.data(), std::uint32_t(palette.size()), &count, payload.data(), 1), "tsom_chunks_reset_palettized");
 	}
 
 	inline void Chunk::UpdateBlock(const Vector3ui& indices, BlockIndex cellType)

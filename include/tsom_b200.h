@@ -157,6 +157,22 @@ int tsom_chunks_get_content(tsom_container* c, const int32_t* chunk_indices, uin
 /* device address of one chunk's 32768 ids (NULL if unknown / no content) */
 const void* tsom_chunk_device_ptr(tsom_container* c, const int32_t chunk_index[3]);
 
+/* ---- save format: Chunk::Serialize / Chunk::Deserialize (src/CommonLib/Chunk.cpp:252-346; callers
+ * src/ServerLib/ServerPlanetEnvironment.cpp:105-129,207-220), device part.  The header of a serialized chunk (version, size,
+ * the NAMES of the block types that occur) is host work — names live in the caller's BlockLibrary (adapter/tsom_adapter.hpp
+ * composes it); the payload, one palette index per block, is produced / consumed on the device.
+ * tsom_chunks_palettize: for chunk i, palette_counts_out[i] = K = number of distinct block types, palette_out[i*palette_stride ..]
+ * = their BlockIndex values ascending (the order the reference writes the names in), payload_out + i*65536 = 32768 palette
+ * indices: uint8 when K <= 8, else uint16 (Chunk.cpp:335-345), big-endian when payload_big_endian != 0.  TSOM_ERR_CAPACITY if
+ * some K exceeds palette_stride (the counts are still written). */
+int tsom_chunks_palettize(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint16_t* palette_out, uint32_t palette_stride,
+                          uint32_t* palette_counts_out, uint8_t* payload_out, int payload_big_endian);
+/* Chunk::Deserialize after the host has parsed the header and mapped the names to BlockIndex values: expands the payloads
+ * (same layout as above) into the chunks' ids like Chunk::Reset (chunks are added if missing, marked invalidated).
+ * TSOM_ERR_INVALID if a payload index is >= its chunk's palette count (the reference indexes out of bounds there). */
+int tsom_chunks_reset_palettized(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint16_t* palettes, uint32_t palette_stride,
+                                 const uint32_t* palette_counts, const uint8_t* payload, int payload_big_endian);
+
 /* ---- generation ---- */
 /* Planet::GenerateChunks (Planet.cpp:385-403): adds chunk_count^3 chunks at (x,y,z) - chunk_count/2 in z,y,x order and
  * fills every one with Planet::GenerateChunk (Planet.cpp:160-383). */

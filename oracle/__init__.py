@@ -90,6 +90,9 @@ def _bind(path: str, full: bool):
     L.orc_mesh_free.argtypes = [C.c_void_p]
     L.orc_box_collider.argtypes = [C.c_void_p, i32p, f32p, C.c_uint32]
     L.orc_box_collider.restype = C.c_uint32
+    L.orc_chunk_serialize.argtypes = [C.c_void_p, i32p, u8p, C.c_uint32]
+    L.orc_chunk_serialize.restype = C.c_uint32
+    L.orc_chunk_deserialize.argtypes = [C.c_void_p, i32p, u8p, C.c_uint32, C.c_char_p]
     L.orc_bench_mesh_isolated.argtypes = [u16p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_bench_mesh_isolated.restype = C.c_double
     L.orc_bench_planet.argtypes = [C.c_uint32, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), u32p]
@@ -287,6 +290,22 @@ class Planet:
         self._L.orc_mesh_copy(h, _p(pos, C.c_float), None if nor is None else _p(nor, C.c_float), None if uvw is None else _p(uvw, C.c_float), _p(ind, C.c_uint32))
         self._L.orc_mesh_free(h)
         return Mesh(pos, nor, uvw, ind)
+
+    def serialize(self, idx) -> bytes:
+        """Chunk::Serialize (Chunk.cpp:312-346): the bytes of the chunk's save file."""
+        buf = np.zeros(1 << 17, np.uint8)
+        n = self._L.orc_chunk_serialize(self._h, _p(_i3(idx), C.c_int32), _p(buf, C.c_uint8), len(buf))
+        return bytes(buf[:n])
+
+    def deserialize(self, idx, data: bytes):
+        """Chunk::Deserialize (Chunk.cpp:252-310) into an existing chunk; raises RuntimeError with the reference's message."""
+        a = np.frombuffer(data, np.uint8).copy()
+        err = C.create_string_buffer(128)
+        rc = self._L.orc_chunk_deserialize(self._h, _p(_i3(idx), C.c_int32), _p(a, C.c_uint8), len(a), err)
+        if rc == 1:
+            raise KeyError(tuple(idx))
+        if rc == 2:
+            raise RuntimeError(err.value.decode())
 
     def box_collider(self, idx, cap=32768):
         out = np.zeros((cap, 6), np.float32)

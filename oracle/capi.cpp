@@ -289,6 +289,39 @@ extern "C"
 		return std::uint32_t(boxes.size());
 	}
 
+	// Chunk::Serialize (Chunk.cpp:312-346) -> bytes written (0: unknown chunk / no content / buffer too small)
+	std::uint32_t orc_chunk_serialize(void* h, const std::int32_t idx[3], std::uint8_t* out, std::uint32_t cap)
+	{
+		const Chunk* c = static_cast<PlanetHandle*>(h)->planet.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c || !c->HasContent())
+			return 0;
+		std::vector<std::uint8_t> bytes;
+		c->Serialize(bytes);
+		if (bytes.size() > cap)
+			return 0;
+		std::memcpy(out, bytes.data(), bytes.size());
+		return std::uint32_t(bytes.size());
+	}
+
+	// Chunk::Deserialize (Chunk.cpp:252-310) into an existing chunk: 0 ok, 1 unknown chunk, 2 rejected (message in err)
+	int orc_chunk_deserialize(void* h, const std::int32_t idx[3], const std::uint8_t* data, std::uint32_t size, char err[128])
+	{
+		Chunk* c = static_cast<PlanetHandle*>(h)->planet.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c)
+			return 1;
+		try
+		{
+			c->Deserialize(data, size);
+		}
+		catch (const std::exception& e)
+		{
+			std::strncpy(err, e.what(), 127);
+			err[127] = 0;
+			return 2;
+		}
+		return 0;
+	}
+
 	// ---- CPU baseline timers (bench.py cpu_baseline / --impl reference).  Return seconds; *facesOut = total faces.
 
 	// mesh (render attributes) n isolated chunks, one task per chunk — BASELINE config 2

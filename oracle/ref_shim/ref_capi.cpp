@@ -203,6 +203,11 @@ extern "C"
 	int orc_planet_generate(void* h, std::uint32_t seed, const std::uint32_t count[3], int nthreads)
 	{
 		Planet& p = static_cast<PlanetHandle*>(h)->planet;
+		for (int cz = 0; cz < int(count[2]); ++cz)
+			for (int cy = 0; cy < int(count[1]); ++cy)
+				for (int cx = 0; cx < int(count[0]); ++cx)
+					if (p.GetChunk({ cx - int(count[0] / 2), cy - int(count[1] / 2), cz - int(count[2] / 2) }))
+						return 1; // Planet::AddChunk asserts that the chunk does not exist yet (Planet.cpp:30)
 		Nz::TaskScheduler sched(nthreads <= 1 ? 1u : unsigned(nthreads));
 		try
 		{
@@ -361,6 +366,27 @@ extern "C"
 			return 0;
 		std::memcpy(out, bs.data.data(), bs.data.size());
 		return std::uint32_t(bs.data.size());
+	}
+
+	// Chunk::Deserialize (Chunk.cpp:252-310) into an existing chunk: 0 ok, 1 unknown chunk, 2 rejected (message in err)
+	int orc_chunk_deserialize(void* hv, const std::int32_t idx[3], const std::uint8_t* data, std::uint32_t size, char err[128])
+	{
+		Chunk* c = static_cast<PlanetHandle*>(hv)->planet.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c)
+			return 1;
+		try
+		{
+			Nz::ByteStream bs;
+			bs.data.assign(data, data + size);
+			c->Deserialize(bs);
+		}
+		catch (const std::exception& e)
+		{
+			std::strncpy(err, e.what(), 127);
+			err[127] = 0;
+			return 2;
+		}
+		return 0;
 	}
 
 	// ---- CPU baseline timers: the reference's own Chunk::BuildMesh / Planet::GenerateChunks, one task per chunk

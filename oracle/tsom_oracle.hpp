@@ -34,6 +34,7 @@
 #include <numeric>
 #include <optional>
 #include <random>
+#include <stdexcept>
 #include <string>
 #include <string_view>
 #include <unordered_map>
@@ -473,6 +474,12 @@ namespace orc
 			// Chunk.cpp:348-366
 			void UpdateBlock(const Vec3ui& indices, BlockIndex newBlock);
 
+			// Chunk.cpp:312-346 / 252-310: the save format.  Stream conventions of Nazara's ByteStream as restated in
+			// oracle/ref_shim/include/Nazara/Core/ByteStream.hpp (UNPINNED third-party behaviour): arithmetic types big-endian,
+			// std::string = UInt32 length + bytes, Vector3ui = three UInt32.
+			void Serialize(std::vector<std::uint8_t>& out) const;
+			void Deserialize(const std::uint8_t* data, std::size_t size); // throws std::runtime_error like the reference
+
 			// corner providers: FlatChunk.cpp:48-54, DeformedChunk.cpp:115-154
 			CornerMode cornerMode = CornerMode::Flat;
 			Vec3f deformationCenter{};
@@ -676,6 +683,95 @@ namespace orc
 		m_blockTypeCount[newBlock]++;
 		if (onBlockUpdated)
 			onBlockUpdated(this, indices, newBlock);
+	}
+
+	namespace stream
+	{
+		inline void PutU8(std::vector<std::uint8_t>& o, std::uint8_t v) { o.push_back(v); }
+		inline void PutU16(std::vector<std::uint8_t>& o, std::uint16_t v) { o.push_back(std::uint8_t(v >> 8)); o.push_back(std::uint8_t(v)); }
+		inline void PutU32(std::vector<std::uint8_t>& o, std::uint32_t v) { for (int s = 24; s >= 0; s -= 8) o.push_back(std::uint8_t(v >> s)); }
+		struct Reader
+		{
+			const std::uint8_t* p;
+			std::size_t n, cur = 0;
+			void Need(std::size_t k) const { if (cur + k > n) throw std::runtime_error("ByteStream: read past end"); }
+			std::uint8_t U8() { Need(1); return p[cur++]; }
+			std::uint16_t U16() { Need(2); std::uint16_t v = std::uint16_t(p[cur] << 8 | p[cur + 1]); cur += 2; return v; }
+			std::uint32_t U32() { Need(4); std::uint32_t v = std::uint32_t(p[cur]) << 24 | std::uint32_t(p[cur + 1]) << 16 | std::uint32_t(p[cur + 2]) << 8 | p[cur + 3]; cur += 4; return v; }
+		};
+	}
+
+	constexpr std::uint32_t ChunkBinaryVersion = 1; // InternalConstants.hpp:24
+
+	// Chunk.cpp:312-346
+	inline void Chunk::Serialize(std::vector<std::uint8_t>& out) const
+	{
+		using namespace stream;
+		PutU32(out, ChunkBinaryVersion);
+		PutU32(out, ChunkSize); PutU32(out, ChunkSize); PutU32(out, ChunkSize);
+
+		std::vector<BlockIndex> serializationIndices(m_blockTypeCount.size());
+		std::uint16_t nextUniqueIndex = 0;
+		for (std::size_t i = 0; i < m_blockTypeCount.size(); ++i)
+		{
+			if (m_blockTypeCount[i] == 0)
+				continue;
+			serializationIndices[i] = nextUniqueIndex++;
+		}
+		PutU16(out, nextUniqueIndex);
+		for (std::size_t i = 0; i < m_blockTypeCount.size(); ++i)
+		{
+			if (m_blockTypeCount[i] == 0)
+				continue;
+			const std::string& name = m_blockLibrary.GetBlockData(BlockIndex(i)).name;
+			PutU32(out, std::uint32_t(name.size()));
+			out.insert(out.end(), name.begin(), name.end());
+		}
+		// "nextUniqueIndex is the number of bits required..." (sic): more than 8 distinct types -> 16-bit indices
+		if (nextUniqueIndex > 8)
+		{
+			for (BlockIndex b : m_blocks)
+				PutU16(out, serializationIndices[b]);
+		}
+		else
+		{
+			for (BlockIndex b : m_blocks)
+				PutU8(out, std::uint8_t(serializationIndices[b]));
+		}
+	}
+
+	// Chunk.cpp:252-310
+	inline void Chunk::Deserialize(const std::uint8_t* data, std::size_t size)
+	{
+		stream::Reader r{ data, size };
+		if (r.U32() != ChunkBinaryVersion)
+			throw std::runtime_error("incompatible chunk version");
+		std::uint32_t sx = r.U32(), sy = r.U32(), sz = r.U32();
+		if (sx != ChunkSize || sy != ChunkSize || sz != ChunkSize)
+			throw std::runtime_error("incompatible chunk size");
+		std::uint16_t blockTypeCount = r.U16();
+		std::vector<BlockIndex> deserializationIndices;
+		deserializationIndices.reserve(blockTypeCount);
+		for (std::uint16_t i = 0; i < blockTypeCount; ++i)
+		{
+			std::uint32_t len = r.U32();
+			r.Need(len);
+			std::string name(reinterpret_cast<const char*>(r.p + r.cur), len);
+			r.cur += len;
+			BlockIndex idx = m_blockLibrary.GetBlockIndex(name);
+			if (idx == InvalidBlockIndex)
+				throw std::runtime_error("unknown block " + name);
+			deserializationIndices.push_back(idx);
+		}
+		std::vector<BlockIndex> blocks(ChunkBlockCount);
+		for (BlockIndex& b : blocks)
+		{
+			std::uint16_t v = blockTypeCount > 8 ? r.U16() : r.U8();
+			if (v >= deserializationIndices.size())
+				throw std::runtime_error("palette index out of range"); // the reference indexes out of bounds here (UB)
+			b = deserializationIndices[v];
+		}
+		Reset([&](BlockIndex* dst) { std::copy(blocks.begin(), blocks.end(), dst); });
 	}
 
 	// ---- Chunk::BuildMesh (Chunk.cpp:20-250)

@@ -102,6 +102,7 @@ def main(mode):
                 faces += assert_mesh_equal(batch.chunk(i), om, what=f"{kw} chunk {k}")["faces"]
         for k in keys:
             assert np.array_equal(gc.BuildBoxCollider(k), op.box_collider(k)), k
+        gc.close()
         ctx.close()
     assert faces > 100_000
     print(f"big library ok ({mode}): {n_types} block types, {faces} faces compared")

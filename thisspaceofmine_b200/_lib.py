@@ -73,6 +73,8 @@ SYMBOLS = {
     "tsom_chunks_reset_device": (C.c_int, [_vp, _i32p, C.c_uint32, _vp]),
     "tsom_chunks_get_content": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p]),
     "tsom_chunk_device_ptr": (_vp, [_vp, _i32p]),
+    "tsom_chunks_palettize": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p, C.c_uint32, _u32p, C.POINTER(C.c_uint8), C.c_int]),
+    "tsom_chunks_reset_palettized": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p, C.c_uint32, _u32p, C.POINTER(C.c_uint8), C.c_int]),
     "tsom_planet_generate": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks)]),
     "tsom_planet_generate_chunks": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks), _i32p, C.c_uint32]),
     "tsom_planet_generate_platform": (C.c_int, [_vp, C.c_int, _i32p, C.POINTER(PlatformBlocks)]),

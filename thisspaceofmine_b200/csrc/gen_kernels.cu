@@ -654,6 +654,194 @@ namespace tsomk
 		edit_apply_kernel<<<grid, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, edits, n, keys, vals, cap - 1u);
 	}
 
+	// ------------------------------------------------------------------------------------------------ save format (Chunk::Serialize)
+	// Device part of Chunk::Serialize / Deserialize (reference src/CommonLib/Chunk.cpp:252-346): the palette of block types that
+	// occur in a chunk (ascending BlockIndex — the order the reference writes the names in, from m_blockTypeCount) and one
+	// palette index per block: uint8 when the chunk has at most 8 distinct types, uint16 otherwise (Chunk.cpp:335-345).
+	// One CTA per chunk: presence bitmap over the 65,536 possible ids in shared memory, popcount prefix -> rank of every id.
+	constexpr int PAL_WORDS = 2048; // 65536 ids / 32
+
+	__global__ void __launch_bounds__(256) palettize_kernel(const uint16_t* __restrict__ blocks, const uint32_t* __restrict__ slots, uint32_t n, uint16_t* __restrict__ palette,
+	                                                        uint32_t stride, uint32_t* __restrict__ counts, uint8_t* __restrict__ payload, int bigEndian)
+	{
+		__shared__ uint32_t present[PAL_WORDS];
+		__shared__ uint16_t rankBase[PAL_WORDS];
+		__shared__ uint32_t warpTot[8];
+		const uint32_t i = blockIdx.x;
+		if (i >= n)
+			return;
+		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		const uint4* src = reinterpret_cast<const uint4*>(blocks + size_t(slots[i]) * NB);
+		for (int w = tid; w < PAL_WORDS; w += 256)
+			present[w] = 0u;
+		__syncthreads();
+
+		unsigned last = 0xFFFFFFFFu;
+		for (int k = 0; k < NB / 8 / 256; ++k)
+		{
+			const uint4 v = src[tid + 256 * k];
+			const uint32_t ws[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				const unsigned id = (ws[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+				if (id != last)
+				{
+					atomicOr(&present[id >> 5], 1u << (id & 31u));
+					last = id;
+				}
+			}
+		}
+		__syncthreads();
+
+		// exclusive prefix of the popcounts: thread t owns words 8t .. 8t+7
+		uint32_t pc[8], sum = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			pc[j] = __popc(present[8 * tid + j]);
+			sum += pc[j];
+		}
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o)
+				incl += v;
+		}
+		if (lane == 31)
+			warpTot[warp] = incl;
+		__syncthreads();
+		uint32_t base = 0, K = 0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w)
+		{
+			if (w < warp)
+				base += warpTot[w];
+			K += warpTot[w];
+		}
+		uint32_t run = base + incl - sum;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			rankBase[8 * tid + j] = uint16_t(run);
+			uint32_t bits = present[8 * tid + j];
+			uint32_t r = run;
+			while (bits)
+			{
+				const int b = __ffs(bits) - 1;
+				bits &= bits - 1u;
+				if (r < stride)
+					palette[size_t(i) * stride + r] = uint16_t((8 * tid + j) * 32 + b);
+				++r;
+			}
+			run += pc[j];
+		}
+		if (tid == 0)
+			counts[i] = K;
+		__syncthreads();
+
+		const bool wide = K > 8u;
+		uint8_t* dst = payload + size_t(i) * (NB * 2);
+		for (int k = 0; k < NB / 8 / 256; ++k)
+		{
+			const uint4 v = src[tid + 256 * k];
+			const uint32_t ws[4] = { v.x, v.y, v.z, v.w };
+			uint32_t idx[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				const unsigned id = (ws[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+				idx[j] = rankBase[id >> 5] + __popc(present[id >> 5] & ((1u << (id & 31u)) - 1u));
+			}
+			if (wide)
+			{
+				uint32_t o[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					uint32_t lo = idx[2 * j], hi = idx[2 * j + 1];
+					if (bigEndian)
+					{
+						lo = ((lo & 0xFFu) << 8) | (lo >> 8);
+						hi = ((hi & 0xFFu) << 8) | (hi >> 8);
+					}
+					o[j] = lo | (hi << 16);
+				}
+				reinterpret_cast<uint4*>(dst)[tid + 256 * k] = make_uint4(o[0], o[1], o[2], o[3]);
+			}
+			else
+			{
+				const uint32_t lo = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+				const uint32_t hi = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+				reinterpret_cast<uint2*>(dst)[tid + 256 * k] = make_uint2(lo, hi);
+			}
+		}
+	}
+
+	__global__ void __launch_bounds__(256) depalettize_kernel(uint16_t* __restrict__ blocks, const uint32_t* __restrict__ slots, uint32_t n, const uint16_t* __restrict__ palette,
+	                                                          uint32_t stride, const uint32_t* __restrict__ counts, const uint8_t* __restrict__ payload, int bigEndian, uint32_t* errFlag)
+	{
+		const uint32_t i = blockIdx.x;
+		if (i >= n)
+			return;
+		const int tid = threadIdx.x;
+		const uint32_t K = counts[i];
+		const bool wide = K > 8u;
+		const uint16_t* pal = palette + size_t(i) * stride;
+		const uint8_t* src = payload + size_t(i) * (NB * 2);
+		uint4* dst = reinterpret_cast<uint4*>(blocks + size_t(slots[i]) * NB);
+		bool bad = false;
+		for (int k = 0; k < NB / 8 / 256; ++k)
+		{
+			uint32_t idx[8];
+			if (wide)
+			{
+				const uint4 v = reinterpret_cast<const uint4*>(src)[tid + 256 * k];
+				const uint32_t ws[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+				{
+					uint32_t x = (ws[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+					if (bigEndian)
+						x = ((x & 0xFFu) << 8) | (x >> 8);
+					idx[j] = x;
+				}
+			}
+			else
+			{
+				const uint2 v = reinterpret_cast<const uint2*>(src)[tid + 256 * k];
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					idx[j] = ((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xFFu;
+			}
+			uint32_t id[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				bad |= idx[j] >= K;
+				id[j] = idx[j] < K ? uint32_t(__ldg(pal + idx[j])) : 0u;
+			}
+			dst[tid + 256 * k] = make_uint4(id[0] | (id[1] << 16), id[2] | (id[3] << 16), id[4] | (id[5] << 16), id[6] | (id[7] << 16));
+		}
+		if (bad)
+			atomicExch(errFlag, 1u);
+	}
+
+	void launch_palettize(const uint16_t* blocks, const uint32_t* slots, uint32_t n, uint16_t* palette, uint32_t stride, uint32_t* counts, uint8_t* payload, int bigEndian, cudaStream_t st)
+	{
+		if (n)
+			palettize_kernel<<<n, 256, 0, st>>>(blocks, slots, n, palette, stride, counts, payload, bigEndian);
+	}
+
+	void launch_depalettize(uint16_t* blocks, const uint32_t* slots, uint32_t n, const uint16_t* palette, uint32_t stride, const uint32_t* counts, const uint8_t* payload, int bigEndian,
+	                        uint32_t* errFlag, cudaStream_t st)
+	{
+		if (n)
+			depalettize_kernel<<<n, 256, 0, st>>>(blocks, slots, n, palette, stride, counts, payload, bigEndian, errFlag);
+	}
+
 	// ------------------------------------------------------------------------------------------------ Planet::GeneratePlatform
 	// A data-dependent sequential edit script (Planet.cpp:405-512); run by one thread against the device-resident blocks.
 	struct PlatformAxis { int forwardAxis, rightAxis, upAxis, forwardDir, rightDir, upDir; };

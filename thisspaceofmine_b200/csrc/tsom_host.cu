@@ -233,6 +233,9 @@ struct tsom_ctx
 	DevBuf<unsigned long long> firstFace, status;
 	DevBuf<float> gravity;
 	DevBuf<tsomk::EditDev> edits;
+	DevBuf<uint8_t> ioPayload;   // save-format payloads (65536 B per chunk)
+	DevBuf<uint16_t> ioPalette;
+	DevBuf<uint32_t> ioCounts;
 	DevBuf<unsigned long long> editKeys; // open-addressing table of the edited blocks of one tsom_apply_edits call
 	DevBuf<uint32_t> editVals;           // ... -> index of the last edit that names the block
 	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
@@ -612,6 +615,9 @@ extern "C"
 		ctx->firstFace.Free();
 		ctx->status.Free();
 		ctx->editKeys.Free();
+		ctx->ioPayload.Free();
+		ctx->ioPalette.Free();
+		ctx->ioCounts.Free();
 		ctx->editVals.Free();
 		ctx->gravity.Free();
 		ctx->edits.Free();
@@ -783,6 +789,25 @@ extern "C"
 
 	uint32_t tsom_container_chunk_count(const tsom_container* c) { return c ? uint32_t(c->slotOf.size()) : 0; }
 
+	// after new ids landed in dBlocks (ctx->jobSlot holds `slots` on the device): x-slabs, content flags, OnReset invalidation
+	static int FinishReset(tsom_container* c, const std::vector<uint32_t>& slots)
+	{
+		tsom_ctx* ctx = c->ctx;
+		const uint32_t n = uint32_t(slots.size());
+		tsomk::launch_build_xslabs(c->dBlocks, c->dXslabs, ctx->jobSlot.ptr, n, ctx->stream);
+		ctx->launches += n ? 1 : 0;
+		TSOM_CUDA(cudaGetLastError());
+		for (uint32_t k = 0; k < n; ++k)
+		{
+			if (!c->hasContent[slots[k]])
+				c->topoDirty = true;
+			c->hasContent[slots[k]] = 1;
+			c->hostInvalid[slots[k]] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
+		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // host staging (`slots`, possibly pageable sources) must outlive the copies
+		return TSOM_OK;
+	}
+
 	static int ResetCommon(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const void* src, cudaMemcpyKind kind)
 	{
 		if (!c || !chunk_indices || !src)
@@ -809,18 +834,7 @@ extern "C"
 		}
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-		tsomk::launch_build_xslabs(c->dBlocks, c->dXslabs, ctx->jobSlot.ptr, n, ctx->stream);
-		ctx->launches += n ? 1 : 0;
-		TSOM_CUDA(cudaGetLastError());
-		for (uint32_t k = 0; k < n; ++k)
-		{
-			if (!c->hasContent[slots[k]])
-				c->topoDirty = true;
-			c->hasContent[slots[k]] = 1;
-			c->hostInvalid[slots[k]] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
-		}
-		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // `slots` and possibly pageable `src` must outlive the copies
-		return TSOM_OK;
+		return FinishReset(c, slots);
 	}
 
 	int tsom_chunks_reset(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint16_t* blocks_host)
@@ -831,6 +845,80 @@ extern "C"
 	int tsom_chunks_reset_device(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const void* blocks_device)
 	{
 		return ResetCommon(c, chunk_indices, n, blocks_device, cudaMemcpyDeviceToDevice);
+	}
+
+	int tsom_chunks_palettize(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint16_t* palette_out, uint32_t palette_stride, uint32_t* palette_counts_out,
+	                          uint8_t* payload_out, int payload_big_endian)
+	{
+		if (!c || !chunk_indices || !palette_out || !palette_counts_out || !payload_out || palette_stride == 0)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			slots[i] = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+			if (slots[i] == 0xFFFFFFFFu || !c->hasContent[slots[i]])
+				return Fail(TSOM_ERR_INVALID, "chunk is unknown or has no content");
+		}
+		TSOM_CUDA(ctx->jobSlot.Ensure(n));
+		TSOM_CUDA(ctx->ioPayload.Ensure(size_t(n) * NB * 2));
+		TSOM_CUDA(ctx->ioPalette.Ensure(size_t(n) * palette_stride));
+		TSOM_CUDA(ctx->ioCounts.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_palettize(c->dBlocks, ctx->jobSlot.ptr, n, ctx->ioPalette.ptr, palette_stride, ctx->ioCounts.ptr, ctx->ioPayload.ptr, payload_big_endian, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(palette_counts_out, ctx->ioCounts.ptr, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(palette_out, ctx->ioPalette.ptr, size_t(n) * palette_stride * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(payload_out, ctx->ioPayload.ptr, size_t(n) * NB * 2, cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (uint32_t i = 0; i < n; ++i)
+			if (palette_counts_out[i] > palette_stride)
+				return Fail(TSOM_ERR_CAPACITY, "a chunk has more distinct block types than palette_stride");
+		return TSOM_OK;
+	}
+
+	int tsom_chunks_reset_palettized(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint16_t* palettes, uint32_t palette_stride, const uint32_t* palette_counts,
+	                                 const uint8_t* payload, int payload_big_endian)
+	{
+		if (!c || !chunk_indices || !palettes || !palette_counts || !payload || palette_stride == 0)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		for (uint32_t i = 0; i < n; ++i)
+			if (palette_counts[i] == 0 || palette_counts[i] > palette_stride)
+				return Fail(TSOM_ERR_INVALID, "palette count must be in [1, palette_stride]");
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		TSOM_CUDA(ctx->jobSlot.Ensure(n));
+		TSOM_CUDA(ctx->ioPayload.Ensure(size_t(n) * NB * 2));
+		TSOM_CUDA(ctx->ioPalette.Ensure(size_t(n) * palette_stride));
+		TSOM_CUDA(ctx->ioCounts.Ensure(n));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->ioCounts.ptr, palette_counts, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->ioPalette.ptr, palettes, size_t(n) * palette_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->ioPayload.ptr, payload, size_t(n) * NB * 2, cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 7, 0, sizeof(uint32_t), ctx->stream));
+		tsomk::launch_depalettize(c->dBlocks, ctx->jobSlot.ptr, n, ctx->ioPalette.ptr, palette_stride, ctx->ioCounts.ptr, ctx->ioPayload.ptr, payload_big_endian, ctx->dSmall + 7, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall + 7, ctx->dSmall + 7, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		int rc = FinishReset(c, slots);
+		if (rc != TSOM_OK)
+			return rc;
+		if (ctx->hSmall[7] != 0)
+			return Fail(TSOM_ERR_INVALID, "a payload index is out of its chunk's palette (malformed chunk data); such blocks were set to Empty");
+		return TSOM_OK;
 	}
 
 	int tsom_chunks_get_content(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint16_t* blocks_host)

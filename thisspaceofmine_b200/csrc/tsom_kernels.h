@@ -121,6 +121,11 @@ namespace tsomk
 	// FlatChunk greedy box collider; boxes = [cap][6] floats, count = number found (may exceed cap)
 	void launch_box_collider(const uint16_t* chunkBlocks, const uint8_t* blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count, cudaStream_t st);
 
+	// ---- save format: palette + per-block palette indices (payload stride 65536 bytes per chunk) ----
+	void launch_palettize(const uint16_t* blocks, const uint32_t* slots, uint32_t n, uint16_t* palette, uint32_t stride, uint32_t* counts, uint8_t* payload, int bigEndian, cudaStream_t st);
+	void launch_depalettize(uint16_t* blocks, const uint32_t* slots, uint32_t n, const uint16_t* palette, uint32_t stride, const uint32_t* counts, const uint8_t* payload, int bigEndian,
+	                        uint32_t* errFlag, cudaStream_t st);
+
 	// ---- multi-GPU halo pull ----
 	struct GhostDesc
 	{

@@ -285,7 +285,8 @@ class ChunkContainer:
 
     def close(self):
         if self._h:
-            L.lib().tsom_container_destroy(self._h)
+            if self.ctx._h:  # a container must not outlive its context; if it did, its device memory went with the context
+                L.lib().tsom_container_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -354,6 +355,69 @@ class ChunkContainer:
         out = np.empty((len(idx), ChunkBlockCount), np.uint16)
         L.check(L.lib().tsom_chunks_get_content(self._h, _p(idx, C.c_int32), len(idx), _p(out, C.c_uint16)))
         return out
+
+    # ---- save format (Chunk::Serialize / Chunk::Deserialize, Chunk.cpp:252-346)
+    ChunkBinaryVersion = 1  # include/CommonLib/InternalConstants.hpp:24
+
+    def SerializeChunks(self, indices, blockLibrary: "BlockLibrary") -> list:
+        """Chunk::Serialize for a batch -> one bytes object per chunk, byte for byte what the reference writes to `<x>_<y>_<z>.chunk`.
+        The device produces the palette and the per-block palette indices; the header (version, size, block NAMES) is composed here.
+        Stream conventions (Nazara ByteStream, restated in oracle/ref_shim): big-endian integers, string = UInt32 length + bytes."""
+        import struct
+
+        idx = _idx(indices)
+        n = len(idx)
+        stride = len(blockLibrary)
+        pal = np.zeros((n, stride), np.uint16)
+        cnt = np.zeros(n, np.uint32)
+        payload = np.zeros((n, 2 * ChunkBlockCount), np.uint8)
+        L.check(L.lib().tsom_chunks_palettize(self._h, _p(idx, C.c_int32), n, _p(pal, C.c_uint16), stride, _p(cnt, C.c_uint32), _p(payload, C.c_uint8), 1))
+        out = []
+        for i in range(n):
+            k = int(cnt[i])
+            head = struct.pack(">IIIIH", self.ChunkBinaryVersion, ChunkSize, ChunkSize, ChunkSize, k)
+            for b in pal[i, :k]:
+                name = blockLibrary.GetBlockData(int(b)).name.encode()
+                head += struct.pack(">I", len(name)) + name
+            out.append(head + payload[i, : ChunkBlockCount * (2 if k > 8 else 1)].tobytes())
+        return out
+
+    def DeserializeChunks(self, indices, blobs, blockLibrary: "BlockLibrary"):
+        """Chunk::Deserialize for a batch: parse the headers (same exceptions as the reference), expand the payloads on the device."""
+        import struct
+
+        idx = _idx(indices)
+        n = len(idx)
+        assert n == len(blobs)
+        stride = max(len(blockLibrary), 1)
+        pal = np.zeros((n, stride), np.uint16)
+        cnt = np.zeros(n, np.uint32)
+        payload = np.zeros((n, 2 * ChunkBlockCount), np.uint8)
+        for i, blob in enumerate(blobs):
+            if len(blob) < 18:
+                raise RuntimeError("ByteStream: read past end")
+            version, sx, sy, sz, k = struct.unpack_from(">IIIIH", blob, 0)
+            if version != self.ChunkBinaryVersion:
+                raise RuntimeError("incompatible chunk version")
+            if (sx, sy, sz) != (ChunkSize,) * 3:
+                raise RuntimeError("incompatible chunk size")
+            cur = 18
+            if k > stride:
+                raise RuntimeError("more block types than the library holds")
+            for j in range(k):
+                (ln,) = struct.unpack_from(">I", blob, cur)
+                name = blob[cur + 4: cur + 4 + ln].decode(errors="replace")
+                cur += 4 + ln
+                b = blockLibrary.GetBlockIndex(name)
+                if b == InvalidBlockIndex:
+                    raise RuntimeError("unknown block " + name)
+                pal[i, j] = b
+            need = ChunkBlockCount * (2 if k > 8 else 1)
+            if len(blob) - cur < need:
+                raise RuntimeError("ByteStream: read past end")
+            payload[i, :need] = np.frombuffer(blob, np.uint8, need, cur)
+            cnt[i] = k
+        L.check(L.lib().tsom_chunks_reset_palettized(self._h, _p(idx, C.c_int32), n, _p(pal, C.c_uint16), stride, _p(cnt, C.c_uint32), _p(payload, C.c_uint8), 1))
 
     # ---- edits
     def UpdateBlocks(self, edits: np.ndarray):
