@@ -388,6 +388,10 @@ def run_b200(args):
                 out["planet"] = planet_bench(T, ctx, args.planet)
             except Exception as e:  # secondary measurement: never lose the headline line
                 out["planet"] = {"error": str(e)}
+            try:
+                out["default_planet"] = default_planet_bench(T, ctx, not args.no_cpu)
+            except Exception as e:
+                out["default_planet"] = {"error": str(e)}
     if args.planet and world > 1:
         # BASELINE configs 3 / 5: ONE planet sharded by chunk index over the ranks (strong scaling), halo slabs over NVLink P2P
         try:
@@ -435,6 +439,37 @@ def planet_bench(T, ctx, count):
                gen_gbs=n * 65536 / (g / 1e3) / 1e9, gen_frac=n * 65536 / (g / 1e3) / 1e9 / peak,
                mesh_gbs=mesh_bytes / ((c + s + e) / 1e3) / 1e9, mesh_frac=mesh_bytes / ((c + s + e) / 1e3) / 1e9 / peak)
     planet.close()
+    return res
+
+
+def default_planet_bench(T, ctx, with_cpu):
+    """BASELINE config[0]: the default serverconfig spawn planet (seed 42, 5x5x5 chunks, src/Server/main.cpp:62,
+    src/ServerLib/ServerPlanetEnvironment.cpp:49-59): generate + mesh every chunk, as server and client do at start-up.
+    GPU: wall clock around GenerateChunks + BuildMeshes through the C ABI (125 chunks: launch-latency bound).
+    CPU: the reference's own Planet::GenerateChunks + Chunk::BuildMesh for every chunk on all host threads (oracle/_ref)."""
+    cc = (5, 5, 5)
+    planet = T.Planet(ctx, capacity=125)
+    grid = T.Planet.chunk_grid(cc)
+    lib = ctx.blockLibrary
+    planet.GenerateChunks(lib, 42, cc)
+    faces = planet.BuildMeshes(grid, views=True).total_faces
+    times = []
+    for _ in range(20):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        planet.GenerateChunks(lib, 42, cc)
+        planet.BuildMeshes(grid, views=False)
+        ctx.synchronize()
+        times.append(time.perf_counter() - t0)
+    planet.close()
+    sec = statistics.median(times)
+    res = {"chunk_count": list(cc), "chunks": 125, "faces": int(faces), "gpu_gen_plus_mesh_ms": sec * 1e3, "gpu_chunks_per_s": 125 / sec}
+    if with_cpu:
+        O, kind = cpu_arm()
+        threads = host_threads()
+        r = min((O.bench_planet(42, cc, threads) for _ in range(3)), key=lambda d: d["gen_s"] + d["mesh_s"])
+        res["cpu_baseline"] = {"kind": kind, "cores": threads, "gen_ms": r["gen_s"] * 1e3, "mesh_ms": r["mesh_s"] * 1e3,
+                               "chunks_per_s": 125 / (r["gen_s"] + r["mesh_s"]), "faces": r["faces"]}
     return res
 
 
