@@ -183,7 +183,8 @@ def cpu_mesh_rate(target_seconds):
     n = max(threads, (n // threads) * threads)
     blocks = cpu_sample(n)
     t, faces = O.bench_mesh_isolated(blocks, threads)
-    return dict(value=n / t, seconds=t, chunks=n, faces=faces, threads=threads, kind=kind)
+    t1, _ = O.bench_mesh_isolated(cpu_sample(8), 1)  # the same code on one thread, for the per-core picture
+    return dict(value=n / t, seconds=t, chunks=n, faces=faces, threads=threads, kind=kind, value_1thread=8 / t1)
 
 
 def run_reference(args):
@@ -375,13 +376,13 @@ def run_b200(args):
                     "note": "tsom_chunks_reset (pinned host ids) + tsom_mesh + tsom_mesh_copy_to_host (pinned host vertices+indices), 256-chunk sub-batches"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mesh_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": "mesh_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "frac_of_nominal_8000": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": emit, "traffic": ncu_traffic(n)},
             "kernels_ms": {"mesh_count": sum(count_ms) / len(count_ms), "mesh_scan": sum(scan_ms) / len(scan_ms), "mesh_emit": emit},
         }
         if not args.no_cpu and world == 1:
             c = cpu_mesh_rate(args.cpu_seconds)
-            out["cpu_baseline"] = {"value": c["value"], "unit": "chunks/s", "cores": c["threads"], "kind": c["kind"],
+            out["cpu_baseline"] = {"value": c["value"], "unit": "chunks/s", "cores": c["threads"], "kind": c["kind"], "value_1thread": c["value_1thread"],
                                    "sample": f"first {c['chunks']} of the 4096 chunks ({c['faces']} faces) in {c['seconds']:.1f} s, {CPU_KIND_NOTE[c['kind']]} with normals+uv, one task per chunk"}
         if args.planet and world == 1:
             try:
@@ -392,6 +393,15 @@ def run_b200(args):
                 out["default_planet"] = default_planet_bench(T, ctx, not args.no_cpu)
             except Exception as e:
                 out["default_planet"] = {"error": str(e)}
+            try:
+                # BASELINE config[3]: 10 k random place/break ops per tick on the 31^3 planet, remesh dirty chunks + neighbours
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_edits
+
+                ea = argparse.Namespace(edge=args.planet, edits=10000, ticks=60, warmup=5, cpu_ticks=0 if args.no_cpu else 1, seed=42)
+                out["edits"] = bench_edits.run(T, ctx, ea)
+            except Exception as e:
+                out["edits"] = {"error": str(e)}
     if args.planet and world > 1:
         # BASELINE configs 3 / 5: ONE planet sharded by chunk index over the ranks (strong scaling), halo slabs over NVLink P2P
         try:

@@ -34,21 +34,10 @@ def make_edits(rng, grid, n):
     return e
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--edge", type=int, default=5)
-    ap.add_argument("--edits", type=int, default=10000)
-    ap.add_argument("--ticks", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--cpu-ticks", type=int, default=3)
-    ap.add_argument("--seed", type=int, default=42)
-    args = ap.parse_args()
-
-    import thisspaceofmine_b200 as T
-
+def run(T, ctx, args):
+    """The measurement itself, on an existing context (bench.py calls it for its `edits` sub-object)."""
     cc = (args.edge,) * 3
     n = args.edge ** 3
-    ctx = T.Context(0)
     planet = T.Planet(ctx, capacity=n)
     planet.GenerateChunks(ctx.blockLibrary, args.seed, cc)
     grid = T.Planet.chunk_grid(cc)
@@ -106,7 +95,24 @@ def main():
             cpu.append((time.perf_counter() - t0) * 1e3)
         out["cpu_baseline"] = {"tick_ms_mean": float(np.mean(cpu)), "ticks": args.cpu_ticks, "cores": threads, "kind": kind,
                                "note": "apply edits + dirty set + Chunk::BuildMesh (render attributes; no collider pass) per dirty chunk, results copied out through ctypes"}
-    print(json.dumps(out))
+    planet.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--edge", type=int, default=5)
+    ap.add_argument("--edits", type=int, default=10000)
+    ap.add_argument("--ticks", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--cpu-ticks", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=42)
+    args = ap.parse_args()
+
+    import thisspaceofmine_b200 as T
+
+    ctx = T.Context(0)
+    print(json.dumps(run(T, ctx, args)))
 
 
 if __name__ == "__main__":
