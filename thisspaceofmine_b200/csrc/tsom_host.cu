@@ -507,7 +507,7 @@ namespace
 		auto grow = [&](auto*& ptr, uint64_t& cap, size_t bytesPerFace) -> int {
 			if (faces <= cap)
 				return TSOM_OK;
-			uint64_t want = std::max<uint64_t>(faces, cap + cap / 2);
+			uint64_t want = std::max<uint64_t>(faces, 2 * cap); // geometric growth: a reallocation costs tens of ms
 			if (ptr)
 				cudaFree(ptr);
 			ptr = nullptr;
@@ -1231,7 +1231,23 @@ extern "C"
 				dirty.push_back(c->idxOf[ns]);
 			}
 		}
-		std::sort(dirty.begin(), dirty.end());
+		c->EnsureHostGrid();
+		if (c->hostGridUsable && dirty.size() * 8 > c->hostGrid.size())
+		{
+			// many dirty chunks: emit them in (x, y, z) order by walking the dense slot grid with x outermost instead of sorting
+			dirty.clear();
+			const size_t nx = size_t(c->gridDim[0]), ny = size_t(c->gridDim[1]), nz = size_t(c->gridDim[2]);
+			for (size_t x = 0; x < nx; ++x)
+				for (size_t y = 0; y < ny; ++y)
+					for (size_t z = 0; z < nz; ++z)
+					{
+						const uint32_t s = c->hostGrid[(z * ny + y) * nx + x];
+						if (s != 0xFFFFFFFFu && seen[s])
+							dirty.push_back(c->idxOf[s]);
+					}
+		}
+		else
+			std::sort(dirty.begin(), dirty.end());
 		*n_out = uint32_t(dirty.size());
 		if (chunk_indices_out)
 		{
