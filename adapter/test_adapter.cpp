@@ -178,6 +178,20 @@ static void TestGpu()
 	CHECK(after[victim] == EmptyBlockIndex);
 	CHECK(planet.CollectInvalidatedChunks().empty());
 
+	// per-tick glue: two edits in different chunks -> one Update() rebuilds both (and only dirty chunks), then nothing is left
+	{
+		std::size_t applied = 0, facesSeen = 0;
+		MeshOptions opt;
+		opt.collider = true;
+		ChunkEntities entities(planet, opt, [&](const ChunkIndices&, const MeshBatch& b, std::size_t i) { ++applied; facesSeen += b.FaceCount(i); });
+		planet.UpdateBlocks({ { ChunkIndices(0, 1, 0), Vector3ui(5, 5, 5), lib.GetBlockIndex("glass") }, { ChunkIndices(1, 0, 0), Vector3ui(0, 7, 7), EmptyBlockIndex } });
+		const std::size_t n = entities.Update();
+		CHECK(n >= 2 && n <= 4); // the two chunks + the Left neighbour of the x == 0 edit
+		CHECK(applied == n && facesSeen > 0);
+		CHECK(entities.Update() == 0);
+		after = chunk.GetContent();
+	}
+
 	// save format: serialize -> deserialize into another chunk -> same ids; a corrupted version is rejected like the reference does
 	{
 		auto bytes = chunk.Serialize(lib);

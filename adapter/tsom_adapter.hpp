@@ -523,6 +523,40 @@ namespace tsom_b200
 			float m_gravity;
 	};
 
+	// ------------------------------------------------------------------------------------------------ ChunkEntities
+	// ChunkEntities::Update (src/CommonLib/ChunkEntities.cpp:73-112) + ClientChunkEntities::ProcessChunkUpdate
+	// (src/ClientLib/ClientChunkEntities.cpp:178-262).  The reference turns every invalidated chunk into collider / mesh tasks and
+	// applies a finished job only when the jobs of its neighbour dependencies have finished too, so that a chunk and its
+	// neighbours never show meshes of different block states.  Here all chunks of a tick are rebuilt from ONE snapshot of the
+	// block store by one launch, so the dependency rule holds by construction: `apply` sees every chunk of the tick at once.
+	class ChunkEntities
+	{
+		public:
+			using ApplyFunc = std::function<void(const ChunkIndices& chunkIndices, const MeshBatch& batch, std::size_t indexInBatch)>;
+
+			ChunkEntities(ChunkContainer& container, MeshOptions options, ApplyFunc apply) :
+			m_container(&container), m_options(options), m_apply(std::move(apply))
+			{
+			}
+
+			// returns the number of chunks rebuilt this tick
+			std::size_t Update()
+			{
+				std::vector<ChunkIndices> dirty = m_container->CollectInvalidatedChunks();
+				if (dirty.empty())
+					return 0;
+				MeshBatch batch = m_container->BuildMeshes(dirty, m_options);
+				for (std::size_t i = 0; i < dirty.size(); ++i)
+					m_apply(dirty[i], batch, i); // faces == 0: the reference destroys the mesh / collider (null mesh, ClientChunkEntities.cpp:161-162)
+				return dirty.size();
+			}
+
+		private:
+			ChunkContainer* m_container;
+			MeshOptions m_options;
+			ApplyFunc m_apply;
+	};
+
 	// ------------------------------------------------------------------------------------------------ Chunk members
 	inline void Chunk::BuildMesh(std::vector<std::uint32_t>& indices, const Vector3f& center, const std::function<VertexAttributes(std::uint32_t count)>& addVertices) const
 	{
