@@ -253,6 +253,7 @@ namespace tsom_b200
 		bool collider = false;               // positions only
 		CornerMode corners = CornerMode::Flat;
 		float deformRadius = 0.f;            // Planet::GetCornerRadius() for DeformedChunk
+		bool ordered = false;                // arena ranges in job order (TSOM_MESH_ORDERED); default: first come, first served
 		const Vector3f* gravityCenters = nullptr; // per chunk `center` argument of Chunk::BuildMesh; null = GetCenter() - GetChunkOffset(chunk)
 	};
 
@@ -422,7 +423,8 @@ namespace tsom_b200
 				batch.m_ctx = m_device->Handle();
 				batch.views.resize(chunks.size());
 				tsom_mesh_params p{};
-				p.flags = (opt.render ? std::uint32_t(TSOM_MESH_RENDER) : 0u) | (opt.collider ? std::uint32_t(TSOM_MESH_COLLIDER) : 0u) | (opt.corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u);
+				p.flags = (opt.render ? std::uint32_t(TSOM_MESH_RENDER) : 0u) | (opt.collider ? std::uint32_t(TSOM_MESH_COLLIDER) : 0u) | (opt.corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u) |
+				          (opt.ordered ? std::uint32_t(TSOM_MESH_ORDERED) : 0u);
 				p.deform_radius = opt.deformRadius;
 				p.gravity_centers = opt.gravityCenters ? &opt.gravityCenters->x : nullptr;
 				if (!chunks.empty())

@@ -51,7 +51,9 @@ enum
 	TSOM_MESH_RENDER = 1,   /* 48-byte vertices + indices: ClientChunkEntities::BuildMesh (src/ClientLib/ClientChunkEntities.cpp:141-176) */
 	TSOM_MESH_COLLIDER = 2, /* positions only + the same indices: DeformedChunk::BuildCollider (src/CommonLib/DeformedChunk.cpp:15-36) */
 	TSOM_MESH_DEFORMED = 4, /* corner provider DeformedChunk::ComputeVoxelCorners (DeformedChunk.cpp:115-154) instead of FlatChunk (FlatChunk.cpp:48-54) */
-	TSOM_MESH_GENERIC_MATH = 8 /* diagnostics: evaluate DrawFace's float math per face even where the exact table-driven flat path applies */
+	TSOM_MESH_GENERIC_MATH = 8, /* diagnostics: evaluate DrawFace's float math per face even where the exact table-driven flat path applies */
+	TSOM_MESH_ORDERED = 16 /* place the chunks' face ranges in the arenas in job order (first_face[i] = sum of face_count[< i]) instead of
+	                          first come, first served; costs a cross-chunk dependency (decoupled look-back) in the kernel */
 };
 
 typedef struct tsom_ctx tsom_ctx;             /* one per process and GPU: stream, block table, mesh arenas */
@@ -195,8 +197,9 @@ int tsom_collect_dirty(tsom_container* c, int32_t* chunk_indices_out, uint32_t c
 
 /* ---- meshing ---- */
 /* Chunk::BuildMesh (src/CommonLib/Chunk.cpp:20-250) for n chunks in ONE batch (chunk_indices NULL: every chunk with
- * content, container order).  Results land in the context's device arenas, face lists dense and in the reference's
- * order; views_out (host, n entries, optional) tells where each chunk's faces are.  Chunks without content get 0 faces. */
+ * content, container order).  Results land in the context's device arenas: every chunk gets one contiguous face range, its
+ * faces in the reference's emission order; the ranges tile [0, total_faces) in no particular order unless TSOM_MESH_ORDERED is
+ * set.  views_out (host, n entries, optional) tells where each chunk's faces are.  Chunks without content get 0 faces. */
 int tsom_mesh(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, tsom_mesh_view* views_out);
 /* device arenas of the last tsom_mesh call on this context */
 int tsom_mesh_arenas(tsom_ctx* ctx, const void** vertices, const void** indices, const void** collider_positions, uint64_t* total_faces);

@@ -157,9 +157,20 @@ def test_batch_order_and_views(ctx):
     chunks = {(2 * i, 0, 0): random_chunk(rng, 0.1 * (i + 1)) for i in range(6)}
     gc, op = _pair(ctx, chunks)
     order = list(chunks)[::-1]
-    batch = gc.BuildMeshes(order)
+    batch = gc.BuildMeshes(order, ordered=True)  # TSOM_MESH_ORDERED: ranges in job order
     assert batch.first_faces[0] == 0
     assert np.array_equal(batch.first_faces[1:], np.cumsum(batch.face_counts.astype(np.uint64))[:-1])
+    for i, idx in enumerate(order):
+        assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"{idx}")
+    # default: first come, first served — the ranges still tile [0, total) without gaps or overlaps
+    batch = gc.BuildMeshes(order)
+    o = np.argsort(batch.first_faces, kind="stable")
+    nz = [i for i in o if batch.face_counts[i] > 0]
+    ends = 0
+    for i in nz:
+        assert batch.first_faces[i] == ends
+        ends += int(batch.face_counts[i])
+    assert ends == batch.total_faces == ctx.arenas()[3]
     for i, idx in enumerate(order):
         assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"{idx}")
 
@@ -221,3 +232,22 @@ def test_hidden_faces_appear_after_edits_resets_and_removals(ctx):
     for i, idx in enumerate(present):
         assert_mesh_equal(batch.chunk(i), op.mesh(idx), what=f"after removal {idx}")
     assert batch.face_counts[present.index((0, 0, 0))] == 1 + 2 * 32 * 32
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+def test_views_are_valid_when_the_arenas_had_to_grow(ordered):
+    """A fresh context has tiny arenas: the first call only counts, grows them and runs again.  With first-come placement the
+    second run places the chunks elsewhere than the first, so the views must come from the second run."""
+    c2 = T.Context(0)
+    try:
+        rng = np.random.default_rng(99)
+        chunks = {(2 * i, 0, 0): random_chunk(rng, 0.5) for i in range(40)}
+        gc, op = _pair(c2, chunks)
+        keys = list(chunks)
+        batch = gc.BuildMeshes(keys, ordered=ordered)
+        assert c2.timings()["mesh_reemit"]
+        for i, idx in enumerate(keys):
+            assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"{idx}")
+        gc.close()
+    finally:
+        c2.close()

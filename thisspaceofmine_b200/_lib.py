@@ -14,7 +14,7 @@ SO_PATH = os.path.join(_HERE, "libtsom_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CAPACITY = range(6)
-MESH_RENDER, MESH_COLLIDER, MESH_DEFORMED, MESH_GENERIC_MATH = 1, 2, 4, 8
+MESH_RENDER, MESH_COLLIDER, MESH_DEFORMED, MESH_GENERIC_MATH, MESH_ORDERED = 1, 2, 4, 8, 16
 
 
 class TsomError(RuntimeError):

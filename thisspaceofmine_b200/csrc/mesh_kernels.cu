@@ -819,6 +819,7 @@ namespace tsomk
 		const LaneConst lc = lane_constants(lane);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
+		const bool ordered = (a.flags & MESH_F_ORDERED) != 0; // arena slices in job order (look-back) instead of first come, first served
 		__syncthreads();
 
 		if (tid == 0)
@@ -904,13 +905,29 @@ namespace tsomk
 
 			__syncthreads(); // ne[] is complete; sm.job has been read by everyone
 
-			// ---- chain the chunk into the arena: decoupled look-back over the jobs before this one (warp 0; the other warps
+			// Unordered mode: no chunk waits on another, so the next ticket (and the two dependent loads behind it) can be taken
+			// now and its latency hides behind this chunk's emission.  (In ordered mode a ticket held during an emission would
+			// delay that job's aggregate and stall the look-back of every later job: there the last finishing warp takes it.)
+			if (!ordered && tid == 32)
+				take_ticket(a, sm);
+
+			// ---- place the chunk in the arena.  Ordered mode: decoupled look-back over the jobs before this one (warp 0; the other warps
 			// already build their first descriptor window and pick firstFace up when they are about to store)
 			unsigned long long firstFace = 0ull;
 			bool haveFirst = false;
 			if (warp == 0)
 			{
-				const unsigned long long excl = chain_lookback<1>(a.status, job, F, lane);
+				unsigned long long excl;
+				if (ordered)
+					excl = chain_lookback<1>(a.status, job, F, lane);
+				else
+				{
+					// first come, first served: one atomic on the arena cursor, no dependency on any other chunk
+					excl = 0ull;
+					if (lane == 0 && F > 0)
+						excl = atomicAdd(a.totalFacesOut, static_cast<unsigned long long>(F));
+					excl = __shfl_sync(FULL, excl, 0);
+				}
 				if (lane == 0)
 				{
 					sm.firstFace = excl;
@@ -918,7 +935,7 @@ namespace tsomk
 					*reinterpret_cast<volatile uint32_t*>(&sm.ffSeq) = job + 1u;
 					a.faceCount[job] = F;
 					a.firstFaceOut[job] = excl;
-					if (job == a.nJobs - 1u)
+					if (ordered && job == a.nJobs - 1u)
 						*a.totalFacesOut = excl + F;
 					if (F > 0 && excl + F > a.arenaFaces)
 						atomicExch(a.overflow, 1u);
@@ -969,7 +986,7 @@ namespace tsomk
 			// next ticket: taken by the LAST warp to finish this chunk, so no extra CTA barrier is needed — and not earlier: a
 			// ticket held during an emission delays this job's aggregate and with it the look-back of every later job (measured).
 			__syncwarp();
-			if (lane == 0)
+			if (ordered && lane == 0)
 			{
 				__threadfence_block();
 				if (atomicAdd(&sm.warpsDone, 1u) == FUSED_WARPS - 1)

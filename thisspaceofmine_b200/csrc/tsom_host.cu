@@ -1397,13 +1397,16 @@ extern "C"
 		if (ctx->hSmall[3] != 0)
 		{
 			ctx->timings[TSOM_TIMING_MESH_REEMIT] = 1.f;
-			// arenas were too small: grow to the exact need and emit again (counts and offsets are still valid)
+			// arenas were too small: the first launch only counted.  Grow to the exact need and run again; the face counts are
+			// the same, the first faces are not (unordered placement is first come, first served), so read the views again.
 			if ((rc = EnsureArenas(ctx, total, flags)) != TSOM_OK)
 				return rc;
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 1, 0, sizeof(uint32_t), ctx->stream));
-			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, sizeof(uint32_t), ctx->stream));
+			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, 3 * sizeof(uint32_t), ctx->stream)); // overflow flag + the 64-bit arena cursor / total
 			TSOM_CUDA(launchFused());
 			TSOM_CUDA(cudaGetLastError());
+			if (views_out)
+				TSOM_CUDA(cudaMemcpyAsync(hFirst, ctx->firstFace.ptr, size_t(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		}
 		ctx->totalFaces = total;

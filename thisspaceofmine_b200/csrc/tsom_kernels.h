@@ -7,7 +7,7 @@
 
 namespace tsomk
 {
-	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u, MESH_F_GENERIC = 8u };
+	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u, MESH_F_GENERIC = 8u, MESH_F_ORDERED = 16u };
 
 	// per-(faceUp, slot, twin) face attributes of a FlatChunk with a power-of-two block size (see mesh_kernels.cu)
 	struct FaceTable
@@ -36,7 +36,7 @@ namespace tsomk
 		uint32_t* jobCounter;                  // work-stealing ticket, zeroed before each launch
 		unsigned long long* status;            // [nJobs] (flag << 62) | faces, zeroed before each launch
 		unsigned long long* firstFaceOut;      // [nJobs]
-		unsigned long long* totalFacesOut;     // inclusive prefix of the last job
+		unsigned long long* totalFacesOut;     // total faces; also the arena cursor of the unordered mode (zeroed before each launch)
 		// arenas
 		float4* vertices;
 		uint2* indices;

@@ -441,9 +441,9 @@ class ChunkContainer:
 
     # ---- meshing
     def BuildMeshes(self, indices=None, render: bool = True, collider: bool = False, deformed: bool = False, deformRadius: float = 0.0,
-                    gravityCenters: Optional[np.ndarray] = None, views: bool = True, genericMath: bool = False) -> MeshBatch:
-        """Chunk::BuildMesh for a whole batch in one call (one count + scan + emit kernel sequence)."""
-        flags = (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0) | (L.MESH_DEFORMED if deformed else 0) | (L.MESH_GENERIC_MATH if genericMath else 0)
+                    gravityCenters: Optional[np.ndarray] = None, views: bool = True, genericMath: bool = False, ordered: bool = False) -> MeshBatch:
+        """Chunk::BuildMesh for a whole batch in one call (one mesh_fused_kernel launch).  `ordered`: arena ranges in job order."""
+        flags = (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0) | (L.MESH_DEFORMED if deformed else 0) | (L.MESH_GENERIC_MATH if genericMath else 0) | (L.MESH_ORDERED if ordered else 0)
         params = L.MeshParams(flags, float(deformRadius), None)
         g = None
         if gravityCenters is not None:
