@@ -42,6 +42,28 @@ def test_generate_chunks_bit_exact(ctx, seed, count):
     _assert_blocks_equal(gp, op, T.Planet.chunk_grid(count))
 
 
+def test_bernoulli_tie_where_the_first_engine_output_decides(ctx):
+    """std::bernoulli_distribution(0.9) over std::minstd_rand burns two engine outputs u1, u2 per draw and is decided by u2 alone
+    (stone iff u2 - 1 < 1932735281) except when u2 - 1 == 1932735281, where u1 decides (about once in 2^31 draws; the kernel's slow
+    path).  Since u2 = x0 * 48271^(2n+2) mod (2^31 - 1), a seed can be solved for that puts the tie on a chosen draw n: here draw
+    5367 of every chunk whose indices sum to 0 — (0,0,0) (every block draws: the full-draw loop), (1,0,-1) (31 of 32 rows draw, whole
+    8-block groups) and (-1,0,1) (31 of 32 columns draw: the mixed group).  With u1 = u2 / 48271 the tie resolves to stone_mossy, the
+    opposite of what the sign of the u2 comparison alone would give."""
+    M, A, K = 2147483647, 48271, 1932735282
+    n = 5 * 1024 + 7 * 32 + 20
+    seed = K * pow(pow(A, -1, M), 2 * n + 2, M) % M
+    assert seed == 786579212
+    x = seed
+    for _ in range(2 * n + 2):
+        x = x * A % M
+    assert x == K  # the tie is really there
+    count = (5, 5, 5)
+    gp, op = _planets(ctx, seed, count)
+    lib = ctx.blockLibrary
+    assert op.get_blocks((0, 0, 0))[n] == lib.GetBlockIndex("stone_mossy")
+    _assert_blocks_equal(gp, op, T.Planet.chunk_grid(count))
+
+
 def test_default_planet_with_platforms_and_meshes(ctx):
     """BASELINE config 1/3: seed 42, 5x5x5, the 4 GeneratePlatform scripts, then every chunk meshed with real neighbours."""
     count = (5, 5, 5)

@@ -86,14 +86,32 @@ namespace tsomk
 	//   Right/Left : A = world Y (up, local z), B = world Z (local y); i = local y, j = local z; noise(a = wy, b = wz)
 	//   Up/Down    : A = world X (local x),     B = world Z (local y); i = local x, j = local y; noise(a = wx, b = wz)
 	//   Back/Front : A = world X (local x),     B = world Y (local z); i = local x, j = local z; noise(a = wx, b = wy)
-	__global__ void __launch_bounds__(1024) terrain_kernel(const TerrainArgs a, int dir, int nA, int nB, int axA, int axB, int axH)
+	// One launch for the six directions: the tiles of direction d are the blocks [terrainOffset[d] / 1024, terrainOffset[d + 1] / 1024).
+	__global__ void __launch_bounds__(1024) terrain_kernel(const TerrainArgs a)
 	{
+		// axis ids: 0 = world X, 1 = world Y (up), 2 = world Z
+		int dir = 0;
+		size_t dirOffset = a.terrainOffset[0];
+#pragma unroll
+		for (int d = 1; d < 6; ++d)
+			if (size_t(blockIdx.x) >= a.terrainOffset[d] / SLAB)
+			{
+				dir = d;
+				dirOffset = a.terrainOffset[d];
+			}
+		// selects, not indexing: a dynamically indexed kernel parameter would be copied to local memory
+		const bool sideX = dir == D_RIGHT || dir == D_LEFT, sideY = dir == D_UP || dir == D_DOWN;
+		const int nA = sideX ? a.tileCount[1] : a.tileCount[0];
+		const int originA = sideX ? a.tileOrigin[1] : a.tileOrigin[0];
+		const int originB = (sideX || sideY) ? a.tileOrigin[2] : a.tileOrigin[1];
+		const int maxHAxis = sideX ? a.maxH[0] : (sideY ? a.maxH[1] : a.maxH[2]);
+
 		__shared__ uint8_t perm[256];
 		if (threadIdx.x < 256)
 			perm[threadIdx.x] = a.perm[dir * 256 + threadIdx.x];
 		__syncthreads();
 
-		const int tile = blockIdx.x;
+		const int tile = int(size_t(blockIdx.x) - dirOffset / SLAB);
 		const int ta = tile % nA, tb = tile / nA;
 		const int i = threadIdx.x & 31, j = threadIdx.x >> 5;
 
@@ -101,13 +119,13 @@ namespace tsomk
 		int wa, wb;
 		if (dir == D_RIGHT || dir == D_LEFT)
 		{
-			wa = (a.tileOrigin[axA] + ta) * CS + j - CS / 2; // world Y from local z = j
-			wb = (a.tileOrigin[axB] + tb) * CS + i - CS / 2; // world Z from local y = i
+			wa = (originA + ta) * CS + j - CS / 2; // world Y from local z = j
+			wb = (originB + tb) * CS + i - CS / 2; // world Z from local y = i
 		}
 		else
 		{
-			wa = (a.tileOrigin[axA] + ta) * CS + i - CS / 2; // world X from local x = i
-			wb = (a.tileOrigin[axB] + tb) * CS + j - CS / 2; // world Z (local y) or world Y (local z) = j
+			wa = (originA + ta) * CS + i - CS / 2; // world X from local x = i
+			wb = (originB + tb) * CS + j - CS / 2; // world Z (local y) or world Y (local z) = j
 		}
 
 		const double scale = double(0.02f);
@@ -115,14 +133,14 @@ namespace tsomk
 		const double height = __dmul_rn(pn_octave01(perm, __dmul_rn(double(wa), scale), __dmul_rn(double(wb), scale)), heightScale);
 
 		// int terrainDepth = std::round(std::min<double>(height * (maxH / 2 - freeSpace) + freeSpace, maxH / 2));  freeSpace is size_t
-		const int half = a.maxH[axH] / 2;
+		const int half = maxHAxis / 2;
 		const unsigned long long span = static_cast<unsigned long long>(static_cast<long long>(half)) - 30ull;
 		double t = __dadd_rn(__dmul_rn(height, __ull2double_rn(span)), 30.0);
 		const double cap = double(half);
 		if (cap < t)
 			t = cap;
 		const int td = int(round(t));
-		a.terrain[a.terrainOffset[dir] + size_t(tile) * SLAB + j * CS + i] = int16_t(td);
+		a.terrain[dirOffset + size_t(tile) * SLAB + j * CS + i] = int16_t(td);
 
 		// per-tile range: lets generate_kernel skip a pass for a whole chunk without touching the tile
 		__shared__ int redMin[32], redMax[32];
@@ -151,7 +169,7 @@ namespace tsomk
 			}
 			if (threadIdx.x == 0)
 			{
-				const size_t t2 = (a.terrainOffset[dir] / SLAB + size_t(tile)) * 2;
+				const size_t t2 = size_t(blockIdx.x) * 2;
 				a.tileRange[t2] = int16_t(mn);
 				a.tileRange[t2 + 1] = int16_t(mx);
 			}
@@ -160,24 +178,31 @@ namespace tsomk
 
 	void launch_terrain(const TerrainArgs& a, cudaStream_t st)
 	{
-		// axis ids: 0 = world X, 1 = world Y (up), 2 = world Z
-		struct { int dir, axA, axB, axH; } plan[6] = {
-			{ D_RIGHT, 1, 2, 0 }, { D_LEFT, 1, 2, 0 }, { D_UP, 0, 2, 1 }, { D_DOWN, 0, 2, 1 }, { D_BACK, 0, 1, 2 }, { D_FRONT, 0, 1, 2 },
-		};
-		for (auto& p : plan)
-		{
-			int nA = a.tileCount[p.axA], nB = a.tileCount[p.axB];
-			terrain_kernel<<<nA * nB, 1024, 0, st>>>(a, p.dir, nA, nB, p.axA, p.axB, p.axH);
-		}
+		// tiles per direction (Direction order): Back / Front X x Y, Down / Up X x Z, Left / Right Y x Z — the layout terrainOffset describes
+		const size_t tiles = 2 * (size_t(a.tileCount[0]) * a.tileCount[1] + size_t(a.tileCount[0]) * a.tileCount[2] + size_t(a.tileCount[1]) * a.tileCount[2]);
+		terrain_kernel<<<unsigned(tiles), 1024, 0, st>>>(a);
 	}
 
 	// ------------------------------------------------------------------------------------------------ std::minstd_rand skip-ahead
 	constexpr uint32_t LCG_A = 48271u;
 	constexpr uint32_t LCG_M = 2147483647u;
 
+	// 32 x 32 -> 64 as ONE IMAD.WIDE: with a plain (u64)x * y the compiler hoists the zero-extension of loop-invariant operands out of
+	// the block loop and then multiplies 64 x 32 (three instructions per product)
+	__host__ __device__ __forceinline__ unsigned long long mulwide(uint32_t x, uint32_t y)
+	{
+#ifdef __CUDA_ARCH__
+		unsigned long long p;
+		asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x), "r"(y));
+		return p;
+#else
+		return static_cast<unsigned long long>(x) * y;
+#endif
+	}
+
 	__host__ __device__ __forceinline__ uint32_t mulmod31(uint32_t x, uint32_t y)
 	{
-		const unsigned long long p = static_cast<unsigned long long>(x) * y;
+		const unsigned long long p = mulwide(x, y);
 		uint32_t s = uint32_t(p & LCG_M) + uint32_t(p >> 31);
 		return s >= LCG_M ? s - LCG_M : s;
 	}
@@ -193,6 +218,49 @@ namespace tsomk
 			e >>= 1;
 		}
 		return r;
+	}
+
+	// x * y mod (2^31 - 1) for y given DOUBLED (y2 = 2y < 2^32): with p = x * y2, hi = (x * y) >> 31 and lo >> 1 = (x * y) & (2^31 - 1),
+	// so the folded sum is one IMAD.WIDE + one LEA.HI, and the final conditional subtraction is an unsigned min (sum - M wraps when
+	// sum < M)
+	__device__ __forceinline__ uint32_t mulmod31_doubled(uint32_t x, uint32_t y2)
+	{
+		const unsigned long long p = mulwide(x, y2);
+		const uint32_t sum = uint32_t(p >> 32) + (uint32_t(p) >> 1);
+		return min(sum, sum - LCG_M);
+	}
+
+	// 0xFFFF in the low half if a is negative, 0xFFFF0000 in the high half if b is negative: prmt with the sign-replicating selector
+	// nibbles (msb set) — __byte_perm masks them off, hence the PTX
+	__device__ __forceinline__ uint32_t sign_halves(uint32_t a, uint32_t b)
+	{
+		uint32_t d;
+		asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(d) : "r"(a), "r"(b));
+		return d;
+	}
+
+	// Eight consecutive drawing blocks of one row: packed ids in w[4]; returns true when one of the draws is a tie (u2 - 1 == bStar,
+	// about once in 2^31 draws) and the caller has to run draw8_ties.  e = bStar + 1 - u2: > 0 stone, < 0 stone_mossy; the sign bytes of
+	// two e's select a packed id pair with one PRMT + one LOP3.
+	__device__ __forceinline__ bool draw8(uint32_t rowMul, const uint32_t (&px2)[8], uint32_t K, uint32_t stonePair, uint32_t deltaPair, uint32_t (&e)[8], uint32_t (&w)[4])
+	{
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			e[j] = K - mulmod31_doubled(rowMul, px2[j]);
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			w[k] = stonePair ^ (deltaPair & sign_halves(e[2 * k], e[2 * k + 1]));
+		return min(min(min(e[0], e[1]), min(e[2], e[3])), min(min(e[4], e[5]), min(e[6], e[7]))) == 0u;
+	}
+
+	// the first engine output of a tied draw decides: u1 = u2 / A = (bStar + 1) * A^-1 — the same for every tie
+	__device__ __forceinline__ void draw8_ties(const uint32_t (&e)[8], uint32_t K, uint32_t aInv, uint32_t aStar, uint32_t stoneId, uint32_t mossyId, uint32_t (&w)[4])
+	{
+		const uint32_t v = (mulmod31(K, aInv) - 1u) < aStar ? stoneId : mossyId;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (e[j] == 0u)
+				w[j >> 1] = (j & 1) ? ((w[j >> 1] & 0xFFFFu) | (v << 16)) : ((w[j >> 1] & 0xFFFF0000u) | v);
 	}
 
 	constexpr int GEN_THREADS = 256;
@@ -379,7 +447,7 @@ namespace tsomk
 		const int dYZ_y = Hy - absWz; // the maxHeight.y - |blockPos.z| term
 
 		int dX[8];
-		uint32_t px[8];
+		uint32_t px2[8];
 		int dXmin = INT_MAX, dXmax = INT_MIN;
 		unsigned shaft = 0u;
 #pragma unroll
@@ -389,7 +457,7 @@ namespace tsomk
 			dX[j] = Hx - abs(wx);
 			dXmin = min(dXmin, dX[j]);
 			dXmax = max(dXmax, dX[j]);
-			px[j] = (anyDraw && x >= ax0 && x <= ax1) ? sm.powX[x - ax0] : 0u;
+			px2[j] = (anyDraw && x >= ax0 && x <= ax1) ? sm.powX[x - ax0] << 1 : 0u; // doubled: see mulmod31_doubled
 			if (abs(wx) <= 2 && absWz <= 2)
 				shaft |= 1u << j;
 		}
@@ -397,6 +465,39 @@ namespace tsomk
 		const uint32_t rowMulY = rowYDraws ? mulmod31(base2, sm.powY[y - ay0]) : 0u;
 		const uint32_t stoneId = a.stone, mossyId = a.stoneMossy, dirtId = a.dirt, grassId = a.grass, snowId = a.snow;
 		const uint32_t bStar = a.bStar;
+
+		const uint32_t K = bStar + 1u;
+		const uint32_t stonePair = stoneId | (stoneId << 16), deltaPair = stonePair ^ (mossyId | (mossyId << 16));
+
+		// ---- chunks in which every block draws and no terrain pass is active (two thirds of a large planet): a loop without the
+		// depth classes and the pass masks.  Per block: x_{2n+2} = rowMul * A^(2x') mod (2^31 - 1) from ONE wide multiply by the doubled
+		// power (hi = p >> 31, lo >> 1 = p & (2^31 - 1)), e = bStar + 1 - u2 (> 0 stone, < 0 stone_mossy, == 0 the first draw decides),
+		// and the sign bytes of two e's select a packed id pair with one PRMT + one LOP3.
+		if (!anyAct && ax0 == 0 && ax1 == CS - 1 && ay0 == 0 && ay1 == CS - 1 && az0 == 0 && az1 == CS - 1)
+		{
+			uint32_t keep[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				keep[k] = ~((((shaft >> (2 * k)) & 1u) * 0xFFFFu) | (((shaft >> (2 * k + 1)) & 1u) * 0xFFFF0000u)); // Planet.cpp:221-222
+			int col = (tid >> 7) * CS + y;
+#pragma unroll 2
+			for (int it = 0; it < CS / 2; ++it, col += 2 * CS)
+			{
+				const uint32_t rowMul = mulmod31(rowMulY, sm.powZ[2 * it + (tid >> 7)]);
+				uint32_t e[8], w[4];
+				if (draw8(rowMul, px2, K, stonePair, deltaPair, e, w))
+					draw8_ties(e, K, a.aInv, a.aStar, stoneId, mossyId, w);
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					w[k] &= keep[k];
+				*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) = make_uint4(w[0], w[1], w[2], w[3]);
+				if (xq == 0)
+					xs[col] = uint16_t(w[0] & 0xFFFFu);
+				if (xq == 3)
+					xs[SLAB + col] = uint16_t(w[3] >> 16);
+			}
+			return;
+		}
 
 		// depth class: 0 Empty (< 30), 1 snow (<= 36), 2 dirt (<= 48), 3 stone / stone_mossy by draw (Planet.cpp:205-219)
 		auto depthClass = [](int d) { return (d >= 30) + (d >= 37) + (d >= 49); };
@@ -416,43 +517,24 @@ namespace tsomk
 				at8 = (sm.at[col] >> xb) & 0xFFu & ~ab8;
 			}
 
-			unsigned id[8];
-			if (mYZ < 30 || ab8 == 0xFFu)
-			{
-#pragma unroll
-				for (int j = 0; j < 8; ++j)
-					id[j] = 0u;
-			}
-			else
+			uint32_t w[4] = { 0u, 0u, 0u, 0u };
+			if (mYZ >= 30 && ab8 != 0xFFu)
 			{
 				const int cMin = depthClass(min(dXmin, mYZ)), cMax = depthClass(min(dXmax, mYZ));
 				if (cMin == 3)
 				{
-					// all eight blocks draw: bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
+					// all eight blocks draw
 					const uint32_t rowMul = mulmod31(rowMulY, sm.powZ[z - az0]);
-					uint32_t u2[8];
-					bool tie = false;
-#pragma unroll
-					for (int j = 0; j < 8; ++j)
-					{
-						u2[j] = mulmod31(rowMul, px[j]);
-						tie |= u2[j] == bStar + 1u;
-						id[j] = u2[j] <= bStar ? stoneId : mossyId;
-					}
-					if (tie) // u2 - 1 == bStar: the first draw decides (about once in 2^31 draws)
-					{
-#pragma unroll
-						for (int j = 0; j < 8; ++j)
-							if (u2[j] == bStar + 1u)
-								id[j] = (mulmod31(u2[j], a.aInv) - 1u) < a.aStar ? stoneId : mossyId;
-					}
+					uint32_t e[8];
+					if (draw8(rowMul, px2, K, stonePair, deltaPair, e, w))
+						draw8_ties(e, K, a.aInv, a.aStar, stoneId, mossyId, w);
 				}
 				else if (cMin == cMax)
 				{
 					const unsigned v = cMin == 0 ? 0u : (cMin == 1 ? snowId : dirtId);
 #pragma unroll
-					for (int j = 0; j < 8; ++j)
-						id[j] = v;
+					for (int k = 0; k < 4; ++k)
+						w[k] = v | (v << 16);
 				}
 				else
 				{
@@ -465,24 +547,21 @@ namespace tsomk
 						unsigned v;
 						if (depth >= 49)
 						{
-							const uint32_t u2 = mulmod31(rowMul, px[j]);
+							// bernoulli(0.9) of draw n == (u2-1, u1-1) lexicographically below (bStar, aStar), u2 = x_{2n+2}
+							const uint32_t u2 = mulmod31_doubled(rowMul, px2[j]);
 							bool stone = u2 <= bStar;
-							if (u2 == bStar + 1u)
+							if (u2 == K) // the first draw decides (about once in 2^31 draws)
 								stone = (mulmod31(u2, a.aInv) - 1u) < a.aStar;
 							v = stone ? stoneId : mossyId;
 						}
 						else
 							v = depth < 30 ? 0u : (depth <= 36 ? snowId : dirtId);
-						id[j] = v;
+						w[j >> 1] |= v << (16 * (j & 1));
 					}
 				}
 			}
 
-			// pack, then the central shaft (after the draw, Planet.cpp:221-222) and the terrain passes on the packed words
-			uint32_t w[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k)
-				w[k] = id[2 * k] | (id[2 * k + 1] << 16);
+			// the central shaft (after the draw, Planet.cpp:221-222) and the terrain passes on the packed words
 			const uint32_t kill = shaft | ab8;
 			if (kill)
 			{

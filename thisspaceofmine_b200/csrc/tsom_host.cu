@@ -1034,7 +1034,7 @@ extern "C"
 		ta.perm = c->dPerm;
 		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 		tsomk::launch_terrain(ta, ctx->stream);
-		ctx->launches += 6;
+		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
