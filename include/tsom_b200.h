@@ -40,7 +40,8 @@ enum tsom_status
 	TSOM_ERR_CUDA = 2,        /* CUDA runtime failure or no device */
 	TSOM_ERR_UNSUPPORTED = 3, /* configuration on which the reference itself asserts (e.g. negative depth, Planet.cpp:199) */
 	TSOM_ERR_NOMEM = 4,
-	TSOM_ERR_CAPACITY = 5     /* container or caller buffer too small */
+	TSOM_ERR_CAPACITY = 5,    /* container or caller buffer too small */
+	TSOM_ERR_INTERNAL = 6     /* a self-check of the library failed (tsom_debug_check_guards) */
 };
 
 enum tsom_direction { TSOM_BACK = 0, TSOM_DOWN = 1, TSOM_FRONT = 2, TSOM_LEFT = 3, TSOM_RIGHT = 4, TSOM_UP = 5 };
@@ -129,7 +130,7 @@ uint64_t tsom_launch_count(tsom_ctx* ctx);
 /* device-side durations (CUDA events on the context's stream) of the kernels of the most recent generate / mesh call */
 enum tsom_timing
 {
-	TSOM_TIMING_TERRAIN_MS = 0,   /* 6 x terrain_kernel */
+	TSOM_TIMING_TERRAIN_MS = 0,   /* terrain_kernel (the six directions in one launch) */
 	TSOM_TIMING_GENERATE_MS = 1,  /* generate_kernel */
 	TSOM_TIMING_MESH_COUNT_MS = 2, /* 0 on the single-pass path (count and scan live inside mesh_fused_kernel) */
 	TSOM_TIMING_MESH_SCAN_MS = 3,
@@ -140,6 +141,9 @@ enum tsom_timing
 int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n);
 /* pre-size the mesh arenas (faces); they also grow on demand */
 int tsom_reserve_faces(tsom_ctx* ctx, uint64_t faces, uint32_t flags);
+/* every arena is allocated with a 256-byte guard filled with 0xA5 behind its last face; returns TSOM_ERR_INTERNAL if a kernel wrote into
+   one (self-check for tests: compute-sanitizer is not always available) */
+int tsom_debug_check_guards(tsom_ctx* ctx);
 
 /* ---- container: Planet / ChunkContainer (include/CommonLib/ChunkContainer.hpp, Planet.hpp) ---- */
 int tsom_container_create(tsom_ctx* ctx, uint32_t capacity_chunks, float tile_size, tsom_container** out);

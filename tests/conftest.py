@@ -13,10 +13,17 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
-def ctx():
+def _session_ctx():
     """One device context for the whole GPU session (tsom_create on cuda:0)."""
     import thisspaceofmine_b200 as T
 
     c = T.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture
+def ctx(_session_ctx):
+    """The session context; after every test the 0xA5 guards behind the mesh arenas must be intact (tsom_debug_check_guards)."""
+    yield _session_ctx
+    _session_ctx.check_guards()

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libtsom_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CAPACITY = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CAPACITY, ERR_INTERNAL = range(7)
 MESH_RENDER, MESH_COLLIDER, MESH_DEFORMED, MESH_GENERIC_MATH, MESH_ORDERED = 1, 2, 4, 8, 16
 
 
@@ -63,6 +63,7 @@ SYMBOLS = {
     "tsom_set_block_table": (C.c_int, [_vp, C.POINTER(BlockDesc), C.c_uint32]),
     "tsom_launch_count": (C.c_uint64, [_vp]),
     "tsom_reserve_faces": (C.c_int, [_vp, C.c_uint64, C.c_uint32]),
+    "tsom_debug_check_guards": (C.c_int, [_vp]),
     "tsom_get_timings": (C.c_int, [_vp, _f32p, C.c_uint32]),
     "tsom_container_create": (C.c_int, [_vp, C.c_uint32, C.c_float, C.POINTER(_vp)]),
     "tsom_container_destroy": (None, [_vp]),

@@ -272,6 +272,7 @@ namespace tsomk
 		uint32_t powX[CS], powY[CS], powZ[CS];
 		uint32_t above[ROWS_PER_CHUNK]; // per x-row (z, y): bit x = emptied by some pass (above a column start)
 		uint32_t at[ROWS_PER_CHUNK];    // per x-row: bit x = sits on a column start (dirt -> grass)
+		uint4 keepOf[256];              // byte of 8 block bits -> the four packed id pairs with the flagged 16-bit halves cleared
 	};
 
 	// 32x32 bit-matrix transpose across a warp: lane i holds row i; afterwards lane j holds column j (bit i = old M[i][j])
@@ -386,6 +387,13 @@ namespace tsomk
 		if (anyAct)
 		{
 			const int lane = tid & 31, warp = tid >> 5;
+			{
+				uint32_t m[4];
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					m[k] = ~((((unsigned(tid) >> (2 * k)) & 1u) * 0xFFFFu) | (((unsigned(tid) >> (2 * k + 1)) & 1u) * 0xFFFF0000u));
+				sm.keepOf[tid] = make_uint4(m[0], m[1], m[2], m[3]);
+			}
 #pragma unroll
 			for (int k = 0; k < ROWS_PER_CHUNK / GEN_THREADS; ++k)
 			{
@@ -466,6 +474,10 @@ namespace tsomk
 		const uint32_t stoneId = a.stone, mossyId = a.stoneMossy, dirtId = a.dirt, grassId = a.grass, snowId = a.snow;
 		const uint32_t bStar = a.bStar;
 
+		uint32_t keep[4]; // the central shaft: Empty after the draw (Planet.cpp:221-222); the same x for every row of this thread
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			keep[k] = ~((((shaft >> (2 * k)) & 1u) * 0xFFFFu) | (((shaft >> (2 * k + 1)) & 1u) * 0xFFFF0000u));
 		const uint32_t K = bStar + 1u;
 		const uint32_t stonePair = stoneId | (stoneId << 16), deltaPair = stonePair ^ (mossyId | (mossyId << 16));
 
@@ -475,10 +487,6 @@ namespace tsomk
 		// and the sign bytes of two e's select a packed id pair with one PRMT + one LOP3.
 		if (!anyAct && ax0 == 0 && ax1 == CS - 1 && ay0 == 0 && ay1 == CS - 1 && az0 == 0 && az1 == CS - 1)
 		{
-			uint32_t keep[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k)
-				keep[k] = ~((((shaft >> (2 * k)) & 1u) * 0xFFFFu) | (((shaft >> (2 * k + 1)) & 1u) * 0xFFFF0000u)); // Planet.cpp:221-222
 			int col = (tid >> 7) * CS + y;
 #pragma unroll 2
 			for (int it = 0; it < CS / 2; ++it, col += 2 * CS)
@@ -499,8 +507,10 @@ namespace tsomk
 			return;
 		}
 
-		// depth class: 0 Empty (< 30), 1 snow (<= 36), 2 dirt (<= 48), 3 stone / stone_mossy by draw (Planet.cpp:205-219)
+		// depth class: 0 Empty (< 30), 1 snow (<= 36), 2 dirt (<= 48), 3 stone / stone_mossy by draw (Planet.cpp:205-219).  The class is
+		// monotone in the depth, so class(min(dX, dYZ)) = min(class(dX), class(dYZ)): the x part is a per-thread constant
 		auto depthClass = [](int d) { return (d >= 30) + (d >= 37) + (d >= 49); };
+		const int cXmin = depthClass(dXmin), cXmax = depthClass(dXmax);
 
 #pragma unroll 1
 		for (int it = 0; it < CS / 2; ++it)
@@ -520,7 +530,8 @@ namespace tsomk
 			uint32_t w[4] = { 0u, 0u, 0u, 0u };
 			if (mYZ >= 30 && ab8 != 0xFFu)
 			{
-				const int cMin = depthClass(min(dXmin, mYZ)), cMax = depthClass(min(dXmax, mYZ));
+				const int cYZ = depthClass(mYZ);
+				const int cMin = min(cXmin, cYZ), cMax = min(cXmax, cYZ);
 				if (cMin == 3)
 				{
 					// all eight blocks draw
@@ -559,25 +570,29 @@ namespace tsomk
 						w[j >> 1] |= v << (16 * (j & 1));
 					}
 				}
-			}
 
-			// the central shaft (after the draw, Planet.cpp:221-222) and the terrain passes on the packed words
-			const uint32_t kill = shaft | ab8;
-			if (kill)
-			{
+				// the central shaft, then the terrain passes on the packed words: Empty above a column start, dirt -> grass on it
 #pragma unroll
 				for (int k = 0; k < 4; ++k)
-					w[k] &= ~((((kill >> (2 * k)) & 1u) * 0xFFFFu) | (((kill >> (2 * k + 1)) & 1u) * 0xFFFF0000u));
-			}
-			if (at8)
-			{
-#pragma unroll
-				for (int k = 0; k < 4; ++k)
+					w[k] &= keep[k];
+				if (ab8)
 				{
-					if (((at8 >> (2 * k)) & 1u) && (w[k] & 0xFFFFu) == dirtId)
-						w[k] = (w[k] & 0xFFFF0000u) | grassId;
-					if (((at8 >> (2 * k + 1)) & 1u) && (w[k] >> 16) == dirtId)
-						w[k] = (w[k] & 0xFFFFu) | (grassId << 16);
+					const uint4 m = sm.keepOf[ab8];
+					w[0] &= m.x;
+					w[1] &= m.y;
+					w[2] &= m.z;
+					w[3] &= m.w;
+				}
+				if (at8 && cMin <= 2 && cMax >= 2) // only a dirt block can turn into grass
+				{
+#pragma unroll
+					for (int k = 0; k < 4; ++k)
+					{
+						if (((at8 >> (2 * k)) & 1u) && (w[k] & 0xFFFFu) == dirtId)
+							w[k] = (w[k] & 0xFFFF0000u) | grassId;
+						if (((at8 >> (2 * k + 1)) & 1u) && (w[k] >> 16) == dirtId)
+							w[k] = (w[k] & 0xFFFFu) | (grassId << 16);
+					}
 				}
 			}
 

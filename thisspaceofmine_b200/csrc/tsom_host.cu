@@ -502,6 +502,8 @@ namespace
 		return TSOM_OK;
 	}
 
+	constexpr size_t ARENA_GUARD_BYTES = 256; // 0xA5 behind the last face of every arena, checked by tsom_debug_check_guards
+
 	int EnsureArenas(tsom_ctx* ctx, uint64_t faces, uint32_t flags)
 	{
 		auto grow = [&](auto*& ptr, uint64_t& cap, size_t bytesPerFace) -> int {
@@ -513,9 +515,14 @@ namespace
 			ptr = nullptr;
 			cap = 0;
 			void* p = nullptr;
-			cudaError_t e = cudaMalloc(&p, want * bytesPerFace);
+			cudaError_t e = cudaMalloc(&p, want * bytesPerFace + ARENA_GUARD_BYTES);
 			if (e != cudaSuccess)
 				return Fail(TSOM_ERR_NOMEM, std::string("mesh arena cudaMalloc: ") + cudaGetErrorString(e));
+			if ((e = cudaMemsetAsync(static_cast<char*>(p) + want * bytesPerFace, 0xA5, ARENA_GUARD_BYTES, ctx->stream)) != cudaSuccess)
+			{
+				cudaFree(p);
+				return Fail(TSOM_ERR_CUDA, std::string("mesh arena guard: ") + cudaGetErrorString(e));
+			}
 			ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(p);
 			cap = want;
 			return TSOM_OK;
@@ -687,6 +694,30 @@ extern "C"
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		return EnsureArenas(ctx, faces, flags);
+	}
+
+	int tsom_debug_check_guards(tsom_ctx* ctx)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "null context");
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		struct { const void* ptr; uint64_t cap; size_t bytesPerFace; const char* name; } arenas[3] = {
+			{ ctx->dIndices, ctx->capIndices, TSOM_FACE_INDEX_BYTES, "index" },
+			{ ctx->dVertices, ctx->capVertices, TSOM_FACE_VERTEX_BYTES, "vertex" },
+			{ ctx->dCollider, ctx->capCollider, TSOM_FACE_COLLIDER_BYTES, "collider" },
+		};
+		for (auto& a : arenas)
+		{
+			if (!a.ptr)
+				continue;
+			unsigned char guard[ARENA_GUARD_BYTES];
+			TSOM_CUDA(cudaMemcpy(guard, static_cast<const char*>(a.ptr) + a.cap * a.bytesPerFace, ARENA_GUARD_BYTES, cudaMemcpyDeviceToHost));
+			for (size_t i = 0; i < ARENA_GUARD_BYTES; ++i)
+				if (guard[i] != 0xA5)
+					return Fail(TSOM_ERR_INTERNAL, std::string("a kernel wrote behind the ") + a.name + " arena (guard byte " + std::to_string(i) + ")");
+		}
+		return TSOM_OK;
 	}
 
 	// ---------------------------------------------------------------------------------------------------- container

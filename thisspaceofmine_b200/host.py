@@ -202,6 +202,10 @@ class Context:
     def reserve_faces(self, faces: int, render=True, collider=False):
         L.check(L.lib().tsom_reserve_faces(self._h, int(faces), (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0)))
 
+    def check_guards(self):
+        """Raises if a kernel wrote behind one of the mesh arenas (each carries a 0xA5 guard behind its last face)."""
+        L.check(L.lib().tsom_debug_check_guards(self._h))
+
     def arenas(self):
         v, i, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
         L.check(L.lib().tsom_mesh_arenas(self._h, C.byref(v), C.byref(i), C.byref(c), C.byref(n)))
