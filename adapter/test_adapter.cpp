@@ -207,6 +207,20 @@ static void TestGpu()
 		CHECK(threw);
 	}
 
+	// wire format: LZ4 block of the block array -> another chunk -> same ids; a truncated block is rejected and changes nothing
+	{
+		auto packet = chunk.Compress();
+		CHECK(!packet.empty() && packet.size() < TSOM_CHUNK_BLOCKS * 2);
+		Chunk copy = planet.AddChunk(lib, ChunkIndices(10, 10, 10));
+		copy.ResetCompressed(packet.data(), packet.size());
+		CHECK(copy.GetContent() == after);
+		bool threw = false;
+		try { copy.ResetCompressed(packet.data(), packet.size() - 3); } catch (const std::runtime_error& e) { threw = std::string(e.what()).find("failed to decompress chunk") == 0; }
+		CHECK(threw);
+		CHECK(copy.GetContent() == after);
+		planet.RemoveChunk(ChunkIndices(10, 10, 10));
+	}
+
 	// greedy box collider of a full chunk: one box covering everything
 	Chunk solid = planet.AddChunk(lib, ChunkIndices(10, 10, 10), [&](BlockIndex* blocks) {
 		for (unsigned int i = 0; i < TSOM_CHUNK_BLOCKS; ++i)

@@ -311,6 +311,13 @@ namespace tsom_b200
 			std::vector<std::uint8_t> Serialize(const BlockLibrary& blockLibrary) const;
 			void Deserialize(const BlockLibrary& blockLibrary, const std::uint8_t* data, std::size_t size);
 
+			// The `content` of Packets::ChunkReset (Packets.cpp:172-212): the block array as one LZ4 block, byte for byte what
+			// BinaryCompressor::Compress produces (LZ4_compress_fast_extState, acceleration 1), made on the device; and the receiving
+			// side (LZ4_decompress_safe + Reset).  ResetCompressed throws with the reference's messages and leaves the chunk untouched
+			// when the block is malformed.  Batches: tsom_chunks_lz4_compress / tsom_chunks_reset_lz4 take any number of chunks.
+			std::vector<std::uint8_t> Compress() const;
+			void ResetCompressed(const std::uint8_t* data, std::size_t size);
+
 			static unsigned int GetBlockLocalIndex(const Vector3ui& i) { return 32u * (32u * i.z + i.y) + i.x; } // Chunk.inl:25-28
 
 		private:
@@ -657,6 +664,22 @@ namespace tsom_b200
 		}
 		out.insert(out.end(), payload.begin(), payload.begin() + TSOM_CHUNK_BLOCKS * (count > 8 ? 2 : 1));
 		return out;
+	}
+
+	inline std::vector<std::uint8_t> Chunk::Compress() const
+	{
+		std::vector<std::uint8_t> out(TSOM_CHUNK_BLOCKS * 2 + TSOM_CHUNK_BLOCKS * 2 / 255 + 16); // LZ4_compressBound
+		std::uint64_t offsets[2] = { 0, 0 };
+		Check(tsom_chunks_lz4_compress(m_owner->Handle(), &m_indices.x, 1, out.data(), out.size(), offsets), "tsom_chunks_lz4_compress");
+		out.resize(std::size_t(offsets[1]));
+		return out;
+	}
+
+	inline void Chunk::ResetCompressed(const std::uint8_t* data, std::size_t size)
+	{
+		const std::uint64_t offsets[2] = { 0, size };
+		if (tsom_chunks_reset_lz4(m_owner->Handle(), &m_indices.x, 1, data, offsets) != TSOM_OK)
+			throw std::runtime_error(tsom_last_error());
 	}
 
 	inline void Chunk::Deserialize(const BlockLibrary& blockLibrary, const std::uint8_t* data, std::size_t size)

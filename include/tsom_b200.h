@@ -179,6 +179,19 @@ int tsom_chunks_palettize(tsom_container* c, const int32_t* chunk_indices, uint3
 int tsom_chunks_reset_palettized(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint16_t* palettes, uint32_t palette_stride,
                                  const uint32_t* palette_counts, const uint8_t* payload, int payload_big_endian);
 
+/* ---- wire format: Packets::ChunkReset (src/CommonLib/Protocol/Packets.cpp:172-212) ----
+ * The reference sends a chunk as ONE LZ4 block of its 65,536-byte block array: BinaryCompressor::Compress =
+ * LZ4_compress_fast_extState(fresh state, acceleration 0 -> 1) (src/CommonLib/Utility/BinaryCompressor.cpp:17-36).
+ * tsom_chunks_lz4_compress produces exactly those bytes on the device, chunk i at streams_out[offsets_out[i] .. offsets_out[i+1]);
+ * offsets_out has n + 1 entries.  TSOM_ERR_CAPACITY if capacity < offsets_out[n] (offsets_out is complete, nothing usable in
+ * streams_out); 65,809 bytes per chunk (LZ4_compressBound) always suffice. */
+int tsom_chunks_lz4_compress(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint8_t* streams_out, uint64_t capacity, uint64_t* offsets_out);
+/* The receiving side (Packets.cpp:197-211 + Chunk::Reset, src/ClientLib/ClientSessionHandler.cpp:156-176): LZ4_decompress_safe of each
+ * block on the device, then the chunks are reset (created if unknown).  All or nothing: TSOM_ERR_INVALID with the reference's message
+ * ("failed to decompress chunk" / "malformed packet ...") if any block is malformed or does not decode to 65,536 bytes.  Deviation:
+ * a match offset of 0, which LZ4_decompress_safe accepts with unspecified output, is rejected. */
+int tsom_chunks_reset_lz4(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint8_t* streams, const uint64_t* offsets);
+
 /* ---- generation ---- */
 /* Planet::GenerateChunks (Planet.cpp:385-403): adds chunk_count^3 chunks at (x,y,z) - chunk_count/2 in z,y,x order and
  * fills every one with Planet::GenerateChunk (Planet.cpp:160-383). */

@@ -64,6 +64,9 @@ def _bind(path: str, full: bool):
     L.orc_blocklib_index.argtypes = [C.c_char_p]
     L.orc_blocklib_register.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
     if full:  # probes of the restatement's internals; the reference build has no such entry points
+        L.orc_lz4_bound.argtypes = [C.c_int]
+        L.orc_lz4_compress.argtypes = [u8p, C.c_int, u8p, C.c_int]
+        L.orc_lz4_decompress.argtypes = [u8p, C.c_int, u8p, C.c_int]
         L.orc_perlin_perm.argtypes = [C.c_uint32, u8p]
         L.orc_perlin_octave01.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_int]
         L.orc_perlin_octave01.restype = C.c_double
@@ -311,6 +314,26 @@ class Planet:
         out = np.zeros((cap, 6), np.float32)
         n = self._L.orc_box_collider(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_float), cap)
         return out[:n].copy()
+
+
+def lz4_compress(data) -> bytes:
+    """BinaryCompressor::Compress (BinaryCompressor.cpp:17-36) = LZ4_compress_fast_extState(acceleration 0 -> 1): restated in
+    oracle/lz4_block.hpp for inputs shorter than 64 KiB + 11 (a chunk's block array is exactly 64 KiB); b"" if it does not apply."""
+    a = np.frombuffer(bytes(data), np.uint8).copy() if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    L = lib()
+    out = np.zeros(max(L.orc_lz4_bound(len(a)), 1), np.uint8)
+    n = L.orc_lz4_compress(_p(a, C.c_uint8), len(a), _p(out, C.c_uint8), len(out))
+    return bytes(out[:n])
+
+
+def lz4_decompress(data: bytes, size: int) -> bytes:
+    """BinaryCompressor::Decompress (BinaryCompressor.cpp:38-47) = LZ4_decompress_safe; raises ValueError on a malformed stream."""
+    a = np.frombuffer(bytes(data), np.uint8).copy()
+    out = np.zeros(max(size, 1), np.uint8)
+    n = lib().orc_lz4_decompress(_p(a, C.c_uint8), len(a), _p(out, C.c_uint8), size)
+    if n < 0:
+        raise ValueError("malformed LZ4 block")
+    return bytes(out[:n])
 
 
 def bench_mesh_isolated(blocks: np.ndarray, nthreads: int, L=None):

@@ -1,6 +1,7 @@
 // oracle/capi.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.  C entry points (ctypes) over tsom_oracle.hpp.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load this library.
 #include "tsom_oracle.hpp"
+#include "lz4_block.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -380,4 +381,8 @@ extern "C"
 			*meshedOut = std::uint32_t(chunks.size());
 		return bad;
 	}
+	// ---- LZ4 block format as used by Packets::ChunkReset (BinaryCompressor.cpp:17-50): see oracle/lz4_block.hpp
+	int orc_lz4_bound(int n) { return tsom_oracle_lz4::compress_bound(n); }
+	int orc_lz4_compress(const std::uint8_t* src, int n, std::uint8_t* dst, int cap) { return tsom_oracle_lz4::compress_block(src, n, dst, cap); }
+	int orc_lz4_decompress(const std::uint8_t* src, int n, std::uint8_t* dst, int cap) { return tsom_oracle_lz4::decompress_block(src, n, dst, cap); }
 }

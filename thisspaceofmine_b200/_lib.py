@@ -76,6 +76,8 @@ SYMBOLS = {
     "tsom_chunk_device_ptr": (_vp, [_vp, _i32p]),
     "tsom_chunks_palettize": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p, C.c_uint32, _u32p, C.POINTER(C.c_uint8), C.c_int]),
     "tsom_chunks_reset_palettized": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p, C.c_uint32, _u32p, C.POINTER(C.c_uint8), C.c_int]),
+    "tsom_chunks_lz4_compress": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tsom_chunks_reset_lz4": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
     "tsom_planet_generate": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks)]),
     "tsom_planet_generate_chunks": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks), _i32p, C.c_uint32]),
     "tsom_planet_generate_platform": (C.c_int, [_vp, C.c_int, _i32p, C.POINTER(PlatformBlocks)]),

@@ -236,6 +236,8 @@ struct tsom_ctx
 	DevBuf<uint8_t> ioPayload;   // save-format payloads (65536 B per chunk)
 	DevBuf<uint16_t> ioPalette;
 	DevBuf<uint32_t> ioCounts;
+	DevBuf<uint8_t> ioStreams;            // LZ4 blocks: per-chunk scratch at a fixed stride, or the packed streams
+	DevBuf<unsigned long long> ioOffsets; // n + 1 offsets of the packed LZ4 blocks
 	DevBuf<unsigned long long> editKeys; // open-addressing table of the edited blocks of one tsom_apply_edits call
 	DevBuf<uint32_t> editVals;           // ... -> index of the last edit that names the block
 	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
@@ -576,6 +578,7 @@ extern "C"
 		ctx->numSMs = prop.multiProcessorCount;
 		TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		TSOM_CUDA(tsomk::mesh_kernels_init());
+		TSOM_CUDA(tsomk::lz4_kernels_init());
 		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
@@ -625,6 +628,8 @@ extern "C"
 		ctx->ioPayload.Free();
 		ctx->ioPalette.Free();
 		ctx->ioCounts.Free();
+		ctx->ioStreams.Free();
+		ctx->ioOffsets.Free();
 		ctx->editVals.Free();
 		ctx->gravity.Free();
 		ctx->edits.Free();
@@ -950,6 +955,109 @@ extern "C"
 		if (ctx->hSmall[7] != 0)
 			return Fail(TSOM_ERR_INVALID, "a payload index is out of its chunk's palette (malformed chunk data); such blocks were set to Empty");
 		return TSOM_OK;
+	}
+
+	// Packets::ChunkReset payloads (Packets.cpp:172-212): one LZ4 block per chunk, the bytes BinaryCompressor::Compress produces.
+	int tsom_chunks_lz4_compress(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint8_t* streams_out, uint64_t capacity, uint64_t* offsets_out)
+	{
+		if (!c || !chunk_indices || !offsets_out || (!streams_out && capacity))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		offsets_out[0] = 0;
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			slots[i] = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+			if (slots[i] == 0xFFFFFFFFu || !c->hasContent[slots[i]])
+				return Fail(TSOM_ERR_INVALID, "chunk is unknown or has no content");
+		}
+		// sub-batches bound the scratch (65,824 B per chunk); each one: compress at a fixed stride -> sizes -> offsets -> pack -> D2H
+		constexpr uint32_t BATCH = 8192;
+		const uint32_t stride = tsomk::lz4_stream_stride();
+		const uint32_t maxBatch = std::min(n, BATCH);
+		TSOM_CUDA(ctx->jobSlot.Ensure(maxBatch));
+		TSOM_CUDA(ctx->ioCounts.Ensure(maxBatch));
+		TSOM_CUDA(ctx->ioOffsets.Ensure(size_t(maxBatch) + 1));
+		TSOM_CUDA(ctx->ioStreams.Ensure(size_t(maxBatch) * stride));
+		TSOM_CUDA(ctx->ioPayload.Ensure(size_t(maxBatch) * stride)); // the packed copy
+		std::vector<uint32_t> sizes(maxBatch);
+		std::vector<unsigned long long> offs(size_t(maxBatch) + 1);
+		uint64_t total = 0;
+		bool fits = true;
+		for (uint32_t first = 0; first < n; first += BATCH)
+		{
+			const uint32_t m = std::min(BATCH, n - first);
+			TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data() + first, size_t(m) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			tsomk::launch_lz4_compress(c->dBlocks, ctx->jobSlot.ptr, m, ctx->ioStreams.ptr, ctx->ioCounts.ptr, ctx->stream);
+			ctx->launches += 1;
+			TSOM_CUDA(cudaGetLastError());
+			TSOM_CUDA(cudaMemcpyAsync(sizes.data(), ctx->ioCounts.ptr, size_t(m) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			offs[0] = 0;
+			for (uint32_t i = 0; i < m; ++i)
+			{
+				offs[i + 1] = offs[i] + sizes[i];
+				offsets_out[first + i + 1] = total + offs[i + 1];
+			}
+			const uint64_t batchBytes = offs[m];
+			if (fits && total + batchBytes <= capacity)
+			{
+				TSOM_CUDA(cudaMemcpyAsync(ctx->ioOffsets.ptr, offs.data(), (size_t(m) + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+				tsomk::launch_lz4_pack(ctx->ioStreams.ptr, ctx->ioOffsets.ptr, m, ctx->ioPayload.ptr, ctx->stream);
+				ctx->launches += 1;
+				TSOM_CUDA(cudaGetLastError());
+				TSOM_CUDA(cudaMemcpyAsync(streams_out + total, ctx->ioPayload.ptr, batchBytes, cudaMemcpyDeviceToHost, ctx->stream));
+				TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			}
+			else
+				fits = false; // keep going for the sizes: offsets_out[n] tells the caller what to allocate
+			total += batchBytes;
+		}
+		if (!fits)
+			return Fail(TSOM_ERR_CAPACITY, "streams_out is too small (offsets_out[n] bytes are needed)");
+		return TSOM_OK;
+	}
+
+	// the receiving side (ClientSessionHandler.cpp:156-176 after Packets.cpp:197-211): LZ4_decompress_safe + Chunk::Reset, all or nothing
+	int tsom_chunks_reset_lz4(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const uint8_t* streams, const uint64_t* offsets)
+	{
+		if (!c || !chunk_indices || !streams || !offsets)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		for (uint32_t i = 0; i < n; ++i)
+			if (offsets[i + 1] < offsets[i])
+				return Fail(TSOM_ERR_INVALID, "offsets must not decrease");
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		const uint64_t base = offsets[0], bytes = offsets[n] - offsets[0];
+		std::vector<unsigned long long> offs(size_t(n) + 1);
+		for (uint32_t i = 0; i <= n; ++i)
+			offs[i] = offsets[i] - base;
+		TSOM_CUDA(ctx->ioStreams.Ensure(std::max<size_t>(bytes, 16)));
+		TSOM_CUDA(ctx->ioOffsets.Ensure(size_t(n) + 1));
+		TSOM_CUDA(ctx->ioCounts.Ensure(n));
+		TSOM_CUDA(ctx->ioPayload.Ensure(size_t(n) * NB * 2));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->ioStreams.ptr, streams + base, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->ioOffsets.ptr, offs.data(), (size_t(n) + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_lz4_decompress(ctx->ioStreams.ptr, ctx->ioOffsets.ptr, n, reinterpret_cast<uint16_t*>(ctx->ioPayload.ptr), ctx->ioCounts.ptr, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		std::vector<uint32_t> status(n);
+		TSOM_CUDA(cudaMemcpyAsync(status.data(), ctx->ioCounts.ptr, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (status[i] == 0xFFFFFFFFu)
+				return Fail(TSOM_ERR_INVALID, "failed to decompress chunk (stream " + std::to_string(i) + "); no chunk was reset"); // Packets.cpp:204-205
+			if (status[i] != NB * 2)
+				return Fail(TSOM_ERR_INVALID, "malformed packet (decompressed size exceeds max packet size: " + std::to_string(status[i]) + " != " + std::to_string(NB * 2) +
+				                                  "); no chunk was reset"); // Packets.cpp:207-208
+		}
+		return ResetCommon(c, chunk_indices, n, ctx->ioPayload.ptr, cudaMemcpyDeviceToDevice);
 	}
 
 	int tsom_chunks_get_content(tsom_container* c, const int32_t* chunk_indices, uint32_t n, uint16_t* blocks_host)

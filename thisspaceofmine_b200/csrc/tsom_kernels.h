@@ -126,6 +126,14 @@ namespace tsomk
 	void launch_depalettize(uint16_t* blocks, const uint32_t* slots, uint32_t n, const uint16_t* palette, uint32_t stride, const uint32_t* counts, const uint8_t* payload, int bigEndian,
 	                        uint32_t* errFlag, cudaStream_t st);
 
+	// ---- wire format: one LZ4 block per chunk (Packets::ChunkReset), lz4_kernels.cu ----
+	cudaError_t lz4_kernels_init();
+	uint32_t lz4_stream_stride(); // bytes reserved per chunk in the scratch of launch_lz4_compress (>= LZ4_compressBound(65536))
+	void launch_lz4_compress(const uint16_t* blocks, const uint32_t* slots, uint32_t n, uint8_t* streams, uint32_t* sizes, cudaStream_t st);
+	void launch_lz4_pack(const uint8_t* streams, const unsigned long long* offsets, uint32_t n, uint8_t* packed, cudaStream_t st);
+	// out: n x 65536 bytes, written only for streams that decode to exactly 65536 bytes; status[i] = decoded size or 0xFFFFFFFF
+	void launch_lz4_decompress(const uint8_t* packed, const unsigned long long* offsets, uint32_t n, uint16_t* out, uint32_t* status, cudaStream_t st);
+
 	// ---- multi-GPU halo pull ----
 	struct GhostDesc
 	{

@@ -423,6 +423,34 @@ class ChunkContainer:
             cnt[i] = k
         L.check(L.lib().tsom_chunks_reset_palettized(self._h, _p(idx, C.c_int32), n, _p(pal, C.c_uint16), stride, _p(cnt, C.c_uint32), _p(payload, C.c_uint8), 1))
 
+    # ---- wire format (Packets::ChunkReset)
+    LZ4_BOUND = ChunkBlockCount * 2 + ChunkBlockCount * 2 // 255 + 16  # LZ4_compressBound(65536)
+
+    def CompressChunks(self, indices) -> list:
+        """The `content` payload of Packets::ChunkReset (Packets.cpp:172-196) for a batch: one LZ4 block per chunk, byte for byte what
+        BinaryCompressor::Compress (= LZ4_compress_fast_extState, acceleration 1) makes of the chunk's block array; built on the device."""
+        idx = _idx(indices)
+        n = len(idx)
+        offs = np.zeros(n + 1, np.uint64)
+        buf = np.zeros(max(n * 16384, self.LZ4_BOUND), np.uint8)  # planet chunks compress to <= 14 KiB; retried at the exact size if not
+        rc = L.lib().tsom_chunks_lz4_compress(self._h, _p(idx, C.c_int32), n, _p(buf, C.c_uint8), len(buf), _p(offs, C.c_uint64))
+        if rc == L.ERR_CAPACITY:
+            buf = np.zeros(int(offs[n]), np.uint8)
+            rc = L.lib().tsom_chunks_lz4_compress(self._h, _p(idx, C.c_int32), n, _p(buf, C.c_uint8), len(buf), _p(offs, C.c_uint64))
+        L.check(rc)
+        return [buf[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+
+    def ResetChunksCompressed(self, indices, streams):
+        """The receiving side of Packets::ChunkReset (Packets.cpp:197-211, ClientSessionHandler.cpp:156-176): LZ4_decompress_safe on the
+        device + Chunk::Reset; raises (and resets nothing) if any block is malformed or is not 65,536 bytes long."""
+        idx = _idx(indices)
+        n = len(idx)
+        assert n == len(streams)
+        offs = np.zeros(n + 1, np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in streams], dtype=np.uint64)
+        buf = np.frombuffer(b"".join(streams) or b"\0", np.uint8).copy()
+        L.check(L.lib().tsom_chunks_reset_lz4(self._h, _p(idx, C.c_int32), n, _p(buf, C.c_uint8), _p(offs, C.c_uint64)))
+
     # ---- edits
     def UpdateBlocks(self, edits: np.ndarray):
         """n x Chunk::UpdateBlock, in order; `edits` is [n, 7] int: cx, cy, cz, x, y, z, block."""
