@@ -4,7 +4,9 @@
 #include "tsom_adapter.hpp"
 
 #include <cstdio>
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 using namespace tsom_b200;
 
@@ -157,6 +159,46 @@ static void TestGpu()
 			CHECK(same);
 			CHECK(collider->indices == indices);
 		}
+	}
+
+	// the reference's calling pattern (ClientChunkEntities.cpp:207-241): many TaskScheduler workers, each calling BuildMesh /
+	// BuildCollider of its own chunk at the same time — here 8 threads over the 27 chunks, 3 rounds, results == the batched run
+	{
+		std::atomic<std::size_t> next{ 0 };
+		std::atomic<int> mismatches{ 0 };
+		auto worker = [&] {
+			for (;;)
+			{
+				const std::size_t job = next.fetch_add(1);
+				if (job >= grid.size() * 3)
+					return;
+				const std::size_t i = job % grid.size();
+				Chunk c = planet.GetChunk(grid[i]);
+				std::vector<VertexStruct> vertices;
+				std::vector<std::uint32_t> indices;
+				const Vector3f center = planet.GetCenter() - planet.GetChunkOffset(grid[i]);
+				c.BuildMesh(indices, center, [&](std::uint32_t count) {
+					vertices.resize(count);
+					Chunk::VertexAttributes a;
+					a.position = &vertices[0].position;
+					a.normal = &vertices[0].normal;
+					a.uv = &vertices[0].uvw;
+					return a;
+				});
+				if (indices != batchIdx[i] || vertices.size() != batchVerts[i].size() ||
+				    (!vertices.empty() && std::memcmp(vertices.data(), batchVerts[i].data(), vertices.size() * sizeof(VertexStruct)) != 0))
+					++mismatches;
+				auto collider = c.BuildCollider();
+				if (collider.has_value() != !vertices.empty() || (collider && collider->indices != indices))
+					++mismatches;
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int t = 0; t < 8; ++t)
+			pool.emplace_back(worker);
+		for (auto& t : pool)
+			t.join();
+		CHECK(mismatches.load() == 0);
 	}
 
 	// edit: break a block, the dirty set holds the chunk (and the masked neighbours), faces change

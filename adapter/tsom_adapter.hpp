@@ -203,6 +203,20 @@ namespace tsom_b200
 			tsom_ctx* Handle() const { return m_ctx; }
 			void Synchronize() const { Check(tsom_synchronize(m_ctx), "tsom_synchronize"); }
 
+			// Keeps "mesh, then copy out of the arenas" together when several threads (the reference's TaskScheduler workers) share
+			// the device: every C entry point locks the context by itself, but the arenas belong to the most recent BuildMeshes.
+			class Lock
+			{
+				public:
+					explicit Lock(const Device& device) : m_ctx(device.m_ctx) { Check(tsom_ctx_lock(m_ctx), "tsom_ctx_lock"); }
+					Lock(const Lock&) = delete;
+					Lock& operator=(const Lock&) = delete;
+					~Lock() { tsom_ctx_unlock(m_ctx); }
+
+				private:
+					tsom_ctx* m_ctx;
+			};
+
 		private:
 			tsom_ctx* m_ctx = nullptr;
 	};
@@ -571,6 +585,7 @@ namespace tsom_b200
 	{
 		MeshOptions opt;
 		opt.gravityCenters = &center;
+		Device::Lock lock(m_owner->GetDevice()); // callable from many workers at once, like the reference's (ClientChunkEntities.cpp:207-241)
 		MeshBatch batch = m_owner->BuildMeshes({ m_indices }, opt);
 		const std::uint32_t faces = batch.FaceCount(0);
 		if (faces == 0)
@@ -599,6 +614,7 @@ namespace tsom_b200
 		MeshOptions opt;
 		opt.render = false;
 		opt.collider = true;
+		Device::Lock lock(m_owner->GetDevice());
 		MeshBatch batch = m_owner->BuildMeshes({ m_indices }, opt);
 		if (batch.FaceCount(0) == 0)
 			return std::nullopt; // the reference returns nullptr for an empty mesh (DeformedChunk.cpp:33-34)

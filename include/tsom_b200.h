@@ -123,6 +123,13 @@ void tsom_destroy(tsom_ctx* ctx);
 /* the cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
 void* tsom_stream(tsom_ctx* ctx);
 int tsom_synchronize(tsom_ctx* ctx);
+/* Threading (the reference calls BuildMesh / BuildCollider from many Nz::TaskScheduler workers, ClientChunkEntities.cpp:207-241): every entry
+ * point takes the context's recursive lock, so calls on one context and its containers serialise and may come from any thread.  Results that
+ * live in context-owned memory — the arenas of tsom_mesh — are replaced by the next tsom_mesh on the same context: a thread that needs
+ * "mesh, then copy out" as one unit brackets the calls with tsom_ctx_lock / tsom_ctx_unlock (same thread, may nest).  Independent work
+ * streams want one context each. */
+int tsom_ctx_lock(tsom_ctx* ctx);
+int tsom_ctx_unlock(tsom_ctx* ctx);
 /* replaces BlockLibrary::GetBlockData (BlockLibrary.hpp:31) on the device: uploads the table once */
 int tsom_set_block_table(tsom_ctx* ctx, const tsom_block_desc* blocks, uint32_t n);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */

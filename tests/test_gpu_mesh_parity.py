@@ -251,3 +251,39 @@ def test_views_are_valid_when_the_arenas_had_to_grow(ordered):
         gc.close()
     finally:
         c2.close()
+
+
+def test_concurrent_callers_on_one_context(ctx):
+    """The reference calls BuildMesh from many TaskScheduler workers at once (ClientChunkEntities.cpp:207-241).  Every C entry point
+    locks the context; a worker brackets "mesh + read the arenas" with tsom_ctx_lock.  6 threads, each with its own container, 12 rounds:
+    every mesh equals the one computed alone."""
+    import threading
+
+    rng = np.random.default_rng(5)
+    pairs = []
+    for t in range(6):
+        chunks = {(2 * i, t, 0): random_chunk(rng, 0.3 + 0.1 * t) for i in range(3)}
+        pairs.append((*_pair(ctx, chunks), list(chunks)))
+    want = [[op.mesh(k) for k in keys] for _, op, keys in pairs]
+    errors = []
+
+    def worker(t):
+        gc, _, keys = pairs[t]
+        try:
+            for _ in range(12):
+                with ctx.locked():
+                    batch = gc.BuildMeshes(keys, collider=True)
+                    got = [batch.chunk(i) for i in range(len(keys))]
+                for i, k in enumerate(keys):
+                    assert_mesh_equal(got[i], want[t][i], f"thread {t} chunk {k}")
+        except Exception as e:  # noqa: BLE001 - reported below
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for gc, _, _ in pairs:
+        gc.close()
+    assert not errors, errors[0]

@@ -62,6 +62,8 @@ SYMBOLS = {
     "tsom_synchronize": (C.c_int, [_vp]),
     "tsom_set_block_table": (C.c_int, [_vp, C.POINTER(BlockDesc), C.c_uint32]),
     "tsom_launch_count": (C.c_uint64, [_vp]),
+    "tsom_ctx_lock": (C.c_int, [_vp]),
+    "tsom_ctx_unlock": (C.c_int, [_vp]),
     "tsom_reserve_faces": (C.c_int, [_vp, C.c_uint64, C.c_uint32]),
     "tsom_debug_check_guards": (C.c_int, [_vp]),
     "tsom_get_timings": (C.c_int, [_vp, _f32p, C.c_uint32]),

@@ -42,6 +42,8 @@ namespace
 			return Fail(TSOM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
 	} while (0)
 
+#define TSOM_LOCK(ctxPtr) std::lock_guard<std::recursive_mutex> tsomLock_((ctxPtr)->mutex)
+
 	constexpr int CS = TSOM_CHUNK_SIZE;
 	constexpr size_t NB = TSOM_CHUNK_BLOCKS;
 	constexpr size_t SLAB = 1024;
@@ -215,6 +217,9 @@ struct tsom_ctx
 	int numSMs = 148;
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
+	// every entry point holds this while it touches the context, its containers or its stream; recursive so that tsom_ctx_lock lets a
+	// caller keep several calls together (mesh + copy out) and entry points may call each other
+	std::recursive_mutex mutex;
 
 	// block table
 	uint8_t* dFlags = nullptr;
@@ -651,7 +656,24 @@ extern "C"
 	{
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	int tsom_ctx_lock(tsom_ctx* ctx)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		ctx->mutex.lock();
+		return TSOM_OK;
+	}
+
+	int tsom_ctx_unlock(tsom_ctx* ctx)
+	{
+		if (!ctx)
+			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		ctx->mutex.unlock();
 		return TSOM_OK;
 	}
 
@@ -661,6 +683,7 @@ extern "C"
 	{
 		if (!ctx || !out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(ctx);
 		for (uint32_t i = 0; i < n && i < TSOM_TIMING_COUNT; ++i)
 			out[i] = ctx->timings[i];
 		return TSOM_OK;
@@ -670,6 +693,7 @@ extern "C"
 	{
 		if (!ctx || !blocks || n == 0 || n > 65535)
 			return Fail(TSOM_ERR_INVALID, "bad block table");
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		std::vector<uint8_t> flags(n);
 		std::vector<uint32_t> tex(size_t(n) * 6);
@@ -696,6 +720,7 @@ extern "C"
 	{
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		return EnsureArenas(ctx, faces, flags);
@@ -705,6 +730,7 @@ extern "C"
 	{
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "null context");
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		struct { const void* ptr; uint64_t cap; size_t bytesPerFace; const char* name; } arenas[3] = {
@@ -731,6 +757,7 @@ extern "C"
 		if (!ctx || !out || capacity_chunks == 0)
 			return Fail(TSOM_ERR_INVALID, "bad container arguments");
 		*out = nullptr;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		auto c = std::make_unique<tsom_container>();
 		c->ctx = ctx;
@@ -765,6 +792,7 @@ extern "C"
 	{
 		if (!c)
 			return;
+		TSOM_LOCK(c->ctx);
 		cudaSetDevice(c->ctx->device);
 		cudaStreamSynchronize(c->ctx->stream);
 		for (auto& [rank, p] : c->peers)
@@ -793,6 +821,7 @@ extern "C"
 	{
 		if (!c || (!chunk_indices && n))
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		for (uint32_t i = 0; i < n; ++i)
 		{
 			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, nullptr);
@@ -810,6 +839,7 @@ extern "C"
 		auto it = c->slotOf.find(k);
 		if (it == c->slotOf.end())
 			return Fail(TSOM_ERR_INVALID, "unknown chunk");
+		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
 		const uint32_t slot = it->second;
 		c->exists[slot] = 0;
@@ -849,6 +879,7 @@ extern "C"
 		if (!c || !chunk_indices || !src)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		std::vector<uint32_t> slots(n);
 		for (uint32_t i = 0; i < n; ++i)
@@ -891,6 +922,7 @@ extern "C"
 		if (n == 0)
 			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		std::vector<uint32_t> slots(n);
 		for (uint32_t i = 0; i < n; ++i)
@@ -925,6 +957,7 @@ extern "C"
 		if (n == 0)
 			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		for (uint32_t i = 0; i < n; ++i)
 			if (palette_counts[i] == 0 || palette_counts[i] > palette_stride)
@@ -966,6 +999,7 @@ extern "C"
 		if (n == 0)
 			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		std::vector<uint32_t> slots(n);
 		for (uint32_t i = 0; i < n; ++i)
@@ -1032,6 +1066,7 @@ extern "C"
 			if (offsets[i + 1] < offsets[i])
 				return Fail(TSOM_ERR_INVALID, "offsets must not decrease");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		const uint64_t base = offsets[0], bytes = offsets[n] - offsets[0];
 		std::vector<unsigned long long> offs(size_t(n) + 1);
@@ -1064,6 +1099,7 @@ extern "C"
 	{
 		if (!c || !chunk_indices || !blocks_host)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
 		for (uint32_t i = 0; i < n; ++i)
 		{
@@ -1080,6 +1116,7 @@ extern "C"
 	{
 		if (!c || !chunk_index)
 			return nullptr;
+		TSOM_LOCK(c->ctx);
 		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
 		if (slot == 0xFFFFFFFFu || !c->hasContent[slot])
 			return nullptr;
@@ -1090,6 +1127,7 @@ extern "C"
 	{
 		if (!c || !chunk_index || !slot_out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
 		if (slot == 0xFFFFFFFFu)
 			return Fail(TSOM_ERR_INVALID, "unknown chunk");
@@ -1105,6 +1143,7 @@ extern "C"
 		if (n == 0)
 			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 
 		int maxH[3];
@@ -1241,6 +1280,7 @@ extern "C"
 		if (!c || !platform_center || !ids || up_direction < 0 || up_direction > 5)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		// dense slot grid over the bounding box of existing chunks
 		int lo[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, hi[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
@@ -1296,6 +1336,7 @@ extern "C"
 		if (n == 0)
 			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(ctx->EnsurePinned(size_t(n) * sizeof(tsomk::EditDev)));
 		auto* staged = static_cast<tsomk::EditDev*>(ctx->hPinned);
@@ -1332,6 +1373,7 @@ extern "C"
 		if (!c || !n_out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		const uint32_t n = c->highWater;
 		std::vector<uint8_t> mask(n, 0);
@@ -1406,6 +1448,7 @@ extern "C"
 		if (!c || !params)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		const uint32_t flags = params->flags;
 		if (!(flags & (TSOM_MESH_RENDER | TSOM_MESH_COLLIDER)))
 			return Fail(TSOM_ERR_INVALID, "flags must request TSOM_MESH_RENDER and/or TSOM_MESH_COLLIDER");
@@ -1565,6 +1608,7 @@ extern "C"
 	{
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_LOCK(ctx);
 		if (vertices)
 			*vertices = ctx->dVertices;
 		if (indices)
@@ -1584,6 +1628,7 @@ extern "C"
 			return Fail(TSOM_ERR_INVALID, "face range exceeds the last mesh result");
 		if (face_count == 0)
 			return TSOM_OK;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		if (vertices)
 		{
@@ -1608,6 +1653,7 @@ extern "C"
 		if (!c || !chunk_index || !n_out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		if (!ctx->dFlags)
 			return Fail(TSOM_ERR_INVALID, "no block table");
 		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
@@ -1635,6 +1681,7 @@ extern "C"
 	{
 		if (!c || !chunk_indices || !remote_slots || !ranks)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		for (uint32_t i = 0; i < n; ++i)
 		{
 			Key k{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] };
@@ -1651,6 +1698,7 @@ extern "C"
 		if (!c || !out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
 		cudaIpcMemHandle_t h0, h1;
 		TSOM_CUDA(cudaIpcGetMemHandle(&h0, c->dBlocks));
@@ -1666,6 +1714,7 @@ extern "C"
 	{
 		if (!c || !handle)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
 		cudaIpcMemHandle_t h0, h1;
 		std::memcpy(&h0, handle->bytes, 64);
@@ -1688,6 +1737,7 @@ extern "C"
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		if (peer->ctx->device != c->ctx->device)
 		{
+			TSOM_LOCK(c->ctx);
 			TSOM_CUDA(cudaSetDevice(c->ctx->device));
 			cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
 			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
@@ -1708,6 +1758,7 @@ extern "C"
 		if (!c)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		int rc = SyncTopology(c);
 		if (rc != TSOM_OK)

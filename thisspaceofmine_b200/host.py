@@ -12,6 +12,7 @@ All block data lives in HBM; every compute call runs sm_100a kernels.  Nothing h
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass, field
 from typing import Iterable, Optional, Sequence
@@ -201,6 +202,15 @@ class Context:
 
     def reserve_faces(self, faces: int, render=True, collider=False):
         L.check(L.lib().tsom_reserve_faces(self._h, int(faces), (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0)))
+
+    @contextlib.contextmanager
+    def locked(self):
+        """tsom_ctx_lock / tsom_ctx_unlock: keeps "mesh, then read the arenas" together when several threads share the context."""
+        L.check(L.lib().tsom_ctx_lock(self._h))
+        try:
+            yield self
+        finally:
+            L.lib().tsom_ctx_unlock(self._h)
 
     def check_guards(self):
         """Raises if a kernel wrote behind one of the mesh arenas (each carries a 0xA5 guard behind its last face)."""
