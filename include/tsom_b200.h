@@ -143,7 +143,8 @@ enum tsom_timing
 	TSOM_TIMING_MESH_SCAN_MS = 3,
 	TSOM_TIMING_MESH_EMIT_MS = 4,  /* mesh_fused_kernel: classify + count + chain + emit */
 	TSOM_TIMING_MESH_REEMIT = 5,  /* 1.0 when the arenas had to grow and the kernel ran twice (the time is then of the first, count-only run) */
-	TSOM_TIMING_COUNT = 6
+	TSOM_TIMING_IO_MS = 6,        /* kernels of the most recent wire-format call: lz4_compress (+ pack, summed over its sub-batches) or lz4_decompress */
+	TSOM_TIMING_COUNT = 7
 };
 int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n);
 /* pre-size the mesh arenas (faces); they also grow on demand */

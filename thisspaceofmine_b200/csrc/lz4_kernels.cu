@@ -71,6 +71,45 @@ namespace tsomk
 			return min(done, limit - a);
 		}
 
+		// The decoder's view of the compressed stream: tokens, offsets and length bytes are read one at a time and each decides where the
+		// next one is, so a global load per byte would put L2 latency on every step.  The warp keeps 256 bytes of the stream in
+		// registers (two words per lane, the second one prefetched) and fetches single bytes with a shuffle.
+		struct StreamWindow
+		{
+			const uint32_t* words; // the stream's first word, rounded down to 4-byte alignment
+			uint32_t shift;        // bytes between that word and the stream's first byte
+			uint32_t base;         // window start (multiple of 128) in bytes from `words`
+			uint32_t cur, next;    // this lane's word of [base, base + 128) and of [base + 128, base + 256)
+
+			__device__ __forceinline__ void init(const uint8_t* src, int lane)
+			{
+				shift = uint32_t(reinterpret_cast<uintptr_t>(src) & 3u);
+				words = reinterpret_cast<const uint32_t*>(src - shift);
+				base = 0u;
+				cur = words[lane];
+				next = words[32 + lane];
+			}
+			__device__ __forceinline__ uint32_t byte(uint32_t ip, int lane)
+			{
+				const uint32_t a = ip + shift;
+				if (a - base >= 128u)
+				{
+					if (a - base < 256u)
+					{
+						base += 128u;
+						cur = next;
+					}
+					else
+					{
+						base = a & ~127u;
+						cur = words[(base >> 2) + lane];
+					}
+					next = words[(base >> 2) + 32 + lane];
+				}
+				return (__shfl_sync(FULL, cur, (a - base) >> 2) >> ((a & 3u) * 8u)) & 255u;
+			}
+		};
+
 		// length bytes of a sequence: 255, 255, ..., rest (all lanes return the advanced offset; lane 0 writes)
 		__device__ __forceinline__ uint32_t put_length(uint8_t* dst, uint32_t op, uint32_t len, int lane)
 		{
@@ -259,7 +298,8 @@ namespace tsomk
 			packed[o + i] = src[i];
 	}
 
-	// One warp per chunk: LZ4_decompress_safe of stream [offsets[i], offsets[i+1]) into shared memory; the 64 KiB land in out[i] only if the
+	// One warp per chunk: LZ4_decompress_safe of stream [offsets[i], offsets[i+1]) into shared memory (`packed` must be readable for 512
+	// bytes past the last stream: the register window reads ahead); the 64 KiB land in out[i] only if the
 	// stream is well formed and decodes to exactly 65,536 bytes.  status[i] = decoded size, or 0xFFFFFFFF for a malformed stream.
 	__global__ void __launch_bounds__(32) lz4_decompress_kernel(const uint8_t* __restrict__ packed, const unsigned long long* __restrict__ offsets, uint32_t n, uint16_t* __restrict__ out,
 	                                                            uint32_t* __restrict__ status)
@@ -279,11 +319,13 @@ namespace tsomk
 			const uint32_t iend = uint32_t(srcSize64);
 			constexpr uint32_t oend = CHUNK_BYTES;
 			uint32_t ip = 0, op = 0;
+			StreamWindow win;
+			win.init(src, lane);
 			for (;;)
 			{
 				if (ip >= iend)
 					break;
-				const uint32_t token = src[ip++];
+				const uint32_t token = win.byte(ip++, lane);
 				// literal length
 				uint32_t length = token >> 4;
 				bool bad = false;
@@ -297,7 +339,7 @@ namespace tsomk
 							bad = true;
 							break;
 						}
-						s = src[ip++];
+						s = win.byte(ip++, lane);
 						length += s;
 					} while (s == 255u);
 				}
@@ -316,7 +358,7 @@ namespace tsomk
 					result = op; // the last sequence holds literals only
 					break;
 				}
-				const uint32_t offset = uint32_t(src[ip]) | (uint32_t(src[ip + 1]) << 8);
+				const uint32_t offset = win.byte(ip, lane) | (win.byte(ip + 1, lane) << 8);
 				ip += 2;
 				if (offset == 0u || offset > op)
 					break;
@@ -331,7 +373,7 @@ namespace tsomk
 							bad = true;
 							break;
 						}
-						s = src[ip++];
+						s = win.byte(ip++, lane);
 						length += s;
 					} while (s == 255u);
 				}

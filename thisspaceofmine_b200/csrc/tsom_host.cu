@@ -1021,15 +1021,20 @@ extern "C"
 		std::vector<unsigned long long> offs(size_t(maxBatch) + 1);
 		uint64_t total = 0;
 		bool fits = true;
+		float kernelMs = 0.f, ms = 0.f;
 		for (uint32_t first = 0; first < n; first += BATCH)
 		{
 			const uint32_t m = std::min(BATCH, n - first);
 			TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data() + first, size_t(m) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 			tsomk::launch_lz4_compress(c->dBlocks, ctx->jobSlot.ptr, m, ctx->ioStreams.ptr, ctx->ioCounts.ptr, ctx->stream);
 			ctx->launches += 1;
 			TSOM_CUDA(cudaGetLastError());
+			TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 			TSOM_CUDA(cudaMemcpyAsync(sizes.data(), ctx->ioCounts.ptr, size_t(m) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess)
+				kernelMs += ms;
 			offs[0] = 0;
 			for (uint32_t i = 0; i < m; ++i)
 			{
@@ -1040,16 +1045,21 @@ extern "C"
 			if (fits && total + batchBytes <= capacity)
 			{
 				TSOM_CUDA(cudaMemcpyAsync(ctx->ioOffsets.ptr, offs.data(), (size_t(m) + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+				TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 				tsomk::launch_lz4_pack(ctx->ioStreams.ptr, ctx->ioOffsets.ptr, m, ctx->ioPayload.ptr, ctx->stream);
 				ctx->launches += 1;
 				TSOM_CUDA(cudaGetLastError());
+				TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 				TSOM_CUDA(cudaMemcpyAsync(streams_out + total, ctx->ioPayload.ptr, batchBytes, cudaMemcpyDeviceToHost, ctx->stream));
 				TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+				if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess)
+					kernelMs += ms;
 			}
 			else
 				fits = false; // keep going for the sizes: offsets_out[n] tells the caller what to allocate
 			total += batchBytes;
 		}
+		ctx->timings[TSOM_TIMING_IO_MS] = kernelMs;
 		if (!fits)
 			return Fail(TSOM_ERR_CAPACITY, "streams_out is too small (offsets_out[n] bytes are needed)");
 		return TSOM_OK;
@@ -1072,18 +1082,21 @@ extern "C"
 		std::vector<unsigned long long> offs(size_t(n) + 1);
 		for (uint32_t i = 0; i <= n; ++i)
 			offs[i] = offsets[i] - base;
-		TSOM_CUDA(ctx->ioStreams.Ensure(std::max<size_t>(bytes, 16)));
+		TSOM_CUDA(ctx->ioStreams.Ensure(bytes + 1024)); // the decoder's register window reads up to 512 bytes ahead
 		TSOM_CUDA(ctx->ioOffsets.Ensure(size_t(n) + 1));
 		TSOM_CUDA(ctx->ioCounts.Ensure(n));
 		TSOM_CUDA(ctx->ioPayload.Ensure(size_t(n) * NB * 2));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->ioStreams.ptr, streams + base, bytes, cudaMemcpyHostToDevice, ctx->stream));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->ioOffsets.ptr, offs.data(), (size_t(n) + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 		tsomk::launch_lz4_decompress(ctx->ioStreams.ptr, ctx->ioOffsets.ptr, n, reinterpret_cast<uint16_t*>(ctx->ioPayload.ptr), ctx->ioCounts.ptr, ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 		std::vector<uint32_t> status(n);
 		TSOM_CUDA(cudaMemcpyAsync(status.data(), ctx->ioCounts.ptr, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_IO_MS], ctx->ev[0], ctx->ev[1]);
 		for (uint32_t i = 0; i < n; ++i)
 		{
 			if (status[i] == 0xFFFFFFFFu)

@@ -196,9 +196,9 @@ class Context:
 
     def timings(self) -> dict:
         """Device-side kernel durations (ms) of the most recent generate / mesh call on this context."""
-        t = (C.c_float * 6)()
-        L.check(L.lib().tsom_get_timings(self._h, t, 6))
-        return dict(terrain_ms=t[0], generate_ms=t[1], mesh_count_ms=t[2], mesh_scan_ms=t[3], mesh_emit_ms=t[4], mesh_reemit=bool(t[5]))
+        t = (C.c_float * 7)()
+        L.check(L.lib().tsom_get_timings(self._h, t, 7))
+        return dict(terrain_ms=t[0], generate_ms=t[1], mesh_count_ms=t[2], mesh_scan_ms=t[3], mesh_emit_ms=t[4], mesh_reemit=bool(t[5]), io_ms=t[6])
 
     def reserve_faces(self, faces: int, render=True, collider=False):
         L.check(L.lib().tsom_reserve_faces(self._h, int(faces), (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0)))

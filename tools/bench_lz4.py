@@ -25,13 +25,15 @@ planet.CompressChunks(grid[: min(n, 64)])  # warm-up (allocations)
 t0 = time.perf_counter()
 streams = planet.CompressChunks(grid)
 t1 = time.perf_counter()
+compress_kernels_ms = ctx.timings()["io_ms"]
 client = T.Planet(ctx, capacity=n)
 client.ResetChunksCompressed(grid[: min(n, 64)], streams[: min(n, 64)])
 t2 = time.perf_counter()
 client.ResetChunksCompressed(grid, streams)
 t3 = time.perf_counter()
+decode_kernel_ms = ctx.timings()["io_ms"]
 out = {"chunks": n, "compressed_bytes": sum(map(len, streams)), "raw_bytes": n * 65536,
-       "gpu_compress_ms": (t1 - t0) * 1e3, "gpu_compress_chunks_per_s": n / (t1 - t0),
+       "gpu_compress_ms": (t1 - t0) * 1e3, "gpu_compress_kernels_ms": compress_kernels_ms, "gpu_decode_kernel_ms": decode_kernel_ms, "gpu_compress_chunks_per_s": n / (t1 - t0),
        "gpu_reset_lz4_ms": (t3 - t2) * 1e3, "gpu_reset_lz4_chunks_per_s": n / (t3 - t2)}
 try:
     import pyarrow as pa
