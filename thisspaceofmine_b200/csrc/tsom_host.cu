@@ -1500,7 +1500,11 @@ extern "C"
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(ctx->faceCount.Ensure(n));
 		TSOM_CUDA(ctx->firstFace.Ensure(n));
-		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		// job i = slot | has-content flag in bit 31: the kernel's ticket needs ONE dependent load behind its atomic, not two
+		std::vector<uint32_t> jobs(n);
+		for (uint32_t i = 0; i < n; ++i)
+			jobs[i] = slots[i] | (c->hasContent[slots[i]] ? 0x80000000u : 0u);
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, jobs.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		if (params->gravity_centers)
 		{
 			TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * 3));

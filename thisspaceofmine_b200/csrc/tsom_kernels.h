@@ -24,7 +24,7 @@ namespace tsomk
 		const unsigned long long* halo;  // [capacity][6] encoded slab pointers (0 = no neighbour)
 		const int4* chunkIdx;            // [capacity] (cx, cy, cz, hasContent)
 		// jobs
-		const uint32_t* jobSlot;         // [nJobs]
+		const uint32_t* jobSlot;         // [nJobs] slot | (chunk has content) << 31
 		const float* gravity;            // [nJobs][3] or nullptr
 		uint32_t nJobs;
 		// block table
