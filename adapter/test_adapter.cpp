@@ -4,6 +4,7 @@
 #include "tsom_adapter.hpp"
 
 #include <cstdio>
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -120,6 +121,25 @@ static void TestGpu()
 	std::vector<std::vector<std::uint32_t>> batchIdx(grid.size());
 	for (std::size_t i = 0; i < grid.size(); ++i)
 		batch.CopyChunk(i, &batchVerts[i], &batchIdx[i], nullptr);
+
+	// GenerateAABB on the device == min / max over the vertices the caller received
+	{
+		const auto boxes = batch.ComputeAABBs();
+		CHECK(boxes.size() == grid.size());
+		for (std::size_t i = 0; i < grid.size(); ++i)
+		{
+			Vector3f lo(0.f, 0.f, 0.f), hi(0.f, 0.f, 0.f);
+			for (std::size_t v = 0; v < batchVerts[i].size(); ++v)
+			{
+				const Vector3f& p = batchVerts[i][v].position;
+				if (v == 0)
+					lo = hi = p;
+				lo = Vector3f(std::min(lo.x, p.x), std::min(lo.y, p.y), std::min(lo.z, p.z));
+				hi = Vector3f(std::max(hi.x, p.x), std::max(hi.y, p.y), std::max(hi.z, p.z));
+			}
+			CHECK(boxes[i].min == lo && boxes[i].max == hi);
+		}
+	}
 
 	for (std::size_t i = 0; i < grid.size(); ++i)
 	{

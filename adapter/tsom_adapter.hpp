@@ -253,6 +253,19 @@ namespace tsom_b200
 				                             colliderPositions ? &colliderPositions->data()->x : nullptr), "tsom_mesh_copy_to_host");
 			}
 
+			// Nz::StaticMesh::GenerateAABB of every chunk (ClientChunkEntities.cpp:168), from the arena: {min, max} of the positions
+			struct Aabb
+			{
+				Vector3f min, max;
+			};
+			std::vector<Aabb> ComputeAABBs() const
+			{
+				std::vector<Aabb> out(views.size());
+				static_assert(sizeof(Aabb) == 6 * sizeof(float), "aabb layout");
+				Check(tsom_mesh_aabb(m_ctx, views.data(), std::uint32_t(views.size()), out.empty() ? nullptr : &out[0].min.x), "tsom_mesh_aabb");
+				return out;
+			}
+
 		private:
 			friend class ChunkContainer;
 			tsom_ctx* m_ctx = nullptr;

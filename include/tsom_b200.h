@@ -231,6 +231,11 @@ int tsom_mesh_arenas(tsom_ctx* ctx, const void** vertices, const void** indices,
 /* copy faces [first_face, first_face + face_count) to host: the std::vector<VertexStruct> / std::vector<UInt32> /
  * std::vector<Vector3f> the reference's callers own.  Any destination may be NULL. */
 int tsom_mesh_copy_to_host(tsom_ctx* ctx, uint64_t first_face, uint64_t face_count, void* vertices, uint32_t* indices, float* collider_positions);
+/* Nz::StaticMesh::GenerateAABB as ClientChunkEntities::BuildMesh calls it on every chunk mesh (src/ClientLib/ClientChunkEntities.cpp:168):
+ * the bounding box of the vertex positions of each view of the last tsom_mesh call, computed on the device from the floats in the arena
+ * (render vertices, or the collider positions of a collider-only call).  aabb_out: n x {min.xyz, max.xyz}; zeros for a view without faces.
+ * (The 12-byte tangent slot stays zero: Chunk::BuildMesh never writes it and StaticMesh::GenerateTangents is third-party.) */
+int tsom_mesh_aabb(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, float* aabb_out);
 /* FlatChunk::BuildCollider greedy box merge (src/CommonLib/FlatChunk.cpp:13-30,56-153): boxes_out = n_boxes x {pos.xyz, size.xyz}
  * in block units (multiply by the block size like FlatChunk.cpp:20-21 does). */
 int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out);

@@ -287,3 +287,29 @@ def test_concurrent_callers_on_one_context(ctx):
     for gc, _, _ in pairs:
         gc.close()
     assert not errors, errors[0]
+
+
+@pytest.mark.parametrize("mode", ["flat", "deformed", "collider_only"])
+def test_aabb_is_the_box_of_the_emitted_positions(ctx, mode):
+    """Nz::StaticMesh::GenerateAABB (ClientChunkEntities.cpp:168) on the device: min / max of exactly the positions in the arena, and
+    within 1e-5 of the box of the oracle's positions; zeros for a chunk without faces."""
+    rng = np.random.default_rng(11)
+    chunks = {(i, 0, 0): random_chunk(rng, 0.02 + 0.2 * i) for i in range(4)}
+    chunks[(9, 9, 9)] = np.zeros(32768, np.uint16)  # no faces
+    gc, op = _pair(ctx, chunks)
+    keys = list(chunks)
+    kw = dict(render=mode != "collider_only", collider=mode == "collider_only", deformed=mode == "deformed", deformRadius=16.0 if mode == "deformed" else 0.0)
+    batch = gc.BuildMeshes(keys, **kw)
+    boxes = batch.aabbs()
+    assert boxes.shape == (len(keys), 6)
+    for i, k in enumerate(keys):
+        m = batch.chunk(i)
+        if m is None:
+            assert not boxes[i].any()
+            continue
+        pos = m.vertices[:, :3] if mode != "collider_only" else m.collider_positions
+        assert np.array_equal(boxes[i, :3], pos.min(0)) and np.array_equal(boxes[i, 3:], pos.max(0)), f"chunk {k}"
+        om = op.mesh(k, deformed=mode == "deformed", deform_radius=kw["deformRadius"])
+        want = np.concatenate([om.position.min(0), om.position.max(0)])
+        assert np.allclose(boxes[i], want, rtol=1e-5, atol=1e-5), f"chunk {k}"
+    gc.close()

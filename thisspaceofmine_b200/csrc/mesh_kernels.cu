@@ -997,6 +997,75 @@ namespace tsomk
 		}
 	}
 
+	// =====================================================================================================================
+	// mesh_aabb_kernel — Nz::StaticMesh::GenerateAABB (src/ClientLib/ClientChunkEntities.cpp:168): the bounding box of a chunk's vertex
+	// positions, taken from the floats tsom_mesh wrote (so it is the box of exactly the vertices the caller uploads), one CTA per chunk.
+	// Source: the render arena (position = first 12 bytes of each 48-byte vertex) or, without it, the collider arena (packed xyz).
+	__global__ void __launch_bounds__(256) mesh_aabb_kernel(const float4* __restrict__ vertices, const float* __restrict__ collider, const unsigned long long* __restrict__ firstFace,
+	                                                        const uint32_t* __restrict__ faceCount, uint32_t n, float* __restrict__ out)
+	{
+		const uint32_t job = blockIdx.x;
+		if (job >= n)
+			return;
+		const unsigned long long first = firstFace[job];
+		const uint32_t nVerts = faceCount[job] * 4u;
+		float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+		for (uint32_t v = threadIdx.x; v < nVerts; v += blockDim.x)
+		{
+			float p[3];
+			if (vertices)
+			{
+				const float4 q = vertices[(first * 4ull + v) * 3ull];
+				p[0] = q.x, p[1] = q.y, p[2] = q.z;
+			}
+			else
+			{
+				const float* q = collider + (first * 4ull + v) * 3ull;
+				p[0] = q[0], p[1] = q[1], p[2] = q[2];
+			}
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				lo[k] = fminf(lo[k], p[k]);
+				hi[k] = fmaxf(hi[k], p[k]);
+			}
+		}
+		__shared__ float red[8][6];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+				hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+			}
+		}
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		if (lane == 0)
+		{
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+			{
+				red[warp][k] = lo[k];
+				red[warp][3 + k] = hi[k];
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < 6)
+		{
+			float r = red[0][threadIdx.x];
+			for (int w = 1; w < 8; ++w)
+				r = threadIdx.x < 3 ? fminf(r, red[w][threadIdx.x]) : fmaxf(r, red[w][threadIdx.x]);
+			out[size_t(job) * 6 + threadIdx.x] = nVerts ? r : 0.f;
+		}
+	}
+
+	void launch_mesh_aabb(const float4* vertices, const float* collider, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n, float* out, cudaStream_t st)
+	{
+		mesh_aabb_kernel<<<n, 256, 0, st>>>(vertices, collider, firstFace, faceCount, n, out);
+	}
+
 	// ---- launchers ----
 	size_t mesh_fused_smem_bytes() { return sizeof(FusedSmem); }
 

@@ -232,6 +232,7 @@ struct tsom_ctx
 	float4* dCollider = nullptr;
 	uint64_t capVertices = 0, capIndices = 0, capCollider = 0;
 	uint64_t totalFaces = 0;
+	uint32_t lastMeshFlags = 0; // TSOM_MESH_RENDER / COLLIDER of the call that filled the arenas
 
 	// per-call scratch
 	DevBuf<uint32_t> jobSlot, faceCount;
@@ -1609,6 +1610,7 @@ extern "C"
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		}
 		ctx->totalFaces = total;
+		ctx->lastMeshFlags = flags;
 		if (views_out)
 		{
 			for (uint32_t i = 0; i < n; ++i)
@@ -1661,6 +1663,39 @@ extern "C"
 				return Fail(TSOM_ERR_INVALID, "last tsom_mesh call did not produce collider positions");
 			TSOM_CUDA(cudaMemcpyAsync(collider_positions, reinterpret_cast<const char*>(ctx->dCollider) + first_face * TSOM_FACE_COLLIDER_BYTES, face_count * TSOM_FACE_COLLIDER_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
 		}
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	int tsom_mesh_aabb(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, float* aabb_out)
+	{
+		if (!ctx || (!views && n) || (!aabb_out && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		TSOM_LOCK(ctx);
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		const bool render = (ctx->lastMeshFlags & TSOM_MESH_RENDER) != 0;
+		if (!render && !(ctx->lastMeshFlags & TSOM_MESH_COLLIDER))
+			return Fail(TSOM_ERR_INVALID, "no mesh result on this context");
+		std::vector<unsigned long long> first(n);
+		std::vector<uint32_t> count(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (views[i].first_face + views[i].face_count > ctx->totalFaces)
+				return Fail(TSOM_ERR_INVALID, "a view exceeds the last mesh result");
+			first[i] = views[i].first_face;
+			count[i] = views[i].face_count;
+		}
+		TSOM_CUDA(ctx->firstFace.Ensure(n));
+		TSOM_CUDA(ctx->faceCount.Ensure(n));
+		TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * 6));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->firstFace.ptr, first.data(), size_t(n) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->faceCount.ptr, count.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_mesh_aabb(render ? ctx->dVertices : nullptr, reinterpret_cast<const float*>(ctx->dCollider), ctx->firstFace.ptr, ctx->faceCount.ptr, n, ctx->gravity.ptr, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(aabb_out, ctx->gravity.ptr, size_t(n) * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		return TSOM_OK;
 	}

@@ -126,6 +126,9 @@ namespace tsomk
 	void launch_depalettize(uint16_t* blocks, const uint32_t* slots, uint32_t n, const uint16_t* palette, uint32_t stride, const uint32_t* counts, const uint8_t* payload, int bigEndian,
 	                        uint32_t* errFlag, cudaStream_t st);
 
+	// ---- Nz::StaticMesh::GenerateAABB: min / max of each chunk's vertex positions (render arena, or the collider arena if vertices == null) ----
+	void launch_mesh_aabb(const float4* vertices, const float* collider, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n, float* out, cudaStream_t st);
+
 	// ---- wire format: one LZ4 block per chunk (Packets::ChunkReset), lz4_kernels.cu ----
 	cudaError_t lz4_kernels_init();
 	uint32_t lz4_stream_stride(); // bytes reserved per chunk in the scratch of launch_lz4_compress (>= LZ4_compressBound(65536))

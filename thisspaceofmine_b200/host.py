@@ -283,6 +283,14 @@ class MeshBatch:
                                                None if coll is None else _p(coll, C.c_float)))
         return ChunkMesh(verts, ind, coll)
 
+    def aabbs(self) -> np.ndarray:
+        """Nz::StaticMesh::GenerateAABB for every chunk of the batch (ClientChunkEntities.cpp:168), computed on the device from the
+        arena -> [n, 6] float32: min.xyz, max.xyz of the vertex positions; zeros for a chunk without faces."""
+        out = np.zeros((len(self._views), 6), np.float32)
+        v = np.ascontiguousarray(self._views)
+        L.check(L.lib().tsom_mesh_aabb(self.ctx._h, C.cast(v.ctypes.data, C.POINTER(L.MeshView)), len(v), _p(out, C.c_float)))
+        return out
+
 
 # ------------------------------------------------------------------------------------------------ ChunkContainer / Planet
 class ChunkContainer:
