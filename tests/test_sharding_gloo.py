@@ -166,3 +166,139 @@ def test_two_rank_sharded_planet_matches_single_process_golden():
     assert all(r[2] for r in res), "sharded block ids differ from the single-process golden"
     g = np.load(os.path.join(GOLDEN, "planet_7_3x3x3.npz"))
     assert sum(r[3] for r in res) == int(g["face_count"].sum())
+
+
+# ------------------------------------------------------------------------------------------------ edits on a sharded planet
+def make_shard_edits(plan, n, seed):
+    """Random edits with many boundary coordinates (0 / 31), so that a good part of them invalidates chunks of the other rank."""
+    rng = np.random.default_rng(seed)
+    e = np.zeros((n, 7), np.int64)
+    e[:, 0:3] = plan.grid[rng.integers(0, plan.n, n)]
+    coords = rng.integers(0, 32, (n, 3))
+    snap = rng.random((n, 3))
+    coords[snap < 0.2] = 0
+    coords[snap > 0.8] = 31
+    e[:, 3:6] = coords
+    e[:, 6] = rng.choice([0, 2, 7, 13], n)
+    return e
+
+
+def test_route_edits_partitions_the_tick():
+    plan = ShardPlan((3, 3, 3), 3)
+    e = make_shard_edits(plan, 500, 3)
+    e[7, 0:3] = (9, 9, 9)  # outside the planet: nobody's
+    owns = [plan.route_edits(r, e)[0] for r in range(3)]
+    total = np.sum(owns, axis=0)
+    assert total[7] == 0 and np.all(np.delete(total, 7) == 1), "every edit inside the planet has exactly one owner"
+    for r in range(3):
+        own, extra = plan.route_edits(r, e)
+        assert np.all(plan.owner[extra] == r)
+        # brute force: my chunks that are the masked neighbour of an edit on a chunk I do not own
+        want = set()
+        for row in e[~own]:
+            lid = int(plan.linear_id(row[0:3])[0])
+            if lid < 0:
+                continue
+            x, y, z = row[3:6]
+            for cond, d in ((x == 0, 3), (x == 31, 4), (y == 0, 2), (y == 31, 0), (z == 0, 1), (z == 31, 5)):
+                if cond:
+                    nb = int(plan.linear_id(row[0:3] + CHUNK_DIR_OFFSET[d])[0])
+                    if nb >= 0 and plan.owner[nb] == r:
+                        want.add(nb)
+        assert set(extra.tolist()) == want
+
+
+def _edit_worker(rank, world, port, result_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        count, seed = (3, 3, 3), 7
+        plan = ShardPlan(count, world)
+        mine = plan.local(rank)
+        mine_set = set(map(tuple, mine.tolist()))
+        rem = plan.remote_neighbours(rank)
+
+        planet = O.Planet(1.0, 16.0)
+        for idx in mine:
+            b, ok = O.generate_chunk(seed, count, idx)
+            assert ok
+            planet.add_chunk(idx, b)
+
+        def exchange_ghosts(first):
+            """every rank publishes the blocks of the chunks its peers mirror (the CPU stand-in for tsom_halo_pull)"""
+            wanted = [None] * world
+            dist.all_gather_object(wanted, {p: ls.tolist() for p, ls in rem.items()})
+            answers = {}
+            for r in range(world):
+                for lid in wanted[r].get(rank, []):
+                    answers[(r, lid)] = planet.get_blocks(plan.grid[lid])
+            got = [None] * world
+            dist.all_gather_object(got, answers)
+            for p in range(world):
+                for (r, lid), blocks in got[p].items():
+                    if r == rank:
+                        (planet.add_chunk if first else planet.reset_chunk)(plan.grid[lid], blocks)
+
+        exchange_ghosts(True)
+        planet.clear_invalidated()
+
+        # the reference run: one process, whole planet
+        whole = O.Planet(1.0, 16.0)
+        assert whole.generate(seed, count, nthreads=2)
+        whole.clear_invalidated()
+
+        ok_dirty = ok_mesh = True
+        nd = 0
+        for tick in range(3):
+            edits = make_shard_edits(plan, 200, 100 + tick)  # the same list on every rank
+            own, extra = plan.route_edits(rank, edits)
+            planet.apply_edits(edits[own])
+            local = planet.collect_dirty()  # my edited chunks + masked neighbours in my container (ghosts included)
+            planet.clear_invalidated()
+            dirty = {tuple(k) for k in local.tolist() if tuple(k) in mine_set} | {tuple(plan.grid[l].tolist()) for l in extra}
+            exchange_ghosts(False)  # refresh the mirrored neighbours before meshing
+            planet.clear_invalidated()
+
+            whole.apply_edits(edits)
+            want = {tuple(k) for k in whole.collect_dirty().tolist()}
+            whole.clear_invalidated()
+            all_dirty = [None] * world
+            dist.all_gather_object(all_dirty, sorted(dirty))
+            union = set().union(*[set(map(tuple, d)) for d in all_dirty])
+            ok_dirty &= union == want and sum(len(d) for d in all_dirty) == len(want)  # complete, and nobody rebuilds another rank's chunk
+            for k in sorted(dirty):
+                a, b = planet.mesh(k), whole.mesh(k)
+                same = (a is None) == (b is None)
+                if same and a is not None:
+                    same = np.array_equal(a.indices, b.indices) and np.array_equal(a.position, b.position) and np.array_equal(a.uvw, b.uvw)
+                ok_mesh &= bool(same)
+            nd += len(dirty)
+        result_q.put((rank, bool(ok_dirty), bool(ok_mesh), nd))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_edit_ticks_match_single_process():
+    """Three ticks of 200 edits on a planet split over two ranks: the owner applies an edit, both sides of a rank boundary rebuild
+    what the reference's neighbour mask says, and every rebuilt mesh equals the single-process one."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_edit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), "sharded dirty sets differ from the single-process dirty set"
+    assert all(r[2] for r in res), "a mesh rebuilt on a shard differs from the single-process mesh"
+    assert all(r[3] > 0 for r in res)

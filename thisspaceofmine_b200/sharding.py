@@ -83,6 +83,30 @@ class ShardPlan:
                     out.setdefault(int(peer), set()).update(int(v) for v in lid[own == peer])
         return {p: np.array(sorted(v), np.int64) for p, v in sorted(out.items())}
 
+    def route_edits(self, rank: int, edits) -> Tuple[np.ndarray, np.ndarray]:
+        """A tick's edits, replicated on every rank ([n, 7] int: cx, cy, cz, x, y, z, block) -> what `rank` has to do with them:
+        (mask of the edits whose chunk it owns — it applies those, in order —, sorted linear ids of ITS chunks that must be rebuilt
+        because a chunk owned by someone else was edited on the boundary layer facing them).  The boundary rule is the reference's
+        neighbour mask (Planet.cpp:39-58): x = 0 Left, x = 31 Right, y = 0 Front, y = 31 Back, z = 0 Down, z = 31 Up (local axes);
+        the owner of an edited chunk finds its own masked neighbours through tsom_collect_dirty, so only the cross-rank pairs are
+        listed here.  Edits outside the planet are owned by nobody."""
+        e = np.asarray(edits, np.int64).reshape(-1, 7)
+        lid = self.linear_id(e[:, 0:3])
+        inside = lid >= 0
+        own = np.zeros(len(e), bool)
+        own[inside] = self.owner[lid[inside]] == rank
+        foreign = inside & ~own
+        touched = []
+        # (local coordinate column, value on the boundary, direction of the neighbour that sees that layer)
+        for col, edge, d in ((3, 0, 3), (3, 31, 4), (4, 0, 2), (4, 31, 0), (5, 0, 1), (5, 31, 5)):
+            sel = foreign & (e[:, col] == edge)
+            if sel.any():
+                n = self.linear_id(e[sel, 0:3] + CHUNK_DIR_OFFSET[d])
+                n = n[n >= 0]
+                touched.append(n[self.owner[n] == rank])
+        extra = np.unique(np.concatenate(touched)) if touched else np.zeros(0, np.int64)
+        return own, extra.astype(np.int64)
+
     def halo_bytes(self, rank: int) -> int:
         """Bytes `rank` pulls per exchange: one 2 KiB slab per (local chunk, direction) whose neighbour is remote."""
         mine = self.local(rank)
@@ -156,5 +180,37 @@ class ShardedPlanet:
         L.check(L.lib().tsom_halo_pull(self.planet._h))
 
     # ---- phase 2: meshing (no communication)
-    def BuildMeshes(self, **kw):
-        return self.planet.BuildMeshes(self.local_grid, **kw)
+    def BuildMeshes(self, indices=None, **kw):
+        return self.planet.BuildMeshes(self.local_grid if indices is None else indices, **kw)
+
+    # ---- edits: every rank sees the tick's edit list, applies the edits of its own chunks and remeshes its own dirty chunks
+    def UpdateBlocks(self, edits):
+        """n x Chunk::UpdateBlock on a sharded planet.  `edits` ([n, 7] int) must be the same on every rank (it is a few hundred KB per
+        tick; the server broadcasts it).  The owner of a chunk applies its edits in order; chunks of this rank that face an edited
+        boundary layer of another rank's chunk are remembered for the next CollectInvalidated."""
+        own, extra = self.plan.route_edits(self.rank, edits)
+        e = np.asarray(edits).reshape(-1, 7)
+        if own.any():
+            self.planet.UpdateBlocks(e[own])
+        self._extra_dirty = np.union1d(getattr(self, "_extra_dirty", np.zeros(0, np.int64)), extra)
+
+    def CollectInvalidated(self, clear: bool = True) -> np.ndarray:
+        """This rank's share of what ChunkEntities::Update would rebuild: its edited chunks, their masked neighbours on this rank, and
+        its chunks next to boundary edits made on other ranks -> [k, 3] int32 sorted by (x, y, z)."""
+        local = self.planet.CollectInvalidated(clear=clear)
+        lids = self.plan.linear_id(local) if len(local) else np.zeros(0, np.int64)
+        lids = lids[(lids >= 0)]
+        lids = lids[self.plan.owner[lids] == self.rank]  # ghost chunks of other ranks are rebuilt by their owners
+        lids = np.union1d(lids, getattr(self, "_extra_dirty", np.zeros(0, np.int64))).astype(np.int64)
+        if clear:
+            self._extra_dirty = np.zeros(0, np.int64)
+        idx = self.plan.grid[lids]
+        order = np.lexsort((idx[:, 2], idx[:, 1], idx[:, 0])) if len(idx) else np.zeros(0, np.int64)
+        return np.ascontiguousarray(idx[order], np.int32)
+
+    def Update(self, **kw):
+        """One tick after UpdateBlocks (collective: every rank calls it): refresh the ghost slabs, rebuild this rank's dirty chunks.
+        Returns (dirty chunk indices, MeshBatch or None)."""
+        dirty = self.CollectInvalidated(clear=True)
+        self.PullHalos()
+        return dirty, (self.planet.BuildMeshes(dirty, **kw) if len(dirty) else None)
