@@ -68,6 +68,8 @@ def _bind(path: str, full: bool):
         L.orc_lz4_compress.argtypes = [u8p, C.c_int, u8p, C.c_int]
         L.orc_lz4_decompress.argtypes = [u8p, C.c_int, u8p, C.c_int]
         L.orc_perlin_perm.argtypes = [C.c_uint32, u8p]
+        L.orc_perlin_noise3d_perm.argtypes = [u8p, C.c_double, C.c_double, C.c_double]
+        L.orc_perlin_noise3d_perm.restype = C.c_double
         L.orc_perlin_octave01.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_int]
         L.orc_perlin_octave01.restype = C.c_double
         L.orc_bernoulli_draws.argtypes = [C.c_uint32, C.c_uint32, u8p]
@@ -314,6 +316,13 @@ class Planet:
         out = np.zeros((cap, 6), np.float32)
         n = self._L.orc_box_collider(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_float), cap)
         return out[:n].copy()
+
+
+def perlin_noise3d_perm(perm, x: float, y: float, z: float) -> float:
+    """siv::PerlinNoise::noise3D over a caller-supplied permutation table (deserialize)."""
+    p = np.ascontiguousarray(perm, dtype=np.uint8)
+    assert p.shape == (256,)
+    return float(lib().orc_perlin_noise3d_perm(_p(p, C.c_uint8), float(x), float(y), float(z)))
 
 
 def lz4_compress(data) -> bytes:

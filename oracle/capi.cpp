@@ -112,6 +112,15 @@ extern "C"
 		std::memcpy(out, p.permutation(), 256);
 	}
 
+	// noise3D over a caller-supplied permutation (siv::PerlinNoise::deserialize): lets the tests check the noise core against Ken Perlin's
+	// published improved-noise reference value
+	double orc_perlin_noise3d_perm(const std::uint8_t perm[256], double x, double y, double z)
+	{
+		PerlinNoise p;
+		p.deserialize(perm);
+		return p.noise3D(x, y, z);
+	}
+
 	double orc_perlin_octave01(std::uint32_t seed, double x, double y, int octaves)
 	{
 		PerlinNoise p;

@@ -324,6 +324,8 @@ namespace orc
 			}
 
 			const std::uint8_t* permutation() const { return m_perm.data(); }
+			// siv::PerlinNoise::deserialize(state): the permutation table is the whole state
+			void deserialize(const std::uint8_t* state) { std::copy(state, state + 256, m_perm.begin()); }
 
 			double noise3D(double x, double y, double z) const
 			{
