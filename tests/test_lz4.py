@@ -190,3 +190,46 @@ def test_gpu_decoder_takes_library_streams_and_rejects_malformed_ones(ctx):
         cont.ResetChunksCompressed(idx[:1], [short])
     assert np.array_equal(cont.GetContent(idx), before), "a rejected batch must not touch any chunk"
     cont.close()
+
+
+@pytest.mark.gpu
+def test_gpu_decoder_on_mutated_streams(ctx):
+    """Bit flips, truncations and extensions of valid blocks: the device decoder accepts exactly the streams the restatement decodes to
+    65,536 bytes (and yields the same bytes); everything else is rejected and leaves the chunk untouched."""
+    import thisspaceofmine_b200 as T
+
+    rng = np.random.default_rng(17)
+    ids = np.where(rng.random(32768) < 0.9, 7, 8).astype(np.uint16)
+    ids[rng.integers(0, 32768, 600)] = 0
+    base = lib_compress(ids.tobytes())
+    cont = T.ChunkContainer(ctx, 1, 1.0)
+    idx = np.zeros((1, 3), np.int32)
+    cont.ResetChunks(idx, ids[None, :])
+    current = ids.copy()
+    accepted = rejected = 0
+    for trial in range(250):
+        s = bytearray(base)
+        kind = trial % 5
+        if kind == 0:
+            s = s[: int(rng.integers(1, len(s)))]                      # truncated
+        elif kind == 1:
+            s += bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))  # trailing garbage
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        s = bytes(s)
+        try:
+            want = O.lz4_decompress(s, N)
+        except ValueError:
+            want = None
+        if want is not None and len(want) == N:
+            cont.ResetChunksCompressed(idx, [s])
+            current = np.frombuffer(want, np.uint16).copy()
+            accepted += 1
+        else:
+            with pytest.raises(T.TsomError):
+                cont.ResetChunksCompressed(idx, [s])
+            rejected += 1
+        assert np.array_equal(cont.GetContent(idx)[0], current), f"trial {trial}"
+    assert accepted > 10 and rejected > 10
+    cont.close()
