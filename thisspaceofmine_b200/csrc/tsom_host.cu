@@ -379,12 +379,27 @@ namespace
 {
 	int AddChunk(tsom_container* c, const Key& k, uint32_t* slotOut)
 	{
-		auto it = c->slotOf.find(k);
-		if (it != c->slotOf.end())
+		if (c->hostGridValid && c->hostGridUsable)
 		{
-			if (slotOut)
-				*slotOut = it->second;
-			return TSOM_OK;
+			// the dense grid is current (nothing was added or removed since it was built): one array read instead of a hash probe —
+			// regenerating or resetting a whole planet asks for every chunk again
+			const uint32_t slot = c->SlotOf(k);
+			if (slot != 0xFFFFFFFFu)
+			{
+				if (slotOut)
+					*slotOut = slot;
+				return TSOM_OK;
+			}
+		}
+		else
+		{
+			auto it = c->slotOf.find(k);
+			if (it != c->slotOf.end())
+			{
+				if (slotOut)
+					*slotOut = it->second;
+				return TSOM_OK;
+			}
 		}
 		uint32_t slot;
 		if (!c->freeSlots.empty())
@@ -1180,25 +1195,6 @@ extern "C"
 				return Fail(TSOM_ERR_UNSUPPORTED, "chunk lies outside +-maxHeight: the reference's depth computation asserts (Nz::SafeCaster, Planet.cpp:199)");
 		}
 
-		std::vector<uint32_t> slots(n);
-		for (uint32_t i = 0; i < n; ++i)
-		{
-			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
-			if (rc != TSOM_OK)
-				return rc;
-		}
-		// generation reads chunkIdx on the device: make sure new chunks are there
-		for (uint32_t i = 0; i < n; ++i)
-		{
-			if (!c->hasContent[slots[i]])
-				c->topoDirty = true;
-			c->hasContent[slots[i]] = 1;
-			c->hostInvalid[slots[i]] = 0x80u | 0x3Fu;
-		}
-		int rc = SyncTopology(c);
-		if (rc != TSOM_OK)
-			return rc;
-
 		// terrain tables over the bounding box
 		tsomk::TerrainArgs ta{};
 		size_t total = 0;
@@ -1230,6 +1226,26 @@ extern "C"
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
+		// ---- host bookkeeping while the terrain kernel runs: slots of the chunks, content flags, topology upload
+		std::vector<uint32_t> slots(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		// generation reads chunkIdx on the device: make sure new chunks are there
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (!c->hasContent[slots[i]])
+				c->topoDirty = true;
+			c->hasContent[slots[i]] = 1;
+			c->hostInvalid[slots[i]] = 0x80u | 0x3Fu;
+		}
+		int rc = SyncTopology(c);
+		if (rc != TSOM_OK)
+			return rc;
+
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 
@@ -1258,13 +1274,14 @@ extern "C"
 		ga.bStar = ctx->bStar;
 		ga.aStar = ctx->aStar;
 		ga.aInv = ctx->aInv;
+		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
 		tsomk::launch_generate(ga, int(n), ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // blocking like Planet::GenerateChunks (WaitForTasks, Planet.cpp:402)
 		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_TERRAIN_MS], ctx->ev[0], ctx->ev[1]);
-		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[1], ctx->ev[2]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[3], ctx->ev[2]);
 		return TSOM_OK;
 	}
 
