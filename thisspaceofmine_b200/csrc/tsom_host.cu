@@ -1519,10 +1519,12 @@ extern "C"
 		TSOM_CUDA(ctx->faceCount.Ensure(n));
 		TSOM_CUDA(ctx->firstFace.Ensure(n));
 		// job i = slot | has-content flag in bit 31: the kernel's ticket needs ONE dependent load behind its atomic, not two
-		std::vector<uint32_t> jobs(n);
+		// (built in the pinned staging buffer, sized here for the views that come back through it after the kernel: the copy is a plain DMA)
+		TSOM_CUDA(ctx->EnsurePinned(std::max<size_t>(size_t(n) * (sizeof(uint32_t) + sizeof(unsigned long long)), 64)));
+		uint32_t* jobs = static_cast<uint32_t*>(ctx->hPinned);
 		for (uint32_t i = 0; i < n; ++i)
 			jobs[i] = slots[i] | (c->hasContent[slots[i]] ? 0x80000000u : 0u);
-		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, jobs.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, jobs, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		if (params->gravity_centers)
 		{
 			TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * 3));
