@@ -81,6 +81,47 @@ def test_default_planet_with_platforms_and_meshes(ctx):
     assert np.array_equal(gp.CollectInvalidated(), op.collect_dirty())
 
 
+def test_default_planet_against_the_references_own_code(ctx):
+    """The same as above, but the CPU side is oracle/_ref: the reference's own Planet.cpp / Chunk.cpp / FlatChunk.cpp compiled from its
+    sources (shipped prebuilt to the GPU box) instead of the restatement — CUDA vs the reference directly, every chunk of the default
+    planet with its four platforms: block ids, dirty set, and every mesh (indices bit-exact, vertices within 1e-5)."""
+    if not O.reference_available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    R = O.reference()
+    count = (5, 5, 5)
+    lib = ctx.blockLibrary
+    gp = T.Planet(ctx, 1.0, 16.0, 9.81, capacity=125)
+    gp.GenerateChunks(lib, 42, count)
+    rp = R.Planet(1.0, 16.0)
+    assert rp.generate(42, count, nthreads=8)
+    for d, c in PLATFORMS:
+        gp.GeneratePlatform(lib, d, c)
+        rp.generate_platform(d, c)
+    grid = T.Planet.chunk_grid(count)
+    _assert_blocks_equal(gp, rp, grid)
+    batch = gp.BuildMeshes(grid, render=True, collider=True)
+    total = 0
+    for i, idx in enumerate(grid):
+        total += assert_mesh_equal(batch.chunk(i), rp.mesh(idx), f"chunk {tuple(idx)}")["faces"]
+    assert total == batch.total_faces and total > 50000
+    assert np.array_equal(gp.CollectInvalidated(), rp.collect_dirty())
+    # a tick of edits on both sides
+    rng = np.random.default_rng(4)
+    edits = np.zeros((2000, 7), np.int64)
+    edits[:, 0:3] = grid[rng.integers(0, len(grid), 2000)]
+    edits[:, 3:6] = rng.integers(0, 32, (2000, 3))
+    edits[:, 6] = rng.choice([0, 2, 7, 13], 2000)
+    rp.clear_invalidated()
+    gp.UpdateBlocks(edits)
+    rp.apply_edits(edits)
+    dirty = gp.CollectInvalidated()
+    assert np.array_equal(dirty, rp.collect_dirty())
+    batch = gp.BuildMeshes(dirty, render=True)
+    for i, idx in enumerate(dirty):
+        assert_mesh_equal(batch.chunk(i), rp.mesh(idx), f"after edits, chunk {tuple(idx)}")
+    gp.close()
+
+
 def test_even_chunk_count_is_rejected(ctx):
     """chunkCount 4 puts blocks beyond +-maxHeight: the reference asserts (Nz::SafeCaster, Planet.cpp:199); we refuse."""
     gp = T.Planet(ctx, capacity=64)

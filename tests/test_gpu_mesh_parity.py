@@ -313,3 +313,36 @@ def test_aabb_is_the_box_of_the_emitted_positions(ctx, mode):
         want = np.concatenate([om.position.min(0), om.position.max(0)])
         assert np.allclose(boxes[i], want, rtol=1e-5, atol=1e-5), f"chunk {k}"
     gc.close()
+
+
+@pytest.mark.parametrize("scenario", ["neighbours_mixed_ids", "deformed", "tile_and_gravity"])
+def test_meshes_against_the_references_own_code(ctx, scenario):
+    """CUDA vs oracle/_ref (the reference's own Chunk.cpp / FlatChunk.cpp / DeformedChunk.cpp compiled from its sources, shipped prebuilt
+    to the GPU box) instead of the restatement: halos with missing / content-less neighbours and transparent, double-sided and
+    non-colliding blocks; deformed corners; a custom block size and gravity centre."""
+    if not O.reference_available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    R = O.reference()
+    rng = np.random.default_rng(21)
+    tile = 0.5 if scenario == "tile_and_gravity" else 1.0
+    chunks = {}
+    for cx in range(-1, 2):
+        for cy in range(0, 2):
+            for cz in range(-1, 1):
+                chunks[(cx, cy, cz)] = random_chunk(rng, 0.55, ids=(2, 3, 7, 8, 9, 13))
+    chunks[(1, 0, 0)] = None
+    del chunks[(0, 1, -1)]
+    gc = T.ChunkContainer(ctx, len(chunks), tile)
+    rp = R.Planet(tile)
+    for idx, b in chunks.items():
+        rp.add_chunk(idx, b)
+        gc.AddChunk(idx, None if b is None else b[None, :])
+    todo = [k for k, v in chunks.items() if v is not None]
+    kw = {}
+    if scenario == "deformed":
+        kw = dict(deformed=True, deformRadius=16.0)
+    if scenario == "tile_and_gravity":
+        kw = dict(gravityCenters=np.tile(np.array([[3.25, -100.0, 17.5]], np.float32), (len(todo), 1)))
+    faces, _ = _compare_all(gc, rp, todo, **kw)
+    assert faces > 10000
+    gc.close()
