@@ -122,6 +122,16 @@ static void TestGpu()
 	for (std::size_t i = 0; i < grid.size(); ++i)
 		batch.CopyChunk(i, &batchVerts[i], &batchIdx[i], nullptr);
 
+	// ComputeVoxelCorners (FlatChunk.cpp:48-54): block (0, 5, 31) of chunk (1, -1, 0), BoxCorner order, y / z crossed
+	{
+		Chunk c = planet.GetChunk(ChunkIndices(1, -1, 0));
+		const auto corners = c.ComputeVoxelCorners(Vector3ui(0, 5, 31));
+		CHECK(corners[std::size_t(Chunk::BoxCorner::LeftBottomFar)] == Vector3f(-16.f, 15.f, -10.f));
+		CHECK(corners[std::size_t(Chunk::BoxCorner::RightBottomFar)] == Vector3f(-16.f, 15.f, -11.f));
+		CHECK(corners[std::size_t(Chunk::BoxCorner::RightTopNear)] == Vector3f(-15.f, 16.f, -11.f));
+		// every vertex of this block's faces in the mesh is one of its corners: checked for all blocks in tests/test_gpu_mesh_parity.py
+	}
+
 	// GenerateAABB on the device == min / max over the vertices the caller received
 	{
 		const auto boxes = batch.ComputeAABBs();

@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <array>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -331,6 +332,13 @@ namespace tsom_b200
 
 			// Chunk::UpdateBlock (Chunk.cpp:348-366); batching many edits per tick: ChunkContainer::UpdateBlocks
 			void UpdateBlock(const Vector3ui& indices, BlockIndex cellType);
+
+			// Chunk::ComputeVoxelCorners (Chunk.hpp:54; FlatChunk.cpp:48-54, DeformedChunk.cpp:115-137), the helper block picking uses
+			// (GameState.cpp:859, PlayerSessionHandler.cpp:367,489): the 8 corners of a block, indexed by BoxCorner; evaluated by the
+			// device functions the mesher uses.  With CornerMode::Deformed the deformation centre is `deformCenter`, or by default the
+			// container centre minus the chunk offset.
+			enum class BoxCorner { LeftBottomFar, LeftTopFar, RightBottomFar, RightTopFar, LeftBottomNear, LeftTopNear, RightBottomNear, RightTopNear };
+			std::array<Vector3f, 8> ComputeVoxelCorners(const Vector3ui& indices, CornerMode corners = CornerMode::Flat, float deformRadius = 0.f, const Vector3f* deformCenter = nullptr) const;
 
 			// Chunk::Serialize / Deserialize (Chunk.cpp:252-346), the `<x>_<y>_<z>.chunk` save format: header composed / parsed
 			// here (big-endian integers, UInt32-prefixed names — Nazara ByteStream conventions), palette + payload on the device.
@@ -692,6 +700,19 @@ namespace tsom_b200
 			out.insert(out.end(), name.begin(), name.end());
 		}
 		out.insert(out.end(), payload.begin(), payload.begin() + TSOM_CHUNK_BLOCKS * (count > 8 ? 2 : 1));
+		return out;
+	}
+
+	inline std::array<Vector3f, 8> Chunk::ComputeVoxelCorners(const Vector3ui& indices, CornerMode corners, float deformRadius, const Vector3f* deformCenter) const
+	{
+		tsom_mesh_params params{};
+		params.flags = corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u;
+		params.deform_radius = deformRadius;
+		params.gravity_centers = deformCenter ? &deformCenter->x : nullptr;
+		const std::uint32_t local[3] = { indices.x, indices.y, indices.z };
+		std::array<Vector3f, 8> out;
+		static_assert(sizeof(out) == 24 * sizeof(float), "corner layout");
+		Check(tsom_voxel_corners(m_owner->Handle(), &m_indices.x, local, 1, &params, &out[0].x), "tsom_voxel_corners");
 		return out;
 	}
 

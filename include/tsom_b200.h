@@ -231,6 +231,14 @@ int tsom_mesh_arenas(tsom_ctx* ctx, const void** vertices, const void** indices,
 /* copy faces [first_face, first_face + face_count) to host: the std::vector<VertexStruct> / std::vector<UInt32> /
  * std::vector<Vector3f> the reference's callers own.  Any destination may be NULL. */
 int tsom_mesh_copy_to_host(tsom_ctx* ctx, uint64_t first_face, uint64_t face_count, void* vertices, uint32_t* indices, float* collider_positions);
+/* Chunk::ComputeVoxelCorners (include/CommonLib/Chunk.hpp:54; FlatChunk.cpp:48-54, DeformedChunk.cpp:115-137) as a batched query: the pure
+ * helper the game's block picking uses (src/Game/States/GameState.cpp:859, src/ServerLib/Session/PlayerSessionHandler.cpp:367,489),
+ * answered by the device functions the mesher itself uses.  Block i = local_indices[3i..] of chunk chunk_indices[3i..] (the chunk need not
+ * exist: the corners depend on its indices only).  params: TSOM_MESH_DEFORMED + deform_radius select DeformedChunk's provider,
+ * gravity_centers (n x 3, optional) is its deformation centre (default: container centre - chunk offset).  corners_out: n x 8 x xyz in
+ * Nz::BoxCorner enum order (LeftBottomFar, LeftTopFar, RightBottomFar, RightTopFar, LeftBottomNear, LeftTopNear, RightBottomNear,
+ * RightTopNear). */
+int tsom_voxel_corners(tsom_container* c, const int32_t* chunk_indices, const uint32_t* local_indices, uint32_t n, const tsom_mesh_params* params, float* corners_out);
 /* Nz::StaticMesh::GenerateAABB as ClientChunkEntities::BuildMesh calls it on every chunk mesh (src/ClientLib/ClientChunkEntities.cpp:168):
  * the bounding box of the vertex positions of each view of the last tsom_mesh call, computed on the device from the floats in the arena
  * (render vertices, or the collider positions of a collider-only call).  aabb_out: n x {min.xyz, max.xyz}; zeros for a view without faces.

@@ -89,6 +89,7 @@ def _bind(path: str, full: bool):
     L.orc_planet_collect_dirty.restype = C.c_uint32
     L.orc_mesh_build.argtypes = [C.c_void_p, i32p, C.c_int, f32p, f32p, C.c_float, C.c_int, C.c_int]
     L.orc_mesh_build.restype = C.c_void_p
+    L.orc_voxel_corners.argtypes = [C.c_void_p, i32p, u32p, C.c_int, f32p, C.c_float, f32p]
     L.orc_mesh_face_count.argtypes = [C.c_void_p]
     L.orc_mesh_face_count.restype = C.c_uint32
     L.orc_mesh_copy.argtypes = [C.c_void_p, f32p, f32p, f32p, u32p]
@@ -311,6 +312,15 @@ class Planet:
             raise KeyError(tuple(idx))
         if rc == 2:
             raise RuntimeError(err.value.decode())
+
+    def voxel_corners(self, idx, local, deformed=False, deform_center=None, deform_radius=0.0) -> np.ndarray:
+        """Chunk::ComputeVoxelCorners (Chunk.hpp:54) of block `local` of chunk `idx` -> [8, 3] float32 in Nz::BoxCorner enum order."""
+        out = np.zeros((8, 3), np.float32)
+        d = None if deform_center is None else _p(np.ascontiguousarray(deform_center, dtype=np.float32), C.c_float)
+        rc = self._L.orc_voxel_corners(self._h, _p(_i3(idx), C.c_int32), _p(_u3(local), C.c_uint32), int(deformed), d, float(deform_radius), _p(out, C.c_float))
+        if rc:
+            raise KeyError(tuple(idx))
+        return out
 
     def box_collider(self, idx, cap=32768):
         out = np.zeros((cap, 6), np.float32)

@@ -269,6 +269,29 @@ extern "C"
 		return m;
 	}
 
+	// Chunk::ComputeVoxelCorners (Chunk.hpp:54; FlatChunk.cpp:48-54 / DeformedChunk.cpp:115-137) of one block: out = 8 corners x xyz in
+	// Nz::BoxCorner enum order.  deformCenter == nullptr: container centre - chunk offset.  Returns 0, or 1 for an unknown chunk.
+	int orc_voxel_corners(void* h, const std::int32_t idx[3], const std::uint32_t local[3], int cornerMode, const float* deformCenter, float deformRadius, float out[24])
+	{
+		Planet& p = static_cast<PlanetHandle*>(h)->planet;
+		Chunk* c = p.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c)
+			return 1;
+		const Vec3f center = p.GetCenter() - p.GetChunkOffset(c->GetIndices());
+		c->cornerMode = cornerMode ? CornerMode::Deformed : CornerMode::Flat;
+		c->deformationCenter = deformCenter ? Vec3f{ deformCenter[0], deformCenter[1], deformCenter[2] } : center;
+		c->deformationRadius = deformRadius;
+		const Corners corners = c->ComputeVoxelCorners({ local[0], local[1], local[2] });
+		int k = 0;
+		for (const Vec3f& v : corners)
+		{
+			out[k++] = v.x;
+			out[k++] = v.y;
+			out[k++] = v.z;
+		}
+		return 0;
+	}
+
 	std::uint32_t orc_mesh_face_count(void* m) { return std::uint32_t(static_cast<MeshHandle*>(m)->out.indices.size() / 6); }
 
 	// any pointer may be null

@@ -322,6 +322,33 @@ extern "C"
 		return m;
 	}
 
+	// the reference's own FlatChunk::ComputeVoxelCorners / DeformedChunk::ComputeVoxelCorners: 8 corners x xyz in Nz::BoxCorner order
+	int orc_voxel_corners(void* hv, const std::int32_t idx[3], const std::uint32_t local[3], int cornerMode, const float* deformCenter, float deformRadius, float out[24])
+	{
+		Planet& p = static_cast<PlanetHandle*>(hv)->planet;
+		Chunk* c = p.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c)
+			return 1;
+		Nz::EnumArray<Nz::BoxCorner, Nz::Vector3f> corners;
+		if (!cornerMode)
+			corners = c->ComputeVoxelCorners(Nz::Vector3ui{ local[0], local[1], local[2] });
+		else
+		{
+			const Nz::Vector3f center = p.GetCenter() - p.GetChunkOffset(c->GetIndices());
+			Nz::Vector3f dc = deformCenter ? Nz::Vector3f(deformCenter[0], deformCenter[1], deformCenter[2]) : center;
+			DeformedChunk deformed(Lib(), p, c->GetIndices(), Nz::Vector3ui{ Planet::ChunkSize }, p.GetTileSize(), dc, deformRadius);
+			corners = deformed.ComputeVoxelCorners(Nz::Vector3ui{ local[0], local[1], local[2] });
+		}
+		int k = 0;
+		for (const Nz::Vector3f& v : corners)
+		{
+			out[k++] = v.x;
+			out[k++] = v.y;
+			out[k++] = v.z;
+		}
+		return 0;
+	}
+
 	std::uint32_t orc_mesh_face_count(void* m) { return std::uint32_t(static_cast<MeshHandle*>(m)->out.indices.size() / 6); }
 
 	void orc_mesh_copy(void* mh, float* pos, float* normal, float* uvw, std::uint32_t* indices)

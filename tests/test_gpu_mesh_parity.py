@@ -346,3 +346,41 @@ def test_meshes_against_the_references_own_code(ctx, scenario):
     faces, _ = _compare_all(gc, rp, todo, **kw)
     assert faces > 10000
     gc.close()
+
+
+@pytest.mark.parametrize("tile", [1.0, 0.5])
+def test_compute_voxel_corners_query(ctx, tile):
+    """Chunk::ComputeVoxelCorners (the block-picking helper) as a batched device query: FlatChunk and DeformedChunk providers, default and
+    caller-supplied deformation centres, against the restatement and — when built — the reference's own code; flat corners exactly,
+    deformed ones within 1e-5."""
+    rng = np.random.default_rng(8)
+    chunk_keys = [(0, 0, 0), (1, -2, 3), (-2, 0, 1)]
+    gc = T.ChunkContainer(ctx, len(chunk_keys), tile)
+    backends = [O] + ([O.reference()] if O.reference_available() else [])
+    planets = []
+    for B in backends:
+        p = B.Planet(tile)
+        for k in chunk_keys:
+            p.add_chunk(k, np.zeros(32768, np.uint16))
+        planets.append(p)
+    for k in chunk_keys:
+        gc.AddChunk(k, None)
+    n = 64
+    ci = np.array([chunk_keys[i] for i in rng.integers(0, len(chunk_keys), n)], np.int32)
+    loc = rng.integers(0, 32, (n, 3)).astype(np.uint32)
+    loc[0], loc[1] = (0, 0, 0), (31, 31, 31)
+    centers = rng.normal(0, 40, (n, 3)).astype(np.float32)
+    for mode, kw, okw in (("flat", {}, {}),
+                          ("deformed", dict(deformed=True, deformRadius=16.0), dict(deformed=True, deform_radius=16.0)),
+                          ("deformed, own centres", dict(deformed=True, deformRadius=7.5, deformCenters=centers), dict(deformed=True, deform_radius=7.5))):
+        got = gc.ComputeVoxelCorners(ci, loc, **kw)
+        assert got.shape == (n, 8, 3)
+        for p in planets:
+            for i in range(n):
+                extra = dict(okw, deform_center=centers[i]) if "own" in mode else okw
+                want = p.voxel_corners(ci[i], loc[i], **extra)
+                if mode == "flat":
+                    assert np.array_equal(got[i], want), (mode, i)
+                else:
+                    assert np.allclose(got[i], want, rtol=1e-5, atol=1e-5), (mode, i)
+    gc.close()

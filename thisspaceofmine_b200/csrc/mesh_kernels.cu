@@ -1066,6 +1066,36 @@ namespace tsomk
 		mesh_aabb_kernel<<<n, 256, 0, st>>>(vertices, collider, firstFace, faceCount, n, out);
 	}
 
+	// =====================================================================================================================
+	// voxel_corners_kernel — Chunk::ComputeVoxelCorners (Chunk.hpp:54) as a query: the pure helper the game uses for block picking
+	// (src/Game/States/GameState.cpp:859, src/ServerLib/Session/PlayerSessionHandler.cpp:367,489), answered by the same device
+	// functions the mesher uses.  One thread per (block, corner); out = n x 8 x xyz in Nz::BoxCorner enum order.
+	__global__ void voxel_corners_kernel(const int4* __restrict__ blocks /* local x, y, z, unused */, const float* __restrict__ centers /* n x 3 */, uint32_t n, float tile, float radius,
+	                                     int deformed, float* __restrict__ out)
+	{
+		const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+		if (t >= n * 8u)
+			return;
+		const uint32_t q = t >> 3, k = t & 7u;
+		constexpr unsigned enumOrder[8] = { 4u, 5u, 0u, 1u, 6u, 7u, 2u, 3u }; // Nz::BoxCorner -> corner code dX | dY << 1 | dZ << 2
+		FaceCtx cx;
+		cx.tile = tile;
+		cx.radius = radius;
+		cx.deformed = deformed != 0;
+		cx.wantAttr = false;
+		cx.gravity = f3(centers[q * 3 + 0], centers[q * 3 + 1], centers[q * 3 + 2]);
+		const int4 b = blocks[q];
+		const F3 p = voxel_corner(cx, b.x, b.y, b.z, enumOrder[k]);
+		out[t * 3 + 0] = p.x;
+		out[t * 3 + 1] = p.y;
+		out[t * 3 + 2] = p.z;
+	}
+
+	void launch_voxel_corners(const int4* blocks, const float* centers, uint32_t n, float tile, float radius, int deformed, float* out, cudaStream_t st)
+	{
+		voxel_corners_kernel<<<(n * 8u + 255u) / 256u, 256, 0, st>>>(blocks, centers, n, tile, radius, deformed, out);
+	}
+
 	// ---- launchers ----
 	size_t mesh_fused_smem_bytes() { return sizeof(FusedSmem); }
 

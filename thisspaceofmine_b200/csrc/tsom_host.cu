@@ -1686,6 +1686,42 @@ extern "C"
 		return TSOM_OK;
 	}
 
+	int tsom_voxel_corners(tsom_container* c, const int32_t* chunk_indices, const uint32_t* local_indices, uint32_t n, const tsom_mesh_params* params, float* corners_out)
+	{
+		if (!c || !params || ((!chunk_indices || !local_indices || !corners_out) && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		TSOM_LOCK(ctx);
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		// staging: n x int4 blocks | n x 3 float centres (pinned), device: status buffer as int4s, gravity buffer as centres + output
+		TSOM_CUDA(ctx->EnsurePinned(size_t(n) * (sizeof(int4) + 3 * sizeof(float))));
+		int4* hBlocks = static_cast<int4*>(ctx->hPinned);
+		float* hCenters = reinterpret_cast<float*>(hBlocks + n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			const uint32_t* l = local_indices + size_t(i) * 3;
+			if (l[0] >= uint32_t(CS) || l[1] >= uint32_t(CS) || l[2] >= uint32_t(CS))
+				return Fail(TSOM_ERR_INVALID, "block indices out of range");
+			hBlocks[i] = make_int4(int(l[0]), int(l[1]), int(l[2]), 0);
+			const int32_t* ci = chunk_indices + size_t(i) * 3;
+			for (int a = 0; a < 3; ++a) // DeformedChunk's deformation centre: the caller's, or container centre - GetChunkOffset (ChunkContainer.inl:53-56)
+				hCenters[i * 3 + a] = params->gravity_centers ? params->gravity_centers[size_t(i) * 3 + a] : c->center[a] - float(ci[a]) * float(CS) * c->tile;
+		}
+		TSOM_CUDA(ctx->status.Ensure(size_t(n) * 2));         // n x int4
+		TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * (3 + 24))); // centres, then the corners
+		TSOM_CUDA(cudaMemcpyAsync(ctx->status.ptr, hBlocks, size_t(n) * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->gravity.ptr, hCenters, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_voxel_corners(reinterpret_cast<const int4*>(ctx->status.ptr), ctx->gravity.ptr, n, c->tile, params->deform_radius, (params->flags & TSOM_MESH_DEFORMED) != 0,
+		                            ctx->gravity.ptr + size_t(n) * 3, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(corners_out, ctx->gravity.ptr + size_t(n) * 3, size_t(n) * 24 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
 	int tsom_mesh_aabb(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, float* aabb_out)
 	{
 		if (!ctx || (!views && n) || (!aabb_out && n))

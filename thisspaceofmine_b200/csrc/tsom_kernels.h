@@ -126,6 +126,9 @@ namespace tsomk
 	void launch_depalettize(uint16_t* blocks, const uint32_t* slots, uint32_t n, const uint16_t* palette, uint32_t stride, const uint32_t* counts, const uint8_t* payload, int bigEndian,
 	                        uint32_t* errFlag, cudaStream_t st);
 
+	// ---- Chunk::ComputeVoxelCorners as a query (block picking): n blocks -> n x 8 corners in Nz::BoxCorner order ----
+	void launch_voxel_corners(const int4* blocks, const float* centers, uint32_t n, float tile, float radius, int deformed, float* out, cudaStream_t st);
+
 	// ---- Nz::StaticMesh::GenerateAABB: min / max of each chunk's vertex positions (render arena, or the collider arena if vertices == null) ----
 	void launch_mesh_aabb(const float4* vertices, const float* collider, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n, float* out, cudaStream_t st);
 

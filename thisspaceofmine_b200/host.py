@@ -506,6 +506,23 @@ class ChunkContainer:
         L.check(L.lib().tsom_mesh(self._h, _p(idx, C.c_int32), len(idx), C.byref(params), None if v is None else C.cast(v.ctypes.data, C.POINTER(L.MeshView))))
         return MeshBatch(self.ctx, idx, v, flags)
 
+    def ComputeVoxelCorners(self, chunkIndices, blockIndices, deformed: bool = False, deformRadius: float = 0.0, deformCenters: Optional[np.ndarray] = None) -> np.ndarray:
+        """Chunk::ComputeVoxelCorners (Chunk.hpp:54) for n blocks: FlatChunk's corner provider, or DeformedChunk's with `deformed`
+        (deformation centre per block in `deformCenters`, default container centre - chunk offset) -> [n, 8, 3] float32 in
+        Nz::BoxCorner enum order.  What the game's block picking calls (GameState.cpp:859, PlayerSessionHandler.cpp:367,489)."""
+        idx = _idx(chunkIndices)
+        loc = np.ascontiguousarray(blockIndices, dtype=np.uint32).reshape(-1, 3)
+        assert len(idx) == len(loc)
+        params = L.MeshParams(L.MESH_DEFORMED if deformed else 0, float(deformRadius), None)
+        g = None
+        if deformCenters is not None:
+            g = np.ascontiguousarray(deformCenters, dtype=np.float32).reshape(-1, 3)
+            assert len(g) == len(idx)
+            params.gravity_centers = _p(g, C.c_float)
+        out = np.zeros((len(idx), 8, 3), np.float32)
+        L.check(L.lib().tsom_voxel_corners(self._h, _p(idx, C.c_int32), _p(loc, C.c_uint32), len(idx), C.byref(params), _p(out, C.c_float)))
+        return out
+
     def BuildBoxCollider(self, indices) -> np.ndarray:
         """FlatChunk::BuildCollider boxes -> [n, 6] float32 (pos.xyz, size.xyz) in block units."""
         idx = _idx(indices)
