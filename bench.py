@@ -386,6 +386,10 @@ def run_b200(args):
                                    "sample": f"first {c['chunks']} of the 4096 chunks ({c['faces']} faces) in {c['seconds']:.1f} s, {CPU_KIND_NOTE[c['kind']]} with normals+uv, one task per chunk"}
         if args.planet and world == 1:
             try:
+                out["variants"] = config1_variants(T, ctx, cont, idx, torch, device, peak)
+            except Exception as e:  # secondary measurement: never lose the headline line
+                out["variants"] = {"error": str(e)}
+            try:
                 out["planet"] = planet_bench(T, ctx, args.planet)
             except Exception as e:  # secondary measurement: never lose the headline line
                 out["planet"] = {"error": str(e)}
@@ -416,6 +420,40 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config1_variants(T, ctx, cont, idx, torch, device, peak):
+    """SURVEY.md §8(d) config 2, the two other fills (kernel time only, 1024 of the container's chunks, 5 launches each):
+    `sparse` p = 0.05 stone, where reading the ids dominates, and `mixed_ids` uniform over {0, 2, 3, 7, 8, 9, 13} = empty, dirt, grass,
+    stone, stone_mossy, forcefield (transparent, no collision), glass (transparent, double sided), which exercises the same-type,
+    transparent-neighbour and twin-face rules (parity of those rules: tests/test_gpu_mesh_parity.py)."""
+    m = 1024
+    sub = np.ascontiguousarray(idx[:m])
+    table = torch.tensor([0, 2, 3, 7, 8, 9, 13], dtype=torch.int16, device=device)
+
+    def mixed(first, count):
+        h = torch.arange(first * NBLK, (first + count) * NBLK, dtype=torch.int64, device=device).view(count, NBLK)
+        h = (h * _s64(0x9E3779B97F4A7C15)) ^ ((h >> 29) & 0x7FFFFFFFF)  # a multiplicative hash of the global block ordinal
+        h = h * _s64(0xBF58476D1CE4E5B9)
+        return table[((h >> 33) & 0x7FFFFFFF) % 7].contiguous()
+
+    fills = {"sparse_p0.05": lambda first, count: device_fill(torch, device, SEED + 2, first, count, p=0.05), "mixed_ids": mixed}
+    res = {}
+    for name, fill in fills.items():
+        for s0 in range(0, m, 256):
+            blk = fill(s0, 256)
+            torch.cuda.synchronize()
+            cont.ResetChunks(sub[s0:s0 + 256], int(blk.data_ptr()))
+            del blk
+        faces = cont.BuildMeshes(sub, views=True).total_faces
+        ms = []
+        for _ in range(5):
+            cont.BuildMeshes(sub, views=False)
+            ms.append(ctx.timings()["mesh_emit_ms"])
+        t = sum(ms) / len(ms)
+        algo = m * CHUNK_READ_BYTES + FACE_BYTES * faces
+        res[name] = {"chunks": m, "faces": int(faces), "kernel_ms": t, "chunks_per_s": m / (t / 1e3), "gbs": algo / (t / 1e3) / 1e9, "frac": algo / (t / 1e3) / 1e9 / peak}
+    return res
 
 
 def planet_bench(T, ctx, count):
