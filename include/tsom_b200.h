@@ -53,8 +53,10 @@ enum
 	TSOM_MESH_COLLIDER = 2, /* positions only + the same indices: DeformedChunk::BuildCollider (src/CommonLib/DeformedChunk.cpp:15-36) */
 	TSOM_MESH_DEFORMED = 4, /* corner provider DeformedChunk::ComputeVoxelCorners (DeformedChunk.cpp:115-154) instead of FlatChunk (FlatChunk.cpp:48-54) */
 	TSOM_MESH_GENERIC_MATH = 8, /* diagnostics: evaluate DrawFace's float math per face even where the exact table-driven flat path applies */
-	TSOM_MESH_ORDERED = 16 /* place the chunks' face ranges in the arenas in job order (first_face[i] = sum of face_count[< i]) instead of
-	                          first come, first served; costs a cross-chunk dependency (decoupled look-back) in the kernel */
+	TSOM_MESH_ORDERED = 16, /* place the chunks' face ranges in the arenas in job order (first_face[i] = sum of face_count[< i]) instead of
+	                           first come, first served; costs a cross-chunk dependency (decoupled look-back) in the kernel */
+	TSOM_MESH_TANGENTS = 32 /* also fill the 12-byte tangent slot of every vertex the way Nz::StaticMesh::GenerateTangents does after
+	                           ClientChunkEntities::BuildMesh (src/ClientLib/ClientChunkEntities.cpp:169); needs TSOM_MESH_RENDER */
 };
 
 typedef struct tsom_ctx tsom_ctx;             /* one per process and GPU: stream, block table, mesh arenas */
@@ -110,7 +112,7 @@ typedef struct tsom_mesh_params
 
 typedef struct tsom_ipc_handle
 {
-	unsigned char bytes[136]; /* 2 x cudaIpcMemHandle_t (blocks, x-slabs) + capacity */
+	unsigned char bytes[200]; /* 3 x cudaIpcMemHandle_t (blocks, x-slabs, halo sync flags) + capacity */
 } tsom_ipc_handle;
 
 /* ---- library ---- */
@@ -137,14 +139,15 @@ uint64_t tsom_launch_count(tsom_ctx* ctx);
 /* device-side durations (CUDA events on the context's stream) of the kernels of the most recent generate / mesh call */
 enum tsom_timing
 {
-	TSOM_TIMING_TERRAIN_MS = 0,   /* terrain_kernel (the six directions in one launch) */
-	TSOM_TIMING_GENERATE_MS = 1,  /* generate_kernel */
-	TSOM_TIMING_MESH_COUNT_MS = 2, /* 0 on the single-pass path (count and scan live inside mesh_fused_kernel) */
-	TSOM_TIMING_MESH_SCAN_MS = 3,
-	TSOM_TIMING_MESH_EMIT_MS = 4,  /* mesh_fused_kernel: classify + count + chain + emit */
-	TSOM_TIMING_MESH_REEMIT = 5,  /* 1.0 when the arenas had to grow and the kernel ran twice (the time is then of the first, count-only run) */
-	TSOM_TIMING_IO_MS = 6,        /* kernels of the most recent wire-format call: lz4_compress (+ pack, summed over its sub-batches) or lz4_decompress */
-	TSOM_TIMING_COUNT = 7
+	TSOM_TIMING_TERRAIN_MS = 0,  /* terrain_kernel (the six directions in one launch) */
+	TSOM_TIMING_GENERATE_MS = 1, /* template_kernel + generate_kernel */
+	TSOM_TIMING_HALO_MS = 2,     /* tsom_halo_pull: wait for the peers' publish flags + halo_pull_kernel */
+	TSOM_TIMING_CLASSIFY_MS = 3, /* job_classify_kernel (marks the jobs whose chunk provably has no face) */
+	TSOM_TIMING_MESH_EMIT_MS = 4, /* mesh_fused_kernel: classify + count + chain + emit */
+	TSOM_TIMING_MESH_REEMIT = 5, /* 1.0 when the arenas had to grow and the kernel ran twice (the time is then of the first, count-only run) */
+	TSOM_TIMING_IO_MS = 6,       /* kernels of the most recent wire-format call: lz4_compress (+ pack, summed over its sub-batches) or lz4_decompress */
+	TSOM_TIMING_COLLIDER_MS = 7, /* box_colliders_kernel of the most recent tsom_box_colliders call */
+	TSOM_TIMING_COUNT = 8
 };
 int tsom_get_timings(tsom_ctx* ctx, float* out, uint32_t n);
 /* pre-size the mesh arenas (faces); they also grow on demand */
@@ -248,17 +251,100 @@ int tsom_mesh_aabb(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, float
  * in block units (multiply by the block size like FlatChunk.cpp:20-21 does). */
 int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out);
 
-/* ---- multi-GPU: one process per GPU, chunks sharded by index, halo slabs pulled over NVLink P2P (no NCCL) ---- */
-/* declare a neighbour chunk that lives on another rank; its facing slabs are refreshed by tsom_halo_pull */
+/* Batched form of the same (the server's physics path: ChunkEntities::UpdateChunkEntity calls BuildCollider for every invalidated chunk,
+ * src/CommonLib/ChunkEntities.cpp:198): ONE launch for n chunks, one CTA per chunk, the boxes of chunk i at
+ * [views_out[i].first_box, + box_count) of a device arena owned by the context, in the reference's order.  No per-chunk synchronisation.
+ * Chunks without content or without a colliding block get 0 boxes (the reference returns a null collider, FlatChunk.cpp:25-26). */
+typedef struct tsom_box_view
+{
+	uint64_t first_box;
+	uint32_t box_count;
+	uint32_t reserved;
+} tsom_box_view;
+int tsom_box_colliders(tsom_container* c, const int32_t* chunk_indices, uint32_t n, tsom_box_view* views_out, uint64_t* total_boxes_out);
+/* boxes [first_box, first_box + box_count) of the last tsom_box_colliders call -> host, 6 floats each (pos.xyz, size.xyz, block units) */
+int tsom_box_colliders_copy_to_host(tsom_ctx* ctx, uint64_t first_box, uint64_t box_count, float* boxes_out);
+
+/* ---- the second ChunkContainer: Ship (include/CommonLib/Ship.hpp, src/CommonLib/Ship.cpp) ----
+ * A container is a Planet by default.  TSOM_CONTAINER_SHIP switches the dirty-neighbour rule of tsom_apply_edits to Ship::AddChunk's
+ * (Ship.cpp:36-54): local z == 0 raises Direction::Up and z == 31 Direction::Down — the opposite of Planet.cpp:50-53. */
+enum tsom_container_kind { TSOM_CONTAINER_PLANET = 0, TSOM_CONTAINER_SHIP = 1 };
+int tsom_container_set_kind(tsom_container* c, int kind);
+/* Ship::Generate (Ship.cpp:115-152): chunk (0,0,0) is added, reset to Empty and the hull box (6x6x4 when small, else 12x12x6, one
+ * forcefield door column) is written with Chunk::UpdateBlock semantics (the chunk ends up invalidated with the masks of those edits). */
+int tsom_ship_generate(tsom_container* c, int small, uint16_t hull_block, uint16_t forcefield_block);
+
+/* ---- multi-GPU: chunks sharded by chunk index, halo slabs pulled over NVLink P2P (no NCCL) ----
+ * A planet is cut into axis-aligned boxes of chunks, one per GPU (tsom_shard_plan).  Each GPU generates and meshes its own box; between
+ * the two phases it copies the 2 KiB facing slab of every neighbour chunk owned by another GPU straight out of the owner's HBM.  The
+ * exchange is ordered on the DEVICE: every container owns two epoch flags in its HBM (blocks-final, slabs-pulled) that the peers poll
+ * over NVLink from a one-warp wait kernel, so no host barrier sits between generation, exchange and meshing.
+ * Two ways to run it: one process per GPU (tsom_ipc_export / tsom_ipc_attach; thisspaceofmine_b200/sharding.py under torchrun), or all
+ * GPUs from ONE process — what a TSOM server is (src/Server/main.cpp:24-62) — through tsom_planet_create_sharded below. */
+
+/* Cuts the chunk_count[0] x [1] x [2] chunk grid of Planet::GenerateChunks (Planet.cpp:385-403) into n_parts boxes by recursive
+ * bisection: the part range is halved, the box is cut across its longest axis at the layer boundary that best balances the
+ * summed chunk weights in proportion to the two part counts.  chunk_weights: optional, one float per chunk in GenerateChunks
+ * order (z, y, x loops) — e.g. a + b * face count of a previous pass; NULL = a shell model (chunks that can hold a surface
+ * weigh more).  boxes_out: n_parts x 6 int32 = lo.xyz, hi.xyz (inclusive) in chunk indices (already minus chunk_count / 2).
+ * TSOM_ERR_INVALID when n_parts exceeds the number of chunks. */
+int tsom_shard_plan(const uint32_t chunk_count[3], uint32_t n_parts, const float* chunk_weights, int32_t* boxes_out);
+
+/* declare neighbour chunks that live on another GPU: rank = the peer's id as given to tsom_ipc_attach / tsom_peer_attach_local,
+ * remote_slot = tsom_chunk_slot of the chunk in the peer's container.  Remote chunks are assumed to have content whenever their
+ * owner has published (a sharded planet generates every chunk before the first exchange). */
 int tsom_container_add_remote_chunks(tsom_container* c, const int32_t* chunk_indices, const uint32_t* remote_slots, const int32_t* ranks, uint32_t n);
 /* slot of a local chunk (what a peer passes as remote_slots) */
 int tsom_chunk_slot(tsom_container* c, const int32_t chunk_index[3], uint32_t* slot_out);
 int tsom_ipc_export(tsom_container* c, tsom_ipc_handle* out);
 int tsom_ipc_attach(tsom_container* c, int rank, const tsom_ipc_handle* handle);
-/* same-process variant (tests, single-process multi-context): attach another container's buffers directly */
+/* same-process variant (single-process multi-GPU, tests): attach another container's buffers directly; enables peer access when
+ * the two contexts sit on different devices */
 int tsom_peer_attach_local(tsom_container* c, int rank, tsom_container* peer);
-/* copy the boundary slabs of all remote neighbours from their owners' HBM into this GPU's ghost slabs */
+/* The exchange, one ROUND per tick, collective over the containers of a planet (every one of them runs every round, also when it
+ * wrote nothing).  All of it is enqueued on the context's stream; neither call waits on the host.
+ *   tsom_halo_publish : "my blocks are final for this round" — raises this container's blocks-final flag to round r.
+ *   tsom_halo_pull    : publishes if this round has not been published yet, waits (on the device) until every attached peer has
+ *                       published round r, copies the facing slabs of all remote neighbours into the local ghost slabs, raises
+ *                       the slabs-pulled flag to r.
+ * Any call that writes blocks (generate, reset, edits, platform ...) after round r first waits, on the device, until every peer has
+ * pulled round r, so a fast GPU cannot overwrite slabs a slower one is still reading.  Nothing may write between a container's
+ * publish and its pull.  Containers that share one context (one stream) must be driven publish-all, then pull-all.
+ * tsom_mesh fails with TSOM_ERR_INVALID while a remote neighbour's slab has never been pulled (topology changed since the last pull).
+ * A peer that does not arrive within 5 s makes the next blocking call on the context fail with TSOM_ERR_INTERNAL. */
+int tsom_halo_publish(tsom_container* c);
 int tsom_halo_pull(tsom_container* c);
+
+/* ---- one planet over several GPUs of ONE process (tsom_create(gpu_ids, n)) ----
+ * Owns one context + container per part.  cuda_devices may name a device more than once (two parts on one GPU: what the
+ * single-GPU parity test does).  Every call fans out to the parts on worker threads and returns when all are done. */
+typedef struct tsom_sharded_planet tsom_sharded_planet;
+int tsom_planet_create_sharded(const int* cuda_devices, uint32_t n_parts, const uint32_t chunk_count[3], float tile_size, const float* chunk_weights,
+                               tsom_sharded_planet** out);
+void tsom_sharded_destroy(tsom_sharded_planet* p);
+uint32_t tsom_sharded_part_count(const tsom_sharded_planet* p);
+tsom_ctx* tsom_sharded_ctx(tsom_sharded_planet* p, uint32_t part);
+tsom_container* tsom_sharded_container(tsom_sharded_planet* p, uint32_t part);
+/* lo.xyz, hi.xyz (inclusive chunk indices) of a part */
+int tsom_sharded_part_box(const tsom_sharded_planet* p, uint32_t part, int32_t box_out[6]);
+/* owner of a chunk (TSOM_ERR_INVALID outside the planet) */
+int tsom_sharded_owner(const tsom_sharded_planet* p, const int32_t chunk_index[3], uint32_t* part_out);
+int tsom_sharded_set_block_table(tsom_sharded_planet* p, const tsom_block_desc* blocks, uint32_t n);
+/* Planet::GenerateChunks (Planet.cpp:385-403) over all parts + one exchange round */
+int tsom_sharded_generate(tsom_sharded_planet* p, uint32_t seed, const tsom_gen_blocks* ids);
+/* n x Chunk::UpdateBlock in order, each routed to the part that owns its chunk (edits outside the planet are skipped) */
+int tsom_sharded_apply_edits(tsom_sharded_planet* p, const tsom_edit* edits, uint32_t n);
+/* tsom_collect_dirty over the whole planet, including the neighbours across part boundaries (Planet.cpp:39-58); sorted by (x,y,z) */
+int tsom_sharded_collect_dirty(tsom_sharded_planet* p, int32_t* chunk_indices_out, uint32_t cap, uint32_t* n_out, int clear);
+/* one exchange round (if blocks changed since the last one), then Chunk::BuildMesh for the n chunks, each on its owner.  views_out[i] is
+ * relative to the arenas of part parts_out[i] (tsom_mesh_arenas(tsom_sharded_ctx(p, part), ...)).  chunk_indices NULL: every chunk of the
+ * planet in GenerateChunks order (n must be the chunk count when views are requested). */
+int tsom_sharded_mesh(tsom_sharded_planet* p, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, tsom_mesh_view* views_out, uint32_t* parts_out);
+int tsom_sharded_mesh_copy_to_host(tsom_sharded_planet* p, uint32_t part, uint64_t first_face, uint64_t face_count, void* vertices, uint32_t* indices, float* collider_positions);
+/* Chunk::GetContent for n chunks, wherever they live */
+int tsom_sharded_get_content(tsom_sharded_planet* p, const int32_t* chunk_indices, uint32_t n, uint16_t* blocks_host);
+/* out: part_count x TSOM_TIMING_COUNT floats (tsom_get_timings of every part) */
+int tsom_sharded_get_timings(tsom_sharded_planet* p, float* out);
 
 #ifdef __cplusplus
 }

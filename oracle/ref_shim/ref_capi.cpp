@@ -1,6 +1,6 @@
 // oracle/ref_shim/ref_capi.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 // C entry points (same names and meaning as oracle/capi.cpp) over THE REFERENCE'S OWN SOURCES: src/CommonLib/{Chunk,FlatChunk,
-// DeformedChunk,Planet,BlockLibrary,ChunkContainer,GravityController}.cpp, compiled unmodified from /root/reference against the
+// DeformedChunk,Planet,Ship,BlockLibrary,ChunkContainer,GravityController}.cpp, compiled unmodified from /root/reference against the
 // stand-in headers of oracle/ref_shim/include (NazaraEngine, siv::PerlinNoise, tsl, fmt are not on this box).
 // What this pins: the restated oracle's STRUCTURE — loop order, neighbour rules, RNG consumption, pass order, platform script,
 // greedy merge, mask rule — against the reference's real code.  What it cannot pin: the arithmetic the shim itself restates
@@ -10,6 +10,8 @@
 #include <CommonLib/DeformedChunk.hpp>
 #include <CommonLib/FlatChunk.hpp>
 #include <CommonLib/Planet.hpp>
+#include <CommonLib/Ship.hpp>
+#include <Nazara/Physics3D/Collider3D.hpp>
 #include <Nazara/Core/ByteStream.hpp>
 #include <Nazara/Core/TaskScheduler.hpp>
 
@@ -469,5 +471,215 @@ extern "C"
 		if (meshedOut)
 			*meshedOut = std::uint32_t(chunks.size());
 		return bad;
+	}
+
+	// ---- a bounded, planet-wide sample of "generate + mesh" for the CPU arm of bench.py -----------------------------------------
+	// Every stride-th chunk of the planet (GenerateChunks order, starting at `offset`) is the sample; its face-adjacent neighbours
+	// are generated once at set-up so that the sample meshes with real halos.  A step regenerates the sample chunks with the
+	// reference's own Planet::GenerateChunk and meshes them with Chunk::BuildMesh, one task per chunk like the reference's callers.
+	struct SampleHandle
+	{
+		PlanetHandle h{ 1.f, 16.f };
+		std::vector<Chunk*> sample;
+		std::uint32_t seed = 0;
+		Nz::Vector3ui count;
+	};
+
+	void* orc_sample_create(std::uint32_t seed, const std::uint32_t count[3], std::uint32_t stride, std::uint32_t offset, int nthreads)
+	{
+		auto s = new SampleHandle;
+		s->seed = seed;
+		s->count = { count[0], count[1], count[2] };
+		Planet& p = s->h.planet;
+		auto inside = [&](const ChunkIndices& c) {
+			return c.x >= -int(count[0] / 2) && c.x < int(count[0]) - int(count[0] / 2) && c.y >= -int(count[1] / 2) && c.y < int(count[1]) - int(count[1] / 2) &&
+			       c.z >= -int(count[2] / 2) && c.z < int(count[2]) - int(count[2] / 2);
+		};
+		std::vector<Chunk*> all;
+		std::size_t k = 0;
+		for (int cz = 0; cz < int(count[2]); ++cz)
+			for (int cy = 0; cy < int(count[1]); ++cy)
+				for (int cx = 0; cx < int(count[0]); ++cx, ++k)
+				{
+					if (k % stride != offset % stride)
+						continue;
+					const ChunkIndices ci{ cx - int(count[0] / 2), cy - int(count[1] / 2), cz - int(count[2] / 2) };
+					Chunk* c = p.GetChunk(ci);
+					if (!c)
+					{
+						c = &p.AddChunk(Lib(), ci);
+						all.push_back(c);
+					}
+					s->sample.push_back(c);
+					for (int d = 0; d < 6; ++d)
+					{
+						const ChunkIndices ni = ci + s_chunkDirOffset[Direction(d)];
+						if (inside(ni) && !p.GetChunk(ni))
+							all.push_back(&p.AddChunk(Lib(), ni));
+					}
+				}
+		try
+		{
+			ParallelFor(all.size(), nthreads, [&](std::size_t i) { p.GenerateChunk(Lib(), *all[i], seed, s->count); });
+		}
+		catch (const Nz::SafeCastError&)
+		{
+			delete s;
+			return nullptr;
+		}
+		return s;
+	}
+
+	std::uint32_t orc_sample_size(void* hv) { return std::uint32_t(static_cast<SampleHandle*>(hv)->sample.size()); }
+
+	// times[0] = generate seconds, times[1] = mesh seconds of the sample; returns its face count
+	std::uint64_t orc_sample_step(void* hv, int nthreads, double times[2])
+	{
+		auto* s = static_cast<SampleHandle*>(hv);
+		Planet& p = s->h.planet;
+		const double t0 = Now();
+		ParallelFor(s->sample.size(), nthreads, [&](std::size_t i) { p.GenerateChunk(Lib(), *s->sample[i], s->seed, s->count); });
+		const double t1 = Now();
+		std::atomic<std::uint64_t> faces{ 0 };
+		ParallelFor(s->sample.size(), nthreads, [&](std::size_t i) {
+			MeshOut out;
+			BuildMeshInto(*s->sample[i], p.GetCenter() - p.GetChunkOffset(s->sample[i]->GetIndices()), true, true, out);
+			faces += out.indices.size() / 6;
+		});
+		const double t2 = Now();
+		times[0] = t1 - t0;
+		times[1] = t2 - t1;
+		return faces;
+	}
+
+	void orc_sample_destroy(void* hv) { delete static_cast<SampleHandle*>(hv); }
+
+	// FlatChunk::BuildCollider for every stride-th chunk of a generated planet, one task per chunk: seconds (boxes counted)
+	double orc_bench_box_colliders(void* hv, const std::uint32_t count[3], std::uint32_t stride, int nthreads, std::uint64_t* boxesOut, std::uint32_t* chunksOut)
+	{
+		Planet& p = static_cast<PlanetHandle*>(hv)->planet;
+		std::vector<const Chunk*> chunks;
+		std::size_t k = 0;
+		for (int cz = 0; cz < int(count[2]); ++cz)
+			for (int cy = 0; cy < int(count[1]); ++cy)
+				for (int cx = 0; cx < int(count[0]); ++cx, ++k)
+					if (k % stride == 0)
+						if (const Chunk* c = p.GetChunk({ cx - int(count[0] / 2), cy - int(count[1] / 2), cz - int(count[2] / 2) }))
+							chunks.push_back(c);
+		std::atomic<std::uint64_t> boxes{ 0 };
+		const double t0 = Now();
+		ParallelFor(chunks.size(), nthreads, [&](std::size_t i) {
+			auto col = chunks[i]->BuildCollider();
+			if (auto* cc = dynamic_cast<Nz::CompoundCollider3D*>(col.get()))
+				boxes += cc->GetGeoms().size();
+		});
+		const double t1 = Now();
+		if (boxesOut)
+			*boxesOut = boxes;
+		if (chunksOut)
+			*chunksOut = std::uint32_t(chunks.size());
+		return t1 - t0;
+	}
+
+	// ---- Ship (include/CommonLib/Ship.hpp, src/CommonLib/Ship.cpp): the second ChunkContainer ------------------------------------
+	struct ShipHandle
+	{
+		Ship ship;
+		std::map<Key, std::uint32_t> invalidated;
+		NazaraSlot(ChunkContainer, OnChunkUpdated, onChunkUpdated);
+
+		explicit ShipHandle(float tile) : ship(tile)
+		{
+			onChunkUpdated.Connect(ship.OnChunkUpdated, [this](ChunkContainer*, Chunk* chunk, DirectionMask mask) {
+				const ChunkIndices& i = chunk->GetIndices();
+				invalidated[Key{ i.x, i.y, i.z }] |= std::uint32_t(mask) | 0x80u; // bit 7: the chunk itself is in the set even with an empty mask
+			});
+		}
+	};
+
+	void* orc_ship_create(float tile) { return new ShipHandle(tile); }
+	void orc_ship_destroy(void* h) { delete static_cast<ShipHandle*>(h); }
+	void orc_ship_generate(void* h, int small) { static_cast<ShipHandle*>(h)->ship.Generate(Lib(), small != 0); }
+
+	int orc_ship_add_chunk(void* h, const std::int32_t idx[3], const std::uint16_t* blocks)
+	{
+		Ship& s = static_cast<ShipHandle*>(h)->ship;
+		ChunkIndices ci{ idx[0], idx[1], idx[2] };
+		if (s.GetChunk(ci))
+			return 1;
+		if (blocks)
+			s.AddChunk(Lib(), ci, [&](BlockIndex* dst) { std::memcpy(dst, blocks, ChunkBlockCount * sizeof(BlockIndex)); });
+		else
+			s.AddChunk(Lib(), ci);
+		return 0;
+	}
+
+	int orc_ship_get_blocks(void* h, const std::int32_t idx[3], std::uint16_t* out)
+	{
+		const Chunk* c = static_cast<ShipHandle*>(h)->ship.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c || !c->HasContent())
+			return 1;
+		std::memcpy(out, c->GetContent(), ChunkBlockCount * sizeof(BlockIndex));
+		return 0;
+	}
+
+	int orc_ship_update_block(void* h, const std::int32_t idx[3], const std::uint32_t local[3], std::uint16_t id)
+	{
+		Chunk* c = static_cast<ShipHandle*>(h)->ship.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c || !c->HasContent())
+			return 1;
+		c->UpdateBlock({ local[0], local[1], local[2] }, id);
+		return 0;
+	}
+
+	// the (chunk, mask | 0x80) pairs collected since the last call, sorted by chunk; cleared
+	std::uint32_t orc_ship_take_invalidated(void* h, std::int32_t* idxOut, std::uint32_t* maskOut, std::uint32_t cap)
+	{
+		auto* s = static_cast<ShipHandle*>(h);
+		std::uint32_t n = 0;
+		for (auto&& [k, m] : s->invalidated)
+		{
+			if (n < cap)
+			{
+				idxOut[n * 3 + 0] = k.x;
+				idxOut[n * 3 + 1] = k.y;
+				idxOut[n * 3 + 2] = k.z;
+				maskOut[n] = m;
+			}
+			++n;
+		}
+		s->invalidated.clear();
+		return n;
+	}
+
+	// Ship::BuildHullCollider (Ship.cpp:63-93), flattened: per box 9 floats = child offset (GetChunkOffset, zero for the single-chunk form),
+	// box centre * blockSize, box lengths * blockSize.  Returns the number of boxes (may exceed cap); 0 = null collider.
+	std::uint32_t orc_ship_hull_collider(void* h, float* out, std::uint32_t cap)
+	{
+		std::shared_ptr<Nz::Collider3D> hull = static_cast<ShipHandle*>(h)->ship.BuildHullCollider();
+		auto* top = dynamic_cast<Nz::CompoundCollider3D*>(hull.get());
+		if (!top)
+			return 0;
+		std::uint32_t n = 0;
+		auto emit = [&](const Nz::Vector3f& chunkOffset, const Nz::CompoundCollider3D::ChildCollider& box) {
+			auto* b = dynamic_cast<Nz::BoxCollider3D*>(box.collider.get());
+			if (n < cap && b)
+			{
+				float* o = out + std::size_t(n) * 9;
+				o[0] = chunkOffset.x; o[1] = chunkOffset.y; o[2] = chunkOffset.z;
+				o[3] = box.offset.x; o[4] = box.offset.y; o[5] = box.offset.z;
+				o[6] = b->GetLengths().x; o[7] = b->GetLengths().y; o[8] = b->GetLengths().z;
+			}
+			++n;
+		};
+		for (const auto& child : top->GetGeoms())
+		{
+			if (auto* inner = dynamic_cast<Nz::CompoundCollider3D*>(child.collider.get()))
+				for (const auto& box : inner->GetGeoms())
+					emit(child.offset, box);
+			else
+				emit(Nz::Vector3f::Zero(), child);
+		}
+		return n;
 	}
 }

@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, "include", "tsom_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|uint32_t|uint64_t|char|void)\s*\*?\s*(tsom_[a-z0-9_]+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|uint32_t|uint64_t|char|tsom_ctx|tsom_container)\s*\*?\s*(tsom_[a-z0-9_]+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 
@@ -53,6 +53,7 @@ def test_struct_layouts_match_the_header():
 #include <stddef.h>
 #include "tsom_b200.h"
 int main(void) {
+  printf("%zu %zu %zu ", sizeof(tsom_box_view), offsetof(tsom_box_view, box_count), (size_t)TSOM_TIMING_COUNT);
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(tsom_block_desc), sizeof(tsom_gen_blocks), sizeof(tsom_platform_blocks), sizeof(tsom_edit),
          offsetof(tsom_edit, block), sizeof(tsom_mesh_view), offsetof(tsom_mesh_view, face_count), sizeof(tsom_mesh_params), offsetof(tsom_mesh_params, gravity_centers),
          sizeof(tsom_ipc_handle));
@@ -64,7 +65,7 @@ int main(void) {
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe])  # also proves the header is plain C
         got = [int(v) for v in subprocess.check_output([exe], text=True).split()]
-    want = [C.sizeof(L.BlockDesc), C.sizeof(L.GenBlocks), C.sizeof(L.PlatformBlocks), C.sizeof(L.Edit), L.Edit.block.offset, C.sizeof(L.MeshView),
+    want = [C.sizeof(L.BoxView), L.BoxView.box_count.offset, L.TIMING_COUNT, C.sizeof(L.BlockDesc), C.sizeof(L.GenBlocks), C.sizeof(L.PlatformBlocks), C.sizeof(L.Edit), L.Edit.block.offset, C.sizeof(L.MeshView),
             L.MeshView.face_count.offset, C.sizeof(L.MeshParams), L.MeshParams.gravity_centers.offset, C.sizeof(L.IpcHandle)]
     assert got == want
 
@@ -98,6 +99,14 @@ def test_null_handles_are_rejected_not_dereferenced():
     assert lib.tsom_mesh(None, None, 0, None, None) != L.OK
     assert lib.tsom_apply_edits(None, None, 0) != L.OK
     assert lib.tsom_halo_pull(None) != L.OK
+    assert lib.tsom_halo_publish(None) != L.OK
+    assert lib.tsom_box_colliders(None, None, 0, None, None) != L.OK
+    assert lib.tsom_sharded_generate(None, 0, None) != L.OK
+    assert lib.tsom_sharded_mesh(None, None, 0, None, None, None) != L.OK
+    assert lib.tsom_sharded_part_count(None) == 0 and not lib.tsom_sharded_ctx(None, 0)
+    lib.tsom_sharded_destroy(None)
+    out = C.c_void_p()
+    assert lib.tsom_planet_create_sharded(None, 2, None, 1.0, None, C.byref(out)) != L.OK and not out.value
     assert lib.tsom_container_chunk_count(None) == 0
     assert lib.tsom_launch_count(None) == 0
     n = C.c_uint32()
@@ -107,10 +116,11 @@ def test_null_handles_are_rejected_not_dereferenced():
 
 def test_numpy_record_layouts_match_the_ctypes_mirror():
     """host.py passes numpy record arrays straight through the C ABI (no per-element Python work): same sizes and offsets."""
-    from thisspaceofmine_b200.host import EDIT_DTYPE, VIEW_DTYPE
+    from thisspaceofmine_b200.host import BOX_VIEW_DTYPE, EDIT_DTYPE, VIEW_DTYPE
 
     assert EDIT_DTYPE.itemsize == C.sizeof(L.Edit)
     assert VIEW_DTYPE.itemsize == C.sizeof(L.MeshView)
+    assert BOX_VIEW_DTYPE.itemsize == C.sizeof(L.BoxView) and BOX_VIEW_DTYPE.fields["box_count"][1] == L.BoxView.box_count.offset
     for name, _ in L.Edit._fields_:
         assert EDIT_DTYPE.fields[name][1] == getattr(L.Edit, name).offset, name
     for name, _ in L.MeshView._fields_:

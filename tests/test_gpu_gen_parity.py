@@ -233,7 +233,11 @@ def test_halo_pull_between_two_shards(ctx):
             ranks = np.full(len(rem), other, np.int32)
             L.check(L.lib().tsom_container_add_remote_chunks(s._h, ri.ctypes.data_as(C.POINTER(C.c_int32)), slots.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                              ranks.ctypes.data_as(C.POINTER(C.c_int32)), len(rem)))
-        L.check(L.lib().tsom_halo_pull(s._h))
+    # both containers share one context (one stream): publish all, then pull all (include/tsom_b200.h, tsom_halo_pull)
+    for s in shards:
+        s.PublishHalo()
+    for s in shards:
+        s.PullHalos()
     for r, s in enumerate(shards):
         batch = s.BuildMeshes(parts[r][0])
         for i, idx in enumerate(parts[r][0]):

@@ -16,15 +16,30 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from thisspaceofmine_b200.sharding import CHUNK_DIR_OFFSET, ShardPlan, chunk_grid, partition  # noqa: E402
+from thisspaceofmine_b200.sharding import CHUNK_DIR_OFFSET, ShardPlan, chunk_grid, plan_boxes  # noqa: E402
 
 
-def test_partition_is_contiguous_and_balanced():
-    for n, w in [(125, 1), (125, 2), (125, 8), (27, 4), (3, 8), (103823, 8)]:
-        r = partition(n, w)
-        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
-        sizes = [e - s for s, e in r]
-        assert max(sizes) - min(sizes) <= 1
+def test_plan_boxes_tile_the_planet_and_balance():
+    """tsom_shard_plan (host code of the C library): the boxes are disjoint, cover every chunk, and split a cubic planet into
+    near-equal parts; an explicit weight array moves the cut to where the weight is."""
+    for cc, w in [((5, 5, 5), 1), ((5, 5, 5), 2), ((5, 5, 5), 8), ((3, 3, 3), 4), ((47, 47, 47), 8), ((31, 31, 31), 3), ((7, 3, 5), 5)]:
+        plan = ShardPlan(cc, w)
+        counts = np.bincount(plan.owner, minlength=w)
+        assert counts.sum() == plan.n and np.all(counts > 0)
+        vol = [int(np.prod(b[3:6] - b[0:3] + 1)) for b in plan.boxes]
+        assert vol == counts.tolist(), "every box holds exactly the chunks it owns (no overlap)"
+        for r in range(w):
+            assert np.array_equal(plan.slot_of(plan.local_ids(r)), np.arange(counts[r])), "slot == position in the owner's box order"
+    b = plan_boxes((47, 47, 47), 8)
+    sizes = np.prod(b[:, 3:6] - b[:, 0:3] + 1, axis=1)
+    assert sizes.max() / sizes.min() < 1.15, "2 x 2 x 2 octants of a cubic planet"
+    # all the weight in the top two z-layers: the first cut isolates them
+    wts = np.ones((9, 9, 9), np.float32)
+    wts[7:, :, :] = 100.0
+    b = plan_boxes((9, 9, 9), 2, wts)
+    assert b[0].tolist() == [-4, -4, -4, 4, 4, 3] and b[1].tolist() == [-4, -4, 4, 4, 4, 4]
+    with pytest.raises(Exception):
+        plan_boxes((1, 1, 2), 3)
 
 
 def test_chunk_grid_is_generatechunks_order():
@@ -46,11 +61,12 @@ def test_remote_neighbours_are_symmetric_and_face_adjacent_only():
                 assert any(tuple((idx - CHUNK_DIR_OFFSET[d]).tolist()) in mine for d in range(6))
             # symmetry: if I need chunks from peer, peer needs chunks from me
             assert r in rem[peer]
-    # z-major ranges: with 5 z-layers over 4 ranks most cuts cross Back/Front only; halo volume is bounded by 2 layers per cut + ragged rows
-    assert plan.halo_bytes(0) <= (25 + 10) * 2048 * 2
-    # slots: position inside the owner's range
-    s, e = plan.ranges[2]
-    assert plan.slot_of(np.arange(s, e)).tolist() == list(range(e - s))
+    # boxes: a rank's halo is the surface of its box that lies inside the planet, one slab per boundary chunk face
+    b = plan.boxes[0]
+    ext = b[3:6] - b[0:3] + 1
+    assert plan.halo_bytes(0) <= 2 * int(ext[0] * ext[1] + ext[0] * ext[2] + ext[1] * ext[2]) * 2048
+    ids = plan.local_ids(2)
+    assert plan.slot_of(ids).tolist() == list(range(len(ids)))
     assert ShardPlan((3, 3, 3), 1).remote_neighbours(0) == {}
 
 
@@ -91,7 +107,7 @@ def _worker(rank, world, port, result_q):
         count = tuple(int(v) for v in g["count"])
         seed = int(g["seed"])
         plan = ShardPlan(count, world)
-        s, e = plan.ranges[rank]
+        ids = plan.local_ids(rank)
         mine = plan.local(rank)
         blocks = {}
         for idx in mine:
@@ -134,8 +150,8 @@ def _worker(rank, world, port, result_q):
             m = planet.mesh(idx)
             faces.append(0 if m is None else m.face_count)
             icrc.append(0 if m is None else _crc(m.indices))
-        ok = np.array_equal(np.array(faces, np.uint32), g["face_count"][s:e]) and np.array_equal(np.array(icrc, np.uint32), g["index_crc"][s:e])
-        bok = all(_crc(blocks[tuple(idx.tolist())]) == g["block_crc"][s + i] for i, idx in enumerate(mine))
+        ok = np.array_equal(np.array(faces, np.uint32), g["face_count"][ids]) and np.array_equal(np.array(icrc, np.uint32), g["index_crc"][ids])
+        bok = all(_crc(blocks[tuple(idx.tolist())]) == g["block_crc"][ids[i]] for i, idx in enumerate(mine))
         result_q.put((rank, bool(ok), bool(bok), int(sum(faces))))
         dist.barrier()
     finally:

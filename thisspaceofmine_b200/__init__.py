@@ -19,5 +19,7 @@ from .host import (  # noqa: F401
     EmptyBlockIndex,
     InvalidBlockIndex,
     MeshBatch,
+    MultiGpuPlanet,
     Planet,
+    Ship,
 )

@@ -14,7 +14,9 @@ SO_PATH = os.path.join(_HERE, "libtsom_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CAPACITY, ERR_INTERNAL = range(7)
-MESH_RENDER, MESH_COLLIDER, MESH_DEFORMED, MESH_GENERIC_MATH, MESH_ORDERED = 1, 2, 4, 8, 16
+MESH_RENDER, MESH_COLLIDER, MESH_DEFORMED, MESH_GENERIC_MATH, MESH_ORDERED, MESH_TANGENTS = 1, 2, 4, 8, 16, 32
+CONTAINER_PLANET, CONTAINER_SHIP = 0, 1
+TIMING_COUNT = 8
 
 
 class TsomError(RuntimeError):
@@ -47,8 +49,12 @@ class MeshParams(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("deform_radius", C.c_float), ("gravity_centers", C.POINTER(C.c_float))]
 
 
+class BoxView(C.Structure):
+    _fields_ = [("first_box", C.c_uint64), ("box_count", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class IpcHandle(C.Structure):
-    _fields_ = [("bytes", C.c_ubyte * 136)]
+    _fields_ = [("bytes", C.c_ubyte * 200)]
 
 
 # every symbol include/tsom_b200.h declares: name -> (restype, argtypes)
@@ -96,7 +102,28 @@ SYMBOLS = {
     "tsom_ipc_export": (C.c_int, [_vp, C.POINTER(IpcHandle)]),
     "tsom_ipc_attach": (C.c_int, [_vp, C.c_int, C.POINTER(IpcHandle)]),
     "tsom_peer_attach_local": (C.c_int, [_vp, C.c_int, _vp]),
+    "tsom_halo_publish": (C.c_int, [_vp]),
     "tsom_halo_pull": (C.c_int, [_vp]),
+    "tsom_box_colliders": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(BoxView), C.POINTER(C.c_uint64)]),
+    "tsom_box_colliders_copy_to_host": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _f32p]),
+    "tsom_container_set_kind": (C.c_int, [_vp, C.c_int]),
+    "tsom_ship_generate": (C.c_int, [_vp, C.c_int, C.c_uint16, C.c_uint16]),
+    "tsom_shard_plan": (C.c_int, [_u32p, C.c_uint32, _f32p, _i32p]),
+    "tsom_planet_create_sharded": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, _u32p, C.c_float, _f32p, C.POINTER(_vp)]),
+    "tsom_sharded_destroy": (None, [_vp]),
+    "tsom_sharded_part_count": (C.c_uint32, [_vp]),
+    "tsom_sharded_ctx": (_vp, [_vp, C.c_uint32]),
+    "tsom_sharded_container": (_vp, [_vp, C.c_uint32]),
+    "tsom_sharded_part_box": (C.c_int, [_vp, C.c_uint32, _i32p]),
+    "tsom_sharded_owner": (C.c_int, [_vp, _i32p, _u32p]),
+    "tsom_sharded_set_block_table": (C.c_int, [_vp, C.POINTER(BlockDesc), C.c_uint32]),
+    "tsom_sharded_generate": (C.c_int, [_vp, C.c_uint32, C.POINTER(GenBlocks)]),
+    "tsom_sharded_apply_edits": (C.c_int, [_vp, C.POINTER(Edit), C.c_uint32]),
+    "tsom_sharded_collect_dirty": (C.c_int, [_vp, _i32p, C.c_uint32, _u32p, C.c_int]),
+    "tsom_sharded_mesh": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(MeshParams), C.POINTER(MeshView), _u32p]),
+    "tsom_sharded_mesh_copy_to_host": (C.c_int, [_vp, C.c_uint32, C.c_uint64, C.c_uint64, _vp, _u32p, _f32p]),
+    "tsom_sharded_get_content": (C.c_int, [_vp, _i32p, C.c_uint32, _u16p]),
+    "tsom_sharded_get_timings": (C.c_int, [_vp, _f32p]),
 }
 
 

@@ -90,11 +90,12 @@ namespace tsomk
 	__global__ void __launch_bounds__(1024) terrain_kernel(const TerrainArgs a)
 	{
 		// axis ids: 0 = world X, 1 = world Y (up), 2 = world Z
+		// the tiles of direction d are the blocks [terrainOffset[d] / 1024, + tiles[d]); directions the call does not need have no tiles
 		int dir = 0;
 		size_t dirOffset = a.terrainOffset[0];
 #pragma unroll
 		for (int d = 1; d < 6; ++d)
-			if (size_t(blockIdx.x) >= a.terrainOffset[d] / SLAB)
+			if (a.tiles[d] != 0u && size_t(blockIdx.x) >= a.terrainOffset[d] / SLAB)
 			{
 				dir = d;
 				dirOffset = a.terrainOffset[d];
@@ -179,8 +180,11 @@ namespace tsomk
 	void launch_terrain(const TerrainArgs& a, cudaStream_t st)
 	{
 		// tiles per direction (Direction order): Back / Front X x Y, Down / Up X x Z, Left / Right Y x Z — the layout terrainOffset describes
-		const size_t tiles = 2 * (size_t(a.tileCount[0]) * a.tileCount[1] + size_t(a.tileCount[0]) * a.tileCount[2] + size_t(a.tileCount[1]) * a.tileCount[2]);
-		terrain_kernel<<<unsigned(tiles), 1024, 0, st>>>(a);
+		size_t tiles = 0;
+		for (int d = 0; d < 6; ++d)
+			tiles += a.tiles[d];
+		if (tiles)
+			terrain_kernel<<<unsigned(tiles), 1024, 0, st>>>(a);
 	}
 
 	// ------------------------------------------------------------------------------------------------ std::minstd_rand skip-ahead
@@ -341,6 +345,9 @@ namespace tsomk
 #pragma unroll
 			for (int p = 0; p < 6; ++p)
 			{
+				act[p] = false;
+				if (!((a.dirMask >> passDir[p]) & 1u))
+					continue; // no tables: the host proved that no chunk of this call reaches the terrain band from this side
 				const size_t tileNo = a.terrainOffset[passDir[p]] / SLAB + tileIdx[p];
 				const int tdMin = a.tileRange[tileNo * 2], tdMax = a.tileRange[tileNo * 2 + 1];
 				const int bd = blockDepth[p];
@@ -365,6 +372,27 @@ namespace tsomk
 		const bool actX = act[0] | act[1], actY = act[2] | act[3], actZ = act[4] | act[5];
 		const bool anyAct = actX | actY | actZ;
 
+		uint16_t* out = a.blocks + size_t(slot) * NB;
+		uint16_t* xs = a.xslabs + size_t(slot) * 2 * SLAB;
+
+		// ---- a chunk that lies wholly outside the base fill (depth < 30 for every block, Planet.cpp:205-206): zeros, nothing else.
+		// depth = min(Hx - |wx|, Hy - |wz|, Hz - |wy|) (y / z crossed, :199-203); its maximum over the chunk is reached where |w| is smallest
+		{
+			auto minAbs = [](int w0) { return (w0 <= 0 && w0 + CS - 1 >= 0) ? 0 : min(abs(w0), abs(w0 + CS - 1)); };
+			const int maxDepth = min(Hx - minAbs(wx0), min(Hy - minAbs(wz0), Hz - minAbs(wy0)));
+			if (maxDepth < 30)
+			{
+				const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+				for (int k = 0; k < NB / 8 / GEN_THREADS; ++k)
+					reinterpret_cast<uint4*>(out)[tid + k * GEN_THREADS] = z4;
+				reinterpret_cast<uint4*>(xs)[tid] = z4; // 2 x 1024 ids = 256 x 16 B
+				if (tid == 0)
+					a.summary[slot] = SUM_EMPTY;
+				return;
+			}
+		}
+
 		// ---- RNG: the blocks that draw (depth - 30 > 18, Planet.cpp:218-219) form a box in local coordinates
 		const int Lx = Hx - 49, Ly = Hy - 49, Lz = Hz - 49; // |wx| <= Lx, |wz| <= Ly, |wy| <= Lz (y/z crossed, :199-203)
 		const int ax0 = max(0, -Lx - wx0), ax1 = min(CS - 1, Lx - wx0);
@@ -372,7 +400,29 @@ namespace tsomk
 		const int az0 = max(0, -Lz - wy0), az1 = min(CS - 1, Lz - wy0); // local z <-> world Y
 		const int NX = ax1 - ax0 + 1, NY = ay1 - ay0 + 1;
 		const bool anyDraw = (NX > 0) && (NY > 0) && (az1 >= az0);
-		if (anyDraw && tid < 3 * CS)
+		const bool fullDraw = !anyAct && ax0 == 0 && ax1 == CS - 1 && ay0 == 0 && ay1 == CS - 1 && az0 == 0 && az1 == CS - 1;
+		// the central shaft (|wx| <= 2 and |wz| <= 2, Planet.cpp:221-222) crosses the chunks with cx == 0 and cz == 0
+		const bool shaftChunk = ci.x == 0 && ci.z == 0;
+
+		// ---- every block draws and there is no shaft: before the terrain passes the chunk is a function of chunkSeed = seed + cx +
+		// cy + cz alone (Planet.cpp:165-168) — its template chunk, which sits in L2 (a 47^3 planet has 139 of them for 90 k such
+		// chunks).  Without an active pass the chunk IS the template; with one, the passes only empty blocks of it (there is no dirt to
+		// turn into grass among stone / stone_mossy), see the masked copy below.
+		const bool fromTemplate = ax0 == 0 && ax1 == CS - 1 && ay0 == 0 && ay1 == CS - 1 && az0 == 0 && az1 == CS - 1 && !shaftChunk && a.templates != nullptr &&
+		                          uint32_t(ci.x + ci.y + ci.z - a.templateSumMin) < a.nTemplates;
+		const uint4* tsrc = reinterpret_cast<const uint4*>(a.templates + size_t(uint32_t(ci.x + ci.y + ci.z - a.templateSumMin)) * TEMPLATE_STRIDE);
+		if (fromTemplate && !anyAct)
+		{
+			uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll 8
+			for (int k = 0; k < NB / 8 / GEN_THREADS; ++k)
+				dst[tid + k * GEN_THREADS] = __ldg(tsrc + tid + k * GEN_THREADS);
+			reinterpret_cast<uint4*>(xs)[tid] = __ldg(tsrc + NB / 8 + tid);
+			if (tid == 0)
+				a.summary[slot] = a.fastSummary;
+			return;
+		}
+		if (anyDraw && !fromTemplate && tid < 3 * CS)
 		{
 			const int j = tid & 31;
 			const unsigned long long stride = tid < CS ? 2ull : (tid < 2 * CS ? 2ull * NX : 2ull * NX * NY);
@@ -437,14 +487,42 @@ namespace tsomk
 			}
 		}
 
+		// ---- template chunk with active passes: template AND NOT "above a column start" (thread = 8 blocks of a row, like below)
+		if (fromTemplate)
+		{
+			const int xq = tid & 3, y = (tid >> 2) & 31, xb = xq * 8;
+			uint32_t orAll = 0u, carved = 0u;
+#pragma unroll 4
+			for (int it = 0; it < CS / 2; ++it)
+			{
+				const int col = (2 * it + (tid >> 7)) * CS + y;
+				uint4 w = __ldg(tsrc + col * (CS / 8) + xq);
+				const uint32_t ab8 = (sm.above[col] >> xb) & 0xFFu;
+				const uint4 m = sm.keepOf[ab8];
+				w.x &= m.x;
+				w.y &= m.y;
+				w.z &= m.z;
+				w.w &= m.w;
+				*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) = w;
+				if (xq == 0)
+					xs[col] = uint16_t(w.x & 0xFFFFu);
+				if (xq == 3)
+					xs[SLAB + col] = uint16_t(w.w >> 16);
+				orAll |= (w.x | w.y) | (w.z | w.w);
+				carved |= ab8;
+			}
+			const int anyBlock = __syncthreads_or(orAll != 0u);
+			const int anyCarved = __syncthreads_or(carved != 0u);
+			if (tid == 0)
+				a.summary[slot] = !anyBlock ? uint8_t(SUM_EMPTY) : (!anyCarved ? a.fastSummary : uint8_t(SUM_UNKNOWN));
+			return;
+		}
+
 		uint32_t chunkSeed = a.seed + uint32_t(ci.x) + uint32_t(ci.y) + uint32_t(ci.z);
 		uint32_t x0 = chunkSeed % LCG_M; // std::linear_congruential_engine::seed: 0 -> 1
 		if (x0 == 0u)
 			x0 = 1u;
 		const uint32_t base2 = mulmod31(x0, mulmod31(LCG_A, LCG_A)); // second engine output of draw 0
-
-		uint16_t* out = a.blocks + size_t(slot) * NB;
-		uint16_t* xs = a.xslabs + size_t(slot) * 2 * SLAB;
 
 		// ---- per-thread constants: this thread always produces x in [8*xq, 8*xq+8) of rows with local y = `y`
 		const int xq = tid & 3;
@@ -485,8 +563,10 @@ namespace tsomk
 		// depth classes and the pass masks.  Per block: x_{2n+2} = rowMul * A^(2x') mod (2^31 - 1) from ONE wide multiply by the doubled
 		// power (hi = p >> 31, lo >> 1 = p & (2^31 - 1)), e = bStar + 1 - u2 (> 0 stone, < 0 stone_mossy, == 0 the first draw decides),
 		// and the sign bytes of two e's select a packed id pair with one PRMT + one LOP3.
-		if (!anyAct && ax0 == 0 && ax1 == CS - 1 && ay0 == 0 && ay1 == CS - 1 && az0 == 0 && az1 == CS - 1)
+		if (fullDraw)
 		{
+			if (tid == 0)
+				a.summary[slot] = shaftChunk ? uint8_t(SUM_UNKNOWN) : a.fastSummary;
 			int col = (tid >> 7) * CS + y;
 #pragma unroll 2
 			for (int it = 0; it < CS / 2; ++it, col += 2 * CS)
@@ -511,6 +591,7 @@ namespace tsomk
 		// monotone in the depth, so class(min(dX, dYZ)) = min(class(dX), class(dYZ)): the x part is a per-thread constant
 		auto depthClass = [](int d) { return (d >= 30) + (d >= 37) + (d >= 49); };
 		const int cXmin = depthClass(dXmin), cXmax = depthClass(dXmax);
+		uint32_t orAll = 0u, minPair = 0xFFFFFFFFu; // OR and per-half minimum of every id pair this thread stores (chunk summary)
 
 #pragma unroll 1
 		for (int it = 0; it < CS / 2; ++it)
@@ -601,7 +682,66 @@ namespace tsomk
 				xs[col] = uint16_t(w[0] & 0xFFFFu);
 			if (xq == 3)
 				xs[SLAB + col] = uint16_t(w[3] >> 16);
+			orAll |= (w[0] | w[1]) | (w[2] | w[3]);
+			minPair = __vminu2(__vminu2(minPair, __vminu2(w[0], w[1])), __vminu2(w[2], w[3]));
 		}
+		// ---- summary: all Empty, or (when the five generator ids are opaque types) no Empty block at all
+		const int anyBlock = __syncthreads_or(orAll != 0u);
+		const int noEmpty = __syncthreads_and((minPair & 0xFFFFu) != 0u && (minPair >> 16) != 0u);
+		if (tid == 0)
+			a.summary[slot] = !anyBlock ? uint8_t(SUM_EMPTY) : ((noEmpty && a.allOpaque) ? uint8_t(SUM_OPAQUE) : uint8_t(SUM_UNKNOWN));
+	}
+
+	// template chunks: every block draws (n = linear block index), no pass, no shaft; template t has chunkSeed = seed + templateSumMin + t
+	__global__ void __launch_bounds__(GEN_THREADS) template_kernel(const GenArgs a, uint16_t* __restrict__ templates)
+	{
+		__shared__ uint32_t powX[CS], powY[CS], powZ[CS];
+		const int tid = threadIdx.x;
+		const uint32_t t = blockIdx.x;
+		if (tid < 3 * CS)
+		{
+			const int j = tid & 31;
+			const unsigned long long stride = tid < CS ? 2ull : (tid < 2 * CS ? 2ull * CS : 2ull * CS * CS);
+			uint32_t* dst = tid < CS ? powX : (tid < 2 * CS ? powY : powZ);
+			dst[j] = powmod31(LCG_A, stride * j);
+		}
+		__syncthreads();
+		const uint32_t chunkSeed = a.seed + uint32_t(a.templateSumMin + int(t));
+		uint32_t x0 = chunkSeed % LCG_M;
+		if (x0 == 0u)
+			x0 = 1u;
+		const uint32_t base2 = mulmod31(x0, mulmod31(LCG_A, LCG_A));
+		const int xq = tid & 3, y = (tid >> 2) & 31, xb = xq * 8;
+		uint32_t px2[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			px2[j] = powX[xb + j] << 1;
+		const uint32_t rowMulY = mulmod31(base2, powY[y]);
+		const uint32_t stoneId = a.stone, mossyId = a.stoneMossy;
+		const uint32_t K = a.bStar + 1u;
+		const uint32_t stonePair = stoneId | (stoneId << 16), deltaPair = stonePair ^ (mossyId | (mossyId << 16));
+		uint16_t* out = templates + size_t(t) * TEMPLATE_STRIDE;
+		uint16_t* xs = out + NB;
+		int col = (tid >> 7) * CS + y;
+#pragma unroll 2
+		for (int it = 0; it < CS / 2; ++it, col += 2 * CS)
+		{
+			const uint32_t rowMul = mulmod31(rowMulY, powZ[2 * it + (tid >> 7)]);
+			uint32_t e[8], w[4];
+			if (draw8(rowMul, px2, K, stonePair, deltaPair, e, w))
+				draw8_ties(e, K, a.aInv, a.aStar, stoneId, mossyId, w);
+			*reinterpret_cast<uint4*>(out + size_t(col) * CS + xb) = make_uint4(w[0], w[1], w[2], w[3]);
+			if (xq == 0)
+				xs[col] = uint16_t(w[0] & 0xFFFFu);
+			if (xq == 3)
+				xs[SLAB + col] = uint16_t(w[3] >> 16);
+		}
+	}
+
+	void launch_templates(const GenArgs& a, uint16_t* templates, cudaStream_t st)
+	{
+		if (a.nTemplates)
+			template_kernel<<<a.nTemplates, GEN_THREADS, 0, st>>>(a, templates);
 	}
 
 	void launch_generate(const GenArgs& a, int grid, cudaStream_t st)
@@ -611,7 +751,8 @@ namespace tsomk
 
 	// ------------------------------------------------------------------------------------------------ x-slab packing
 	// xslabs[slot][0][z][y] = ids[z][y][0], xslabs[slot][1][z][y] = ids[z][y][31]: what the Left/Right neighbours stage as halo
-	__global__ void __launch_bounds__(256) build_xslabs_kernel(const uint16_t* __restrict__ blocks, uint16_t* __restrict__ xslabs, const uint32_t* __restrict__ slots, uint32_t n)
+	__global__ void __launch_bounds__(256) build_xslabs_kernel(const uint16_t* __restrict__ blocks, uint16_t* __restrict__ xslabs, uint8_t* __restrict__ summary,
+	                                                           const uint32_t* __restrict__ slots, uint32_t n)
 	{
 		const uint32_t i = blockIdx.x;
 		if (i >= n)
@@ -624,39 +765,35 @@ namespace tsomk
 			dst[c] = src[c * CS];
 			dst[SLAB + c] = src[c * CS + CS - 1];
 		}
+		if (threadIdx.x == 0)
+			summary[slot] = SUM_UNKNOWN; // new content of unknown make-up
 	}
 
-	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, const uint32_t* slots, uint32_t n, cudaStream_t st)
+	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, uint8_t* summary, const uint32_t* slots, uint32_t n, cudaStream_t st)
 	{
 		if (n)
-			build_xslabs_kernel<<<n, 256, 0, st>>>(blocks, xslabs, slots, n);
+			build_xslabs_kernel<<<n, 256, 0, st>>>(blocks, xslabs, summary, slots, n);
 	}
 
 	// ------------------------------------------------------------------------------------------------ edits
 	// Chunk::UpdateBlock (Chunk.cpp:348-366) + the neighbour-mask rule of Planet.cpp:39-58, single-writer form (platform script)
-	__device__ __forceinline__ void device_update_block(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint32_t slot, int x, int y, int z, uint16_t id)
+	// neighbour mask of one edited block: Planet.cpp:39-58, or Ship.cpp:36-54 (Up / Down swapped) when `ship`
+	__device__ __forceinline__ unsigned edit_mask(int x, int y, int z, bool ship)
 	{
-		blocks[size_t(slot) * NB + (z * CS + y) * CS + x] = id;
 		unsigned mask = 0x80u; // bit 7: "is in m_invalidatedChunks" (a mask of 0 still invalidates the chunk itself)
 		if (x == 0)
-		{
-			xslabs[size_t(slot) * 2 * SLAB + z * CS + y] = id;
 			mask |= 1u << D_LEFT;
-		}
 		else if (x == CS - 1)
-		{
-			xslabs[size_t(slot) * 2 * SLAB + SLAB + z * CS + y] = id;
 			mask |= 1u << D_RIGHT;
-		}
 		if (y == 0)
 			mask |= 1u << D_FRONT;
 		else if (y == CS - 1)
 			mask |= 1u << D_BACK;
 		if (z == 0)
-			mask |= 1u << D_DOWN;
+			mask |= 1u << (ship ? D_UP : D_DOWN);
 		else if (z == CS - 1)
-			mask |= 1u << D_UP;
-		invalidMask[slot] |= uint8_t(mask);
+			mask |= 1u << (ship ? D_DOWN : D_UP);
+		return mask;
 	}
 
 	// Batched edits: one thread per edit.  Only the order of edits to the SAME block matters (the later one wins), so a first
@@ -694,8 +831,8 @@ namespace tsomk
 		}
 	}
 
-	__global__ void __launch_bounds__(EDIT_THREADS) edit_apply_kernel(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* __restrict__ edits, uint32_t n,
-	                                                                  const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t capMask)
+	__global__ void __launch_bounds__(EDIT_THREADS) edit_apply_kernel(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint8_t* summary, const EditDev* __restrict__ edits,
+	                                                                  uint32_t n, const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t capMask, int shipMask)
 	{
 		const uint32_t i = blockIdx.x * EDIT_THREADS + threadIdx.x;
 		if (i >= n)
@@ -710,42 +847,27 @@ namespace tsomk
 
 		const int x = int(e.packed & 31u), y = int((e.packed >> 5) & 31u), z = int((e.packed >> 10) & 31u);
 		const uint16_t id = uint16_t(e.packed >> 16);
-		const bool last = vals[h] == i;
-		if (last)
+		if (vals[h] == i)
+		{
 			blocks[size_t(e.slot) * NB + (z * CS + y) * CS + x] = id;
-		unsigned mask = 0x80u; // bit 7: "is in m_invalidatedChunks" (a mask of 0 still invalidates the chunk itself)
-		if (x == 0)
-		{
-			if (last)
+			if (x == 0)
 				xslabs[size_t(e.slot) * 2 * SLAB + z * CS + y] = id;
-			mask |= 1u << D_LEFT;
-		}
-		else if (x == CS - 1)
-		{
-			if (last)
+			else if (x == CS - 1)
 				xslabs[size_t(e.slot) * 2 * SLAB + SLAB + z * CS + y] = id;
-			mask |= 1u << D_RIGHT;
 		}
-		if (y == 0)
-			mask |= 1u << D_FRONT;
-		else if (y == CS - 1)
-			mask |= 1u << D_BACK;
-		if (z == 0)
-			mask |= 1u << D_DOWN;
-		else if (z == CS - 1)
-			mask |= 1u << D_UP;
+		summary[e.slot] = SUM_UNKNOWN;
 		// every edit raises its mask, overwritten or not (each UpdateBlock call fires OnBlockUpdated, Chunk.cpp:365)
-		atomicOr(reinterpret_cast<unsigned int*>(invalidMask) + (e.slot >> 2), mask << (8u * (e.slot & 3u)));
+		atomicOr(reinterpret_cast<unsigned int*>(invalidMask) + (e.slot >> 2), edit_mask(x, y, z, shipMask != 0) << (8u * (e.slot & 3u)));
 	}
 
-	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
-	                        uint32_t cap, cudaStream_t st)
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint8_t* summary, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
+	                        uint32_t cap, int shipMask, cudaStream_t st)
 	{
 		if (!n)
 			return;
 		const int grid = int((n + EDIT_THREADS - 1) / EDIT_THREADS);
 		edit_claim_kernel<<<grid, EDIT_THREADS, 0, st>>>(edits, n, keys, vals, cap - 1u);
-		edit_apply_kernel<<<grid, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, edits, n, keys, vals, cap - 1u);
+		edit_apply_kernel<<<grid, EDIT_THREADS, 0, st>>>(blocks, xslabs, invalidMask, summary, edits, n, keys, vals, cap - 1u, shipMask);
 	}
 
 	// ------------------------------------------------------------------------------------------------ save format (Chunk::Serialize)
@@ -937,7 +1059,10 @@ namespace tsomk
 	}
 
 	// ------------------------------------------------------------------------------------------------ Planet::GeneratePlatform
-	// A data-dependent sequential edit script (Planet.cpp:405-512); run by one thread against the device-resident blocks.
+	// The edit script of Planet.cpp:405-512 on the device-resident blocks, one CTA, one thread per platform cell (15 x 15).
+	// Why it parallelises: every cell of every layer names its own block (right / forward / up are three different axes), so no edit
+	// of the script overwrites or reads the result of another one; the only sequential part is WHEN the pillar loop stops (the first
+	// layer that places nothing), which is one CTA-wide OR per layer.
 	struct PlatformAxis { int forwardAxis, rightAxis, upAxis, forwardDir, rightDir, upDir; };
 	__constant__ PlatformAxis c_dirAxis[6] = {
 		{ 1, 0, 2,  1,  1,  1 }, { 2, 0, 1,  1,  1, -1 }, { 1, 0, 2, -1,  1, -1 },
@@ -973,178 +1098,284 @@ namespace tsomk
 		return a.slotGrid[((chunk[2] - a.gridOrigin[2]) * a.gridDim[1] + (chunk[1] - a.gridOrigin[1])) * a.gridDim[0] + (chunk[0] - a.gridOrigin[0])];
 	}
 
-	__global__ void platform_kernel(const PlatformArgs a)
+	// Chunk::UpdateBlock (Chunk.cpp:348-366) + the neighbour-mask rule of Planet.cpp:39-58 from many threads at once (distinct blocks)
+	__device__ __forceinline__ void platform_update_block(const PlatformArgs& a, uint32_t slot, const int local[3], uint16_t id)
 	{
-		if (threadIdx.x != 0 || blockIdx.x != 0)
-			return;
-		const int platformSize = 15;
-		const unsigned freeHeight = 10;
+		const int x = local[0], y = local[1], z = local[2];
+		a.blocks[size_t(slot) * NB + (z * CS + y) * CS + x] = id;
+		if (x == 0)
+			a.xslabs[size_t(slot) * 2 * SLAB + z * CS + y] = id;
+		else if (x == CS - 1)
+			a.xslabs[size_t(slot) * 2 * SLAB + SLAB + z * CS + y] = id;
+		a.summary[slot] = SUM_UNKNOWN;
+		atomicOr(reinterpret_cast<unsigned int*>(a.invalidMask) + (slot >> 2), edit_mask(x, y, z, false) << (8u * (slot & 3u)));
+	}
+
+	__global__ void __launch_bounds__(256) platform_kernel(const PlatformArgs a)
+	{
+		constexpr int platformSize = 15;
+		constexpr int freeHeight = 10;
 		const PlatformAxis ax = c_dirAxis[a.upDirection];
+		const int tid = threadIdx.x;
+		// thread = cell (x, z): 16 lanes per row of the platform, lane 15 of each row idle
+		const int x = tid & 15, z = tid >> 4;
+		const bool cell = x < platformSize && z < platformSize;
+		const bool border = x == 0 || x == platformSize - 1 || z == 0 || z == platformSize - 1;
+		const bool corner = (x == 0 || x == platformSize - 1) && (z == 0 || z == platformSize - 1);
 
-		int coord[3] = { a.center[0], a.center[1], a.center[2] };
-		coord[ax.rightAxis] += -ax.rightDir * platformSize / 2;
-		coord[ax.forwardAxis] += -ax.forwardDir * platformSize / 2;
-		int orig[3] = { coord[0], coord[1], coord[2] };
+		int orig[3] = { a.center[0], a.center[1], a.center[2] };
+		orig[ax.rightAxis] += -ax.rightDir * platformSize / 2;
+		orig[ax.forwardAxis] += -ax.forwardDir * platformSize / 2;
 
-		for (unsigned y = 0; y < freeHeight; ++y)
-		{
-			const int startingZ = coord[ax.forwardAxis];
-			for (int z = 0; z < platformSize; ++z)
-			{
-				const int startingX = coord[ax.rightAxis];
-				for (int x = 0; x < platformSize; ++x)
+		// ---- the deck and the free space above it (Planet.cpp:427-460): layer 0 copper border / stone bricks, layers 1..9 Empty; the
+		// loop leaves after the layer whose up coordinate is 0 when up points to negative coordinates (:454-455)
+		int layers = freeHeight;
+		if (ax.upDir < 0)
+			for (int y = 0; y < freeHeight; ++y)
+				if (orig[ax.upAxis] + y * ax.upDir == 0)
 				{
-					uint16_t id;
-					if (y != 0)
-						id = 0;
-					else if (x == 0 || x == platformSize - 1 || z == 0 || z == platformSize - 1)
-						id = a.copper;
-					else
-						id = a.stoneBricks;
-					int local[3];
-					int slot = platform_locate(a, coord, local);
-					if (slot >= 0)
-						device_update_block(a.blocks, a.xslabs, a.invalidMask, uint32_t(slot), local[0], local[1], local[2], id);
-					coord[ax.rightAxis] += ax.rightDir;
+					layers = y + 1;
+					break;
 				}
-				coord[ax.rightAxis] = startingX;
-				coord[ax.forwardAxis] += ax.forwardDir;
+		if (cell)
+		{
+			for (int y = 0; y < layers; ++y)
+			{
+				int coord[3] = { orig[0], orig[1], orig[2] };
+				coord[ax.rightAxis] += x * ax.rightDir;
+				coord[ax.forwardAxis] += z * ax.forwardDir;
+				coord[ax.upAxis] += y * ax.upDir;
+				const uint16_t id = y != 0 ? uint16_t(0) : (border ? a.copper : a.stoneBricks);
+				int local[3];
+				const int slot = platform_locate(a, coord, local);
+				if (slot >= 0)
+					platform_update_block(a, uint32_t(slot), local, id);
 			}
-			if (coord[ax.upAxis] == 0 && ax.upDir < 0)
-				break;
-			coord[ax.upAxis] += ax.upDir;
-			coord[ax.forwardAxis] = startingZ;
 		}
 
-		coord[0] = orig[0];
-		coord[1] = orig[1];
-		coord[2] = orig[2];
+		// ---- the pillars below (Planet.cpp:462-511): layer y = 1, 2, ... until a layer places nothing.  Inside a row the reference
+		// advances the right coordinate only behind a cell whose chunk exists (`continue` before the increment, :478-482): cell x sits at
+		// orig + x * rightDir while every earlier cell of its row found its chunk, and the row is stuck on the first absent one.
 		for (unsigned y = 1;; ++y)
 		{
-			coord[ax.upAxis] -= ax.upDir;
-			bool hasEmpty = false;
-			const int startingZ = coord[ax.forwardAxis];
-			for (int z = 0; z < platformSize; ++z)
+			int coord[3] = { orig[0], orig[1], orig[2] };
+			coord[ax.rightAxis] += x * ax.rightDir;
+			coord[ax.forwardAxis] += z * ax.forwardDir;
+			coord[ax.upAxis] -= int(y) * ax.upDir;
+			int local[3] = { 0, 0, 0 };
+			const int slot = cell ? platform_locate(a, coord, local) : -1;
+			const uint32_t have = __ballot_sync(0xffffffffu, slot >= 0 || x >= platformSize);
+			const uint32_t rowHave = (have >> (16 * ((tid >> 4) & 1))) & 0x7FFFu;
+			const int firstAbsent = (~rowHave & 0x7FFFu) ? __ffs(~rowHave & 0x7FFFu) - 1 : platformSize;
+			bool place = false;
+			if (cell && x < firstAbsent)
 			{
-				const int startingX = coord[ax.rightAxis];
-				for (int x = 0; x < platformSize; ++x)
-				{
-					int local[3];
-					int slot = platform_locate(a, coord, local);
-					if (slot < 0)
-						continue; // before the x position advances, as Planet.cpp:478-482
-					coord[ax.rightAxis] += ax.rightDir;
-
-					if (y % 3 == 0)
-					{
-						if (x != 0 && x != platformSize - 1 && z != 0 && z != platformSize - 1)
-							continue;
-					}
-					else
-					{
-						if (a.blocks[size_t(slot) * NB + (local[2] * CS + local[1]) * CS + local[0]] != 0)
-							continue;
-						if ((x != 0 && x != platformSize - 1) || (z != 0 && z != platformSize - 1))
-							continue;
-					}
-					hasEmpty = true;
-					device_update_block(a.blocks, a.xslabs, a.invalidMask, uint32_t(slot), local[0], local[1], local[2], a.planks);
-				}
-				coord[ax.rightAxis] = startingX;
-				coord[ax.forwardAxis] += ax.forwardDir;
+				if (y % 3 == 0)
+					place = border;
+				else
+					place = corner && a.blocks[size_t(slot) * NB + (local[2] * CS + local[1]) * CS + local[0]] == 0;
 			}
-			if (!hasEmpty)
+			if (place)
+				platform_update_block(a, uint32_t(slot), local, a.planks);
+			if (!__syncthreads_or(place))
 				break;
-			coord[ax.forwardAxis] = startingZ;
 		}
 	}
 
-	void launch_platform(const PlatformArgs& a, cudaStream_t st) { platform_kernel<<<1, 32, 0, st>>>(a); }
+	void launch_platform(const PlatformArgs& a, cudaStream_t st) { platform_kernel<<<1, 256, 0, st>>>(a); }
 
 	// ------------------------------------------------------------------------------------------------ FlatChunk::BuildCollider
-	// Greedy box merge (FlatChunk.cpp:56-153): order dependent, so one thread walks the bitmask exactly like the reference;
-	// the mask itself (Chunk::OnChunkReset, Chunk.cpp:368-384) is built by the whole CTA with ballots.
-	__global__ void __launch_bounds__(256) box_collider_kernel(const uint16_t* __restrict__ ids, const uint8_t* __restrict__ blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count)
-	{
-		__shared__ uint32_t mask[ROWS_PER_CHUNK];
-		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-		for (int r = warp; r < ROWS_PER_CHUNK; r += 8)
-		{
-			unsigned id = ids[r * CS + lane];
-			unsigned f = blkFlags[id < nTypes ? id : nTypes - 1];
-			uint32_t m = __ballot_sync(0xffffffffu, (f & BF_COLLIDES) != 0);
-			if (lane == 0)
-				mask[r] = m;
-		}
-		__syncthreads();
-		if (threadIdx.x != 0)
-			return;
+	// Greedy box merge (FlatChunk.cpp:56-153) for a batch of chunks, one WARP per chunk.  The merge is order dependent (the next box
+	// starts at the first cell still set in z, y, x order), so the boxes are found one after the other exactly like the reference
+	// does; what the 32 lanes share is the work inside one step: the 32x32 rows of the collision mask are built with ballots
+	// (Chunk::OnChunkReset / GetCollisionCellMask, Chunk.cpp:368-384), the Y extension tests 32 rows with one ballot, the Z extension
+	// one layer per ballot, and the clear is one row per lane.  A box is one 30-bit word (x, y, z, sizes - 1) in the job's scratch.
+	constexpr int BOXC_WARPS = 4;
 
+	__global__ void __launch_bounds__(BOXC_WARPS * 32) box_colliders_kernel(const uint16_t* __restrict__ blocks, const uint32_t* __restrict__ jobSlot, uint32_t n,
+	                                                                       const uint8_t* __restrict__ blkFlags, uint32_t nTypes, uint32_t* __restrict__ scratch, uint32_t* __restrict__ counts)
+	{
+		__shared__ uint32_t maskAll[BOXC_WARPS][ROWS_PER_CHUNK];
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		const uint32_t job = blockIdx.x * BOXC_WARPS + warp;
+		if (job >= n)
+			return;
+		const uint32_t entry = jobSlot[job];
+		if (!(entry & JOB_HAS_CONTENT))
+		{
+			if (lane == 0)
+				counts[job] = 0u;
+			return;
+		}
+		uint32_t* mask = maskAll[warp];
+		const uint16_t* ids = blocks + size_t(entry & JOB_SLOT_MASK) * NB;
+		constexpr uint32_t FULL = 0xffffffffu;
+		// collision bits: lane = 8 consecutive ids of a row (16-byte load), 4 lanes per row, 8 rows per step
+		for (int r0 = 0; r0 < ROWS_PER_CHUNK; r0 += 8)
+		{
+			const int row = r0 + (lane >> 2), seg = lane & 3;
+			const uint4 w = *reinterpret_cast<const uint4*>(ids + size_t(row) * CS + seg * 8);
+			const uint32_t ws[4] = { w.x, w.y, w.z, w.w };
+			uint32_t bits = 0;
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				const unsigned id = (ws[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+				if (__ldg(blkFlags + (id < nTypes ? id : nTypes - 1)) & BF_COLLIDES)
+					bits |= 1u << j;
+			}
+			bits <<= seg * 8;
+			bits |= __shfl_xor_sync(FULL, bits, 1);
+			bits |= __shfl_xor_sync(FULL, bits, 2);
+			if (seg == 0)
+				mask[row] = bits;
+		}
+		__syncwarp();
+
+		uint32_t* out = scratch + size_t(job) * BOX_SCRATCH_STRIDE;
 		uint32_t nBoxes = 0;
 		for (int z = 0; z < CS; ++z)
 		{
-			for (int y = 0; y < CS; ++y)
+			// rows of this layer that still hold a cell
+			uint32_t live = __ballot_sync(FULL, mask[z * CS + lane] != 0u);
+			while (live)
 			{
-				int x = 0;
-				while (x < CS)
+				const int y = __ffs(live) - 1;
+				uint32_t row = mask[z * CS + y];
+				while (row)
 				{
-					uint32_t m = mask[z * CS + y] >> x;
-					if (!m)
-						break;
-					x += __ffs(m) - 1;          // start of the run
-					uint32_t run = mask[z * CS + y] >> x;
-					int len = (~run == 0u) ? 32 - x : __ffs(~run) - 1;
-					if (len > CS - x)
-						len = CS - x;
-					const int sx = x, endX = x + len - 1;
+					const int sx = __ffs(row) - 1;
+					const uint32_t run = row >> sx;
+					const int len = (~run == 0u) ? CS - sx : __ffs(~run) - 1;
 					const uint32_t rowBits = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << sx;
-					int endY = y, endZ = z;
-					for (endY += 1; endY < CS; ++endY)
-						if ((mask[z * CS + endY] & rowBits) != rowBits)
-							break;
-					endY--;
-					for (endZ += 1; endZ < CS; ++endZ)
+					// grow on Y: rows y + 1 + lane of layer z
+					const int yy = y + 1 + lane;
+					const uint32_t okY = __ballot_sync(FULL, yy < CS && (mask[z * CS + (yy < CS ? yy : 0)] & rowBits) == rowBits);
+					const int endY = y + ((~okY == 0u) ? 32 : __ffs(~okY) - 1);
+					// grow on Z: layer by layer, lane = row y + lane of the box
+					const int ny = endY - y + 1;
+					int endZ = z;
+					for (int zz = z + 1; zz < CS; ++zz)
 					{
-						bool ok = true;
-						for (int yy = y; yy <= endY; ++yy)
-							if ((mask[endZ * CS + yy] & rowBits) != rowBits)
-							{
-								ok = false;
-								break;
-							}
-						if (!ok)
+						const bool ok = lane >= ny || (mask[zz * CS + y + (lane < ny ? lane : 0)] & rowBits) == rowBits;
+						if (!__all_sync(FULL, ok))
 							break;
+						endZ = zz;
 					}
-					endZ--;
 					for (int zz = z; zz <= endZ; ++zz)
-						for (int yy = y; yy <= endY; ++yy)
-							mask[zz * CS + yy] &= ~rowBits;
-					if (nBoxes < cap)
-					{
-						float* o = boxes + size_t(nBoxes) * 6;
-						const float half = float(CS) * 0.5f;
-						o[0] = float(sx) - half;
-						o[1] = float(z) - half;
-						o[2] = float(y) - half;
-						o[3] = float(endX + 1) - float(sx);
-						o[4] = float(endZ + 1) - float(z);
-						o[5] = float(endY + 1) - float(y);
-					}
+						if (lane < ny)
+							mask[zz * CS + y + lane] &= ~rowBits;
+					__syncwarp();
+					if (lane == 0 && nBoxes < BOX_SCRATCH_STRIDE)
+						out[nBoxes] = uint32_t(sx) | (uint32_t(y) << 5) | (uint32_t(z) << 10) | (uint32_t(len - 1) << 15) | (uint32_t(endY - y) << 20) | (uint32_t(endZ - z) << 25);
 					++nBoxes;
-					x = endX + 1;
+					row = mask[z * CS + y];
 				}
+				// the rows of this layer may have been cleared by the boxes just made
+				live = __ballot_sync(FULL, mask[z * CS + lane] != 0u) & ~((2u << y) - 1u);
 			}
 		}
-		*count = nBoxes;
+		if (lane == 0)
+			counts[job] = nBoxes;
 	}
 
-	void launch_box_collider(const uint16_t* chunkBlocks, const uint8_t* blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count, cudaStream_t st)
+	// decode the boxes of job j to their final place: arena[first[j] + k] = {pos.xyz, size.xyz} in the reference's axes (x, z, y):
+	// pos = start - dims / 2, size = end + 1 - start (FlatChunk.cpp:121-127)
+	__global__ void __launch_bounds__(256) box_pack_kernel(const uint32_t* __restrict__ scratch, const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ first, uint32_t n,
+	                                                       float* __restrict__ arena)
 	{
-		box_collider_kernel<<<1, 256, 0, st>>>(chunkBlocks, blkFlags, nTypes, boxes, cap, count);
+		const uint32_t job = blockIdx.x;
+		if (job >= n)
+			return;
+		const uint32_t cnt = min(counts[job], BOX_SCRATCH_STRIDE);
+		const uint32_t* src = scratch + size_t(job) * BOX_SCRATCH_STRIDE;
+		float* dst = arena + first[job] * 6ull;
+		const float half = float(CS) * 0.5f;
+		for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+		{
+			const uint32_t b = src[k];
+			const int sx = int(b & 31u), sy = int((b >> 5) & 31u), sz = int((b >> 10) & 31u);
+			const int lx = int((b >> 15) & 31u) + 1, ly = int((b >> 20) & 31u) + 1, lz = int((b >> 25) & 31u) + 1;
+			float* o = dst + size_t(k) * 6;
+			o[0] = float(sx) - half;
+			o[1] = float(sz) - half;
+			o[2] = float(sy) - half;
+			o[3] = float(sx + lx) - float(sx);
+			o[4] = float(sz + lz) - float(sz);
+			o[5] = float(sy + ly) - float(sy);
+		}
 	}
 
-	// ------------------------------------------------------------------------------------------------ P2P halo pull
-	// One CTA per ghost slab: 2 KiB read straight from the owner GPU's HBM over NVLink (peer-mapped pointer), written locally.
+	void launch_box_colliders(const uint16_t* blocks, const uint32_t* jobSlot, uint32_t n, const uint8_t* blkFlags, uint32_t nTypes, uint32_t* scratch, uint32_t* counts, cudaStream_t st)
+	{
+		if (n)
+			box_colliders_kernel<<<(n + BOXC_WARPS - 1) / BOXC_WARPS, BOXC_WARPS * 32, 0, st>>>(blocks, jobSlot, n, blkFlags, nTypes, scratch, counts);
+	}
+
+	void launch_box_pack(const uint32_t* scratch, const uint32_t* counts, const unsigned long long* first, uint32_t n, float* arena, cudaStream_t st)
+	{
+		if (n)
+			box_pack_kernel<<<n, 256, 0, st>>>(scratch, counts, first, n, arena);
+	}
+
+	// ------------------------------------------------------------------------------------------------ P2P halo exchange
+	// Ordering between GPUs lives on the device: every container owns epoch flags in its own HBM (blocks-final, slabs-pulled); the peers
+	// poll them over NVLink.  A flag is raised by a one-thread kernel behind the producing kernels on the same stream (the kernel boundary
+	// makes their writes visible device-wide, the system-scope fence + release store order them for the peers).
+	__global__ void flag_publish_kernel(uint32_t* flag, uint32_t value)
+	{
+		if (threadIdx.x == 0 && blockIdx.x == 0)
+		{
+			__threadfence_system();
+			asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+		}
+	}
+
+	__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+	{
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+		return v;
+	}
+
+	__device__ __forceinline__ unsigned long long global_timer_ns()
+	{
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+		return t;
+	}
+
+	// one warp: lane i waits until *flags[i] >= value (epochs only grow).  Gives up after timeoutNs and raises *err, so that a
+	// peer that died shows up as an error on the host instead of a hung GPU.
+	__global__ void flag_wait_kernel(const uint32_t* const* flags, uint32_t n, uint32_t value, unsigned long long timeoutNs, uint32_t* err)
+	{
+		const unsigned long long t0 = global_timer_ns();
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			const uint32_t* f = flags[i];
+			while (int32_t(ld_acquire_sys(f) - value) < 0)
+			{
+				if (global_timer_ns() - t0 > timeoutNs)
+				{
+					atomicExch(err, 1u + i);
+					break;
+				}
+				__nanosleep(200);
+			}
+		}
+		__threadfence_system();
+	}
+
+	void launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t st) { flag_publish_kernel<<<1, 32, 0, st>>>(flag, value); }
+
+	void launch_flag_wait(const uint32_t* const* flags, uint32_t n, uint32_t value, unsigned long long timeoutNs, uint32_t* err, cudaStream_t st)
+	{
+		if (n)
+			flag_wait_kernel<<<1, 32, 0, st>>>(flags, n, value, timeoutNs, err);
+	}
+
+	// One CTA per ghost slab: 2 KiB read straight from the owner GPU's HBM over NVLink (peer-mapped pointer, cache-volatile loads: the
+	// owner rewrites these addresses every round), written locally.
 	__global__ void __launch_bounds__(128) halo_pull_kernel(const GhostDesc* __restrict__ descs, uint32_t n, uint16_t* __restrict__ ghostSlabs)
 	{
 		const uint32_t i = blockIdx.x;
@@ -1157,7 +1388,7 @@ namespace tsomk
 			src = reinterpret_cast<const uint4*>(d.src) + t;
 		else
 			src = reinterpret_cast<const uint4*>(d.src + size_t(t >> 2) * SLAB) + (t & 3);
-		reinterpret_cast<uint4*>(ghostSlabs + size_t(d.ghost) * SLAB)[t] = *src;
+		reinterpret_cast<uint4*>(ghostSlabs + size_t(d.ghost) * SLAB)[t] = __ldcv(src);
 	}
 
 	void launch_halo_pull(const GhostDesc* descs, uint32_t n, uint16_t* ghostSlabs, cudaStream_t st)

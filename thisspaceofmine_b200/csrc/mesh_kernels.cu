@@ -780,8 +780,9 @@ namespace tsomk
 	{
 		const uint32_t j = atomicAdd(a.jobCounter, 1u);
 		const uint32_t entry = j < a.nJobs ? a.jobSlot[j] : 0u;
-		sm.slot = entry & 0x7FFFFFFFu;
-		sm.hasContent = entry >> 31;
+		sm.slot = entry & JOB_SLOT_MASK;
+		// a chunk whose summary proves that it has no face (job_classify_kernel) is treated like one without content: 0 faces, no stage
+		sm.hasContent = (entry & (JOB_HAS_CONTENT | JOB_SKIP)) == JOB_HAS_CONTENT ? 1u : 0u;
 		sm.job = j;
 	}
 
@@ -1094,6 +1095,44 @@ namespace tsomk
 	void launch_voxel_corners(const int4* blocks, const float* centers, uint32_t n, float tile, float radius, int deformed, float* out, cudaStream_t st)
 	{
 		voxel_corners_kernel<<<(n * 8u + 255u) / 256u, 256, 0, st>>>(blocks, centers, n, tile, radius, deformed, out);
+	}
+
+	// =====================================================================================================================
+	// job_classify_kernel — one thread per job: a chunk that is all Empty, or all opaque with six all-opaque neighbours, has no face
+	// (Chunk.cpp:190-201: a face needs a non-Empty block next to a transparent one or to a missing chunk).  The summaries come for free
+	// from the producers (generate_kernel); two thirds of a large planet are such chunks and skip their 64 KiB stage this way.
+	__global__ void __launch_bounds__(256) job_classify_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n, const uint8_t* __restrict__ summary,
+	                                                           const int32_t* __restrict__ nbrSlot)
+	{
+		const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+		if (j >= n)
+			return;
+		uint32_t entry = src[j] & ~JOB_SKIP;
+		if (entry & JOB_HAS_CONTENT)
+		{
+			const uint32_t slot = entry & JOB_SLOT_MASK;
+			const uint8_t s = summary[slot];
+			bool skip = s == SUM_EMPTY;
+			if (s == SUM_OPAQUE)
+			{
+				skip = true;
+#pragma unroll
+				for (int d = 0; d < 6; ++d)
+				{
+					const int32_t ns = nbrSlot[size_t(slot) * 6 + d];
+					skip = skip && ns >= 0 && summary[ns] == SUM_OPAQUE;
+				}
+			}
+			if (skip)
+				entry |= JOB_SKIP;
+		}
+		dst[j] = entry;
+	}
+
+	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, cudaStream_t st)
+	{
+		if (n)
+			job_classify_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(src, dst, n, summary, nbrSlot);
 	}
 
 	// ---- launchers ----

@@ -16,6 +16,7 @@
 #include <new>
 #include <random>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <unordered_map>
 #include <vector>
@@ -82,6 +83,35 @@ namespace
 			cudaError_t e = cudaMalloc(&p, want * sizeof(T));
 			if (e != cudaSuccess)
 				return e;
+			if (ptr)
+				cudaFree(ptr);
+			ptr = p;
+			cap = want;
+			return cudaSuccess;
+		}
+		// same, keeping the first `keep` elements (the copy is ordered on `st`, which is synchronised before the old buffer goes)
+		cudaError_t EnsureKeep(size_t n, size_t keep, cudaStream_t st)
+		{
+			if (n <= cap)
+				return cudaSuccess;
+			size_t want = std::max(n, cap * 2);
+			T* p = nullptr;
+			cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+			if (e != cudaSuccess)
+				return e;
+			if (ptr && keep)
+			{
+				e = cudaMemcpyAsync(p, ptr, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+				if (e == cudaSuccess)
+					e = cudaStreamSynchronize(st);
+				if (e != cudaSuccess)
+				{
+					cudaFree(p);
+					return e;
+				}
+			}
+			else if (ptr)
+				cudaStreamSynchronize(st);
 			if (ptr)
 				cudaFree(ptr);
 			ptr = p;
@@ -225,6 +255,8 @@ struct tsom_ctx
 	uint8_t* dFlags = nullptr;
 	uint32_t* dTex = nullptr;
 	uint32_t nTypes = 0;
+	std::vector<uint8_t> hostFlags; // BF_* per type, host copy (the generator derives the chunk summaries it may write from it)
+	uint32_t tableEpoch = 0;        // bumped by tsom_set_block_table: chunk summaries made under another table are void
 
 	// arenas (faces)
 	float4* dVertices = nullptr;
@@ -246,8 +278,25 @@ struct tsom_ctx
 	DevBuf<unsigned long long> ioOffsets; // n + 1 offsets of the packed LZ4 blocks
 	DevBuf<unsigned long long> editKeys; // open-addressing table of the edited blocks of one tsom_apply_edits call
 	DevBuf<uint32_t> editVals;           // ... -> index of the last edit that names the block
-	uint32_t* dSmall = nullptr; // [0] count ticket [1] emit ticket [2] nWork [3] overflow [4..5] totalFaces(u64) [6] box count
+	uint32_t* dSmall = nullptr; // [1] job ticket [3] overflow [4..5] totalFaces(u64) [7] palette error [8] exchange time-out (peer + 1)
 	uint32_t* hSmall = nullptr; // pinned mirror
+
+	// box collider arena of the last tsom_box_colliders call: 6 floats per box
+	float* dBoxes = nullptr;
+	uint64_t capBoxes = 0, totalBoxes = 0;
+	DevBuf<uint32_t> boxScratch, boxCounts;
+	DevBuf<unsigned long long> boxFirst;
+
+	// a mesh call in flight between MeshEnqueue and MeshFinish
+	struct PendingMesh
+	{
+		bool active = false;
+		uint32_t n = 0, flags = 0;
+		bool wantViews = false;
+		tsomk::MeshArgs args{};
+	} pendingMesh;
+	bool pendingGenerate = false;
+	bool pendingHalo = false; // events of a tsom_halo_pull were recorded and not read yet
 	void* hPinned = nullptr;    // pinned staging for small result read-backs
 	size_t hPinnedBytes = 0;
 
@@ -259,7 +308,7 @@ struct tsom_ctx
 	float faceTableTile = 0.f;
 
 	// device-side timing of the last calls (CUDA events on `stream`)
-	cudaEvent_t ev[6] = {};
+	cudaEvent_t ev[12] = {}; // 0,1 terrain  2,3 generate  4,5 mesh  6,7 halo  8,9 classify / io / collider
 	float timings[TSOM_TIMING_COUNT] = {};
 
 	cudaError_t EnsurePinned(size_t bytes)
@@ -284,11 +333,17 @@ struct tsom_container
 	float tile = 1.f;
 	float center[3] = { 0.f, 0.f, 0.f };
 
+	int kind = TSOM_CONTAINER_PLANET;
+
 	uint16_t* dBlocks = nullptr;
 	uint16_t* dXslabs = nullptr;
 	unsigned long long* dHalo = nullptr;
 	int4* dChunkIdx = nullptr;
 	uint8_t* dInvalid = nullptr;
+	uint8_t* dSummary = nullptr;  // [capacity] tsomk::SUM_*
+	int32_t* dNbr = nullptr;      // [capacity][6] slot of the face-adjacent local chunk with content, -1 otherwise
+	uint32_t* dSync = nullptr;    // [0] blocks-final epoch [1] slabs-pulled epoch (polled by the peers over NVLink)
+	uint32_t summaryTableEpoch = 0;
 
 	std::unordered_map<Key, uint32_t, KeyHash> slotOf;
 	std::vector<Key> idxOf;
@@ -296,6 +351,27 @@ struct tsom_container
 	std::vector<uint32_t> freeSlots;
 	uint32_t highWater = 0;
 	bool topoDirty = true;
+	uint64_t topoVersion = 1; // bumped whenever the set of chunks or a content flag changes (keys of the job-list caches below)
+
+	// the index list of the last generate / mesh call and its device-resident job list: a whole-planet regenerate + remesh names the
+	// same chunks every time, so the per-chunk host work (slot lookup, job entry, upload) is one memcmp
+	struct JobCache
+	{
+		std::vector<int32_t> idx;
+		DevBuf<uint32_t> jobs;
+		std::vector<uint32_t> hostSlots;
+		uint64_t version = 0;
+		uint32_t n = 0;
+		bool Matches(const int32_t* chunk_indices, uint32_t count, uint64_t ver) const
+		{
+			return version == ver && n == count && count != 0 && std::memcmp(idx.data(), chunk_indices, size_t(count) * 3 * sizeof(int32_t)) == 0;
+		}
+	} genCache, meshCache;
+	struct GenPlan // what depends on the chunk list only, cached with genCache
+	{
+		int lo[3], hi[3], sumMin, sumMax;
+	} genPlan{};
+	DevBuf<uint16_t> templates;
 
 	// remote neighbours (other ranks) and the ghost slabs that mirror their boundary layers
 	struct Remote
@@ -308,17 +384,40 @@ struct tsom_container
 	{
 		const uint16_t* blocks = nullptr;
 		const uint16_t* xslabs = nullptr;
+		const uint32_t* sync = nullptr;
 		bool ipc = false;
 	};
 	std::map<int, Peer> peers;
 	DevBuf<uint16_t> ghostSlabs;
 	DevBuf<tsomk::GhostDesc> ghostDescs;
 	uint32_t nGhost = 0;
+	// a (remote chunk, direction) keeps its ghost slab for the lifetime of the container: a topology change leaves pulled slabs valid
+	struct GhostKey
+	{
+		Key k;
+		int d;
+		bool operator==(const GhostKey& o) const { return k == o.k && d == o.d; }
+	};
+	struct GhostKeyHash
+	{
+		size_t operator()(const GhostKey& g) const { return KeyHash()(g.k) * 6 + size_t(g.d); }
+	};
+	std::unordered_map<GhostKey, uint32_t, GhostKeyHash> ghostIndex;
+	std::vector<tsomk::GhostDesc> ghostList;
+	bool ghostsStale = false; // a ghost slab exists that was never pulled: tsom_mesh refuses until the next tsom_halo_pull
+
+	// device-side ordering of the exchange (see tsom_halo_pull in tsom_b200.h)
+	uint32_t epoch = 0, pulledEpoch = 0;
+	bool published = false, dirtySincePublish = false, needWriteWait = false;
+	DevBuf<const uint32_t*> peerGenFlags, peerPullFlags;
+	bool peerFlagsDirty = true;
 
 	// terrain tables of the last generate call
 	DevBuf<int16_t> terrain, tileRange;
 	uint8_t* dPerm = nullptr;
+	uint8_t* hPerm = nullptr; // pinned staging of the six permutation tables
 	DevBuf<int> slotGrid;
+	uint64_t slotGridVersion = 0; // topoVersion the device slot grid of GeneratePlatform was built for
 
 	// dense chunk-index -> slot grid over the bounding box of the existing chunks (O(1) lookups for per-tick batches: edits,
 	// dirty sets, mesh jobs); rebuilt lazily after the set of chunks changed, skipped for very sparse containers
@@ -377,6 +476,12 @@ struct tsom_container
 
 namespace
 {
+	inline void TopoChanged(tsom_container* c)
+	{
+		c->topoDirty = true;
+		++c->topoVersion;
+	}
+
 	int AddChunk(tsom_container* c, const Key& k, uint32_t* slotOut)
 	{
 		if (c->hostGridValid && c->hostGridUsable)
@@ -419,13 +524,13 @@ namespace
 		c->exists[slot] = 1;
 		c->hasContent[slot] = 0;
 		c->hostInvalid[slot] = 0;
-		c->topoDirty = true;
+		TopoChanged(c);
 		if (slotOut)
 			*slotOut = slot;
 		return TSOM_OK;
 	}
 
-	// (re)build the per-chunk index and halo pointer tables and the ghost list, then upload them
+	// (re)build the per-chunk index, neighbour and halo pointer tables and the ghost list, then upload them
 	int SyncTopology(tsom_container* c)
 	{
 		if (!c->topoDirty)
@@ -434,7 +539,13 @@ namespace
 		const uint32_t n = c->highWater;
 		std::vector<int4> idx(n);
 		std::vector<unsigned long long> halo(size_t(n) * 6, 0ull);
-		std::vector<tsomk::GhostDesc> ghosts;
+		std::vector<int32_t> nbr(size_t(n) * 6, -1);
+		struct GhostUse
+		{
+			uint32_t s, d, ghost;
+		};
+		std::vector<GhostUse> ghostUses;
+		bool ghostListChanged = false;
 
 		for (uint32_t s = 0; s < n; ++s)
 		{
@@ -452,10 +563,9 @@ namespace
 				const Key nk{ k.x + kChunkDirOffset[d][0], k.y + kChunkDirOffset[d][1], k.z + kChunkDirOffset[d][2] };
 				// which boundary layer of the neighbour faces us
 				const bool far = (d == TSOM_DOWN || d == TSOM_FRONT || d == TSOM_LEFT); // neighbour's layer 31
-				auto it = c->slotOf.find(nk);
-				if (it != c->slotOf.end())
+				const uint32_t ns = c->SlotOf(nk);
+				if (ns != 0xFFFFFFFFu)
 				{
-					const uint32_t ns = it->second;
 					if (!c->hasContent[ns])
 						continue; // !HasContent() => face drawn, same as no neighbour (Chunk.cpp:165-166)
 					const uint16_t* nb = c->dBlocks + size_t(ns) * NB;
@@ -468,8 +578,11 @@ namespace
 					else
 						e = reinterpret_cast<unsigned long long>(nx + (far ? SLAB : 0)) | tsomk_halo_contig();
 					halo[size_t(s) * 6 + d] = e;
+					nbr[size_t(s) * 6 + d] = int32_t(ns);
 					continue;
 				}
+				if (c->remotes.empty())
+					continue;
 				auto rt = c->remotes.find(nk);
 				if (rt != c->remotes.end())
 				{
@@ -479,7 +592,6 @@ namespace
 					const uint16_t* nb = pt->second.blocks + size_t(rt->second.slot) * NB;
 					const uint16_t* nx = pt->second.xslabs + size_t(rt->second.slot) * 2 * SLAB;
 					tsomk::GhostDesc g;
-					g.ghost = uint32_t(ghosts.size());
 					if (d == TSOM_UP || d == TSOM_DOWN)
 					{
 						g.src = nb + (far ? 31 * SLAB : 0);
@@ -495,34 +607,108 @@ namespace
 						g.src = nx + (far ? SLAB : 0);
 						g.contig = 1;
 					}
-					ghosts.push_back(g);
-					halo[size_t(s) * 6 + d] = 1ull; // patched below once the ghost buffer address is known
+					// stable ghost index per (remote chunk, direction): slabs that were pulled stay where they are
+					const tsom_container::GhostKey gk{ nk, d };
+					auto git = c->ghostIndex.find(gk);
+					if (git == c->ghostIndex.end())
+					{
+						g.ghost = uint32_t(c->ghostList.size());
+						c->ghostIndex.emplace(gk, g.ghost);
+						c->ghostList.push_back(g);
+						c->ghostsStale = true; // nothing has been pulled into this slab yet
+						ghostListChanged = true;
+					}
+					else
+					{
+						g.ghost = git->second;
+						if (c->ghostList[g.ghost].src != g.src || c->ghostList[g.ghost].contig != g.contig)
+						{
+							c->ghostList[g.ghost] = g; // the peer was re-attached or the chunk moved to another slot
+							c->ghostsStale = true;
+							ghostListChanged = true;
+						}
+					}
+					ghostUses.push_back(GhostUse{ s, uint32_t(d), g.ghost });
 				}
 			}
 		}
 
-		c->nGhost = uint32_t(ghosts.size());
+		c->nGhost = uint32_t(c->ghostList.size());
 		if (c->nGhost)
 		{
-			TSOM_CUDA(c->ghostSlabs.Ensure(size_t(c->nGhost) * SLAB));
+			TSOM_CUDA(c->ghostSlabs.EnsureKeep(size_t(c->nGhost) * SLAB, c->ghostSlabs.cap, ctx->stream));
 			TSOM_CUDA(c->ghostDescs.Ensure(c->nGhost));
-			TSOM_CUDA(cudaMemcpyAsync(c->ghostDescs.ptr, ghosts.data(), ghosts.size() * sizeof(tsomk::GhostDesc), cudaMemcpyHostToDevice, ctx->stream));
-			// second pass: ghost order == encounter order above
-			uint32_t g = 0;
-			for (uint32_t s = 0; s < n; ++s)
-				for (int d = 0; d < 6; ++d)
-					if (halo[size_t(s) * 6 + d] == 1ull)
-						halo[size_t(s) * 6 + d] = reinterpret_cast<unsigned long long>(c->ghostSlabs.ptr + size_t(g++) * SLAB) | tsomk_halo_contig();
+			if (ghostListChanged)
+				TSOM_CUDA(cudaMemcpyAsync(c->ghostDescs.ptr, c->ghostList.data(), c->ghostList.size() * sizeof(tsomk::GhostDesc), cudaMemcpyHostToDevice, ctx->stream));
+			for (const GhostUse& u : ghostUses)
+				halo[size_t(u.s) * 6 + u.d] = reinterpret_cast<unsigned long long>(c->ghostSlabs.ptr + size_t(u.ghost) * SLAB) | tsomk_halo_contig();
 		}
 
 		if (n)
 		{
 			TSOM_CUDA(cudaMemcpyAsync(c->dChunkIdx, idx.data(), size_t(n) * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
 			TSOM_CUDA(cudaMemcpyAsync(c->dHalo, halo.data(), halo.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaMemcpyAsync(c->dNbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the host vectors die at scope exit
 		}
 		c->topoDirty = false;
 		return TSOM_OK;
+	}
+
+	// ---- device-side ordering of the halo exchange (tsom_halo_publish / tsom_halo_pull, see tsom_b200.h)
+	constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 5ull * 1000ull * 1000ull * 1000ull;
+
+	int SyncPeerFlags(tsom_container* c)
+	{
+		if (!c->peerFlagsDirty)
+			return TSOM_OK;
+		const size_t np = c->peers.size();
+		if (np)
+		{
+			std::vector<const uint32_t*> gen, pull;
+			for (auto& [rank, p] : c->peers)
+			{
+				gen.push_back(p.sync + 0);
+				pull.push_back(p.sync + 1);
+			}
+			TSOM_CUDA(c->peerGenFlags.Ensure(np));
+			TSOM_CUDA(c->peerPullFlags.Ensure(np));
+			TSOM_CUDA(cudaMemcpyAsync(c->peerGenFlags.ptr, gen.data(), np * sizeof(const uint32_t*), cudaMemcpyHostToDevice, c->ctx->stream));
+			TSOM_CUDA(cudaMemcpyAsync(c->peerPullFlags.ptr, pull.data(), np * sizeof(const uint32_t*), cudaMemcpyHostToDevice, c->ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(c->ctx->stream));
+		}
+		c->peerFlagsDirty = false;
+		return TSOM_OK;
+	}
+
+	// Called by everything that writes block ids: once per round, before the first write, wait (on the device) until every peer
+	// has pulled the slabs of the last published round — a fast GPU must not overwrite what a slower one is still reading.
+	int BeforeBlockWrite(tsom_container* c)
+	{
+		c->dirtySincePublish = true;
+		if (!c->needWriteWait)
+			return TSOM_OK;
+		c->needWriteWait = false;
+		if (c->peers.empty())
+			return TSOM_OK;
+		int rc = SyncPeerFlags(c);
+		if (rc != TSOM_OK)
+			return rc;
+		tsomk::launch_flag_wait(c->peerPullFlags.ptr, uint32_t(c->peers.size()), c->pulledEpoch, EXCHANGE_TIMEOUT_NS, c->ctx->dSmall + 8, c->ctx->stream);
+		c->ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		return TSOM_OK;
+	}
+
+	// after a stream synchronisation that brought dSmall[8] to the host: did a wait kernel give up?
+	int CheckExchangeTimeout(tsom_ctx* ctx)
+	{
+		if (ctx->hSmall[8] == 0u)
+			return TSOM_OK;
+		const uint32_t who = ctx->hSmall[8] - 1u;
+		ctx->hSmall[8] = 0u;
+		cudaMemsetAsync(ctx->dSmall + 8, 0, sizeof(uint32_t), ctx->stream);
+		return Fail(TSOM_ERR_INTERNAL, "halo exchange timed out: attached peer #" + std::to_string(who) + " did not publish / pull its round within 5 s");
 	}
 
 	constexpr size_t ARENA_GUARD_BYTES = 256; // 0xA5 behind the last face of every arena, checked by tsom_debug_check_guards
@@ -594,25 +780,42 @@ extern "C"
 		if (prop.major < 10)
 			return Fail(TSOM_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100-class; this library ships sm_100a code only");
 
-		auto ctx = std::make_unique<tsom_ctx>();
+		// a failure below goes through tsom_destroy, which releases whatever was created so far
+		tsom_ctx* ctx = new (std::nothrow) tsom_ctx();
+		if (!ctx)
+			return Fail(TSOM_ERR_NOMEM, "out of host memory");
 		ctx->device = cuda_device;
 		ctx->numSMs = prop.multiProcessorCount;
-		TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-		TSOM_CUDA(tsomk::mesh_kernels_init());
-		TSOM_CUDA(tsomk::lz4_kernels_init());
-		TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
-		TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
-		TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
-		for (auto& e : ctx->ev)
-			TSOM_CUDA(cudaEventCreate(&e));
-		TSOM_CUDA(cudaMalloc(&ctx->dFaceTable, sizeof(tsomk::FaceTable)));
+		auto init = [&]() -> int {
+			TSOM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+			TSOM_CUDA(tsomk::mesh_kernels_init());
+			TSOM_CUDA(tsomk::lz4_kernels_init());
+			TSOM_CUDA(cudaMalloc(&ctx->dSmall, 16 * sizeof(uint32_t)));
+			TSOM_CUDA(cudaMemset(ctx->dSmall, 0, 16 * sizeof(uint32_t)));
+			TSOM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->hSmall), 16 * sizeof(uint32_t)));
+			std::memset(ctx->hSmall, 0, 16 * sizeof(uint32_t));
+			for (auto& e : ctx->ev)
+				TSOM_CUDA(cudaEventCreate(&e));
+			TSOM_CUDA(cudaMalloc(&ctx->dFaceTable, sizeof(tsomk::FaceTable)));
+			return TSOM_OK;
+		};
+		int rc = init();
+		if (rc != TSOM_OK)
+		{
+			const std::string msg = g_lastError;
+			tsom_destroy(ctx);
+			return Fail(rc, msg);
+		}
 
 		const F3h normals[6] = { { 0.f, 0.f, 1.f }, { 0.f, -1.f, 0.f }, { 0.f, 0.f, -1.f }, { -1.f, 0.f, 0.f }, { 1.f, 0.f, 0.f }, { 0.f, 1.f, 0.f } };
 		for (int d = 0; d < 6; ++d)
 			RotationBetween(normals[d], F3h{ 0.f, 1.f, 0.f }, ctx->quat[d]);
 
 		if (!DeriveBernoulliThreshold(ctx->bStar, ctx->aStar))
+		{
+			tsom_destroy(ctx);
 			return Fail(TSOM_ERR_UNSUPPORTED, "std::bernoulli_distribution(0.9) over std::minstd_rand is not a two-level integer threshold on this standard library");
+		}
 		{
 			// 48271^-1 mod (2^31 - 1) by Fermat
 			auto mulmod = [](uint64_t a, uint64_t b) { return (a * b) % 2147483647ull; };
@@ -626,7 +829,7 @@ extern "C"
 			}
 			ctx->aInv = uint32_t(r);
 		}
-		*out = ctx.release();
+		*out = ctx;
 		return TSOM_OK;
 	}
 
@@ -635,7 +838,8 @@ extern "C"
 		if (!ctx)
 			return;
 		cudaSetDevice(ctx->device);
-		cudaStreamSynchronize(ctx->stream);
+		if (ctx->stream)
+			cudaStreamSynchronize(ctx->stream);
 		cudaFree(ctx->dFlags);
 		cudaFree(ctx->dTex);
 		cudaFree(ctx->dVertices);
@@ -654,15 +858,21 @@ extern "C"
 		ctx->editVals.Free();
 		ctx->gravity.Free();
 		ctx->edits.Free();
+		cudaFree(ctx->dBoxes);
+		ctx->boxScratch.Free();
+		ctx->boxCounts.Free();
+		ctx->boxFirst.Free();
 		cudaFree(ctx->dSmall);
 		cudaFree(ctx->dFaceTable);
 		for (auto& e : ctx->ev)
 			if (e)
 				cudaEventDestroy(e);
-		cudaFreeHost(ctx->hSmall);
+		if (ctx->hSmall)
+			cudaFreeHost(ctx->hSmall);
 		if (ctx->hPinned)
 			cudaFreeHost(ctx->hPinned);
-		cudaStreamDestroy(ctx->stream);
+		if (ctx->stream)
+			cudaStreamDestroy(ctx->stream);
 		delete ctx;
 	}
 
@@ -729,6 +939,8 @@ extern "C"
 		TSOM_CUDA(cudaMemcpy(ctx->dFlags, flags.data(), n, cudaMemcpyHostToDevice));
 		TSOM_CUDA(cudaMemcpy(ctx->dTex, tex.data(), tex.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		ctx->nTypes = n;
+		ctx->hostFlags = flags;
+		++ctx->tableEpoch; // chunk summaries made under the previous table no longer hold
 		return TSOM_OK;
 	}
 
@@ -780,22 +992,33 @@ extern "C"
 		c->capacity = capacity_chunks;
 		c->tile = tile_size;
 		cudaError_t e;
+		const size_t maskBytes = (size_t(capacity_chunks) + 3u) & ~size_t(3); // edit_apply_kernel ORs whole 32-bit words
 		if ((e = cudaMalloc(&c->dBlocks, size_t(capacity_chunks) * NB * sizeof(uint16_t))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dXslabs, size_t(capacity_chunks) * 2 * SLAB * sizeof(uint16_t))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dHalo, size_t(capacity_chunks) * 6 * sizeof(unsigned long long))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dChunkIdx, size_t(capacity_chunks) * sizeof(int4))) != cudaSuccess ||
-		    (e = cudaMalloc(&c->dInvalid, capacity_chunks)) != cudaSuccess ||
-		    (e = cudaMalloc(&c->dPerm, 6 * 256)) != cudaSuccess)
+		    (e = cudaMalloc(&c->dInvalid, maskBytes)) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dSummary, maskBytes)) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dNbr, size_t(capacity_chunks) * 6 * sizeof(int32_t))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dSync, 64 * sizeof(uint32_t))) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dPerm, 6 * 256)) != cudaSuccess ||
+		    (e = cudaMallocHost(reinterpret_cast<void**>(&c->hPerm), 6 * 256)) != cudaSuccess)
 		{
 			cudaFree(c->dBlocks);
 			cudaFree(c->dXslabs);
 			cudaFree(c->dHalo);
 			cudaFree(c->dChunkIdx);
 			cudaFree(c->dInvalid);
+			cudaFree(c->dSummary);
+			cudaFree(c->dNbr);
+			cudaFree(c->dSync);
 			cudaFree(c->dPerm);
 			return Fail(TSOM_ERR_NOMEM, std::string("container cudaMalloc: ") + cudaGetErrorString(e));
 		}
-		TSOM_CUDA(cudaMemset(c->dInvalid, 0, capacity_chunks));
+		TSOM_CUDA(cudaMemset(c->dInvalid, 0, maskBytes));
+		TSOM_CUDA(cudaMemset(c->dSummary, 0, maskBytes));
+		TSOM_CUDA(cudaMemset(c->dSync, 0, 64 * sizeof(uint32_t)));
+		c->summaryTableEpoch = ctx->tableEpoch;
 		c->idxOf.resize(capacity_chunks);
 		c->exists.assign(capacity_chunks, 0);
 		c->hasContent.assign(capacity_chunks, 0);
@@ -817,6 +1040,7 @@ extern "C"
 			{
 				cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.blocks));
 				cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.xslabs));
+				cudaIpcCloseMemHandle(const_cast<uint32_t*>(p.sync));
 			}
 		}
 		cudaFree(c->dBlocks);
@@ -824,9 +1048,19 @@ extern "C"
 		cudaFree(c->dHalo);
 		cudaFree(c->dChunkIdx);
 		cudaFree(c->dInvalid);
+		cudaFree(c->dSummary);
+		cudaFree(c->dNbr);
+		cudaFree(c->dSync);
 		cudaFree(c->dPerm);
+		if (c->hPerm)
+			cudaFreeHost(c->hPerm);
 		c->ghostSlabs.Free();
 		c->ghostDescs.Free();
+		c->peerGenFlags.Free();
+		c->peerPullFlags.Free();
+		c->genCache.jobs.Free();
+		c->meshCache.jobs.Free();
+		c->templates.Free();
 		c->terrain.Free();
 		c->tileRange.Free();
 		c->slotGrid.Free();
@@ -851,11 +1085,11 @@ extern "C"
 	{
 		if (!c || !chunk_index)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		Key k{ chunk_index[0], chunk_index[1], chunk_index[2] };
 		auto it = c->slotOf.find(k);
 		if (it == c->slotOf.end())
 			return Fail(TSOM_ERR_INVALID, "unknown chunk");
-		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
 		const uint32_t slot = it->second;
 		c->exists[slot] = 0;
@@ -865,7 +1099,16 @@ extern "C"
 		c->freeSlots.push_back(slot);
 		c->slotOf.erase(it);
 		c->hostGridValid = false;
-		c->topoDirty = true;
+		TopoChanged(c);
+		return TSOM_OK;
+	}
+
+	int tsom_container_set_kind(tsom_container* c, int kind)
+	{
+		if (!c || (kind != TSOM_CONTAINER_PLANET && kind != TSOM_CONTAINER_SHIP))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
+		c->kind = kind;
 		return TSOM_OK;
 	}
 
@@ -876,13 +1119,13 @@ extern "C"
 	{
 		tsom_ctx* ctx = c->ctx;
 		const uint32_t n = uint32_t(slots.size());
-		tsomk::launch_build_xslabs(c->dBlocks, c->dXslabs, ctx->jobSlot.ptr, n, ctx->stream);
+		tsomk::launch_build_xslabs(c->dBlocks, c->dXslabs, c->dSummary, ctx->jobSlot.ptr, n, ctx->stream);
 		ctx->launches += n ? 1 : 0;
 		TSOM_CUDA(cudaGetLastError());
 		for (uint32_t k = 0; k < n; ++k)
 		{
 			if (!c->hasContent[slots[k]])
-				c->topoDirty = true;
+				TopoChanged(c);
 			c->hasContent[slots[k]] = 1;
 			c->hostInvalid[slots[k]] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
 		}
@@ -901,6 +1144,11 @@ extern "C"
 		for (uint32_t i = 0; i < n; ++i)
 		{
 			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		{
+			int rc = BeforeBlockWrite(c);
 			if (rc != TSOM_OK)
 				return rc;
 		}
@@ -994,6 +1242,11 @@ extern "C"
 		TSOM_CUDA(cudaMemcpyAsync(ctx->ioPalette.ptr, palettes, size_t(n) * palette_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->ioPayload.ptr, payload, size_t(n) * NB * 2, cudaMemcpyHostToDevice, ctx->stream));
 		TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 7, 0, sizeof(uint32_t), ctx->stream));
+		{
+			int rc = BeforeBlockWrite(c);
+			if (rc != TSOM_OK)
+				return rc;
+		}
 		tsomk::launch_depalettize(c->dBlocks, ctx->jobSlot.ptr, n, ctx->ioPalette.ptr, palette_stride, ctx->ioCounts.ptr, ctx->ioPayload.ptr, payload_big_endian, ctx->dSmall + 7, ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
@@ -1165,95 +1418,119 @@ extern "C"
 	}
 
 	// ---------------------------------------------------------------------------------------------------- generation
-	int tsom_planet_generate_chunks(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids, const int32_t* chunk_indices, uint32_t n)
+	// Everything of Planet::GenerateChunk(s) up to the last launch; GenerateFinish waits for it.  (Split so that one host thread can
+	// keep several GPUs busy: tsom_sharded_generate enqueues on every part before it waits on any.)  Caller holds the context lock.
+	static int GenerateEnqueue(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids, const int32_t* chunk_indices, uint32_t n)
 	{
-		if (!c || !chunk_count || !ids || (!chunk_indices && n))
-			return Fail(TSOM_ERR_INVALID, "bad arguments");
-		if (n == 0)
-			return TSOM_OK;
 		tsom_ctx* ctx = c->ctx;
-		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 
 		int maxH[3];
 		for (int k = 0; k < 3; ++k)
 			maxH[k] = ((int(chunk_count[k]) + 1) / 2) * CS; // Planet.cpp:176-177
 
-		// bounding box of the requested chunks + the reference's own precondition (Nz::SafeCaster at Planet.cpp:199: depth >= 0)
-		int lo[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, hi[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
-		for (uint32_t i = 0; i < n; ++i)
+		auto& cache = c->genCache;
+		if (!cache.Matches(chunk_indices, n, c->topoVersion))
 		{
-			const int32_t* ci = chunk_indices + size_t(i) * 3;
-			for (int k = 0; k < 3; ++k)
+			// bounding box of the requested chunks + the reference's own precondition (Nz::SafeCaster at Planet.cpp:199: depth >= 0)
+			tsom_container::GenPlan plan{ { INT32_MAX, INT32_MAX, INT32_MAX }, { INT32_MIN, INT32_MIN, INT32_MIN }, INT32_MAX, INT32_MIN };
+			for (uint32_t i = 0; i < n; ++i)
 			{
-				lo[k] = std::min(lo[k], ci[k]);
-				hi[k] = std::max(hi[k], ci[k]);
+				const int32_t* ci = chunk_indices + size_t(i) * 3;
+				for (int k = 0; k < 3; ++k)
+				{
+					plan.lo[k] = std::min(plan.lo[k], ci[k]);
+					plan.hi[k] = std::max(plan.hi[k], ci[k]);
+				}
+				plan.sumMin = std::min(plan.sumMin, ci[0] + ci[1] + ci[2]);
+				plan.sumMax = std::max(plan.sumMax, ci[0] + ci[1] + ci[2]);
+				// world coordinate ranges: X from cx, Y(up) from cy, Z from cz; depth crosses Y/Z (Planet.cpp:199-203)
+				auto maxAbs = [](int cidx) { int a = cidx * CS - CS / 2, b = a + CS - 1; return std::max(std::abs(a), std::abs(b)); };
+				if (maxAbs(ci[0]) > maxH[0] || maxAbs(ci[2]) > maxH[1] || maxAbs(ci[1]) > maxH[2])
+					return Fail(TSOM_ERR_UNSUPPORTED, "chunk lies outside +-maxHeight: the reference's depth computation asserts (Nz::SafeCaster, Planet.cpp:199)");
 			}
-			// world coordinate ranges: X from cx, Y(up) from cy, Z from cz; depth crosses Y/Z (Planet.cpp:199-203)
-			auto maxAbs = [](int cidx) { int a = cidx * CS - CS / 2, b = a + CS - 1; return std::max(std::abs(a), std::abs(b)); };
-			if (maxAbs(ci[0]) > maxH[0] || maxAbs(ci[2]) > maxH[1] || maxAbs(ci[1]) > maxH[2])
-				return Fail(TSOM_ERR_UNSUPPORTED, "chunk lies outside +-maxHeight: the reference's depth computation asserts (Nz::SafeCaster, Planet.cpp:199)");
+			std::vector<uint32_t> slots(n);
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
+				if (rc != TSOM_OK)
+					return rc;
+			}
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				if (!c->hasContent[slots[i]])
+					TopoChanged(c);
+				c->hasContent[slots[i]] = 1;
+			}
+			TSOM_CUDA(cache.jobs.Ensure(n));
+			TSOM_CUDA(cudaMemcpyAsync(cache.jobs.ptr, slots.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // `slots` dies at scope exit
+			cache.idx.assign(chunk_indices, chunk_indices + size_t(n) * 3);
+			cache.n = n;
+			cache.version = c->topoVersion;
+			c->genPlan = plan;
+			cache.hostSlots = std::move(slots);
 		}
+		for (uint32_t s : cache.hostSlots)
+			c->hostInvalid[s] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
+		const tsom_container::GenPlan& plan = c->genPlan;
 
-		// terrain tables over the bounding box
+		// generation reads chunkIdx on the device: make sure new chunks are there
+		int rc = SyncTopology(c);
+		if (rc != TSOM_OK)
+			return rc;
+		if ((rc = BeforeBlockWrite(c)) != TSOM_OK)
+			return rc;
+
+		// terrain tables over the bounding box, only for the sides from which a chunk of this call can be carved: the pass of a
+		// side touches a chunk only if blockDepth - terrainDepth < 32 for some column, and terrainDepth <= maxH / 2 (Planet.cpp:241-247)
 		tsomk::TerrainArgs ta{};
 		size_t total = 0;
 		for (int k = 0; k < 3; ++k)
 		{
-			ta.tileOrigin[k] = lo[k];
-			ta.tileCount[k] = hi[k] - lo[k] + 1;
+			ta.tileOrigin[k] = plan.lo[k];
+			ta.tileCount[k] = plan.hi[k] - plan.lo[k] + 1;
 			ta.maxH[k] = maxH[k];
 		}
 		const size_t tilesX = size_t(ta.tileCount[1]) * ta.tileCount[2], tilesY = size_t(ta.tileCount[0]) * ta.tileCount[2], tilesZ = size_t(ta.tileCount[0]) * ta.tileCount[1];
 		const size_t tiles[6] = { tilesZ, tilesY, tilesZ, tilesX, tilesX, tilesY }; // Direction order: Back Down Front Left Right Up
+		uint32_t dirMask = 0;
+		{
+			// smallest blockDepth a chunk of the box can have per side (Planet.cpp:237,262,287,312,337,362)
+			auto nearPlus = [&](int axis) { return maxH[axis] - (plan.hi[axis] * CS - CS / 2) + 1; };
+			auto nearMinus = [&](int axis) { return maxH[axis] + (plan.lo[axis] * CS - CS / 2 + CS - 1) + 1; };
+			const int minDepth[6] = { nearPlus(2), nearMinus(1), nearMinus(2), nearMinus(0), nearPlus(0), nearPlus(1) }; // Back +Z, Down -Y, Front -Z, Left -X, Right +X, Up +Y
+			const int axisOf[6] = { 2, 1, 2, 0, 0, 1 };
+			for (int d = 0; d < 6; ++d)
+				if (minDepth[d] - maxH[axisOf[d]] / 2 < CS)
+					dirMask |= 1u << d;
+		}
 		for (int d = 0; d < 6; ++d)
 		{
 			ta.terrainOffset[d] = total;
-			total += tiles[d] * SLAB;
+			ta.tiles[d] = (dirMask >> d) & 1u ? uint32_t(tiles[d]) : 0u;
+			total += size_t(ta.tiles[d]) * SLAB;
 		}
-		TSOM_CUDA(c->terrain.Ensure(total));
-		TSOM_CUDA(c->tileRange.Ensure(total / SLAB * 2));
+		TSOM_CUDA(c->terrain.Ensure(std::max<size_t>(total, SLAB)));
+		TSOM_CUDA(c->tileRange.Ensure(std::max<size_t>(total / SLAB * 2, 2)));
 		ta.terrain = c->terrain.ptr;
 		ta.tileRange = c->tileRange.ptr;
-		uint8_t perm[6 * 256];
+		uint8_t* perm = c->hPerm; // pinned, owned by the container: the copy below may still be queued when this call returns
 		for (int d = 0; d < 6; ++d)
 			PerlinPermutation(seed + unsigned(d), perm + d * 256); // Planet.cpp:179-181
-		TSOM_CUDA(cudaMemcpyAsync(c->dPerm, perm, sizeof(perm), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(c->dPerm, perm, 6 * 256, cudaMemcpyHostToDevice, ctx->stream));
 		ta.perm = c->dPerm;
 		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 		tsomk::launch_terrain(ta, ctx->stream);
-		ctx->launches += 1;
+		ctx->launches += total ? 1 : 0;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-
-		// ---- host bookkeeping while the terrain kernel runs: slots of the chunks, content flags, topology upload
-		std::vector<uint32_t> slots(n);
-		for (uint32_t i = 0; i < n; ++i)
-		{
-			int rc = AddChunk(c, Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] }, &slots[i]);
-			if (rc != TSOM_OK)
-				return rc;
-		}
-		// generation reads chunkIdx on the device: make sure new chunks are there
-		for (uint32_t i = 0; i < n; ++i)
-		{
-			if (!c->hasContent[slots[i]])
-				c->topoDirty = true;
-			c->hasContent[slots[i]] = 1;
-			c->hostInvalid[slots[i]] = 0x80u | 0x3Fu;
-		}
-		int rc = SyncTopology(c);
-		if (rc != TSOM_OK)
-			return rc;
-
-		TSOM_CUDA(ctx->jobSlot.Ensure(n));
-		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, slots.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 
 		tsomk::GenArgs ga{};
 		ga.blocks = c->dBlocks;
 		ga.xslabs = c->dXslabs;
 		ga.chunkIdx = c->dChunkIdx;
-		ga.jobSlot = ctx->jobSlot.ptr;
+		ga.jobSlot = cache.jobs.ptr;
 		ga.nJobs = n;
 		ga.seed = seed;
 		for (int k = 0; k < 3; ++k)
@@ -1266,6 +1543,7 @@ extern "C"
 		ga.tileRange = c->tileRange.ptr;
 		for (int d = 0; d < 6; ++d)
 			ga.terrainOffset[d] = ta.terrainOffset[d];
+		ga.dirMask = dirMask;
 		ga.dirt = ids->dirt;
 		ga.grass = ids->grass;
 		ga.stone = ids->stone;
@@ -1274,15 +1552,59 @@ extern "C"
 		ga.bStar = ctx->bStar;
 		ga.aStar = ctx->aStar;
 		ga.aInv = ctx->aInv;
-		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+		// chunk summaries the generator may write, from the block table (none without a table: everything stays SUM_UNKNOWN)
+		auto opaque = [&](uint16_t id) { return id != 0 && id < ctx->hostFlags.size() && !(ctx->hostFlags[id] & 4u /* BF_TRANSPARENT */); };
+		ga.summary = c->dSummary;
+		ga.fastSummary = (opaque(ids->stone) && opaque(ids->stone_mossy)) ? tsomk::SUM_OPAQUE : tsomk::SUM_UNKNOWN;
+		ga.allOpaque = (opaque(ids->dirt) && opaque(ids->grass) && opaque(ids->stone) && opaque(ids->stone_mossy) && opaque(ids->snow)) ? 1 : 0;
+		// template chunks: one per value of cx + cy + cz in the request; worth it when many chunks share each of them
+		ga.templates = nullptr;
+		ga.templateSumMin = plan.sumMin;
+		ga.nTemplates = 0;
+		const uint32_t nTemplates = uint32_t(plan.sumMax - plan.sumMin + 1);
+		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+		if (n >= 4u * nTemplates)
+		{
+			TSOM_CUDA(c->templates.Ensure(size_t(nTemplates) * tsomk::TEMPLATE_STRIDE));
+			ga.nTemplates = nTemplates;
+			tsomk::launch_templates(ga, c->templates.ptr, ctx->stream);
+			ctx->launches += 1;
+			TSOM_CUDA(cudaGetLastError());
+			ga.templates = c->templates.ptr;
+		}
 		tsomk::launch_generate(ga, int(n), ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
-		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall + 8, ctx->dSmall + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->pendingGenerate = true;
+		return TSOM_OK;
+	}
+
+	static int GenerateFinish(tsom_container* c)
+	{
+		tsom_ctx* ctx = c->ctx;
+		if (!ctx->pendingGenerate)
+			return TSOM_OK;
+		ctx->pendingGenerate = false;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // blocking like Planet::GenerateChunks (WaitForTasks, Planet.cpp:402)
 		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_TERRAIN_MS], ctx->ev[0], ctx->ev[1]);
-		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[3], ctx->ev[2]);
-		return TSOM_OK;
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[2], ctx->ev[3]);
+		return CheckExchangeTimeout(ctx);
+	}
+
+	int tsom_planet_generate_chunks(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids, const int32_t* chunk_indices, uint32_t n)
+	{
+		if (!c || !chunk_count || !ids || (!chunk_indices && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		TSOM_LOCK(c->ctx);
+		int rc = GenerateEnqueue(c, seed, chunk_count, ids, chunk_indices, n);
+		if (rc != TSOM_OK)
+			return rc;
+		return GenerateFinish(c);
 	}
 
 	int tsom_planet_generate(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids)
@@ -1336,15 +1658,26 @@ extern "C"
 		}
 		if (cells > (size_t(1) << 28))
 			return Fail(TSOM_ERR_UNSUPPORTED, "chunk bounding box too large for the platform slot grid");
-		std::vector<int> grid(cells, -1);
-		for (auto& [k, s] : c->slotOf)
-			if (c->hasContent[s])
-				grid[(size_t(k.z - lo[2]) * pa.gridDim[1] + size_t(k.y - lo[1])) * pa.gridDim[0] + size_t(k.x - lo[0])] = int(s);
-		TSOM_CUDA(c->slotGrid.Ensure(cells));
-		TSOM_CUDA(cudaMemcpyAsync(c->slotGrid.ptr, grid.data(), cells * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		if (c->slotGridVersion != c->topoVersion)
+		{
+			std::vector<int> grid(cells, -1);
+			for (auto& [k, s] : c->slotOf)
+				if (c->hasContent[s])
+					grid[(size_t(k.z - lo[2]) * pa.gridDim[1] + size_t(k.y - lo[1])) * pa.gridDim[0] + size_t(k.x - lo[0])] = int(s);
+			TSOM_CUDA(c->slotGrid.Ensure(cells));
+			TSOM_CUDA(cudaMemcpyAsync(c->slotGrid.ptr, grid.data(), cells * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // `grid` dies at scope exit
+			c->slotGridVersion = c->topoVersion;
+		}
+		{
+			int rc = BeforeBlockWrite(c);
+			if (rc != TSOM_OK)
+				return rc;
+		}
 		pa.blocks = c->dBlocks;
 		pa.xslabs = c->dXslabs;
 		pa.invalidMask = c->dInvalid;
+		pa.summary = c->dSummary;
 		pa.slotGrid = c->slotGrid.ptr;
 		pa.upDirection = up_direction;
 		for (int a = 0; a < 3; ++a)
@@ -1392,7 +1725,13 @@ extern "C"
 		TSOM_CUDA(ctx->editVals.Ensure(cap));
 		TSOM_CUDA(cudaMemsetAsync(ctx->editKeys.ptr, 0xFF, size_t(cap) * sizeof(unsigned long long), ctx->stream));
 		TSOM_CUDA(cudaMemsetAsync(ctx->editVals.ptr, 0, size_t(cap) * sizeof(uint32_t), ctx->stream));
-		tsomk::launch_apply_edits(c->dBlocks, c->dXslabs, c->dInvalid, ctx->edits.ptr, n, ctx->editKeys.ptr, ctx->editVals.ptr, cap, ctx->stream);
+		{
+			int rc = BeforeBlockWrite(c);
+			if (rc != TSOM_OK)
+				return rc;
+		}
+		tsomk::launch_apply_edits(c->dBlocks, c->dXslabs, c->dInvalid, c->dSummary, ctx->edits.ptr, n, ctx->editKeys.ptr, ctx->editVals.ptr, cap, c->kind == TSOM_CONTAINER_SHIP ? 1 : 0,
+		                          ctx->stream);
 		ctx->launches += 2;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the pinned staging buffer is reused by the next call
@@ -1412,18 +1751,16 @@ extern "C"
 		{
 			TSOM_CUDA(ctx->EnsurePinned(n));
 			TSOM_CUDA(cudaMemcpyAsync(ctx->hPinned, c->dInvalid, n, cudaMemcpyDeviceToHost, ctx->stream));
-			if (clear)
-				TSOM_CUDA(cudaMemsetAsync(c->dInvalid, 0, n, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 			std::memcpy(mask.data(), ctx->hPinned, n);
 		}
+		const bool wantClear = clear != 0;
+		clear = 0; // decided below: a list that does not fit the caller's buffer must not be lost
 		std::vector<Key> dirty;
 		std::vector<uint8_t> seen(n, 0);
 		for (uint32_t s = 0; s < n; ++s)
 		{
 			const uint8_t m = mask[s] | c->hostInvalid[s];
-			if (clear)
-				c->hostInvalid[s] = 0;
 			if (!(m & 0x80u) || !c->exists[s] || !c->hasContent[s])
 				continue;
 			if (!seen[s])
@@ -1461,6 +1798,14 @@ extern "C"
 		else
 			std::sort(dirty.begin(), dirty.end());
 		*n_out = uint32_t(dirty.size());
+		if (wantClear)
+		{
+			if (chunk_indices_out && dirty.size() > cap)
+				return Fail(TSOM_ERR_CAPACITY, "chunk_indices_out holds " + std::to_string(cap) + " chunks, " + std::to_string(dirty.size()) + " are invalidated; nothing was cleared");
+			std::fill(c->hostInvalid.begin(), c->hostInvalid.begin() + n, uint8_t(0));
+			if (n)
+				TSOM_CUDA(cudaMemsetAsync(c->dInvalid, 0, n, ctx->stream));
+		}
 		if (chunk_indices_out)
 		{
 			for (uint32_t i = 0; i < dirty.size() && i < cap; ++i)
@@ -1474,39 +1819,87 @@ extern "C"
 	}
 
 	// ---------------------------------------------------------------------------------------------------- meshing
-	int tsom_mesh(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, tsom_mesh_view* views_out)
+	static cudaError_t LaunchFused(tsom_ctx* ctx, tsomk::MeshArgs& a, uint32_t n, uint32_t flags)
 	{
-		if (!c || !params)
-			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		a.vertices = ctx->dVertices;
+		a.indices = ctx->dIndices;
+		a.collider = ctx->dCollider;
+		a.arenaFaces = ArenaFaces(ctx, flags);
+		a.jobCounter = ctx->dSmall + 1;
+		a.status = ctx->status.ptr;
+		a.firstFaceOut = ctx->firstFace.ptr;
+		a.totalFacesOut = reinterpret_cast<unsigned long long*>(ctx->dSmall + 4);
+		if (flags & TSOM_MESH_ORDERED)
+		{
+			cudaError_t e = cudaMemsetAsync(ctx->status.ptr, 0, size_t(n) * sizeof(unsigned long long), ctx->stream);
+			if (e != cudaSuccess)
+				return e;
+		}
+		tsomk::launch_mesh_fused(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
+		ctx->launches += 1;
+		return cudaGetLastError();
+	}
+
+	// Chunk::BuildMesh for a batch up to the launch and the queued read-back; MeshFinish waits and fills the views.  Caller holds the lock.
+	static int MeshEnqueue(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, bool wantViews, uint32_t* nOut)
+	{
 		tsom_ctx* ctx = c->ctx;
-		TSOM_LOCK(ctx);
 		const uint32_t flags = params->flags;
 		if (!(flags & (TSOM_MESH_RENDER | TSOM_MESH_COLLIDER)))
 			return Fail(TSOM_ERR_INVALID, "flags must request TSOM_MESH_RENDER and/or TSOM_MESH_COLLIDER");
+		if ((flags & TSOM_MESH_TANGENTS) && !(flags & TSOM_MESH_RENDER))
+			return Fail(TSOM_ERR_INVALID, "TSOM_MESH_TANGENTS needs TSOM_MESH_RENDER");
 		if (!ctx->dFlags)
 			return Fail(TSOM_ERR_INVALID, "no block table: call tsom_set_block_table first");
 		TSOM_CUDA(cudaSetDevice(ctx->device));
+		ctx->pendingMesh.active = false;
 
-		std::vector<uint32_t> slots;
+		// ---- job list: slot | has-content flag, one entry per chunk (cached on the device while the same list is meshed again)
+		auto& cache = c->meshCache;
 		if (chunk_indices)
 		{
-			slots.resize(n);
-			for (uint32_t i = 0; i < n; ++i)
+			if (!cache.Matches(chunk_indices, n, c->topoVersion))
 			{
-				slots[i] = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
-				if (slots[i] == 0xFFFFFFFFu)
-					return Fail(TSOM_ERR_INVALID, "tsom_mesh: unknown chunk");
+				std::vector<uint32_t> jobs(n);
+				for (uint32_t i = 0; i < n; ++i)
+				{
+					const uint32_t slot = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+					if (slot == 0xFFFFFFFFu)
+						return Fail(TSOM_ERR_INVALID, "tsom_mesh: unknown chunk");
+					jobs[i] = slot | (c->hasContent[slot] ? tsomk::JOB_HAS_CONTENT : 0u);
+				}
+				cache.n = 0;
+				if (n)
+				{
+					TSOM_CUDA(cache.jobs.Ensure(n));
+					TSOM_CUDA(cudaMemcpyAsync(cache.jobs.ptr, jobs.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+					TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // `jobs` dies at scope exit
+					cache.idx.assign(chunk_indices, chunk_indices + size_t(n) * 3);
+					cache.n = n;
+					cache.version = c->topoVersion;
+				}
 			}
 		}
 		else
 		{
+			// every chunk with content, container order
+			std::vector<uint32_t> jobs;
 			for (uint32_t s = 0; s < c->highWater; ++s)
 				if (c->exists[s] && c->hasContent[s])
-					slots.push_back(s);
-			if (views_out && n != slots.size())
+					jobs.push_back(s | tsomk::JOB_HAS_CONTENT);
+			if (wantViews && n != jobs.size())
 				return Fail(TSOM_ERR_INVALID, "tsom_mesh: with chunk_indices == NULL, n must equal the number of chunks with content");
-			n = uint32_t(slots.size());
+			n = uint32_t(jobs.size());
+			cache.n = 0; // not keyed by an index list
+			if (n)
+			{
+				TSOM_CUDA(cache.jobs.Ensure(n));
+				TSOM_CUDA(cudaMemcpyAsync(cache.jobs.ptr, jobs.data(), size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+				TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			}
 		}
+		if (nOut)
+			*nOut = n;
 		ctx->totalFaces = 0;
 		if (n == 0)
 			return TSOM_OK;
@@ -1514,17 +1907,20 @@ extern "C"
 		int rc = SyncTopology(c);
 		if (rc != TSOM_OK)
 			return rc;
+		if (c->ghostsStale)
+			return Fail(TSOM_ERR_INVALID, "tsom_mesh: a neighbour chunk on another GPU has never been pulled (the topology changed): call tsom_halo_pull first");
+		if (c->summaryTableEpoch != ctx->tableEpoch)
+		{
+			// the block table changed since the summaries were written: opaque may no longer mean opaque
+			TSOM_CUDA(cudaMemsetAsync(c->dSummary, 0, c->capacity, ctx->stream));
+			c->summaryTableEpoch = ctx->tableEpoch;
+		}
 
 		TSOM_CUDA(ctx->jobSlot.Ensure(n));
 		TSOM_CUDA(ctx->faceCount.Ensure(n));
 		TSOM_CUDA(ctx->firstFace.Ensure(n));
-		// job i = slot | has-content flag in bit 31: the kernel's ticket needs ONE dependent load behind its atomic, not two
-		// (built in the pinned staging buffer, sized here for the views that come back through it after the kernel: the copy is a plain DMA)
+		TSOM_CUDA(ctx->status.Ensure(n));
 		TSOM_CUDA(ctx->EnsurePinned(std::max<size_t>(size_t(n) * (sizeof(uint32_t) + sizeof(unsigned long long)), 64)));
-		uint32_t* jobs = static_cast<uint32_t*>(ctx->hPinned);
-		for (uint32_t i = 0; i < n; ++i)
-			jobs[i] = slots[i] | (c->hasContent[slots[i]] ? 0x80000000u : 0u);
-		TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, jobs, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		if (params->gravity_centers)
 		{
 			TSOM_CUDA(ctx->gravity.Ensure(size_t(n) * 3));
@@ -1534,7 +1930,15 @@ extern "C"
 		if (ArenaFaces(ctx, flags) == 0 && (rc = EnsureArenas(ctx, 1u << 16, flags)) != TSOM_OK)
 			return rc;
 
-		tsomk::MeshArgs a{};
+		// ---- chunks that provably have no face (summaries of the producers) are marked and skip their 64 KiB stage
+		TSOM_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
+		tsomk::launch_job_classify(cache.jobs.ptr, ctx->jobSlot.ptr, n, c->dSummary, c->dNbr, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
+
+		tsomk::MeshArgs& a = ctx->pendingMesh.args;
+		a = tsomk::MeshArgs{};
 		a.blocks = c->dBlocks;
 		a.halo = c->dHalo;
 		a.chunkIdx = c->dChunkIdx;
@@ -1567,50 +1971,51 @@ extern "C"
 			a.faceTable = ctx->dFaceTable;
 		}
 
-		auto launchFused = [&]() -> cudaError_t {
-			a.vertices = ctx->dVertices;
-			a.indices = ctx->dIndices;
-			a.collider = ctx->dCollider;
-			a.arenaFaces = ArenaFaces(ctx, flags);
-			a.jobCounter = ctx->dSmall + 1;
-			a.status = ctx->status.ptr;
-			a.firstFaceOut = ctx->firstFace.ptr;
-			a.totalFacesOut = reinterpret_cast<unsigned long long*>(ctx->dSmall + 4);
-			cudaError_t e = cudaMemsetAsync(ctx->status.ptr, 0, size_t(n) * sizeof(unsigned long long), ctx->stream);
-			if (e != cudaSuccess)
-				return e;
-			tsomk::launch_mesh_fused(a, int(std::min<uint32_t>(n, uint32_t(2 * ctx->numSMs))), ctx->stream);
-			ctx->launches += 1;
-			return cudaSuccess;
-		};
+		// single pass: the count and the scan live inside mesh_fused_kernel
+		TSOM_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+		TSOM_CUDA(LaunchFused(ctx, a, n, flags));
+		TSOM_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
 
-		// single pass: the count and the scan live inside mesh_fused_kernel (their timing slots read 0)
-		TSOM_CUDA(ctx->status.Ensure(n));
-		TSOM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-		TSOM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-		TSOM_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-		TSOM_CUDA(launchFused());
-		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-		TSOM_CUDA(cudaGetLastError());
-
-		// read back totals (+ views)
-		const size_t viewBytes = views_out ? size_t(n) * (sizeof(uint32_t) + sizeof(unsigned long long)) : 0;
-		TSOM_CUDA(ctx->EnsurePinned(std::max<size_t>(viewBytes, 64)));
-		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall, ctx->dSmall, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		// queue the read-back of the totals (+ views)
+		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall, ctx->dSmall, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		auto* hFirst = static_cast<unsigned long long*>(ctx->hPinned);
 		auto* hCount = reinterpret_cast<uint32_t*>(hFirst + n);
-		if (views_out)
+		if (wantViews)
 		{
 			TSOM_CUDA(cudaMemcpyAsync(hFirst, ctx->firstFace.ptr, size_t(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 			TSOM_CUDA(cudaMemcpyAsync(hCount, ctx->faceCount.ptr, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		}
+		ctx->pendingMesh.active = true;
+		ctx->pendingMesh.n = n;
+		ctx->pendingMesh.flags = flags;
+		ctx->pendingMesh.wantViews = wantViews;
+		return TSOM_OK;
+	}
+
+	static int MeshFinish(tsom_container* c, tsom_mesh_view* views_out)
+	{
+		tsom_ctx* ctx = c->ctx;
+		if (!ctx->pendingMesh.active)
+			return TSOM_OK;
+		ctx->pendingMesh.active = false;
+		const uint32_t n = ctx->pendingMesh.n, flags = ctx->pendingMesh.flags;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 
-		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_COUNT_MS], ctx->ev[0], ctx->ev[1]);
-		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_SCAN_MS], ctx->ev[1], ctx->ev[2]);
-		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_EMIT_MS], ctx->ev[2], ctx->ev[3]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_CLASSIFY_MS], ctx->ev[8], ctx->ev[9]);
+		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_EMIT_MS], ctx->ev[4], ctx->ev[5]);
 		ctx->timings[TSOM_TIMING_MESH_REEMIT] = 0.f;
+		if (ctx->pendingHalo)
+		{
+			cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_HALO_MS], ctx->ev[6], ctx->ev[7]);
+			ctx->pendingHalo = false;
+		}
+		int rc = CheckExchangeTimeout(ctx);
+		if (rc != TSOM_OK)
+			return rc;
 
+		auto* hFirst = static_cast<unsigned long long*>(ctx->hPinned);
+		auto* hCount = reinterpret_cast<uint32_t*>(hFirst + n);
 		unsigned long long total;
 		std::memcpy(&total, ctx->hSmall + 4, sizeof(total));
 		if (ctx->hSmall[3] != 0)
@@ -1622,15 +2027,14 @@ extern "C"
 				return rc;
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 1, 0, sizeof(uint32_t), ctx->stream));
 			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 3, 0, 3 * sizeof(uint32_t), ctx->stream)); // overflow flag + the 64-bit arena cursor / total
-			TSOM_CUDA(launchFused());
-			TSOM_CUDA(cudaGetLastError());
-			if (views_out)
+			TSOM_CUDA(LaunchFused(ctx, ctx->pendingMesh.args, n, flags));
+			if (ctx->pendingMesh.wantViews)
 				TSOM_CUDA(cudaMemcpyAsync(hFirst, ctx->firstFace.ptr, size_t(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
 		}
 		ctx->totalFaces = total;
 		ctx->lastMeshFlags = flags;
-		if (views_out)
+		if (views_out && ctx->pendingMesh.wantViews)
 		{
 			for (uint32_t i = 0; i < n; ++i)
 			{
@@ -1640,6 +2044,17 @@ extern "C"
 			}
 		}
 		return TSOM_OK;
+	}
+
+	int tsom_mesh(tsom_container* c, const int32_t* chunk_indices, uint32_t n, const tsom_mesh_params* params, tsom_mesh_view* views_out)
+	{
+		if (!c || !params)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
+		int rc = MeshEnqueue(c, chunk_indices, n, params, views_out != nullptr, nullptr);
+		if (rc != TSOM_OK)
+			return rc;
+		return MeshFinish(c, views_out);
 	}
 
 	int tsom_mesh_arenas(tsom_ctx* ctx, const void** vertices, const void** indices, const void** collider_positions, uint64_t* total_faces)
@@ -1662,15 +2077,15 @@ extern "C"
 	{
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "ctx is null");
+		TSOM_LOCK(ctx);
 		if (first_face + face_count > ctx->totalFaces)
 			return Fail(TSOM_ERR_INVALID, "face range exceeds the last mesh result");
 		if (face_count == 0)
 			return TSOM_OK;
-		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		if (vertices)
 		{
-			if (!ctx->dVertices)
+			if (!ctx->dVertices || !(ctx->lastMeshFlags & TSOM_MESH_RENDER))
 				return Fail(TSOM_ERR_INVALID, "last tsom_mesh call did not produce render vertices");
 			TSOM_CUDA(cudaMemcpyAsync(vertices, reinterpret_cast<const char*>(ctx->dVertices) + first_face * TSOM_FACE_VERTEX_BYTES, face_count * TSOM_FACE_VERTEX_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
 		}
@@ -1678,7 +2093,7 @@ extern "C"
 			TSOM_CUDA(cudaMemcpyAsync(indices, reinterpret_cast<const char*>(ctx->dIndices) + first_face * TSOM_FACE_INDEX_BYTES, face_count * TSOM_FACE_INDEX_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
 		if (collider_positions)
 		{
-			if (!ctx->dCollider)
+			if (!ctx->dCollider || !(ctx->lastMeshFlags & TSOM_MESH_COLLIDER))
 				return Fail(TSOM_ERR_INVALID, "last tsom_mesh call did not produce collider positions");
 			TSOM_CUDA(cudaMemcpyAsync(collider_positions, reinterpret_cast<const char*>(ctx->dCollider) + first_face * TSOM_FACE_COLLIDER_BYTES, face_count * TSOM_FACE_COLLIDER_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
 		}
@@ -1755,32 +2170,155 @@ extern "C"
 		return TSOM_OK;
 	}
 
-	int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out)
+	// FlatChunk::BuildCollider for a batch: box_colliders_kernel (one warp per chunk) into a packed scratch, sizes to the host, offsets
+	// back, box_pack_kernel into the dense arena.  Sub-batches bound the scratch (64 KiB per chunk); one synchronisation per sub-batch.
+	int tsom_box_colliders(tsom_container* c, const int32_t* chunk_indices, uint32_t n, tsom_box_view* views_out, uint64_t* total_boxes_out)
 	{
-		if (!c || !chunk_index || !n_out)
+		if (!c || (!chunk_indices && n))
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		tsom_ctx* ctx = c->ctx;
 		TSOM_LOCK(ctx);
 		if (!ctx->dFlags)
 			return Fail(TSOM_ERR_INVALID, "no block table");
-		uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
+		ctx->totalBoxes = 0;
+		if (total_boxes_out)
+			*total_boxes_out = 0;
+		if (n == 0)
+			return TSOM_OK;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		std::vector<uint32_t> jobs(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			const uint32_t slot = c->SlotOf(Key{ chunk_indices[i * 3], chunk_indices[i * 3 + 1], chunk_indices[i * 3 + 2] });
+			if (slot == 0xFFFFFFFFu)
+				return Fail(TSOM_ERR_INVALID, "tsom_box_colliders: unknown chunk");
+			jobs[i] = slot | (c->hasContent[slot] ? tsomk::JOB_HAS_CONTENT : 0u);
+		}
+		constexpr uint32_t BATCH = 8192;
+		const uint32_t maxBatch = std::min(n, BATCH);
+		TSOM_CUDA(ctx->jobSlot.Ensure(maxBatch));
+		TSOM_CUDA(ctx->boxCounts.Ensure(maxBatch));
+		TSOM_CUDA(ctx->boxFirst.Ensure(maxBatch));
+		TSOM_CUDA(ctx->boxScratch.Ensure(size_t(maxBatch) * tsomk::BOX_SCRATCH_STRIDE));
+		TSOM_CUDA(ctx->EnsurePinned(size_t(maxBatch) * (sizeof(uint32_t) + sizeof(unsigned long long))));
+		auto* hFirst = static_cast<unsigned long long*>(ctx->hPinned);
+		auto* hCount = reinterpret_cast<uint32_t*>(hFirst + maxBatch);
+		uint64_t total = 0;
+		float kernelMs = 0.f, ms = 0.f;
+		for (uint32_t first = 0; first < n; first += BATCH)
+		{
+			const uint32_t m = std::min(BATCH, n - first);
+			TSOM_CUDA(cudaMemcpyAsync(ctx->jobSlot.ptr, jobs.data() + first, size_t(m) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			TSOM_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
+			tsomk::launch_box_colliders(c->dBlocks, ctx->jobSlot.ptr, m, ctx->dFlags, ctx->nTypes, ctx->boxScratch.ptr, ctx->boxCounts.ptr, ctx->stream);
+			ctx->launches += 1;
+			TSOM_CUDA(cudaGetLastError());
+			TSOM_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
+			TSOM_CUDA(cudaMemcpyAsync(hCount, ctx->boxCounts.ptr, size_t(m) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess)
+				kernelMs += ms;
+			const uint64_t batchFirst = total;
+			for (uint32_t i = 0; i < m; ++i)
+			{
+				hFirst[i] = total;
+				if (views_out)
+				{
+					views_out[first + i].first_box = total;
+					views_out[first + i].box_count = hCount[i];
+					views_out[first + i].reserved = 0;
+				}
+				total += hCount[i];
+			}
+			if (total > batchFirst)
+			{
+				if (total > ctx->capBoxes)
+				{
+					// grow the arena, keeping the boxes of the earlier sub-batches
+					const uint64_t want = std::max<uint64_t>(total, 2 * ctx->capBoxes);
+					float* p = nullptr;
+					cudaError_t e = cudaMalloc(&p, want * 6 * sizeof(float));
+					if (e != cudaSuccess)
+						return Fail(TSOM_ERR_NOMEM, std::string("box arena cudaMalloc: ") + cudaGetErrorString(e));
+					if (ctx->dBoxes && batchFirst)
+						cudaMemcpy(p, ctx->dBoxes, batchFirst * 6 * sizeof(float), cudaMemcpyDeviceToDevice);
+					cudaFree(ctx->dBoxes);
+					ctx->dBoxes = p;
+					ctx->capBoxes = want;
+				}
+				TSOM_CUDA(cudaMemcpyAsync(ctx->boxFirst.ptr, hFirst, size_t(m) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+				TSOM_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
+				tsomk::launch_box_pack(ctx->boxScratch.ptr, ctx->boxCounts.ptr, ctx->boxFirst.ptr, m, ctx->dBoxes, ctx->stream);
+				ctx->launches += 1;
+				TSOM_CUDA(cudaGetLastError());
+				TSOM_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
+				TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // the pinned offsets are rewritten by the next sub-batch
+				if (cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess)
+					kernelMs += ms;
+			}
+		}
+		ctx->timings[TSOM_TIMING_COLLIDER_MS] = kernelMs;
+		ctx->totalBoxes = total;
+		if (total_boxes_out)
+			*total_boxes_out = total;
+		return TSOM_OK;
+	}
+
+	int tsom_box_colliders_copy_to_host(tsom_ctx* ctx, uint64_t first_box, uint64_t box_count, float* boxes_out)
+	{
+		if (!ctx || (!boxes_out && box_count))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(ctx);
+		if (first_box + box_count > ctx->totalBoxes)
+			return Fail(TSOM_ERR_INVALID, "box range exceeds the last tsom_box_colliders result");
+		if (box_count == 0)
+			return TSOM_OK;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		TSOM_CUDA(cudaMemcpyAsync(boxes_out, ctx->dBoxes + first_box * 6, box_count * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	// one chunk, the reference's call shape (FlatChunk::BuildCollider): the batched path with n = 1
+	int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out)
+	{
+		if (!c || !chunk_index || !n_out)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
+		const uint32_t slot = c->SlotOf(Key{ chunk_index[0], chunk_index[1], chunk_index[2] });
 		if (slot == 0xFFFFFFFFu || !c->hasContent[slot])
 			return Fail(TSOM_ERR_INVALID, "chunk is unknown or has no content");
-		TSOM_CUDA(cudaSetDevice(ctx->device));
-		const uint32_t maxBoxes = 16384; // a 32^3 checkerboard: every other cell is its own box
-		TSOM_CUDA(ctx->gravity.Ensure(size_t(maxBoxes) * 6));
-		tsomk::launch_box_collider(c->dBlocks + size_t(slot) * NB, ctx->dFlags, ctx->nTypes, ctx->gravity.ptr, maxBoxes, ctx->dSmall + 6, ctx->stream);
-		ctx->launches += 1;
-		TSOM_CUDA(cudaGetLastError());
-		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall + 6, ctx->dSmall + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
-		const uint32_t nb = ctx->hSmall[6];
-		*n_out = nb;
-		if (boxes_out && nb)
-		{
-			TSOM_CUDA(cudaMemcpy(boxes_out, ctx->gravity.ptr, size_t(std::min(nb, std::min(cap, maxBoxes))) * 6 * sizeof(float), cudaMemcpyDeviceToHost));
-		}
+		tsom_box_view v{};
+		int rc = tsom_box_colliders(c, chunk_index, 1, &v, nullptr);
+		if (rc != TSOM_OK)
+			return rc;
+		*n_out = v.box_count;
+		if (boxes_out && v.box_count)
+			return tsom_box_colliders_copy_to_host(c->ctx, v.first_box, std::min<uint64_t>(v.box_count, cap), boxes_out);
 		return TSOM_OK;
+	}
+
+	// Ship::Generate (Ship.cpp:115-152): chunk (0,0,0) reset to Empty, then the hull written block by block.  The final content is a
+	// pure function of (small, ids); it is composed here and handed to the device like any Chunk::Reset, after which the chunk is
+	// invalidated with DirectionMask_All (OnReset) — a superset of the masks the UpdateBlock calls raise.
+	int tsom_ship_generate(tsom_container* c, int small, uint16_t hull_block, uint16_t forcefield_block)
+	{
+		if (!c)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		std::vector<uint16_t> blocks(NB, 0);
+		const unsigned boxSize = small ? 6 : 12, height = small ? 4 : 6;
+		const unsigned sx = CS / 2 - boxSize / 2, sy = CS / 2 - boxSize / 2, sz = CS / 2 - height / 2;
+		for (unsigned z = 0; z < height; ++z)
+			for (unsigned y = 0; y < boxSize; ++y)
+				for (unsigned x = 0; x < boxSize; ++x)
+				{
+					if (x != 0 && x != boxSize - 1 && y != 0 && y != boxSize - 1 && z != 0 && z != height - 1)
+						continue;
+					const bool door = x == 0 && y == boxSize / 2 && z > 0 && z < height - 1;
+					blocks[(size_t(sz + z) * CS + (sy + y)) * CS + (sx + x)] = door ? forcefield_block : hull_block;
+				}
+		const int32_t origin[3] = { 0, 0, 0 };
+		return tsom_chunks_reset(c, origin, 1, blocks.data());
 	}
 
 	// ---------------------------------------------------------------------------------------------------- multi-GPU
@@ -1796,7 +2334,7 @@ extern "C"
 				return Fail(TSOM_ERR_INVALID, "remote chunk is already a local chunk");
 			c->remotes[k] = tsom_container::Remote{ ranks[i], remote_slots[i] };
 		}
-		c->topoDirty = true;
+		TopoChanged(c);
 		return TSOM_OK;
 	}
 
@@ -1805,16 +2343,29 @@ extern "C"
 		if (!c || !out)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+		static_assert(sizeof(tsom_ipc_handle) >= 3 * 64 + 4, "tsom_ipc_handle size");
 		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
-		cudaIpcMemHandle_t h0, h1;
+		cudaIpcMemHandle_t h0, h1, h2;
 		TSOM_CUDA(cudaIpcGetMemHandle(&h0, c->dBlocks));
 		TSOM_CUDA(cudaIpcGetMemHandle(&h1, c->dXslabs));
+		TSOM_CUDA(cudaIpcGetMemHandle(&h2, c->dSync));
 		std::memset(out, 0, sizeof(*out));
 		std::memcpy(out->bytes, &h0, 64);
 		std::memcpy(out->bytes + 64, &h1, 64);
-		std::memcpy(out->bytes + 128, &c->capacity, 4);
+		std::memcpy(out->bytes + 128, &h2, 64);
+		std::memcpy(out->bytes + 192, &c->capacity, 4);
 		return TSOM_OK;
+	}
+
+	static void ClosePeer(tsom_container::Peer& p)
+	{
+		if (!p.ipc)
+			return;
+		cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.blocks));
+		cudaIpcCloseMemHandle(const_cast<uint16_t*>(p.xslabs));
+		cudaIpcCloseMemHandle(const_cast<uint32_t*>(p.sync));
+		p = tsom_container::Peer{};
 	}
 
 	int tsom_ipc_attach(tsom_container* c, int rank, const tsom_ipc_handle* handle)
@@ -1823,18 +2374,28 @@ extern "C"
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
 		TSOM_LOCK(c->ctx);
 		TSOM_CUDA(cudaSetDevice(c->ctx->device));
-		cudaIpcMemHandle_t h0, h1;
+		auto old = c->peers.find(rank);
+		if (old != c->peers.end())
+		{
+			TSOM_CUDA(cudaStreamSynchronize(c->ctx->stream));
+			ClosePeer(old->second); // re-attaching a rank: release the previous mappings first
+		}
+		cudaIpcMemHandle_t h0, h1, h2;
 		std::memcpy(&h0, handle->bytes, 64);
 		std::memcpy(&h1, handle->bytes + 64, 64);
-		void *p0 = nullptr, *p1 = nullptr;
+		std::memcpy(&h2, handle->bytes + 128, 64);
+		void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
 		TSOM_CUDA(cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess));
 		TSOM_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
+		TSOM_CUDA(cudaIpcOpenMemHandle(&p2, h2, cudaIpcMemLazyEnablePeerAccess));
 		tsom_container::Peer p;
 		p.blocks = static_cast<const uint16_t*>(p0);
 		p.xslabs = static_cast<const uint16_t*>(p1);
+		p.sync = static_cast<const uint32_t*>(p2);
 		p.ipc = true;
 		c->peers[rank] = p;
-		c->topoDirty = true;
+		c->peerFlagsDirty = true;
+		TopoChanged(c);
 		return TSOM_OK;
 	}
 
@@ -1842,22 +2403,49 @@ extern "C"
 	{
 		if (!c || !peer)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		if (peer->ctx->device != c->ctx->device)
 		{
-			TSOM_LOCK(c->ctx);
 			TSOM_CUDA(cudaSetDevice(c->ctx->device));
 			cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
 			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
 				return Fail(TSOM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
 			cudaGetLastError();
 		}
+		auto old = c->peers.find(rank);
+		if (old != c->peers.end())
+			ClosePeer(old->second);
 		tsom_container::Peer p;
 		p.blocks = peer->dBlocks;
 		p.xslabs = peer->dXslabs;
+		p.sync = peer->dSync;
 		p.ipc = false;
 		c->peers[rank] = p;
-		c->topoDirty = true;
+		c->peerFlagsDirty = true;
+		TopoChanged(c);
 		return TSOM_OK;
+	}
+
+	// "my blocks are final for this round": raise the blocks-final flag to round pulledEpoch + 1 behind everything queued so far
+	static int HaloPublish(tsom_container* c)
+	{
+		tsom_ctx* ctx = c->ctx;
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		c->epoch = c->pulledEpoch + 1u;
+		tsomk::launch_flag_publish(c->dSync + 0, c->epoch, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		c->published = true;
+		c->dirtySincePublish = false;
+		return TSOM_OK;
+	}
+
+	int tsom_halo_publish(tsom_container* c)
+	{
+		if (!c)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
+		return HaloPublish(c);
 	}
 
 	int tsom_halo_pull(tsom_container* c)
@@ -1870,13 +2458,37 @@ extern "C"
 		int rc = SyncTopology(c);
 		if (rc != TSOM_OK)
 			return rc;
+		if ((rc = SyncPeerFlags(c)) != TSOM_OK)
+			return rc;
+		if (!c->published || c->dirtySincePublish)
+			if ((rc = HaloPublish(c)) != TSOM_OK)
+				return rc;
+		TSOM_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+		if (!c->peers.empty())
+		{
+			// wait, on the device, until every peer's blocks are final for this round
+			tsomk::launch_flag_wait(c->peerGenFlags.ptr, uint32_t(c->peers.size()), c->epoch, EXCHANGE_TIMEOUT_NS, ctx->dSmall + 8, ctx->stream);
+			ctx->launches += 1;
+			TSOM_CUDA(cudaGetLastError());
+		}
 		if (c->nGhost)
 		{
 			tsomk::launch_halo_pull(c->ghostDescs.ptr, c->nGhost, c->ghostSlabs.ptr, ctx->stream);
 			ctx->launches += 1;
 			TSOM_CUDA(cudaGetLastError());
 		}
-		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
-		return TSOM_OK;
+		tsomk::launch_flag_publish(c->dSync + 1, c->epoch, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+		ctx->pendingHalo = true;
+		c->pulledEpoch = c->epoch;
+		c->published = false;
+		c->needWriteWait = true;
+		c->ghostsStale = false;
+		return TSOM_OK; // nothing waited for on the host: the next blocking call on this context reports a time-out
 	}
+
 }
+
+#include "tsom_sharded.inl"

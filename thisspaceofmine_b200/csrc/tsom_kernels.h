@@ -7,7 +7,18 @@
 
 namespace tsomk
 {
-	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u, MESH_F_GENERIC = 8u, MESH_F_ORDERED = 16u };
+	enum : uint32_t { MESH_F_RENDER = 1u, MESH_F_COLLIDER = 2u, MESH_F_DEFORMED = 4u, MESH_F_GENERIC = 8u, MESH_F_ORDERED = 16u, MESH_F_TANGENTS = 32u };
+
+	// per-chunk content summary (one byte per slot), written by the producers at no extra pass over the ids: lets the mesher skip the
+	// 64 KiB stage of chunks that provably have no face
+	enum : uint8_t
+	{
+		SUM_UNKNOWN = 0, // anything (every reset / edit puts a chunk back here)
+		SUM_EMPTY = 1,   // every block is Empty
+		SUM_OPAQUE = 2   // every block is non-Empty and not transparent
+	};
+	// job entry of the mesher: slot | JOB_SKIP (no face, proven from the summaries) | JOB_HAS_CONTENT
+	constexpr uint32_t JOB_SLOT_MASK = 0x3FFFFFFFu, JOB_SKIP = 0x40000000u, JOB_HAS_CONTENT = 0x80000000u;
 
 	// per-(faceUp, slot, twin) face attributes of a FlatChunk with a power-of-two block size (see mesh_kernels.cu)
 	struct FaceTable
@@ -24,7 +35,7 @@ namespace tsomk
 		const unsigned long long* halo;  // [capacity][6] encoded slab pointers (0 = no neighbour)
 		const int4* chunkIdx;            // [capacity] (cx, cy, cz, hasContent)
 		// jobs
-		const uint32_t* jobSlot;         // [nJobs] slot | (chunk has content) << 31
+		const uint32_t* jobSlot;         // [nJobs] slot | JOB_SKIP | JOB_HAS_CONTENT
 		const float* gravity;            // [nJobs][3] or nullptr
 		uint32_t nJobs;
 		// block table
@@ -57,6 +68,9 @@ namespace tsomk
 	cudaError_t mesh_kernels_init();
 	size_t mesh_fused_smem_bytes();
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st);
+	// dst[j] = src[j] | JOB_SKIP when the chunk of job j provably has no face: it is SUM_EMPTY, or SUM_OPAQUE with six existing
+	// SUM_OPAQUE neighbours (nbrSlot: [capacity][6] slot of the face-adjacent chunk with content in this container, -1 otherwise)
+	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, cudaStream_t st);
 
 	// ---- generation ----
 	struct GenArgs
@@ -76,13 +90,24 @@ namespace tsomk
 		uint16_t dirt, grass, stone, stoneMossy, snow;
 		uint32_t bStar, aStar;   // integer form of `bernoulli(0.9)` over two minstd draws
 		uint32_t aInv;           // 48271^-1 mod (2^31 - 1)
+		uint32_t dirMask;        // bit d: the terrain tables of Direction d exist (else no chunk of this call can be carved from that side)
+		uint8_t* summary;        // [capacity] SUM_*
+		uint8_t fastSummary;     // summary of a chunk made of stone / stone_mossy only: SUM_OPAQUE when both are opaque types
+		uint8_t allOpaque;       // 1 when dirt, grass, stone, stone_mossy and snow are all opaque types: no Empty block => SUM_OPAQUE
+		// chunks in which every block draws and no pass is active depend on cx + cy + cz only (chunkSeed, Planet.cpp:165): they are
+		// copies of template chunk (cx + cy + cz - templateSumMin), [nTemplates][32768 ids + 2 x 1024 x-slab ids]; nullptr = compute
+		const uint16_t* templates;
+		int templateSumMin;
+		uint32_t nTemplates;
 	};
+	constexpr size_t TEMPLATE_STRIDE = 32768 + 2 * 1024; // ids per template chunk
 
 	struct TerrainArgs
 	{
 		int16_t* terrain;
 		int16_t* tileRange;
 		size_t terrainOffset[6];
+		uint32_t tiles[6];   // tiles per direction; 0 = direction not needed by this call
 		int tileOrigin[3];
 		int tileCount[3];
 		int maxH[3];
@@ -91,9 +116,10 @@ namespace tsomk
 
 	void launch_terrain(const TerrainArgs& a, cudaStream_t st);
 	void launch_generate(const GenArgs& a, int grid, cudaStream_t st);
+	void launch_templates(const GenArgs& a, uint16_t* templates, cudaStream_t st);
 
 	// ---- chunk maintenance ----
-	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, const uint32_t* slots, uint32_t n, cudaStream_t st);
+	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, uint8_t* summary, const uint32_t* slots, uint32_t n, cudaStream_t st);
 
 	struct EditDev
 	{
@@ -101,14 +127,16 @@ namespace tsomk
 		uint32_t packed; // x | y<<5 | z<<10 | block<<16
 	};
 	// keys / vals: open-addressing table (capacity `cap`, a power of two >= 2n; keys preset to ~0, vals to 0)
-	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
-	                        uint32_t cap, cudaStream_t st);
+	// shipMask: Ship::AddChunk's neighbour rule (z == 0 -> Up, z == 31 -> Down, Ship.cpp:48-51) instead of Planet's (Planet.cpp:50-53)
+	void launch_apply_edits(uint16_t* blocks, uint16_t* xslabs, uint8_t* invalidMask, uint8_t* summary, const EditDev* edits, uint32_t n, unsigned long long* keys, uint32_t* vals,
+	                        uint32_t cap, int shipMask, cudaStream_t st);
 
 	struct PlatformArgs
 	{
 		uint16_t* blocks;
 		uint16_t* xslabs;
 		uint8_t* invalidMask;
+		uint8_t* summary;
 		const int* slotGrid; // dense grid of slots (-1 absent / no content) covering [gridOrigin, gridOrigin + gridDim)
 		int gridOrigin[3];
 		int gridDim[3];
@@ -118,8 +146,11 @@ namespace tsomk
 	};
 	void launch_platform(const PlatformArgs& a, cudaStream_t st);
 
-	// FlatChunk greedy box collider; boxes = [cap][6] floats, count = number found (may exceed cap)
-	void launch_box_collider(const uint16_t* chunkBlocks, const uint8_t* blkFlags, uint32_t nTypes, float* boxes, uint32_t cap, uint32_t* count, cudaStream_t st);
+	// FlatChunk greedy box collider for n chunks (one CTA each): the boxes of job j go to scratch[j][0 .. count[j]) (one packed 30-bit word per box,
+	// BOX_SCRATCH_STRIDE words per job); launch_box_pack then moves them to their final places first[j] in the dense arena
+	constexpr uint32_t BOX_SCRATCH_STRIDE = 16384; // a 32^3 checkerboard: every other cell is its own box
+	void launch_box_colliders(const uint16_t* blocks, const uint32_t* jobSlot, uint32_t n, const uint8_t* blkFlags, uint32_t nTypes, uint32_t* scratch, uint32_t* counts, cudaStream_t st);
+	void launch_box_pack(const uint32_t* scratch, const uint32_t* counts, const unsigned long long* first, uint32_t n, float* arena, cudaStream_t st);
 
 	// ---- save format: palette + per-block palette indices (payload stride 65536 bytes per chunk) ----
 	void launch_palettize(const uint16_t* blocks, const uint32_t* slots, uint32_t n, uint16_t* palette, uint32_t stride, uint32_t* counts, uint8_t* payload, int bigEndian, cudaStream_t st);
@@ -148,4 +179,7 @@ namespace tsomk
 		uint32_t ghost;      // destination ghost slab index
 	};
 	void launch_halo_pull(const GhostDesc* descs, uint32_t n, uint16_t* ghostSlabs, cudaStream_t st);
+	// epoch flags of the device-side exchange ordering (gen_kernels.cu)
+	void launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t st);
+	void launch_flag_wait(const uint32_t* const* flags, uint32_t n, uint32_t value, unsigned long long timeoutNs, uint32_t* err, cudaStream_t st);
 }

@@ -45,6 +45,7 @@ def _p(a: np.ndarray, t):
 # numpy mirrors of tsom_edit / tsom_mesh_view (include/tsom_b200.h), so batches cross the C ABI without per-element Python work
 EDIT_DTYPE = np.dtype([("chunk", np.int32, 3), ("x", np.uint8), ("y", np.uint8), ("z", np.uint8), ("reserved", np.uint8), ("block", np.uint16), ("reserved2", np.uint16)])
 VIEW_DTYPE = np.dtype([("first_face", np.uint64), ("face_count", np.uint32), ("reserved", np.uint32)])
+BOX_VIEW_DTYPE = np.dtype([("first_box", np.uint64), ("box_count", np.uint32), ("reserved", np.uint32)])
 
 
 def pack_edits(edits) -> np.ndarray:
@@ -54,6 +55,11 @@ def pack_edits(edits) -> np.ndarray:
     raw["chunk"] = e[:, 0:3]
     raw["x"], raw["y"], raw["z"], raw["block"] = e[:, 3], e[:, 4], e[:, 5], e[:, 6]
     return raw
+
+
+def _mesh_flags(render, collider, deformed, genericMath, ordered, tangents) -> int:
+    return ((L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0) | (L.MESH_DEFORMED if deformed else 0) | (L.MESH_GENERIC_MATH if genericMath else 0)
+            | (L.MESH_ORDERED if ordered else 0) | (L.MESH_TANGENTS if tangents else 0))
 
 
 def _idx(v) -> np.ndarray:
@@ -160,21 +166,31 @@ class BlockLibrary:
         return arr
 
 
+def _timings_dict(t) -> dict:
+    """enum tsom_timing (include/tsom_b200.h) -> names"""
+    return dict(terrain_ms=t[0], generate_ms=t[1], halo_ms=t[2], classify_ms=t[3], mesh_emit_ms=t[4], mesh_reemit=bool(t[5]), io_ms=t[6], collider_ms=t[7])
+
+
 # ------------------------------------------------------------------------------------------------ device context
 class Context:
     """One per process and GPU (tsom_ctx): stream, device block table, mesh arenas."""
 
-    def __init__(self, device: int = 0, blockLibrary: Optional[BlockLibrary] = None):
-        self._h = C.c_void_p()
-        L.check(L.lib().tsom_create(device, C.byref(self._h)))
+    def __init__(self, device: int = 0, blockLibrary: Optional[BlockLibrary] = None, _borrowed=None):
+        self._owned = _borrowed is None
         self.device = device
         self.blockLibrary = blockLibrary or BlockLibrary()
+        if _borrowed is not None:  # a context owned by a tsom_sharded_planet
+            self._h = C.c_void_p(_borrowed)
+            return
+        self._h = C.c_void_p()
+        L.check(L.lib().tsom_create(device, C.byref(self._h)))
         descs = self.blockLibrary.to_descs()
         L.check(L.lib().tsom_set_block_table(self._h, descs, len(descs)))
 
     def close(self):
         if self._h:
-            L.lib().tsom_destroy(self._h)
+            if self._owned:
+                L.lib().tsom_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -196,9 +212,9 @@ class Context:
 
     def timings(self) -> dict:
         """Device-side kernel durations (ms) of the most recent generate / mesh call on this context."""
-        t = (C.c_float * 7)()
-        L.check(L.lib().tsom_get_timings(self._h, t, 7))
-        return dict(terrain_ms=t[0], generate_ms=t[1], mesh_count_ms=t[2], mesh_scan_ms=t[3], mesh_emit_ms=t[4], mesh_reemit=bool(t[5]), io_ms=t[6])
+        t = (C.c_float * L.TIMING_COUNT)()
+        L.check(L.lib().tsom_get_timings(self._h, t, L.TIMING_COUNT))
+        return _timings_dict(t)
 
     def reserve_faces(self, faces: int, render=True, collider=False):
         L.check(L.lib().tsom_reserve_faces(self._h, int(faces), (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0)))
@@ -491,9 +507,10 @@ class ChunkContainer:
 
     # ---- meshing
     def BuildMeshes(self, indices=None, render: bool = True, collider: bool = False, deformed: bool = False, deformRadius: float = 0.0,
-                    gravityCenters: Optional[np.ndarray] = None, views: bool = True, genericMath: bool = False, ordered: bool = False) -> MeshBatch:
-        """Chunk::BuildMesh for a whole batch in one call (one mesh_fused_kernel launch).  `ordered`: arena ranges in job order."""
-        flags = (L.MESH_RENDER if render else 0) | (L.MESH_COLLIDER if collider else 0) | (L.MESH_DEFORMED if deformed else 0) | (L.MESH_GENERIC_MATH if genericMath else 0) | (L.MESH_ORDERED if ordered else 0)
+                    gravityCenters: Optional[np.ndarray] = None, views: bool = True, genericMath: bool = False, ordered: bool = False, tangents: bool = False) -> MeshBatch:
+        """Chunk::BuildMesh for a whole batch in one call (one mesh_fused_kernel launch).  `ordered`: arena ranges in job order;
+        `tangents`: also what Nz::StaticMesh::GenerateTangents adds afterwards (ClientChunkEntities.cpp:169)."""
+        flags = _mesh_flags(render, collider, deformed, genericMath, ordered, tangents)
         params = L.MeshParams(flags, float(deformRadius), None)
         g = None
         if gravityCenters is not None:
@@ -530,6 +547,27 @@ class ChunkContainer:
         n = C.c_uint32()
         L.check(L.lib().tsom_box_collider(self._h, _p(idx, C.c_int32), _p(out, C.c_float), len(out), C.byref(n)))
         return out[: n.value].copy()
+
+    def BuildBoxColliders(self, indices, copy: bool = True):
+        """FlatChunk::BuildCollider for a batch of chunks in ONE call (what ChunkEntities::UpdateChunkEntity asks per invalidated chunk,
+        ChunkEntities.cpp:198) -> (first_box [n] uint64, box_count [n] uint32, boxes [total, 6] float32 or None when copy is False)."""
+        idx = _idx(indices)
+        views = np.zeros(len(idx), BOX_VIEW_DTYPE)
+        total = C.c_uint64()
+        L.check(L.lib().tsom_box_colliders(self._h, _p(idx, C.c_int32), len(idx), C.cast(views.ctypes.data, C.POINTER(L.BoxView)), C.byref(total)))
+        boxes = None
+        if copy:
+            boxes = np.zeros((int(total.value), 6), np.float32)
+            if total.value:
+                L.check(L.lib().tsom_box_colliders_copy_to_host(self.ctx._h, 0, total.value, _p(boxes, C.c_float)))
+        return views["first_box"], views["box_count"], boxes
+
+    # ---- multi-GPU exchange (see tsom_halo_publish / tsom_halo_pull in include/tsom_b200.h)
+    def PublishHalo(self):
+        L.check(L.lib().tsom_halo_publish(self._h))
+
+    def PullHalos(self):
+        L.check(L.lib().tsom_halo_pull(self._h))
 
 
 class Planet(ChunkContainer):
@@ -587,3 +625,152 @@ class ChunkEntities:
         if len(dirty) == 0:
             return None
         return self.container.BuildMeshes(dirty, render=self.render, collider=self.collider)
+
+
+# ------------------------------------------------------------------------------------------------ Ship
+class Ship(ChunkContainer):
+    """Ship (include/CommonLib/Ship.hpp, src/CommonLib/Ship.cpp): the second ChunkContainer of the reference — a handful of FlatChunks
+    whose block edits raise Ship::AddChunk's neighbour mask (local z == 0 -> Direction::Up, z == 31 -> Direction::Down, Ship.cpp:36-54:
+    the opposite of Planet's) and whose physics body is the compound of its chunks' box colliders (Ship::BuildHullCollider)."""
+
+    def __init__(self, ctx: Context, tileSize: float = 1.0, capacity: int = 8):
+        super().__init__(ctx, capacity, tileSize)
+        L.check(L.lib().tsom_container_set_kind(self._h, L.CONTAINER_SHIP))
+        self._order: list = []  # chunk indices in insertion order (the reference iterates a hopscotch_map: no defined order)
+
+    def AddChunk(self, blockLibrary: BlockLibrary, indices, blocks: Optional[np.ndarray] = None):
+        """Ship::AddChunk (Ship.cpp:21-61); `blocks` plays the initCallback."""
+        super().AddChunk(indices, blocks)
+        key = tuple(int(v) for v in np.asarray(indices).reshape(3))
+        if key not in self._order:
+            self._order.append(key)
+
+    def RemoveChunk(self, indices):
+        super().RemoveChunk(indices)
+        key = tuple(int(v) for v in np.asarray(indices).reshape(3))
+        if key in self._order:
+            self._order.remove(key)
+
+    def Generate(self, blockLibrary: BlockLibrary, small: bool):
+        """Ship::Generate (Ship.cpp:115-152): chunk (0,0,0) with the hull box and its forcefield door; nothing without a "hull" block."""
+        hull = blockLibrary.GetBlockIndex("hull")
+        if (0, 0, 0) not in self._order:
+            super().AddChunk((0, 0, 0))
+            self._order.append((0, 0, 0))
+        if hull == InvalidBlockIndex:
+            return
+        L.check(L.lib().tsom_ship_generate(self._h, int(bool(small)), hull, blockLibrary.GetBlockIndex("forcefield")))
+
+    def BuildHullCollider(self):
+        """Ship::BuildHullCollider (Ship.cpp:63-93): every chunk's FlatChunk::BuildCollider in ONE batched call.
+        -> None when no chunk has a colliding block; with one chunk its boxes [n, 6] (pos.xyz, size.xyz in block units, as
+        FlatChunk::BuildCollider's compound lists them); with several a list of (GetChunkOffset(indices), boxes) children."""
+        if not self._order:
+            return None
+        idx = np.array(self._order, np.int32)
+        first, count, boxes = self.BuildBoxColliders(idx)
+        per_chunk = [boxes[int(f):int(f) + int(c)] for f, c in zip(first, count)]
+        if len(self._order) > 1:
+            children = [(self.GetChunkOffset(k), b) for k, b in zip(self._order, per_chunk) if len(b)]
+            return children or None
+        return per_chunk[0] if len(per_chunk[0]) else None
+
+
+# ------------------------------------------------------------------------------------------------ one planet over several GPUs, one process
+class MultiGpuPlanet:
+    """tsom_planet_create_sharded: a Planet cut into one box of chunks per GPU, all GPUs driven from THIS process (a TSOM server is one
+    process, src/Server/main.cpp:24-62).  Same call surface as Planet for the whole-planet operations; meshes come back per chunk
+    with the part (GPU) whose arenas hold them.  `devices` may name a GPU twice (two parts on one GPU)."""
+
+    def __init__(self, devices: Sequence[int], chunkCount: Sequence[int], tileSize: float = 1.0, blockLibrary: Optional[BlockLibrary] = None, weights: Optional[np.ndarray] = None):
+        self.chunkCount = tuple(int(v) for v in chunkCount)
+        self.blockLibrary = blockLibrary or BlockLibrary()
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        cc = np.ascontiguousarray(self.chunkCount, dtype=np.uint32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32).reshape(-1)
+        self._h = C.c_void_p()
+        L.check(L.lib().tsom_planet_create_sharded(dev, len(devices), _p(cc, C.c_uint32), float(tileSize), None if w is None else _p(w, C.c_float), C.byref(self._h)))
+        descs = self.blockLibrary.to_descs()
+        L.check(L.lib().tsom_sharded_set_block_table(self._h, descs, len(descs)))
+        self.parts = int(L.lib().tsom_sharded_part_count(self._h))
+        self.grid = Planet.chunk_grid(self.chunkCount)
+
+    def close(self):
+        if self._h:
+            L.lib().tsom_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def part_box(self, part: int) -> np.ndarray:
+        b = np.zeros(6, np.int32)
+        L.check(L.lib().tsom_sharded_part_box(self._h, part, _p(b, C.c_int32)))
+        return b
+
+    def part_context(self, part: int) -> Context:
+        return Context(blockLibrary=self.blockLibrary, _borrowed=L.lib().tsom_sharded_ctx(self._h, part))
+
+    def owner(self, indices) -> np.ndarray:
+        idx = _idx(indices)
+        out = np.zeros(len(idx), np.uint32)
+        o = C.c_uint32()
+        for i in range(len(idx)):
+            L.check(L.lib().tsom_sharded_owner(self._h, _p(idx[i:i + 1], C.c_int32), C.byref(o)))
+            out[i] = o.value
+        return out
+
+    def GenerateChunks(self, seed: int):
+        """Planet::GenerateChunks (Planet.cpp:385-403) over all GPUs + one halo exchange round."""
+        lib = self.blockLibrary
+        ids = L.GenBlocks(*(lib.GetBlockIndex(n) for n in ("dirt", "grass", "stone", "stone_mossy", "snow")))
+        L.check(L.lib().tsom_sharded_generate(self._h, seed & 0xFFFFFFFF, C.byref(ids)))
+
+    def UpdateBlocks(self, edits):
+        raw = np.ascontiguousarray(edits) if isinstance(edits, np.ndarray) and edits.dtype == EDIT_DTYPE else pack_edits(edits)
+        L.check(L.lib().tsom_sharded_apply_edits(self._h, C.cast(raw.ctypes.data, C.POINTER(L.Edit)), len(raw)))
+
+    def CollectInvalidated(self, clear: bool = True) -> np.ndarray:
+        n = C.c_uint32()
+        out = np.zeros((len(self.grid), 3), np.int32)
+        L.check(L.lib().tsom_sharded_collect_dirty(self._h, _p(out, C.c_int32), len(out), C.byref(n), int(clear)))
+        return out[: n.value].copy()
+
+    def GetContent(self, indices) -> np.ndarray:
+        idx = _idx(indices)
+        out = np.empty((len(idx), ChunkBlockCount), np.uint16)
+        L.check(L.lib().tsom_sharded_get_content(self._h, _p(idx, C.c_int32), len(idx), _p(out, C.c_uint16)))
+        return out
+
+    def BuildMeshes(self, indices=None, render: bool = True, collider: bool = False, deformed: bool = False, deformRadius: float = 0.0, views: bool = True,
+                    genericMath: bool = False, tangents: bool = False):
+        """Chunk::BuildMesh for the listed chunks (None: the whole planet in GenerateChunks order), each on the GPU that owns it.
+        -> (views [n] VIEW_DTYPE, parts [n] uint32, flags); a chunk's faces are read with `chunk_mesh`."""
+        flags = _mesh_flags(render, collider, deformed, genericMath, False, tangents)
+        params = L.MeshParams(flags, float(deformRadius), None)
+        idx = None if indices is None else _idx(indices)
+        n = len(self.grid) if idx is None else len(idx)
+        v = np.zeros(n, VIEW_DTYPE) if views else None
+        parts = np.zeros(n, np.uint32) if views else None
+        L.check(L.lib().tsom_sharded_mesh(self._h, None if idx is None else _p(idx, C.c_int32), n, C.byref(params), None if v is None else C.cast(v.ctypes.data, C.POINTER(L.MeshView)),
+                                          None if parts is None else _p(parts, C.c_uint32)))
+        return v, parts, flags
+
+    def chunk_mesh(self, view, part: int, flags: int) -> Optional[ChunkMesh]:
+        f = int(view["face_count"])
+        if f == 0:
+            return None
+        verts = np.empty((4 * f, 12), np.float32) if flags & L.MESH_RENDER else None
+        coll = np.empty((4 * f, 3), np.float32) if flags & L.MESH_COLLIDER else None
+        ind = np.empty(6 * f, np.uint32)
+        L.check(L.lib().tsom_sharded_mesh_copy_to_host(self._h, int(part), int(view["first_face"]), f, None if verts is None else verts.ctypes.data_as(C.c_void_p), _p(ind, C.c_uint32),
+                                                       None if coll is None else _p(coll, C.c_float)))
+        return ChunkMesh(verts, ind, coll)
+
+    def timings(self) -> list:
+        t = np.zeros((self.parts, L.TIMING_COUNT), np.float32)
+        L.check(L.lib().tsom_sharded_get_timings(self._h, _p(t, C.c_float)))
+        return [_timings_dict(row) for row in t]

@@ -1,13 +1,16 @@
-"""Whole-planet sharding across GPUs: one process per GPU, chunks split by linear chunk id, halo slabs pulled over NVLink P2P.
+"""Whole-planet sharding across GPUs, one process per GPU: the planet is cut into one axis-aligned box of chunks per rank
+(``tsom_shard_plan``: recursive bisection balanced by chunk weights), halo slabs are pulled over NVLink P2P.
 
-Chunks are independent given the boundary layers of their six face-adjacent neighbours (reference src/CommonLib/Chunk.cpp:104-172),
-so a planet is cut into contiguous ranges of the linear chunk id ``i = (z * ny + y) * nx + x`` — the order Planet::GenerateChunks
-walks (reference src/CommonLib/Planet.cpp:387-393).  Each rank generates and meshes its own range; between the two phases it copies
-the 2 KiB facing slab of every neighbour chunk owned by another rank straight out of that rank's HBM (cudaIpc mapping + a copy
-kernel, ``tsom_halo_pull``).  There is no collective on the data path; ``torch.distributed`` only carries the 136-byte IPC handles
-once and the barriers that order "peer finished writing" before "I read".
+Chunks are independent given the boundary layers of their six face-adjacent neighbours (reference src/CommonLib/Chunk.cpp:104-172).
+Each rank generates and meshes its own box (chunks in the z, y, x order Planet::GenerateChunks walks, reference
+src/CommonLib/Planet.cpp:387-393); between the two phases it copies the 2 KiB facing slab of every neighbour chunk owned by another
+rank straight out of that rank's HBM (cudaIpc mapping + a copy kernel, ``tsom_halo_pull``).  The exchange is ordered ON THE DEVICE:
+every container owns two epoch flags in its HBM that the peers poll over NVLink (see ``tsom_halo_pull`` in include/tsom_b200.h), so
+there is neither a collective nor a host barrier on the data path; ``torch.distributed`` only carries the 200-byte IPC handles once.
 
-``ShardPlan`` is pure integer host logic (tested on CPU with gloo, world_size 2); ``ShardedPlanet`` drives the C ABI.
+``ShardPlan`` is integer host logic over the boxes the C library plans (tested on CPU with gloo, world_size 2); ``ShardedPlanet``
+drives the C ABI.  The same plan and the same exchange run inside ONE process through ``tsom_planet_create_sharded``
+(``thisspaceofmine_b200.MultiGpuPlanet``).
 """
 from __future__ import annotations
 
@@ -27,31 +30,37 @@ def chunk_grid(chunkCount: Sequence[int]) -> np.ndarray:
     return np.stack([x.ravel() - nx // 2, y.ravel() - ny // 2, z.ravel() - nz // 2], axis=1).astype(np.int32)
 
 
-def partition(n: int, world: int) -> List[Tuple[int, int]]:
-    """Contiguous, balanced ranges [start, end) of the linear chunk id; the first n % world ranks get one extra chunk."""
-    if world < 1:
-        raise ValueError("world must be >= 1")
-    base, extra = divmod(n, world)
-    out, s = [], 0
-    for r in range(world):
-        e = s + base + (1 if r < extra else 0)
-        out.append((s, e))
-        s = e
-    return out
+def plan_boxes(chunkCount: Sequence[int], world: int, weights=None) -> np.ndarray:
+    """tsom_shard_plan: [world, 6] int32 = lo.xyz, hi.xyz (inclusive chunk indices) of every rank's box.  Pure host code of the
+    library (no GPU needed)."""
+    from . import _lib as L
+
+    cc = np.ascontiguousarray(chunkCount, dtype=np.uint32)
+    boxes = np.zeros((int(world), 6), np.int32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32).reshape(-1)
+    L.check(L.lib().tsom_shard_plan(cc.ctypes.data_as(C.POINTER(C.c_uint32)), int(world), None if w is None else w.ctypes.data_as(C.POINTER(C.c_float)),
+                                    boxes.ctypes.data_as(C.POINTER(C.c_int32))))
+    return boxes
 
 
 class ShardPlan:
-    """Who owns which chunk, and which neighbour chunks each rank must mirror."""
+    """Who owns which chunk (one box per rank), and which neighbour chunks each rank must mirror."""
 
-    def __init__(self, chunkCount: Sequence[int], world: int):
+    def __init__(self, chunkCount: Sequence[int], world: int, weights=None):
+        if world < 1:
+            raise ValueError("world must be >= 1")
         self.chunkCount = tuple(int(v) for v in chunkCount)
         self.world = int(world)
         self.grid = chunk_grid(self.chunkCount)
         self.n = len(self.grid)
-        self.ranges = partition(self.n, self.world)
-        self.owner = np.empty(self.n, np.int32)
-        for r, (s, e) in enumerate(self.ranges):
-            self.owner[s:e] = r
+        self.boxes = plan_boxes(self.chunkCount, self.world, weights)
+        self.owner = np.full(self.n, -1, np.int32)
+        self._ids: List[np.ndarray] = []
+        for r, b in enumerate(self.boxes):
+            inside = np.all((self.grid >= b[0:3]) & (self.grid <= b[3:6]), axis=1)
+            self.owner[inside] = r
+            self._ids.append(np.nonzero(inside)[0].astype(np.int64))  # ascending linear id == z, y, x loops inside the box
+        assert np.all(self.owner >= 0), "the boxes tile the planet"
 
     def linear_id(self, idx) -> np.ndarray:
         """Linear chunk id of chunk indices [k, 3]; -1 outside the planet."""
@@ -61,14 +70,20 @@ class ShardPlan:
         ok = (x >= 0) & (x < nx) & (y >= 0) & (y < ny) & (z >= 0) & (z < nz)
         return np.where(ok, (z * ny + y) * nx + x, -1)
 
+    def local_ids(self, rank: int) -> np.ndarray:
+        """Linear ids (GenerateChunks order) of the chunks of `rank`, in the order it adds them to its container."""
+        return self._ids[rank]
+
     def local(self, rank: int) -> np.ndarray:
-        s, e = self.ranges[rank]
-        return self.grid[s:e]
+        return self.grid[self._ids[rank]]
 
     def slot_of(self, linear: np.ndarray) -> np.ndarray:
-        """Slot of a chunk inside its owner's container: chunks are added in range order into an empty container."""
-        starts = np.array([s for s, _ in self.ranges], np.int64)
-        return (np.asarray(linear, np.int64) - starts[self.owner[linear]]).astype(np.uint32)
+        """Slot of a chunk inside its owner's container: chunks are added in box order (z, y, x loops) into an empty container."""
+        lin = np.asarray(linear, np.int64).reshape(-1)
+        idx = self.grid[lin].astype(np.int64)
+        b = self.boxes[self.owner[lin]].astype(np.int64)
+        ex, ey = b[:, 3] - b[:, 0] + 1, b[:, 4] - b[:, 1] + 1
+        return (((idx[:, 2] - b[:, 2]) * ey + (idx[:, 1] - b[:, 1])) * ex + (idx[:, 0] - b[:, 0])).astype(np.uint32)
 
     def remote_neighbours(self, rank: int) -> Dict[int, np.ndarray]:
         """peer rank -> sorted unique linear ids of the chunks it owns that are face-adjacent to a chunk of `rank`."""
@@ -121,11 +136,11 @@ class ShardPlan:
 class ShardedPlanet:
     """One rank's share of a Planet (Planet::GenerateChunks + Chunk::BuildMesh over the rank's chunk range)."""
 
-    def __init__(self, ctx, chunkCount: Sequence[int], rank: int, world: int, tileSize: float = 1.0, group=None):
+    def __init__(self, ctx, chunkCount: Sequence[int], rank: int, world: int, tileSize: float = 1.0, group=None, weights=None):
         from .host import Planet
 
         self.ctx, self.rank, self.world, self.group = ctx, int(rank), int(world), group
-        self.plan = ShardPlan(chunkCount, world)
+        self.plan = ShardPlan(chunkCount, world, weights)
         self.local_grid = np.ascontiguousarray(self.plan.local(rank))
         self.planet = Planet(ctx, tileSize, capacity=max(len(self.local_grid), 1))
         self._connected = False
@@ -169,14 +184,14 @@ class ShardedPlanet:
         self._connected = True
 
     def PullHalos(self):
-        """Barrier (every peer finished writing its blocks) -> copy the remote boundary slabs into the local ghost slabs."""
+        """One exchange round (collective: every rank runs every round).  Queued on the context's stream and ordered on the device —
+        wait for the peers' blocks-final flags, copy the remote boundary slabs into the local ghost slabs, raise the slabs-pulled
+        flag; no host barrier, no stream synchronisation."""
         from . import _lib as L
 
         if self.world == 1:
             return
         self.ConnectPeers()
-        self.ctx.synchronize()
-        self._dist().barrier(group=self.group)
         L.check(L.lib().tsom_halo_pull(self.planet._h))
 
     # ---- phase 2: meshing (no communication)
