@@ -247,6 +247,15 @@ int tsom_voxel_corners(tsom_container* c, const int32_t* chunk_indices, const ui
  * (render vertices, or the collider positions of a collider-only call).  aabb_out: n x {min.xyz, max.xyz}; zeros for a view without faces.
  * (The 12-byte tangent slot stays zero: Chunk::BuildMesh never writes it and StaticMesh::GenerateTangents is third-party.) */
 int tsom_mesh_aabb(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, float* aabb_out);
+/* Per-view checksums of the last tsom_mesh result, computed on the device: out[2i] over the 32-bit words of view i's vertices (the
+ * collider positions after a collider-only call), out[2i + 1] over its indices.  Position-weighted 64-bit sums that do not depend on
+ * where the faces sit in the arena: mesh(N GPUs) is compared with mesh(1 GPU) chunk by chunk without moving the arenas to the host
+ * (bench.py's sharded_parity).  Zero for a view without faces. */
+int tsom_mesh_checksums(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, uint64_t* out);
+/* The index buffer of a chunk with face_count faces — a pure function of the face ordinal, 4k + {0,2,1,1,2,3} (src/CommonLib/Chunk.cpp:95-101)
+ * — written by host threads: a caller that wants the std::vector<UInt32> of Chunk::BuildMesh can leave the 24 B per face on the device
+ * (tsom_mesh_copy_to_host with indices == NULL) instead of carrying them across PCIe.  No device needed. */
+int tsom_mesh_indices_for_faces(uint64_t face_count, uint32_t* indices_out);
 /* FlatChunk::BuildCollider greedy box merge (src/CommonLib/FlatChunk.cpp:13-30,56-153): boxes_out = n_boxes x {pos.xyz, size.xyz}
  * in block units (multiply by the block size like FlatChunk.cpp:20-21 does). */
 int tsom_box_collider(tsom_container* c, const int32_t chunk_index[3], float* boxes_out, uint32_t cap, uint32_t* n_out);

@@ -102,6 +102,26 @@ def _bind(path: str, full: bool):
     L.orc_bench_mesh_isolated.argtypes = [u16p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_bench_mesh_isolated.restype = C.c_double
     L.orc_bench_planet.argtypes = [C.c_uint32, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), u32p]
+    L.orc_sample_create.argtypes = [C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_int]
+    L.orc_sample_create.restype = C.c_void_p
+    L.orc_sample_size.argtypes = [C.c_void_p]
+    L.orc_sample_size.restype = C.c_uint32
+    L.orc_sample_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.orc_sample_step.restype = C.c_uint64
+    L.orc_sample_destroy.argtypes = [C.c_void_p]
+    L.orc_bench_box_colliders.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64), u32p]
+    L.orc_bench_box_colliders.restype = C.c_double
+    L.orc_ship_create.argtypes = [C.c_float]
+    L.orc_ship_create.restype = C.c_void_p
+    L.orc_ship_destroy.argtypes = [C.c_void_p]
+    L.orc_ship_generate.argtypes = [C.c_void_p, C.c_int]
+    L.orc_ship_add_chunk.argtypes = [C.c_void_p, i32p, u16p]
+    L.orc_ship_get_blocks.argtypes = [C.c_void_p, i32p, u16p]
+    L.orc_ship_update_block.argtypes = [C.c_void_p, i32p, u32p, C.c_uint16]
+    L.orc_ship_take_invalidated.argtypes = [C.c_void_p, i32p, u32p, C.c_uint32]
+    L.orc_ship_take_invalidated.restype = C.c_uint32
+    L.orc_ship_hull_collider.argtypes = [C.c_void_p, f32p, C.c_uint32]
+    L.orc_ship_hull_collider.restype = C.c_uint32
     return L
 
 
@@ -328,6 +348,78 @@ class Planet:
         return out[:n].copy()
 
 
+class Ship:
+    """Handle on an oracle Ship (ChunkContainer of FlatChunks, Ship.cpp): the Up/Down-swapped dirty mask, Generate, hull collider."""
+
+    def __init__(self, tile: float = 1.0, L=None):
+        self._L = L or lib()
+        self._h = C.c_void_p(self._L.orc_ship_create(tile))
+        self.tile = tile
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_ship_destroy(self._h)
+            self._h = None
+
+    def generate(self, small: bool):
+        self._L.orc_ship_generate(self._h, int(small))
+
+    def add_chunk(self, idx, blocks=None):
+        b = None if blocks is None else _p(np.ascontiguousarray(blocks, dtype=np.uint16), C.c_uint16)
+        return self._L.orc_ship_add_chunk(self._h, _p(_i3(idx), C.c_int32), b)
+
+    def get_blocks(self, idx):
+        out = np.zeros(NBLK, np.uint16)
+        rc = self._L.orc_ship_get_blocks(self._h, _p(_i3(idx), C.c_int32), _p(out, C.c_uint16))
+        return out if rc == 0 else None
+
+    def update_block(self, idx, local, block_id):
+        return self._L.orc_ship_update_block(self._h, _p(_i3(idx), C.c_int32), _p(_u3(local), C.c_uint32), int(block_id))
+
+    def take_invalidated(self, cap=4096):
+        """{chunk index: direction mask | 0x80} raised since the last call (what ChunkEntities collects from OnChunkUpdated); cleared."""
+        idx = np.zeros((cap, 3), np.int32)
+        mask = np.zeros(cap, np.uint32)
+        n = self._L.orc_ship_take_invalidated(self._h, _p(idx, C.c_int32), _p(mask, C.c_uint32), cap)
+        return {tuple(int(v) for v in idx[i]): int(mask[i]) for i in range(n)}
+
+    def hull_collider(self, cap=1 << 16) -> np.ndarray:
+        """Ship::BuildHullCollider flattened -> [n, 9] float32: child offset, box centre, box lengths (world units); n == 0: null."""
+        out = np.zeros((cap, 9), np.float32)
+        n = self._L.orc_ship_hull_collider(self._h, _p(out, C.c_float), cap)
+        return out[:n].copy()
+
+
+class PlanetSample:
+    """A bounded, planet-wide sample of "generate + mesh" (every stride-th chunk, neighbours generated once at set-up): the workload of
+    bench.py's CPU arm.  step() regenerates and meshes the sample, one task per chunk on nthreads workers."""
+
+    def __init__(self, seed, chunk_count, stride, offset=0, nthreads=1, L=None):
+        self._L = L or lib()
+        self._h = C.c_void_p(self._L.orc_sample_create(seed & 0xFFFFFFFF, _p(_u3(chunk_count), C.c_uint32), int(stride), int(offset), int(nthreads)))
+        if not self._h:
+            raise RuntimeError("planet sample: unsupported planet")
+        self.size = int(self._L.orc_sample_size(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_sample_destroy(self._h)
+            self._h = None
+
+    def step(self, nthreads):
+        t = (C.c_double * 2)()
+        faces = int(self._L.orc_sample_step(self._h, int(nthreads), t))
+        return dict(gen_s=t[0], mesh_s=t[1], faces=faces, chunks=self.size)
+
+
+def bench_box_colliders(planet: "Planet", chunk_count, nthreads, stride=1, L=None):
+    """Time FlatChunk::BuildCollider over every stride-th chunk of a generated planet (the backend is the planet's) -> (seconds, boxes, chunks)."""
+    boxes = C.c_uint64(0)
+    chunks = C.c_uint32(0)
+    t = planet._L.orc_bench_box_colliders(planet._h, _p(_u3(chunk_count), C.c_uint32), int(stride), int(nthreads), C.byref(boxes), C.byref(chunks))
+    return float(t), int(boxes.value), int(chunks.value)
+
+
 def perlin_noise3d_perm(perm, x: float, y: float, z: float) -> float:
     """siv::PerlinNoise::noise3D over a caller-supplied permutation table (deserialize)."""
     p = np.ascontiguousarray(perm, dtype=np.uint8)
@@ -377,8 +469,9 @@ class _Reference:
 
     def __getattr__(self, name):
         target = globals()[name]
-        if name == "Planet":
-            return lambda *a, **k: Planet(*a, L=ref_lib(), **k)
+        if name in ("Planet", "Ship", "PlanetSample"):
+            cls = target
+            return lambda *a, **k: cls(*a, L=ref_lib(), **k)
         if callable(target):
             return lambda *a, **k: target(*a, L=ref_lib(), **k)
         return target

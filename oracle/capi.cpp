@@ -417,4 +417,187 @@ extern "C"
 	int orc_lz4_bound(int n) { return tsom_oracle_lz4::compress_bound(n); }
 	int orc_lz4_compress(const std::uint8_t* src, int n, std::uint8_t* dst, int cap) { return tsom_oracle_lz4::compress_block(src, n, dst, cap); }
 	int orc_lz4_decompress(const std::uint8_t* src, int n, std::uint8_t* dst, int cap) { return tsom_oracle_lz4::decompress_block(src, n, dst, cap); }
+
+	// ---- a bounded, planet-wide sample of "generate + mesh" for the CPU arm of bench.py (same entry points as oracle/ref_shim) ----
+	struct SampleHandle
+	{
+		PlanetHandle h{ 1.f, 16.f };
+		std::vector<Chunk*> sample;
+		std::uint32_t seed = 0;
+		Vec3ui count{};
+	};
+
+	void* orc_sample_create(std::uint32_t seed, const std::uint32_t count[3], std::uint32_t stride, std::uint32_t offset, int nthreads)
+	{
+		auto s = new SampleHandle;
+		s->seed = seed;
+		s->count = Vec3ui{ count[0], count[1], count[2] };
+		Planet& p = s->h.planet;
+		auto inside = [&](const Vec3i& c) {
+			return c.x >= -int(count[0] / 2) && c.x < int(count[0]) - int(count[0] / 2) && c.y >= -int(count[1] / 2) && c.y < int(count[1]) - int(count[1] / 2) &&
+			       c.z >= -int(count[2] / 2) && c.z < int(count[2]) - int(count[2] / 2);
+		};
+		std::vector<Chunk*> all;
+		std::size_t k = 0;
+		for (int cz = 0; cz < int(count[2]); ++cz)
+			for (int cy = 0; cy < int(count[1]); ++cy)
+				for (int cx = 0; cx < int(count[0]); ++cx, ++k)
+				{
+					if (k % stride != offset % stride)
+						continue;
+					const Vec3i ci{ cx - int(count[0] / 2), cy - int(count[1] / 2), cz - int(count[2] / 2) };
+					Chunk* c = p.GetChunk(ci);
+					if (!c)
+					{
+						c = &p.AddChunk(Lib(), ci);
+						all.push_back(c);
+					}
+					s->sample.push_back(c);
+					for (int d = 0; d < 6; ++d)
+					{
+						const Vec3i ni{ ci.x + s_chunkDirOffset[d].x, ci.y + s_chunkDirOffset[d].y, ci.z + s_chunkDirOffset[d].z };
+						if (inside(ni) && !p.GetChunk(ni))
+							all.push_back(&p.AddChunk(Lib(), ni));
+					}
+				}
+		std::atomic<int> bad{ 0 };
+		std::vector<std::vector<BlockIndex>> tmp(all.size());
+		ParallelFor(all.size(), nthreads, [&](std::size_t i) {
+			tmp[i].resize(ChunkBlockCount);
+			if (!Planet::GenerateChunkBlocks(Lib(), all[i]->GetIndices(), seed, s->count, tmp[i].data()))
+				bad = 1;
+		});
+		for (std::size_t i = 0; i < all.size(); ++i)
+			all[i]->Reset([&](BlockIndex* dst) { std::memcpy(dst, tmp[i].data(), ChunkBlockCount * sizeof(BlockIndex)); });
+		if (bad)
+		{
+			delete s;
+			return nullptr;
+		}
+		return s;
+	}
+
+	std::uint32_t orc_sample_size(void* hv) { return std::uint32_t(static_cast<SampleHandle*>(hv)->sample.size()); }
+
+	std::uint64_t orc_sample_step(void* hv, int nthreads, double times[2])
+	{
+		auto* s = static_cast<SampleHandle*>(hv);
+		Planet& p = s->h.planet;
+		const double t0 = Now();
+		std::vector<std::vector<BlockIndex>> tmp(s->sample.size());
+		ParallelFor(s->sample.size(), nthreads, [&](std::size_t i) {
+			tmp[i].resize(ChunkBlockCount);
+			Planet::GenerateChunkBlocks(Lib(), s->sample[i]->GetIndices(), s->seed, s->count, tmp[i].data());
+		});
+		for (std::size_t i = 0; i < s->sample.size(); ++i)
+			s->sample[i]->Reset([&](BlockIndex* dst) { std::memcpy(dst, tmp[i].data(), ChunkBlockCount * sizeof(BlockIndex)); });
+		const double t1 = Now();
+		std::atomic<std::uint64_t> faces{ 0 };
+		ParallelFor(s->sample.size(), nthreads, [&](std::size_t i) {
+			MeshOut out;
+			s->sample[i]->BuildMesh(out, p.GetCenter() - p.GetChunkOffset(s->sample[i]->GetIndices()), true, true);
+			faces += out.indices.size() / 6;
+		});
+		const double t2 = Now();
+		times[0] = t1 - t0;
+		times[1] = t2 - t1;
+		return faces;
+	}
+
+	void orc_sample_destroy(void* hv) { delete static_cast<SampleHandle*>(hv); }
+
+	double orc_bench_box_colliders(void* hv, const std::uint32_t count[3], std::uint32_t stride, int nthreads, std::uint64_t* boxesOut, std::uint32_t* chunksOut)
+	{
+		Planet& p = static_cast<PlanetHandle*>(hv)->planet;
+		std::vector<const Chunk*> chunks;
+		std::size_t k = 0;
+		for (int cz = 0; cz < int(count[2]); ++cz)
+			for (int cy = 0; cy < int(count[1]); ++cy)
+				for (int cx = 0; cx < int(count[0]); ++cx, ++k)
+					if (k % stride == 0)
+						if (const Chunk* c = p.GetChunk({ cx - int(count[0] / 2), cy - int(count[1] / 2), cz - int(count[2] / 2) }))
+							chunks.push_back(c);
+		std::atomic<std::uint64_t> boxes{ 0 };
+		const double t0 = Now();
+		ParallelFor(chunks.size(), nthreads, [&](std::size_t i) { boxes += chunks[i]->BuildBoxCollider().size(); });
+		const double t1 = Now();
+		if (boxesOut)
+			*boxesOut = boxes;
+		if (chunksOut)
+			*chunksOut = std::uint32_t(chunks.size());
+		return t1 - t0;
+	}
+
+	// ---- Ship (same entry points as oracle/ref_shim) ----
+	struct ShipHandle
+	{
+		Ship ship;
+		explicit ShipHandle(float tile) : ship(tile) {}
+	};
+
+	void* orc_ship_create(float tile) { return new ShipHandle(tile); }
+	void orc_ship_destroy(void* h) { delete static_cast<ShipHandle*>(h); }
+	void orc_ship_generate(void* h, int small) { static_cast<ShipHandle*>(h)->ship.Generate(Lib(), small != 0); }
+
+	int orc_ship_add_chunk(void* h, const std::int32_t idx[3], const std::uint16_t* blocks)
+	{
+		Ship& s = static_cast<ShipHandle*>(h)->ship;
+		Vec3i ci{ idx[0], idx[1], idx[2] };
+		if (s.GetChunk(ci))
+			return 1;
+		Chunk& c = s.AddChunk(Lib(), ci);
+		if (blocks)
+			c.Reset([&](BlockIndex* dst) { std::memcpy(dst, blocks, ChunkBlockCount * sizeof(BlockIndex)); });
+		return 0;
+	}
+
+	int orc_ship_get_blocks(void* h, const std::int32_t idx[3], std::uint16_t* out)
+	{
+		const Chunk* c = static_cast<ShipHandle*>(h)->ship.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c || !c->HasContent())
+			return 1;
+		std::memcpy(out, c->Blocks().data(), ChunkBlockCount * sizeof(BlockIndex));
+		return 0;
+	}
+
+	int orc_ship_update_block(void* h, const std::int32_t idx[3], const std::uint32_t local[3], std::uint16_t id)
+	{
+		Chunk* c = static_cast<ShipHandle*>(h)->ship.GetChunk({ idx[0], idx[1], idx[2] });
+		if (!c || !c->HasContent())
+			return 1;
+		c->UpdateBlock({ local[0], local[1], local[2] }, id);
+		return 0;
+	}
+
+	std::uint32_t orc_ship_take_invalidated(void* h, std::int32_t* idxOut, std::uint32_t* maskOut, std::uint32_t cap)
+	{
+		Ship& s = static_cast<ShipHandle*>(h)->ship;
+		std::uint32_t n = 0;
+		for (auto&& [k, m] : s.invalidated)
+		{
+			if (n < cap)
+			{
+				idxOut[n * 3 + 0] = k.x;
+				idxOut[n * 3 + 1] = k.y;
+				idxOut[n * 3 + 2] = k.z;
+				maskOut[n] = std::uint32_t(m) | 0x80u;
+			}
+			++n;
+		}
+		s.invalidated.clear();
+		return n;
+	}
+
+	std::uint32_t orc_ship_hull_collider(void* h, float* out, std::uint32_t cap)
+	{
+		auto boxes = static_cast<ShipHandle*>(h)->ship.BuildHullCollider();
+		for (std::uint32_t i = 0; i < boxes.size() && i < cap; ++i)
+		{
+			float* o = out + std::size_t(i) * 9;
+			o[0] = boxes[i].chunkOffset.x; o[1] = boxes[i].chunkOffset.y; o[2] = boxes[i].chunkOffset.z;
+			o[3] = boxes[i].center.x; o[4] = boxes[i].center.y; o[5] = boxes[i].center.z;
+			o[6] = boxes[i].lengths.x; o[7] = boxes[i].lengths.y; o[8] = boxes[i].lengths.z;
+		}
+		return std::uint32_t(boxes.size());
+	}
 }

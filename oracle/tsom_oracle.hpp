@@ -472,6 +472,14 @@ namespace orc
 
 			// Chunk.inl:109-123 + Chunk.cpp:368-384
 			template<typename F> void Reset(F&& f);
+			// Chunk.inl:97-107: all Empty, no OnReset signal
+			void ResetEmpty()
+			{
+				m_blocks.assign(ChunkBlockCount, EmptyBlockIndex);
+				m_collisionCellMask.assign(ChunkBlockCount, 0);
+				m_blockTypeCount.assign(EmptyBlockIndex + 1, 0);
+				m_blockTypeCount[EmptyBlockIndex] = ChunkBlockCount;
+			}
 
 			// Chunk.cpp:348-366
 			void UpdateBlock(const Vec3ui& indices, BlockIndex newBlock);
@@ -1302,5 +1310,76 @@ namespace orc
 		private:
 			float m_cornerRadius;
 			float m_gravity;
+	};
+
+	// ---------------------------------------------------------------- Ship (Ship.cpp) — the second ChunkContainer of the reference
+	class Ship : public ChunkContainer
+	{
+		public:
+			explicit Ship(float tileSize) : ChunkContainer(tileSize) {}
+
+			// Ship.cpp:21-61: FlatChunk + the dirty-mask rule with Up / Down swapped relative to Planet (z == 0 -> Up, z == 31 -> Down, :48-51)
+			Chunk& AddChunk(const BlockLibrary& lib, const Vec3i& indices)
+			{
+				auto chunk = std::make_unique<Chunk>(lib, *this, indices, m_tileSize);
+				chunk->onReset = [this](Chunk* c) { OnChunkUpdated(c, 0x3F); };
+				chunk->onBlockUpdated = [this](Chunk* c, const Vec3ui& i, BlockIndex)
+				{
+					std::uint8_t mask = 0;
+					if (i.x == 0) mask |= 1u << Left; else if (i.x == ChunkSize - 1) mask |= 1u << Right;
+					if (i.y == 0) mask |= 1u << Front; else if (i.y == ChunkSize - 1) mask |= 1u << Back;
+					if (i.z == 0) mask |= 1u << Up; else if (i.z == ChunkSize - 1) mask |= 1u << Down;
+					OnChunkUpdated(c, mask);
+				};
+				Chunk* ptr = chunk.get();
+				m_chunks[indices] = std::move(chunk);
+				return *ptr;
+			}
+
+			// Ship.cpp:115-152
+			void Generate(const BlockLibrary& lib, bool small)
+			{
+				Chunk& chunk = AddChunk(lib, { 0, 0, 0 });
+				BlockIndex hull = lib.GetBlockIndex("hull");
+				if (hull == InvalidBlockIndex)
+					return;
+				BlockIndex forcefield = lib.GetBlockIndex("forcefield");
+				const unsigned boxSize = small ? 6 : 12, height = small ? 4 : 6;
+				const Vec3ui start{ ChunkSize / 2 - boxSize / 2, ChunkSize / 2 - boxSize / 2, ChunkSize / 2 - height / 2 };
+				chunk.ResetEmpty(); // Chunk::Reset() without a callback does not fire OnReset (Chunk.inl:97-107)
+				for (unsigned z = 0; z < height; ++z)
+					for (unsigned y = 0; y < boxSize; ++y)
+						for (unsigned x = 0; x < boxSize; ++x)
+						{
+							if (x != 0 && x != boxSize - 1 && y != 0 && y != boxSize - 1 && z != 0 && z != height - 1)
+								continue;
+							const Vec3ui pos{ start.x + x, start.y + y, start.z + z };
+							if (x == 0 && y == boxSize / 2 && z > 0 && z < height - 1)
+								chunk.UpdateBlock(pos, forcefield);
+							else
+								chunk.UpdateBlock(pos, hull);
+						}
+			}
+
+			// Ship.cpp:63-93, flattened: (child offset, box centre * blockSize, box lengths * blockSize) per box (FlatChunk.cpp:13-30);
+			// one chunk: its own compound (offset zero); several: one child per chunk with a collider, offset = GetChunkOffset
+			struct HullBox { Vec3f chunkOffset, center, lengths; };
+			std::vector<HullBox> BuildHullCollider() const
+			{
+				std::vector<HullBox> out;
+				const bool compound = m_chunks.size() > 1;
+				for (auto&& [idx, chunk] : m_chunks)
+				{
+					if (!chunk->HasContent())
+						continue;
+					const Vec3f off = compound ? GetChunkOffset(idx) : Vec3f{};
+					for (const Chunk::ColliderBox& b : chunk->BuildBoxCollider())
+					{
+						const Vec3f c{ b.pos.x + b.size.x / 2.f, b.pos.y + b.size.y / 2.f, b.pos.z + b.size.z / 2.f }; // Nz::Boxf::GetCenter
+						out.push_back({ off, c * m_tileSize, b.size * m_tileSize });
+					}
+				}
+				return out;
+			}
 	};
 }

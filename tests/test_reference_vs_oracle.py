@@ -201,3 +201,53 @@ def test_edit_stream_and_dirty_sets(R):
         assert np.array_equal(po.get_blocks(idx), pr.get_blocks(idx)), idx
     for idx in [(0, 0, 0), (2, 2, 2), (-1, 2, 0)]:
         assert_same_mesh(po.mesh(idx), pr.mesh(idx), f"after edits {idx}")
+
+
+def test_ship_mask_rule_generate_and_hull_collider():
+    """Ship.cpp compiled from the reference vs the restatement: Ship::Generate's blocks, the Up / Down-swapped neighbour mask of
+    Ship::AddChunk (Ship.cpp:36-54) per edit, and Ship::BuildHullCollider for one and for several chunks (Ship.cpp:63-93)."""
+    R = O.reference()
+    rng = np.random.default_rng(5)
+    for small in (True, False):
+        a, b = O.Ship(2.0), R.Ship(2.0)
+        a.generate(small)
+        b.generate(small)
+        assert np.array_equal(a.get_blocks((0, 0, 0)), b.get_blocks((0, 0, 0)))
+        assert a.take_invalidated() == b.take_invalidated()
+        for _ in range(200):
+            loc = rng.choice([0, 1, 15, 30, 31], 3)
+            blk = int(rng.choice([0, 4, 9, 13]))
+            assert a.update_block((0, 0, 0), loc, blk) == 0 and b.update_block((0, 0, 0), loc, blk) == 0
+            assert a.take_invalidated() == b.take_invalidated(), loc
+        assert np.array_equal(a.get_blocks((0, 0, 0)), b.get_blocks((0, 0, 0)))
+        ha, hb = a.hull_collider(), b.hull_collider()
+        assert len(ha) > 0 and np.array_equal(ha, hb)
+        # a second chunk turns the hull into a compound of per-chunk compounds with chunk offsets
+        extra = (rng.random(32768) < 0.3).astype(np.uint16) * 4
+        assert a.add_chunk((1, 0, -1), extra) == 0 and b.add_chunk((1, 0, -1), extra) == 0
+        ha, hb = a.hull_collider(), b.hull_collider()
+        key = lambda h: h[np.lexsort(h.T[::-1])]  # the reference iterates a hash map: compare as sets of rows
+        assert len(ha) == len(hb) and np.array_equal(key(ha), key(hb))
+        assert {tuple(r) for r in ha[:, 0:3].tolist()} == {(0.0, 0.0, 0.0), (64.0, 0.0, -64.0)}
+    empty = R.Ship(1.0)
+    assert len(empty.hull_collider()) == 0 and len(O.Ship(1.0).hull_collider()) == 0
+
+
+def test_planet_sample_and_collider_bench_agree():
+    """The CPU arm's workload (a planet-wide sample of generate + mesh) gives the same faces on the restatement and on the reference's
+    own code, and equals meshing those chunks inside the whole planet."""
+    R = O.reference()
+    count = (5, 5, 5)
+    a, b = O.PlanetSample(42, count, 7, 3, nthreads=2), R.PlanetSample(42, count, 7, 3, nthreads=2)
+    ra, rb = a.step(2), b.step(2)
+    assert ra["chunks"] == rb["chunks"] == len(range(3, 125, 7)) and ra["faces"] == rb["faces"] > 0
+    whole = O.Planet()
+    assert whole.generate(42, count, nthreads=2)
+    grid = [(x - 2, y - 2, z - 2) for z in range(5) for y in range(5) for x in range(5)]
+    want = sum((whole.mesh(grid[k]).face_count if whole.mesh(grid[k]) is not None else 0) for k in range(3, 125, 7))
+    assert ra["faces"] == want
+    rw = R.Planet()
+    assert rw.generate(42, count, nthreads=2)
+    ta, na, ca = O.bench_box_colliders(whole, count, 2)
+    tb, nb, cb = R.bench_box_colliders(rw, count, 2)
+    assert (na, ca) == (nb, cb) and ca == 125 and na > 0

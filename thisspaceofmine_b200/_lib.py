@@ -95,6 +95,8 @@ SYMBOLS = {
     "tsom_mesh_arenas": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "tsom_mesh_copy_to_host": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _u32p, _f32p]),
     "tsom_mesh_aabb": (C.c_int, [_vp, C.POINTER(MeshView), C.c_uint32, _f32p]),
+    "tsom_mesh_checksums": (C.c_int, [_vp, C.POINTER(MeshView), C.c_uint32, C.POINTER(C.c_uint64)]),
+    "tsom_mesh_indices_for_faces": (C.c_int, [C.c_uint64, _u32p]),
     "tsom_voxel_corners": (C.c_int, [_vp, _i32p, _u32p, C.c_uint32, C.POINTER(MeshParams), _f32p]),
     "tsom_box_collider": (C.c_int, [_vp, _i32p, _f32p, C.c_uint32, _u32p]),
     "tsom_container_add_remote_chunks": (C.c_int, [_vp, _i32p, _u32p, _i32p, C.c_uint32]),

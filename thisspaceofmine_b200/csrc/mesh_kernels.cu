@@ -1062,6 +1062,57 @@ namespace tsomk
 		}
 	}
 
+	// =====================================================================================================================
+	// mesh_checksum_kernel — one CTA per view: two 64-bit position-weighted sums, over the 32-bit words of the chunk's vertices (or
+	// collider positions) and over its indices.  Independent of where the chunk's faces sit in the arena, so meshes built by
+	// different launches / different GPUs compare chunk by chunk on the device (sharded parity without moving the arenas to the host).
+	__global__ void __launch_bounds__(256) mesh_checksum_kernel(const uint32_t* __restrict__ vertexWords, uint32_t wordsPerFace, const uint32_t* __restrict__ indices,
+	                                                            const unsigned long long* __restrict__ firstFace, const uint32_t* __restrict__ faceCount, uint32_t n,
+	                                                            unsigned long long* __restrict__ out)
+	{
+		const uint32_t job = blockIdx.x;
+		if (job >= n)
+			return;
+		const unsigned long long first = firstFace[job];
+		const unsigned long long nv = static_cast<unsigned long long>(faceCount[job]) * wordsPerFace, ni = static_cast<unsigned long long>(faceCount[job]) * 6ull;
+		auto term = [](uint32_t w, unsigned long long i) { return (static_cast<unsigned long long>(w) + 0x9E3779B97F4A7C15ull) * (2ull * i + 1ull); };
+		unsigned long long hv = 0ull, hi = 0ull;
+		const uint32_t* v = vertexWords + first * wordsPerFace;
+		for (unsigned long long i = threadIdx.x; i < nv; i += blockDim.x)
+			hv += term(v[i], i);
+		const uint32_t* ix = indices + first * 6ull;
+		for (unsigned long long i = threadIdx.x; i < ni; i += blockDim.x)
+			hi += term(ix[i], i);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			hv += __shfl_xor_sync(0xffffffffu, hv, o);
+			hi += __shfl_xor_sync(0xffffffffu, hi, o);
+		}
+		__shared__ unsigned long long red[8][2];
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		if (lane == 0)
+		{
+			red[warp][0] = hv;
+			red[warp][1] = hi;
+		}
+		__syncthreads();
+		if (threadIdx.x < 2)
+		{
+			unsigned long long r = 0ull;
+			for (int w = 0; w < 8; ++w)
+				r += red[w][threadIdx.x];
+			out[size_t(job) * 2 + threadIdx.x] = r;
+		}
+	}
+
+	void launch_mesh_checksum(const uint32_t* vertexWords, uint32_t wordsPerFace, const uint32_t* indices, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n,
+	                          unsigned long long* out, cudaStream_t st)
+	{
+		if (n)
+			mesh_checksum_kernel<<<n, 256, 0, st>>>(vertexWords, wordsPerFace, indices, firstFace, faceCount, n, out);
+	}
+
 	void launch_mesh_aabb(const float4* vertices, const float* collider, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n, float* out, cudaStream_t st)
 	{
 		mesh_aabb_kernel<<<n, 256, 0, st>>>(vertices, collider, firstFace, faceCount, n, out);

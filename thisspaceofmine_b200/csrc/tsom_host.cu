@@ -2170,6 +2170,74 @@ extern "C"
 		return TSOM_OK;
 	}
 
+	int tsom_mesh_checksums(tsom_ctx* ctx, const tsom_mesh_view* views, uint32_t n, uint64_t* out)
+	{
+		if (!ctx || (!views && n) || (!out && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		TSOM_LOCK(ctx);
+		TSOM_CUDA(cudaSetDevice(ctx->device));
+		const bool render = (ctx->lastMeshFlags & TSOM_MESH_RENDER) != 0;
+		if (!render && !(ctx->lastMeshFlags & TSOM_MESH_COLLIDER))
+			return Fail(TSOM_ERR_INVALID, "no mesh result on this context");
+		TSOM_CUDA(ctx->EnsurePinned(size_t(n) * (sizeof(unsigned long long) + sizeof(uint32_t))));
+		auto* hFirst = static_cast<unsigned long long*>(ctx->hPinned);
+		auto* hCount = reinterpret_cast<uint32_t*>(hFirst + n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (views[i].first_face + views[i].face_count > ctx->totalFaces)
+				return Fail(TSOM_ERR_INVALID, "a view exceeds the last mesh result");
+			hFirst[i] = views[i].first_face;
+			hCount[i] = views[i].face_count;
+		}
+		TSOM_CUDA(ctx->firstFace.Ensure(n));
+		TSOM_CUDA(ctx->faceCount.Ensure(n));
+		TSOM_CUDA(ctx->status.Ensure(size_t(n) * 2));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->firstFace.ptr, hFirst, size_t(n) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+		TSOM_CUDA(cudaMemcpyAsync(ctx->faceCount.ptr, hCount, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		tsomk::launch_mesh_checksum(reinterpret_cast<const uint32_t*>(render ? static_cast<const void*>(ctx->dVertices) : static_cast<const void*>(ctx->dCollider)), render ? 48u : 12u,
+		                            reinterpret_cast<const uint32_t*>(ctx->dIndices), ctx->firstFace.ptr, ctx->faceCount.ptr, n, ctx->status.ptr, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaMemcpyAsync(out, ctx->status.ptr, size_t(n) * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		return TSOM_OK;
+	}
+
+	int tsom_mesh_indices_for_faces(uint64_t face_count, uint32_t* indices_out)
+	{
+		if (!indices_out && face_count)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (face_count > 0xFFFFFFFFull / 4ull)
+			return Fail(TSOM_ERR_INVALID, "a chunk's vertex ordinals do not fit 32 bits");
+		auto fill = [indices_out](uint64_t f0, uint64_t f1) {
+			for (uint64_t f = f0; f < f1; ++f)
+			{
+				uint32_t* o = indices_out + f * 6;
+				const uint32_t b = uint32_t(f) * 4u;
+				o[0] = b;
+				o[1] = b + 2u;
+				o[2] = b + 1u;
+				o[3] = b + 1u;
+				o[4] = b + 2u;
+				o[5] = b + 3u;
+			}
+		};
+		const unsigned workers = face_count < (1u << 20) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		if (workers == 1)
+		{
+			fill(0, face_count);
+			return TSOM_OK;
+		}
+		std::vector<std::thread> pool;
+		for (unsigned w = 0; w < workers; ++w)
+			pool.emplace_back(fill, face_count * w / workers, face_count * (w + 1) / workers);
+		for (auto& t : pool)
+			t.join();
+		return TSOM_OK;
+	}
+
 	// FlatChunk::BuildCollider for a batch: box_colliders_kernel (one warp per chunk) into a packed scratch, sizes to the host, offsets
 	// back, box_pack_kernel into the dense arena.  Sub-batches bound the scratch (64 KiB per chunk); one synchronisation per sub-batch.
 	int tsom_box_colliders(tsom_container* c, const int32_t* chunk_indices, uint32_t n, tsom_box_view* views_out, uint64_t* total_boxes_out)
@@ -2299,15 +2367,19 @@ extern "C"
 	}
 
 	// Ship::Generate (Ship.cpp:115-152): chunk (0,0,0) reset to Empty, then the hull written block by block.  The final content is a
-	// pure function of (small, ids); it is composed here and handed to the device like any Chunk::Reset, after which the chunk is
-	// invalidated with DirectionMask_All (OnReset) — a superset of the masks the UpdateBlock calls raise.
+	// pure function of (small, ids); it is composed here and handed to the device in one copy.  What the reference leaves behind in
+	// m_invalidatedChunks is kept too: Chunk::Reset() without a callback fires no OnReset (Chunk.inl:97-107), so the chunk is
+	// invalidated by its UpdateBlock calls alone — the chunk itself plus the OR of their neighbour masks (Ship.cpp:36-54).
 	int tsom_ship_generate(tsom_container* c, int small, uint16_t hull_block, uint16_t forcefield_block)
 	{
 		if (!c)
 			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
 		std::vector<uint16_t> blocks(NB, 0);
 		const unsigned boxSize = small ? 6 : 12, height = small ? 4 : 6;
 		const unsigned sx = CS / 2 - boxSize / 2, sy = CS / 2 - boxSize / 2, sz = CS / 2 - height / 2;
+		uint8_t mask = 0x80u;
+		const bool ship = c->kind == TSOM_CONTAINER_SHIP;
 		for (unsigned z = 0; z < height; ++z)
 			for (unsigned y = 0; y < boxSize; ++y)
 				for (unsigned x = 0; x < boxSize; ++x)
@@ -2315,10 +2387,19 @@ extern "C"
 					if (x != 0 && x != boxSize - 1 && y != 0 && y != boxSize - 1 && z != 0 && z != height - 1)
 						continue;
 					const bool door = x == 0 && y == boxSize / 2 && z > 0 && z < height - 1;
-					blocks[(size_t(sz + z) * CS + (sy + y)) * CS + (sx + x)] = door ? forcefield_block : hull_block;
+					const unsigned px = sx + x, py = sy + y, pz = sz + z;
+					blocks[(size_t(pz) * CS + py) * CS + px] = door ? forcefield_block : hull_block;
+					if (px == 0) mask |= 1u << TSOM_LEFT; else if (px == unsigned(CS) - 1) mask |= 1u << TSOM_RIGHT;
+					if (py == 0) mask |= 1u << TSOM_FRONT; else if (py == unsigned(CS) - 1) mask |= 1u << TSOM_BACK;
+					if (pz == 0) mask |= 1u << (ship ? TSOM_UP : TSOM_DOWN); else if (pz == unsigned(CS) - 1) mask |= 1u << (ship ? TSOM_DOWN : TSOM_UP);
 				}
 		const int32_t origin[3] = { 0, 0, 0 };
-		return tsom_chunks_reset(c, origin, 1, blocks.data());
+		int rc = tsom_chunks_reset(c, origin, 1, blocks.data());
+		if (rc != TSOM_OK)
+			return rc;
+		const uint32_t slot = c->SlotOf(Key{ 0, 0, 0 });
+		c->hostInvalid[slot] = mask;
+		return TSOM_OK;
 	}
 
 	// ---------------------------------------------------------------------------------------------------- multi-GPU

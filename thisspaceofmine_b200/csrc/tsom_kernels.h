@@ -163,6 +163,10 @@ namespace tsomk
 	// ---- Nz::StaticMesh::GenerateAABB: min / max of each chunk's vertex positions (render arena, or the collider arena if vertices == null) ----
 	void launch_mesh_aabb(const float4* vertices, const float* collider, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n, float* out, cudaStream_t st);
 
+	// ---- per-view checksums of a mesh result (vertex words or collider positions; indices), see mesh_checksum_kernel ----
+	void launch_mesh_checksum(const uint32_t* vertexWords, uint32_t wordsPerFace, const uint32_t* indices, const unsigned long long* firstFace, const uint32_t* faceCount, uint32_t n,
+	                          unsigned long long* out, cudaStream_t st);
+
 	// ---- wire format: one LZ4 block per chunk (Packets::ChunkReset), lz4_kernels.cu ----
 	cudaError_t lz4_kernels_init();
 	uint32_t lz4_stream_stride(); // bytes reserved per chunk in the scratch of launch_lz4_compress (>= LZ4_compressBound(65536))

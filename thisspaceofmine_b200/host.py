@@ -299,6 +299,14 @@ class MeshBatch:
                                                None if coll is None else _p(coll, C.c_float)))
         return ChunkMesh(verts, ind, coll)
 
+    def checksums(self) -> np.ndarray:
+        """tsom_mesh_checksums: [n, 2] uint64 — a position-weighted sum over each chunk's vertex words (collider positions after a
+        collider-only call) and one over its indices, computed on the device; independent of where the faces sit in the arena."""
+        out = np.zeros((len(self._views), 2), np.uint64)
+        v = np.ascontiguousarray(self._views)
+        L.check(L.lib().tsom_mesh_checksums(self.ctx._h, C.cast(v.ctypes.data, C.POINTER(L.MeshView)), len(v), out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
     def aabbs(self) -> np.ndarray:
         """Nz::StaticMesh::GenerateAABB for every chunk of the batch (ClientChunkEntities.cpp:168), computed on the device from the
         arena -> [n, 6] float32: min.xyz, max.xyz of the vertex positions; zeros for a chunk without faces."""
