@@ -4,6 +4,8 @@
 #include "tsom_adapter.hpp"
 
 #include <cstdio>
+#include <cstdlib>
+#include <cmath>
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -309,6 +311,129 @@ static void TestGpu()
 	std::printf("adapter GPU pass: %llu faces over %zu chunks\n", (unsigned long long)faces, grid.size());
 }
 
+// round 2: the sharded planet in one process (parts may share a GPU: devices = {0, 0, 0} works on a single-GPU box), the Ship container,
+// batched box colliders, tangents.  `devices` comes from the command line: --gpu [n_parts]
+// number of usable devices through the C ABI alone (the adapter does not include CUDA headers)
+static void cudaDevicesVisible(int* n)
+{
+	*n = 0;
+	for (int d = 0; d < 16; ++d)
+	{
+		tsom_ctx* c = nullptr;
+		if (tsom_create(d, &c) != TSOM_OK)
+			break;
+		tsom_destroy(c);
+		++*n;
+	}
+}
+
+static void TestGpuSharded(const std::vector<int>& devices)
+{
+	BlockLibrary lib;
+	Device device(lib, 0);
+	const Vector3ui count(3, 3, 3);
+	const auto grid = Planet::ChunkGrid(count);
+
+	// one GPU, one container: the reference run
+	Planet planet(device, 1.f, 16.f, 9.81f, 32);
+	planet.GenerateChunks(lib, 7, count);
+	MeshOptions opt;
+	opt.collider = true;
+	MeshBatch whole = planet.BuildMeshes(grid, opt);
+
+	// the same planet cut into devices.size() parts
+	ShardedPlanet sharded(lib, devices, count, 1.f);
+	CHECK(sharded.GetPartCount() == devices.size());
+	sharded.GenerateChunks(lib, 7);
+	ShardedMeshBatch parts = sharded.BuildMeshes(grid, opt);
+	std::size_t differing = 0;
+	for (std::size_t i = 0; i < grid.size(); ++i)
+	{
+		CHECK(parts.parts[i] == sharded.GetOwner(grid[i]));
+		std::vector<VertexStruct> va, vb;
+		std::vector<std::uint32_t> ia, ib;
+		std::vector<Vector3f> ca, cb;
+		whole.CopyChunk(i, &va, &ia, &ca);
+		parts.CopyChunk(i, &vb, &ib, &cb);
+		if (ia != ib || va.size() != vb.size() || (!va.empty() && std::memcmp(va.data(), vb.data(), va.size() * sizeof(VertexStruct)) != 0) ||
+		    (!ca.empty() && std::memcmp(ca.data(), cb.data(), ca.size() * sizeof(Vector3f)) != 0))
+			++differing;
+		CHECK(sharded.GetContent(grid[i]) == planet.GetChunk(grid[i]).GetContent());
+	}
+	CHECK(differing == 0);
+
+	// an edit on a part boundary: both sides of the cut are rebuilt, like on the single container
+	planet.CollectInvalidatedChunks();
+	sharded.CollectInvalidatedChunks();
+	std::vector<ChunkContainer::BlockUpdate> edits;
+	for (const ChunkIndices& c : grid)
+		edits.push_back({ c, Vector3ui(0, 31, 0), EmptyBlockIndex });
+	planet.UpdateBlocks(edits);
+	sharded.UpdateBlocks(edits);
+	auto dirtyA = planet.CollectInvalidatedChunks();
+	auto dirtyB = sharded.CollectInvalidatedChunks();
+	CHECK(dirtyA.size() == 27 && dirtyA.size() == dirtyB.size());
+	for (std::size_t i = 0; i < dirtyA.size() && i < dirtyB.size(); ++i)
+		CHECK(dirtyA[i] == dirtyB[i]);
+	MeshBatch wholeAfter = planet.BuildMeshes(grid, opt);
+	ShardedMeshBatch partsAfter = sharded.BuildMeshes(grid, opt);
+	for (std::size_t i = 0; i < grid.size(); ++i)
+		CHECK(wholeAfter.FaceCount(i) == partsAfter.FaceCount(i));
+
+	// indices synthesised on the host == indices copied from the device; tangents fill the 12-byte slot with unit vectors
+	{
+		MeshOptions t;
+		t.tangents = true;
+		MeshBatch b = planet.BuildMeshes({ grid[13] }, t);
+		std::vector<VertexStruct> v, v2;
+		std::vector<std::uint32_t> fromDevice, synthesized;
+		b.CopyChunk(0, &v, &fromDevice, nullptr);
+		b.CopyChunkSynthesizeIndices(0, &v2, synthesized);
+		CHECK(!fromDevice.empty() && fromDevice == synthesized);
+		bool unit = !v.empty();
+		for (const VertexStruct& q : v)
+		{
+			const float len = std::sqrt(q.tangent.x * q.tangent.x + q.tangent.y * q.tangent.y + q.tangent.z * q.tangent.z);
+			unit = unit && std::fabs(len - 1.f) < 1e-5f;
+		}
+		CHECK(unit);
+	}
+
+	// batched box colliders == one call per chunk
+	{
+		auto all = planet.BuildBoxColliders(grid);
+		std::size_t boxes = 0;
+		for (std::size_t i = 0; i < grid.size(); i += 5)
+		{
+			auto one = planet.GetChunk(grid[i]).BuildBoxCollider();
+			CHECK(one.size() == all[i].size());
+			for (std::size_t k = 0; k < one.size() && k < all[i].size(); ++k)
+				CHECK(one[k].position == all[i][k].position && one[k].size == all[i][k].size);
+			boxes += one.size();
+		}
+		CHECK(boxes > 0);
+	}
+
+	// Ship: Generate, the Up / Down-swapped mask, the hull compound
+	{
+		Ship ship(device, 2.f);
+		ship.Generate(lib, true);
+		auto hull = ship.BuildHullCollider();
+		CHECK(hull.size() == 1 && !hull[0].boxes.empty() && hull[0].offset == Vector3f(0.f, 0.f, 0.f));
+		auto d = ship.CollectInvalidatedChunks();
+		CHECK(d.size() == 1 && d[0] == ChunkIndices(0, 0, 0));
+		ship.AddChunk(lib, ChunkIndices(0, 1, 0), [&](BlockIndex* b) { b[0] = lib.GetBlockIndex("hull"); });
+		ship.AddChunk(lib, ChunkIndices(0, -1, 0), [&](BlockIndex* b) { b[0] = lib.GetBlockIndex("hull"); });
+		ship.CollectInvalidatedChunks();
+		ship.UpdateBlocks({ { ChunkIndices(0, 0, 0), Vector3ui(5, 5, 0), lib.GetBlockIndex("hull") } }); // local z == 0: Up on a Ship (Ship.cpp:48-49)
+		d = ship.CollectInvalidatedChunks();
+		CHECK(d.size() == 2 && d[0] == ChunkIndices(0, 0, 0) && d[1] == ChunkIndices(0, 1, 0));
+		hull = ship.BuildHullCollider();
+		CHECK(hull.size() == 3 && hull[1].offset == Vector3f(0.f, 64.f, 0.f));
+	}
+	std::printf("adapter sharded GPU pass: %zu parts\n", devices.size());
+}
+
 int main(int argc, char** argv)
 {
 	const bool gpu = argc > 1 && std::strcmp(argv[1], "--gpu") == 0;
@@ -332,6 +457,14 @@ int main(int argc, char** argv)
 		try
 		{
 			TestGpu();
+			// parts of the sharded planet: one per visible GPU when there are several, else --gpu N parts on GPU 0 (default 3)
+			int nDev = 0;
+			cudaDevicesVisible(&nDev);
+			const int nParts = argc > 2 ? std::atoi(argv[2]) : (nDev > 1 ? nDev : 3);
+			std::vector<int> devices;
+			for (int i = 0; i < nParts; ++i)
+				devices.push_back(nDev > 1 ? i % nDev : 0);
+			TestGpuSharded(devices);
 		}
 		catch (const std::exception& e)
 		{

@@ -254,6 +254,14 @@ namespace tsom_b200
 				                             colliderPositions ? &colliderPositions->data()->x : nullptr), "tsom_mesh_copy_to_host");
 			}
 
+			// The same without carrying the indices across PCIe: they are a pure function of the face ordinal (Chunk.cpp:95-101)
+			void CopyChunkSynthesizeIndices(std::size_t i, std::vector<VertexStruct>* vertices, std::vector<std::uint32_t>& indices) const
+			{
+				CopyChunk(i, vertices, nullptr, nullptr);
+				indices.resize(std::size_t(views[i].face_count) * 6);
+				Check(tsom_mesh_indices_for_faces(views[i].face_count, indices.data()), "tsom_mesh_indices_for_faces");
+			}
+
 			// Nz::StaticMesh::GenerateAABB of every chunk (ClientChunkEntities.cpp:168), from the arena: {min, max} of the positions
 			struct Aabb
 			{
@@ -282,6 +290,7 @@ namespace tsom_b200
 		CornerMode corners = CornerMode::Flat;
 		float deformRadius = 0.f;            // Planet::GetCornerRadius() for DeformedChunk
 		bool ordered = false;                // arena ranges in job order (TSOM_MESH_ORDERED); default: first come, first served
+		bool tangents = false;               // also what Nz::StaticMesh::GenerateTangents adds (ClientChunkEntities.cpp:169)
 		const Vector3f* gravityCenters = nullptr; // per chunk `center` argument of Chunk::BuildMesh; null = GetCenter() - GetChunkOffset(chunk)
 	};
 
@@ -466,13 +475,41 @@ namespace tsom_b200
 				batch.views.resize(chunks.size());
 				tsom_mesh_params p{};
 				p.flags = (opt.render ? std::uint32_t(TSOM_MESH_RENDER) : 0u) | (opt.collider ? std::uint32_t(TSOM_MESH_COLLIDER) : 0u) | (opt.corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u) |
-				          (opt.ordered ? std::uint32_t(TSOM_MESH_ORDERED) : 0u);
+				          (opt.ordered ? std::uint32_t(TSOM_MESH_ORDERED) : 0u) | (opt.tangents ? std::uint32_t(TSOM_MESH_TANGENTS) : 0u);
 				p.deform_radius = opt.deformRadius;
 				p.gravity_centers = opt.gravityCenters ? &opt.gravityCenters->x : nullptr;
 				if (!chunks.empty())
 					Check(tsom_mesh(m_container, &chunks[0].x, std::uint32_t(chunks.size()), &p, batch.views.data()), "tsom_mesh");
 				Check(tsom_mesh_arenas(m_device->Handle(), nullptr, nullptr, nullptr, &batch.totalFaces), "tsom_mesh_arenas");
 				return batch;
+			}
+
+			// FlatChunk::BuildCollider for all `chunks` in ONE call (the server's physics path asks it per invalidated chunk,
+			// ChunkEntities.cpp:198): boxes[i] = chunk i's greedy boxes {position, size}, scaled by the block size like FlatChunk.cpp:20-21;
+			// empty <=> the reference returns a null collider
+			std::vector<std::vector<Chunk::Box>> BuildBoxColliders(const std::vector<ChunkIndices>& chunks)
+			{
+				std::vector<std::vector<Chunk::Box>> out(chunks.size());
+				if (chunks.empty())
+					return out;
+				std::vector<tsom_box_view> views(chunks.size());
+				std::uint64_t total = 0;
+				Device::Lock lock(*m_device);
+				Check(tsom_box_colliders(m_container, &chunks[0].x, std::uint32_t(chunks.size()), views.data(), &total), "tsom_box_colliders");
+				std::vector<float> raw(std::size_t(total) * 6);
+				if (total)
+					Check(tsom_box_colliders_copy_to_host(m_device->Handle(), 0, total, raw.data()), "tsom_box_colliders_copy_to_host");
+				for (std::size_t i = 0; i < chunks.size(); ++i)
+				{
+					out[i].resize(views[i].box_count);
+					for (std::uint32_t k = 0; k < views[i].box_count; ++k)
+					{
+						const float* b = raw.data() + (views[i].first_box + k) * 6;
+						out[i][k].position = Vector3f(b[0], b[1], b[2]) * m_tileSize;
+						out[i][k].size = Vector3f(b[3], b[4], b[5]) * m_tileSize;
+					}
+				}
+				return out;
 			}
 
 			tsom_container* Handle() const { return m_container; }
@@ -565,6 +602,199 @@ namespace tsom_b200
 
 			float m_cornerRadius;
 			float m_gravity;
+	};
+
+	// ------------------------------------------------------------------------------------------------ Ship
+	// Ship (include/CommonLib/Ship.hpp, src/CommonLib/Ship.cpp): the reference's second ChunkContainer.  Its block edits raise the
+	// neighbour mask of Ship.cpp:36-54 (local z == 0 -> Direction::Up, z == 31 -> Direction::Down: the opposite of Planet's), its
+	// physics body is the compound of its chunks' box colliders.
+	class Ship : public ChunkContainer
+	{
+		public:
+			Ship(Device& device, float tileSize, std::uint32_t capacityChunks = 8) : ChunkContainer(device, tileSize, capacityChunks)
+			{
+				Check(tsom_container_set_kind(m_container, TSOM_CONTAINER_SHIP), "tsom_container_set_kind");
+			}
+
+			// Ship::AddChunk (Ship.cpp:21-61)
+			Chunk AddChunk(const BlockLibrary& /*blockLibrary*/, const ChunkIndices& indices, const std::function<void(BlockIndex* blocks)>& initCallback = nullptr)
+			{
+				const std::int32_t idx[3] = { indices.x, indices.y, indices.z };
+				if (initCallback)
+				{
+					std::vector<BlockIndex> blocks(TSOM_CHUNK_BLOCKS, EmptyBlockIndex);
+					initCallback(blocks.data());
+					Check(tsom_chunks_reset(m_container, idx, 1, blocks.data()), "tsom_chunks_reset");
+				}
+				else
+					Check(tsom_container_add_chunks(m_container, idx, 1), "tsom_container_add_chunks");
+				if (std::find(m_chunks.begin(), m_chunks.end(), indices) == m_chunks.end())
+					m_chunks.push_back(indices);
+				return Chunk(*this, indices);
+			}
+
+			void RemoveChunk(const ChunkIndices& indices) // Ship.cpp:154-161
+			{
+				ChunkContainer::RemoveChunk(indices);
+				m_chunks.erase(std::remove(m_chunks.begin(), m_chunks.end(), indices), m_chunks.end());
+			}
+
+			// Ship::Generate (Ship.cpp:115-152)
+			void Generate(const BlockLibrary& blockLibrary, bool small)
+			{
+				if (std::find(m_chunks.begin(), m_chunks.end(), ChunkIndices(0, 0, 0)) == m_chunks.end())
+					AddChunk(blockLibrary, ChunkIndices(0, 0, 0));
+				const BlockIndex hull = blockLibrary.GetBlockIndex("hull");
+				if (hull == InvalidBlockIndex)
+					return;
+				Check(tsom_ship_generate(m_container, small ? 1 : 0, hull, blockLibrary.GetBlockIndex("forcefield")), "tsom_ship_generate");
+			}
+
+			// Ship::BuildHullCollider (Ship.cpp:63-93): one child per chunk that has a collider — its boxes and GetChunkOffset — built by
+			// ONE batched call; an empty result <=> nullptr.  (With a single chunk the reference returns that chunk's compound itself:
+			// the one child here, offset zero.)
+			struct HullChild
+			{
+				Vector3f offset;
+				std::vector<Chunk::Box> boxes;
+			};
+			std::vector<HullChild> BuildHullCollider()
+			{
+				std::vector<HullChild> out;
+				std::vector<std::vector<Chunk::Box>> boxes = BuildBoxColliders(m_chunks);
+				for (std::size_t i = 0; i < m_chunks.size(); ++i)
+					if (!boxes[i].empty())
+						out.push_back(HullChild{ m_chunks.size() > 1 ? GetChunkOffset(m_chunks[i]) : Vector3f(0.f, 0.f, 0.f), std::move(boxes[i]) });
+				return out;
+			}
+
+		private:
+			std::vector<ChunkIndices> m_chunks; // insertion order (the reference iterates a hash map: no defined order)
+	};
+
+	// ------------------------------------------------------------------------------------------------ a planet over several GPUs
+	// tsom_planet_create_sharded: ONE process — what a TSOM server is (src/Server/main.cpp:24-62) — drives all GPUs.  The planet is
+	// cut into one box of chunks per GPU; generation, the halo exchange over NVLink and meshing run on all of them at once.  A chunk's
+	// mesh lives in the arenas of the GPU that owns it: ShardedMeshBatch::CopyChunk fetches it from there.
+	class ShardedPlanet;
+	class ShardedMeshBatch
+	{
+		public:
+			std::vector<tsom_mesh_view> views;
+			std::vector<std::uint32_t> parts;
+
+			std::uint32_t FaceCount(std::size_t i) const { return views[i].face_count; }
+			void CopyChunk(std::size_t i, std::vector<VertexStruct>* vertices, std::vector<std::uint32_t>* indices, std::vector<Vector3f>* colliderPositions) const
+			{
+				const tsom_mesh_view& v = views[i];
+				if (vertices)
+					vertices->resize(std::size_t(v.face_count) * 4);
+				if (indices)
+					indices->resize(std::size_t(v.face_count) * 6);
+				if (colliderPositions)
+					colliderPositions->resize(std::size_t(v.face_count) * 4);
+				if (v.face_count == 0)
+					return;
+				Check(tsom_sharded_mesh_copy_to_host(m_planet, parts[i], v.first_face, v.face_count, vertices ? vertices->data() : nullptr, indices ? indices->data() : nullptr,
+				                                     colliderPositions ? &colliderPositions->data()->x : nullptr), "tsom_sharded_mesh_copy_to_host");
+			}
+
+		private:
+			friend class ShardedPlanet;
+			tsom_sharded_planet* m_planet = nullptr;
+	};
+
+	class ShardedPlanet
+	{
+		public:
+			ShardedPlanet(const BlockLibrary& blockLibrary, const std::vector<int>& cudaDevices, const Vector3ui& chunkCount, float tileSize) : m_chunkCount(chunkCount), m_tileSize(tileSize)
+			{
+				const std::uint32_t cc[3] = { chunkCount.x, chunkCount.y, chunkCount.z };
+				Check(tsom_planet_create_sharded(cudaDevices.data(), std::uint32_t(cudaDevices.size()), cc, tileSize, nullptr, &m_planet), "tsom_planet_create_sharded");
+				auto descs = blockLibrary.ToDescs();
+				Check(tsom_sharded_set_block_table(m_planet, descs.data(), std::uint32_t(descs.size())), "tsom_sharded_set_block_table");
+			}
+			ShardedPlanet(const ShardedPlanet&) = delete;
+			ShardedPlanet& operator=(const ShardedPlanet&) = delete;
+			~ShardedPlanet() { tsom_sharded_destroy(m_planet); }
+
+			std::uint32_t GetPartCount() const { return tsom_sharded_part_count(m_planet); }
+			std::uint32_t GetOwner(const ChunkIndices& indices) const
+			{
+				std::uint32_t part = 0;
+				Check(tsom_sharded_owner(m_planet, &indices.x, &part), "tsom_sharded_owner");
+				return part;
+			}
+			Vector3f GetChunkOffset(const ChunkIndices& indices) const { return Vector3f(float(indices.x), float(indices.y), float(indices.z)) * float(ChunkContainer::ChunkSize) * m_tileSize; }
+
+			// Planet::GenerateChunks (Planet.cpp:385-403) on all GPUs + one halo exchange round
+			void GenerateChunks(const BlockLibrary& lib, std::uint32_t seed)
+			{
+				tsom_gen_blocks ids;
+				ids.dirt = lib.GetBlockIndex("dirt");
+				ids.grass = lib.GetBlockIndex("grass");
+				ids.stone = lib.GetBlockIndex("stone");
+				ids.stone_mossy = lib.GetBlockIndex("stone_mossy");
+				ids.snow = lib.GetBlockIndex("snow");
+				Check(tsom_sharded_generate(m_planet, seed, &ids), "tsom_sharded_generate");
+			}
+
+			void UpdateBlocks(const std::vector<ChunkContainer::BlockUpdate>& updates)
+			{
+				std::vector<tsom_edit> edits(updates.size());
+				for (std::size_t i = 0; i < updates.size(); ++i)
+				{
+					edits[i] = tsom_edit{};
+					edits[i].chunk[0] = updates[i].chunk.x;
+					edits[i].chunk[1] = updates[i].chunk.y;
+					edits[i].chunk[2] = updates[i].chunk.z;
+					edits[i].x = std::uint8_t(updates[i].indices.x);
+					edits[i].y = std::uint8_t(updates[i].indices.y);
+					edits[i].z = std::uint8_t(updates[i].indices.z);
+					edits[i].block = updates[i].cellType;
+				}
+				Check(tsom_sharded_apply_edits(m_planet, edits.data(), std::uint32_t(edits.size())), "tsom_sharded_apply_edits");
+			}
+
+			std::vector<ChunkIndices> CollectInvalidatedChunks()
+			{
+				std::uint32_t n = 0;
+				Check(tsom_sharded_collect_dirty(m_planet, nullptr, 0, &n, 0), "tsom_sharded_collect_dirty");
+				std::vector<ChunkIndices> out(n);
+				Check(tsom_sharded_collect_dirty(m_planet, n ? &out[0].x : nullptr, n, &n, 1), "tsom_sharded_collect_dirty");
+				return out;
+			}
+
+			// Chunk::BuildMesh for `chunks`, each on the GPU that owns it (all GPUs at once)
+			ShardedMeshBatch BuildMeshes(const std::vector<ChunkIndices>& chunks, const MeshOptions& opt = MeshOptions())
+			{
+				ShardedMeshBatch batch;
+				batch.m_planet = m_planet;
+				batch.views.resize(chunks.size());
+				batch.parts.resize(chunks.size());
+				tsom_mesh_params p{};
+				p.flags = (opt.render ? std::uint32_t(TSOM_MESH_RENDER) : 0u) | (opt.collider ? std::uint32_t(TSOM_MESH_COLLIDER) : 0u) | (opt.corners == CornerMode::Deformed ? std::uint32_t(TSOM_MESH_DEFORMED) : 0u) |
+				          (opt.tangents ? std::uint32_t(TSOM_MESH_TANGENTS) : 0u);
+				p.deform_radius = opt.deformRadius;
+				p.gravity_centers = opt.gravityCenters ? &opt.gravityCenters->x : nullptr;
+				if (!chunks.empty())
+					Check(tsom_sharded_mesh(m_planet, &chunks[0].x, std::uint32_t(chunks.size()), &p, batch.views.data(), batch.parts.data()), "tsom_sharded_mesh");
+				return batch;
+			}
+
+			std::vector<BlockIndex> GetContent(const ChunkIndices& indices) const
+			{
+				std::vector<BlockIndex> out(TSOM_CHUNK_BLOCKS);
+				Check(tsom_sharded_get_content(m_planet, &indices.x, 1, out.data()), "tsom_sharded_get_content");
+				return out;
+			}
+
+			tsom_sharded_planet* Handle() const { return m_planet; }
+
+		private:
+			tsom_sharded_planet* m_planet = nullptr;
+			Vector3ui m_chunkCount;
+			float m_tileSize;
 	};
 
 	// ------------------------------------------------------------------------------------------------ ChunkEntities

@@ -53,6 +53,7 @@ FILL_P = 0.5
 STONE = 7
 NBLK = 32768
 MICRO_CHUNKS = 4096
+CHUNKS_PER_GPU = MICRO_CHUNKS  # config[1] (tests/test_gpu_fullsize.py checks the microbench workload at full size)
 FACE_BYTES = 216  # 4 x 48 B vertices + 6 x 4 B indices
 METRIC = "chunks_generated_and_meshed_per_sec"
 
@@ -329,8 +330,9 @@ def run_b200(args):
     faces_total = allsum(faces_local)
 
     # ---- ramp the clocks (a fresh box reads ~5 % low for its first second), then exactly W warm-up steps, then exactly K timed steps
+    # (the ranks agree on when the ramp ends: a step is collective, every rank must run the same number of them)
     ramp_steps, t_ramp = 0, time.perf_counter()
-    while time.perf_counter() - t_ramp < args.ramp_seconds:
+    while allmax(1.0 if time.perf_counter() - t_ramp < args.ramp_seconds else 0.0) > 0.0:
         step()
         ramp_steps += 1
     for _ in range(args.warmup):

@@ -320,9 +320,13 @@ int tsom_peer_attach_local(tsom_container* c, int rank, tsom_container* peer);
  * pulled round r, so a fast GPU cannot overwrite slabs a slower one is still reading.  Nothing may write between a container's
  * publish and its pull.  Containers that share one context (one stream) must be driven publish-all, then pull-all.
  * tsom_mesh fails with TSOM_ERR_INVALID while a remote neighbour's slab has never been pulled (topology changed since the last pull).
- * A peer that does not arrive within 5 s makes the next blocking call on the context fail with TSOM_ERR_INTERNAL. */
+ * Peers attached with tsom_peer_attach_local (same process) are waited for with CUDA events whenever their publish / pull has already
+ * been enqueued by the host — publish-all, then pull-all guarantees it — so that path never polls; peers in other processes are polled.
+ * A polled peer that does not arrive within the time-out (5 s unless tsom_halo_set_timeout changed it) makes the next blocking call on
+ * the context fail with TSOM_ERR_INTERNAL instead of hanging the GPU. */
 int tsom_halo_publish(tsom_container* c);
 int tsom_halo_pull(tsom_container* c);
+int tsom_halo_set_timeout(tsom_container* c, uint32_t milliseconds);
 
 /* ---- one planet over several GPUs of ONE process (tsom_create(gpu_ids, n)) ----
  * Owns one context + container per part.  cuda_devices may name a device more than once (two parts on one GPU: what the

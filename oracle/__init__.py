@@ -102,6 +102,7 @@ def _bind(path: str, full: bool):
     L.orc_bench_mesh_isolated.argtypes = [u16p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_bench_mesh_isolated.restype = C.c_double
     L.orc_bench_planet.argtypes = [C.c_uint32, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), u32p]
+    L.orc_generate_tangents.argtypes = [f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p]
     L.orc_sample_create.argtypes = [C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_int]
     L.orc_sample_create.restype = C.c_void_p
     L.orc_sample_size.argtypes = [C.c_void_p]
@@ -418,6 +419,17 @@ def bench_box_colliders(planet: "Planet", chunk_count, nthreads, stride=1, L=Non
     chunks = C.c_uint32(0)
     t = planet._L.orc_bench_box_colliders(planet._h, _p(_u3(chunk_count), C.c_uint32), int(stride), int(nthreads), C.byref(boxes), C.byref(chunks))
     return float(t), int(boxes.value), int(chunks.value)
+
+
+def generate_tangents(mesh: "Mesh", L=None) -> np.ndarray:
+    """Nz::SubMesh::GenerateTangents on a chunk mesh (ClientChunkEntities.cpp:169; restated in oracle/nazara_tangents.hpp, unpinned
+    third-party arithmetic) -> [4F, 3] float32."""
+    pos = np.ascontiguousarray(mesh.position, np.float32)
+    uvw = np.ascontiguousarray(mesh.uvw, np.float32)
+    ind = np.ascontiguousarray(mesh.indices, np.uint32)
+    out = np.zeros_like(pos)
+    (L or lib()).orc_generate_tangents(_p(pos, C.c_float), _p(uvw, C.c_float), _p(ind, C.c_uint32), len(pos), len(ind), _p(out, C.c_float))
+    return out
 
 
 def perlin_noise3d_perm(perm, x: float, y: float, z: float) -> float:

@@ -3,6 +3,7 @@
 #include "tsom_oracle.hpp"
 #include "lz4_block.hpp"
 
+#include "nazara_tangents.hpp"
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -599,5 +600,11 @@ extern "C"
 			o[6] = boxes[i].lengths.x; o[7] = boxes[i].lengths.y; o[8] = boxes[i].lengths.z;
 		}
 		return std::uint32_t(boxes.size());
+	}
+
+	// Nz::SubMesh::GenerateTangents (ClientChunkEntities.cpp:169): restated in oracle/nazara_tangents.hpp, unpinned third-party arithmetic
+	void orc_generate_tangents(const float* pos, const float* uvw, const std::uint32_t* indices, std::uint32_t vertexCount, std::uint32_t indexCount, float* tangentsOut)
+	{
+		nazara_tangents::Generate(pos, uvw, indices, vertexCount, indexCount, tangentsOut);
 	}
 }

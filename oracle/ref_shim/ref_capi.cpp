@@ -15,6 +15,7 @@
 #include <Nazara/Core/ByteStream.hpp>
 #include <Nazara/Core/TaskScheduler.hpp>
 
+#include "../nazara_tangents.hpp"
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -681,5 +682,11 @@ extern "C"
 				emit(Nz::Vector3f::Zero(), child);
 		}
 		return n;
+	}
+
+	// Nz::SubMesh::GenerateTangents (ClientChunkEntities.cpp:169): restated in oracle/nazara_tangents.hpp, unpinned third-party arithmetic
+	void orc_generate_tangents(const float* pos, const float* uvw, const std::uint32_t* indices, std::uint32_t vertexCount, std::uint32_t indexCount, float* tangentsOut)
+	{
+		nazara_tangents::Generate(pos, uvw, indices, vertexCount, indexCount, tangentsOut);
 	}
 }

@@ -124,7 +124,7 @@ def test_sharded_edit_ticks_match_the_oracle():
 
 def test_mesh_refuses_unpulled_ghosts_and_exchange_times_out(ctx):
     """tsom_mesh must not cull against a remote slab that was never pulled, and a peer that never publishes shows up as
-    TSOM_ERR_INTERNAL after the 5 s device-side time-out instead of hanging the GPU."""
+    TSOM_ERR_INTERNAL after the device-side time-out (200 ms here, 5 s by default) instead of hanging the GPU."""
     import ctypes as C
 
     import thisspaceofmine_b200 as T
@@ -148,7 +148,8 @@ def test_mesh_refuses_unpulled_ghosts_and_exchange_times_out(ctx):
         b.PublishHalo()
         a.PullHalos()
         assert a.BuildMeshes(ia).face_counts.tolist() == [5 * 1024]
-        # next round: b never publishes -> a's pull gives up after 5 s and the next blocking call reports it
+        # next round: b never publishes -> a's pull polls b's flag, gives up after the time-out and the next blocking call reports it
+        L.check(L.lib().tsom_halo_set_timeout(a._h, 200))
         a.PullHalos()
         with pytest.raises(T.TsomError) as e:
             a.BuildMeshes(ia)

@@ -106,6 +106,7 @@ SYMBOLS = {
     "tsom_peer_attach_local": (C.c_int, [_vp, C.c_int, _vp]),
     "tsom_halo_publish": (C.c_int, [_vp]),
     "tsom_halo_pull": (C.c_int, [_vp]),
+    "tsom_halo_set_timeout": (C.c_int, [_vp, C.c_uint32]),
     "tsom_box_colliders": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(BoxView), C.POINTER(C.c_uint64)]),
     "tsom_box_colliders_copy_to_host": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _f32p]),
     "tsom_container_set_kind": (C.c_int, [_vp, C.c_int]),

@@ -180,15 +180,46 @@ namespace tsomk
 		float slice;
 	};
 
-	// 4 vertices as 12 float4 {px py pz nx | ny nz u v | w 0 0 0}; the tangent slot stays zero (never written by Chunk::BuildMesh)
-	__device__ __forceinline__ void store_face(float4* out, const FaceOut& f)
+	// Nz::SubMesh::GenerateTangents as ClientChunkEntities::BuildMesh runs it after Chunk::BuildMesh (ClientChunkEntities.cpp:169), for
+	// one face.  NazaraEngine is not in the reference tree: this restates the engine's algorithm (UNPINNED third-party arithmetic, single
+	// CPU statement in oracle/nazara_tangents.hpp): every triangle adds coef * (dv0 * duv1.y - dv1 * duv0.y), coef = 1 / (duv0.x * duv1.y -
+	// duv1.x * duv0.y), to its three vertices, then every vertex tangent is normalised.  A face owns its 4 vertices and its two triangles
+	// (0, 2, 1) and (1, 2, 3) (Chunk.cpp:95-101), so the sums close inside the face: v0 <- A, v1 and v2 <- A + B, v3 <- B.
+	__device__ __forceinline__ F3 triangle_tangent(const F3& p0, const F3& p1, const F3& p2, float u0, float v0, float u1, float v1, float u2, float v2)
 	{
+		const F3 dv0 = p1 - p0, dv1 = p2 - p0;
+		const float du0 = u1 - u0, dw0 = v1 - v0, du1 = u2 - u0, dw1 = v2 - v0;
+		const float coef = 1.f / (du0 * dw1 - du1 * dw0);
+		return f3(coef * (dv0.x * dw1 + dv1.x * (-dw0)), coef * (dv0.y * dw1 + dv1.y * (-dw0)), coef * (dv0.z * dw1 + dv1.z * (-dw0)));
+	}
+
+	__device__ __forceinline__ void face_tangents(const FaceOut& f, F3 t[4])
+	{
+		const F3 tA = triangle_tangent(f.pos[0], f.pos[2], f.pos[1], f.u[0], f.v[0], f.u[2], f.v[2], f.u[1], f.v[1]);
+		const F3 tB = triangle_tangent(f.pos[1], f.pos[2], f.pos[3], f.u[1], f.v[1], f.u[2], f.v[2], f.u[3], f.v[3]);
+		const F3 zero = f3(0.f, 0.f, 0.f);
+		t[0] = normalize(zero + tA);
+		t[1] = normalize((zero + tA) + tB);
+		t[2] = normalize((zero + tA) + tB);
+		t[3] = normalize(zero + tB);
+	}
+
+	// 4 vertices as 12 float4 {px py pz nx | ny nz u v | w tx ty tz}; the tangent slot stays zero (Chunk::BuildMesh never writes it)
+	// unless the caller asked for what GenerateTangents adds afterwards
+	__device__ __forceinline__ void store_face(float4* out, const FaceOut& f, bool wantTangents)
+	{
+		F3 t[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			t[i] = f3(0.f, 0.f, 0.f);
+		if (wantTangents)
+			face_tangents(f, t);
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 		{
 			out[i * 3 + 0] = make_float4(f.pos[i].x, f.pos[i].y, f.pos[i].z, f.n.x);
 			out[i * 3 + 1] = make_float4(f.n.y, f.n.z, f.u[i], f.v[i]);
-			out[i * 3 + 2] = make_float4(f.slice, 0.f, 0.f, 0.f);
+			out[i * 3 + 2] = make_float4(f.slice, t[i].x, t[i].y, t[i].z);
 		}
 	}
 
@@ -198,6 +229,31 @@ namespace tsomk
 		F3 blockCenter, fc;
 		face_geometry(cx, x, y, z, slot, twin, blockCenter, o.pos, fc);
 
+		o.n = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			o.u[i] = o.v[i] = 0.f;
+		o.slice = 0.f;
+		if (cx.wantAttr)
+		{
+			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
+			int texDir;
+			face_attrs(a.quat, faceUp, blockCenter, o.pos, fc, o.n, texDir, o.u, o.v);
+			o.slice = float(tex_slice(a, id, texDir));
+		}
+	}
+
+	// DrawFace with the block's geometry already known: the four quad corners (in emission order) and the block centre
+	__device__ __forceinline__ void draw_face_cached(const MeshArgs& a, const FaceCtx& cx, const F3& blockCenter, const F3 pos[4], unsigned id, FaceOut& o)
+	{
+		F3 fc = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			o.pos[i] = pos[i];
+			fc = fc + pos[i];
+		}
+		fc = fc / 4.f;
 		o.n = f3(0.f, 0.f, 0.f);
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
@@ -618,9 +674,12 @@ namespace tsomk
 
 	// Build the faces of the window [w0, w0 + nw) from their descriptors, one per lane, and stream them out through the warp's 16-face
 	// staging tile with coalesced 16-byte stores (vertices, collider positions, indices).
-	template<class B>
+	// LEAN: the table-driven flat path without tangents, compiled without the generic corner / attribute / tangent code (the
+	// instantiation a planet remesh runs; the other one carries everything else)
+	template<bool LEAN, class B>
 	__device__ __forceinline__ void store_window(const MeshArgs& a, const B& sm, const FaceTable& table, bool fastFlat, const FaceCtx& cx, uint32_t w0, uint32_t nw, uint32_t kA,
-	                                             const uint16_t* desc, float4* stage, unsigned long long firstFace, const LaneConst& lc, bool wantRender, bool wantCollider, int lane)
+	                                             const uint16_t* desc, float4* stage, unsigned long long firstFace, const LaneConst& lc, bool wantRender, bool wantCollider, bool wantTangents,
+	                                             int lane)
 	{
 		// ---- build one face per lane, stream out through the 16-face staging tile
 		const uint32_t nTiles = (nw + 31u) >> 5;
@@ -630,18 +689,89 @@ namespace tsomk
 			const uint32_t nf = min(32u, nw - tt * 32u);
 			const bool valid = f < nw;
 			FaceOut fo;
+			uint32_t row = 0u;
+			int x = 0, s = 0;
+			bool twin = false;
 			if (valid)
 			{
 				const uint32_t de = desc[f];
-				const uint32_t row = sm.ne[kA + (de >> 9)] >> NE_ROW_SHIFT;
-				const int x = int(de & 31u), y = int(row & 31u), z = int(row >> 5);
-				const int s = int((de >> 5) & 7u);
-				const bool twin = ((de >> 8) & 1u) != 0u;
-				const unsigned id = sm.ids[row * CS + x];
-				if (fastFlat)
-					draw_face_flat_r(a, cx, table, x, y, z, s, twin, id, fo);
-				else
-					draw_face_r(a, cx, x, y, z, s, twin, id, fo);
+				row = sm.ne[kA + (de >> 9)] >> NE_ROW_SHIFT;
+				x = int(de & 31u);
+				s = int((de >> 5) & 7u);
+				twin = ((de >> 8) & 1u) != 0u;
+			}
+			if (LEAN || fastFlat)
+			{
+				if (valid)
+					draw_face_flat_r(a, cx, table, x, int(row & 31u), int(row >> 5), s, twin, sm.ids[row * CS + x], fo);
+			}
+			else
+			{
+				// Generic corner providers (DeformedChunk: a normalisation per corner): the 8 corners and the centre of a block are the
+				// same for all of its faces (up to 12), and the faces of a block are neighbours in the emission order.  The warp finds
+				// the distinct blocks of the tile, spreads their 8 * nBlocks corner evaluations over its 32 lanes and shares the
+				// results through the staging tile, which is idle at this point: [0, 32) block keys, then 9 F3 per block (8 corners by
+				// code dX | dY << 1 | dZ << 2, centre), 16 blocks per round.
+				constexpr uint32_t FULLM = 0xffffffffu;
+				uint32_t* keys = reinterpret_cast<uint32_t*>(stage);
+				float* cache = reinterpret_cast<float*>(stage) + 32;
+				const uint32_t key = valid ? ((row << 5) | uint32_t(x)) : 0xFFFFFFFFu;
+				const uint32_t prev = __shfl_up_sync(FULLM, key, 1);
+				const bool leader = valid && (lane == 0 || key != prev);
+				const uint32_t leaders = __ballot_sync(FULLM, leader);
+				const uint32_t nBlocks = __popc(leaders);
+				const uint32_t myBlock = __popc(leaders & (0xFFFFFFFFu >> (31 - lane))) - 1u; // ordinal of this lane's block in the tile
+				if (leader)
+					keys[myBlock] = key;
+				__syncwarp();
+				F3 pos[4], blockCenter = f3(0.f, 0.f, 0.f);
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					pos[i] = f3(0.f, 0.f, 0.f);
+				for (uint32_t b0 = 0; b0 < nBlocks; b0 += 16u)
+				{
+					const uint32_t nb = min(16u, nBlocks - b0);
+					for (uint32_t e = uint32_t(lane); e < nb * 8u; e += 32u)
+					{
+						const uint32_t k = keys[b0 + (e >> 3)];
+						const F3 c = voxel_corner(cx, int(k & 31u), int((k >> 5) & 31u), int(k >> 10), e & 7u);
+						float* dst = cache + ((e >> 3) * 9u + (e & 7u)) * 3u;
+						dst[0] = c.x;
+						dst[1] = c.y;
+						dst[2] = c.z;
+					}
+					__syncwarp();
+					if (uint32_t(lane) < nb)
+					{
+						// block centre: the 8 corners summed in the enum order of Nz::BoxCorner (codes 4, 5, 0, 1, 6, 7, 2, 3), / 8 (Chunk.cpp:186-188)
+						const float* cb = cache + uint32_t(lane) * 27u;
+						F3 sum = f3(0.f, 0.f, 0.f);
+						constexpr int order[8] = { 4, 5, 0, 1, 6, 7, 2, 3 };
+#pragma unroll
+						for (int q = 0; q < 8; ++q)
+							sum = sum + f3(cb[order[q] * 3 + 0], cb[order[q] * 3 + 1], cb[order[q] * 3 + 2]);
+						sum = sum / 8.f;
+						float* dst = cache + (uint32_t(lane) * 9u + 8u) * 3u;
+						dst[0] = sum.x;
+						dst[1] = sum.y;
+						dst[2] = sum.z;
+					}
+					__syncwarp();
+					if (valid && myBlock >= b0 && myBlock < b0 + nb)
+					{
+						const float* cb = cache + (myBlock - b0) * 27u;
+						blockCenter = f3(cb[24], cb[25], cb[26]);
+#pragma unroll
+						for (int i = 0; i < 4; ++i)
+						{
+							const unsigned code = c_faceCorners[s][twin ? (i ^ 1) : i];
+							pos[i] = f3(cb[code * 3 + 0], cb[code * 3 + 1], cb[code * 3 + 2]);
+						}
+					}
+					__syncwarp();
+				}
+				if (valid)
+					draw_face_cached(a, cx, blockCenter, pos, sm.ids[row * CS + x], fo);
 			}
 			const unsigned long long face0 = firstFace + w0 + tt * 32u;
 #pragma unroll
@@ -651,7 +781,7 @@ namespace tsomk
 					break;
 				const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
 				if (valid && (uint32_t(lane) >> 4) == h)
-					store_face(stage + (lane & 15) * STAGE_FACE_F4, fo);
+					store_face(stage + (lane & 15) * STAGE_FACE_F4, fo, !LEAN && wantTangents);
 				__syncwarp();
 				const unsigned long long faceH = face0 + h * HALF_FACES;
 				if (wantRender)
@@ -786,6 +916,7 @@ namespace tsomk
 		sm.job = j;
 	}
 
+	template<bool LEAN>
 	__global__ void __launch_bounds__(FUSED_THREADS, 2) mesh_fused_kernel(const MeshArgs a)
 	{
 		extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -813,6 +944,7 @@ namespace tsomk
 		const LaneConst lc = lane_constants(lane);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
+		const bool wantTangents = (a.flags & MESH_F_TANGENTS) != 0;
 		const bool ordered = (a.flags & MESH_F_ORDERED) != 0; // arena slices in job order (look-back) instead of first come, first served
 		__syncthreads();
 
@@ -979,7 +1111,7 @@ namespace tsomk
 					if (firstFace + F > a.arenaFaces)
 						break; // arena too small: this launch only counts (the host grows the arena and runs the kernel again)
 
-					store_window(a, sm, sm.table, fastFlat, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, lane);
+					store_window<LEAN>(a, sm, sm.table, fastFlat, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, wantTangents, lane);
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}
@@ -1191,14 +1323,20 @@ namespace tsomk
 
 	cudaError_t mesh_kernels_init()
 	{
-		cudaError_t e = cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)));
-		if (e != cudaSuccess)
+		cudaError_t e;
+		if ((e = cudaFuncSetAttribute(mesh_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)))) != cudaSuccess ||
+		    (e = cudaFuncSetAttribute(mesh_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess ||
+		    (e = cudaFuncSetAttribute(mesh_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)))) != cudaSuccess)
 			return e;
-		return cudaFuncSetAttribute(mesh_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+		return cudaFuncSetAttribute(mesh_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 	}
 
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st)
 	{
-		mesh_fused_kernel<<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+		// the lean instantiation: table-driven flat path, no tangents
+		if (a.faceTable != nullptr && !(a.flags & MESH_F_TANGENTS))
+			mesh_fused_kernel<true><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+		else
+			mesh_fused_kernel<false><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
 	}
 }

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -386,6 +387,7 @@ struct tsom_container
 		const uint16_t* xslabs = nullptr;
 		const uint32_t* sync = nullptr;
 		bool ipc = false;
+		tsom_container* local = nullptr; // same-process peer: ordered with CUDA events instead of polling its flags
 	};
 	std::map<int, Peer> peers;
 	DevBuf<uint16_t> ghostSlabs;
@@ -407,6 +409,11 @@ struct tsom_container
 	bool ghostsStale = false; // a ghost slab exists that was never pulled: tsom_mesh refuses until the next tsom_halo_pull
 
 	// device-side ordering of the exchange (see tsom_halo_pull in tsom_b200.h)
+	// Peers in other processes poll the epoch flags in dSync over NVLink.  Peers in THIS process wait on the events below instead
+	// (cudaStreamWaitEvent): nothing then depends on two kernels of different streams being resident at the same time.
+	cudaEvent_t evGen = nullptr, evPull = nullptr;       // recorded behind the blocks-final / slabs-pulled flag writes
+	std::atomic<uint32_t> evGenEpoch{ 0 }, evPullEpoch{ 0 }; // round of the last record, as enqueued by the host
+	uint32_t exchangeTimeoutMs = 5000;
 	uint32_t epoch = 0, pulledEpoch = 0;
 	bool published = false, dirtySincePublish = false, needWriteWait = false;
 	DevBuf<const uint32_t*> peerGenFlags, peerPullFlags;
@@ -656,21 +663,20 @@ namespace
 	}
 
 	// ---- device-side ordering of the halo exchange (tsom_halo_publish / tsom_halo_pull, see tsom_b200.h)
-	constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 5ull * 1000ull * 1000ull * 1000ull;
 
 	int SyncPeerFlags(tsom_container* c)
 	{
 		if (!c->peerFlagsDirty)
 			return TSOM_OK;
-		const size_t np = c->peers.size();
+		std::vector<const uint32_t*> gen, pull;
+		for (auto& [rank, p] : c->peers)
+		{
+			gen.push_back(p.sync + 0);
+			pull.push_back(p.sync + 1);
+		}
+		const size_t np = gen.size();
 		if (np)
 		{
-			std::vector<const uint32_t*> gen, pull;
-			for (auto& [rank, p] : c->peers)
-			{
-				gen.push_back(p.sync + 0);
-				pull.push_back(p.sync + 1);
-			}
 			TSOM_CUDA(c->peerGenFlags.Ensure(np));
 			TSOM_CUDA(c->peerPullFlags.Ensure(np));
 			TSOM_CUDA(cudaMemcpyAsync(c->peerGenFlags.ptr, gen.data(), np * sizeof(const uint32_t*), cudaMemcpyHostToDevice, c->ctx->stream));
@@ -678,6 +684,40 @@ namespace
 			TSOM_CUDA(cudaStreamSynchronize(c->ctx->stream));
 		}
 		c->peerFlagsDirty = false;
+		return TSOM_OK;
+	}
+
+	// Make this container's stream wait until every peer has reached `round` of the flag at `which` (0 blocks-final, 1 slabs-pulled).
+	// A peer of this process whose host has already enqueued that round is waited for with its event; everybody else (peers in other
+	// processes, or a local peer that is behind on the host) through the polling kernel, which gives up after the time-out.
+	int WaitForPeers(tsom_container* c, int which, uint32_t round)
+	{
+		if (c->peers.empty())
+			return TSOM_OK;
+		tsom_ctx* ctx = c->ctx;
+		bool poll = false;
+		for (auto& [rank, p] : c->peers)
+		{
+			if (p.local)
+			{
+				const uint32_t done = which == 0 ? p.local->evGenEpoch.load() : p.local->evPullEpoch.load();
+				if (int32_t(done - round) >= 0)
+				{
+					TSOM_CUDA(cudaStreamWaitEvent(ctx->stream, which == 0 ? p.local->evGen : p.local->evPull, 0));
+					continue;
+				}
+			}
+			poll = true;
+		}
+		if (!poll)
+			return TSOM_OK;
+		int rc = SyncPeerFlags(c);
+		if (rc != TSOM_OK)
+			return rc;
+		// (a peer already waited for by event passes the poll at once: its flag write precedes its event)
+		tsomk::launch_flag_wait(which == 0 ? c->peerGenFlags.ptr : c->peerPullFlags.ptr, uint32_t(c->peers.size()), round, 1000000ull * c->exchangeTimeoutMs, ctx->dSmall + 8, ctx->stream);
+		ctx->launches += 1;
+		TSOM_CUDA(cudaGetLastError());
 		return TSOM_OK;
 	}
 
@@ -689,15 +729,8 @@ namespace
 		if (!c->needWriteWait)
 			return TSOM_OK;
 		c->needWriteWait = false;
-		if (c->peers.empty())
-			return TSOM_OK;
-		int rc = SyncPeerFlags(c);
-		if (rc != TSOM_OK)
-			return rc;
-		tsomk::launch_flag_wait(c->peerPullFlags.ptr, uint32_t(c->peers.size()), c->pulledEpoch, EXCHANGE_TIMEOUT_NS, c->ctx->dSmall + 8, c->ctx->stream);
-		c->ctx->launches += 1;
-		TSOM_CUDA(cudaGetLastError());
-		return TSOM_OK;
+		TSOM_CUDA(cudaSetDevice(c->ctx->device));
+		return WaitForPeers(c, 1, c->pulledEpoch);
 	}
 
 	// after a stream synchronisation that brought dSmall[8] to the host: did a wait kernel give up?
@@ -708,7 +741,7 @@ namespace
 		const uint32_t who = ctx->hSmall[8] - 1u;
 		ctx->hSmall[8] = 0u;
 		cudaMemsetAsync(ctx->dSmall + 8, 0, sizeof(uint32_t), ctx->stream);
-		return Fail(TSOM_ERR_INTERNAL, "halo exchange timed out: attached peer #" + std::to_string(who) + " did not publish / pull its round within 5 s");
+		return Fail(TSOM_ERR_INTERNAL, "halo exchange timed out: attached peer #" + std::to_string(who) + " did not publish / pull its round in time");
 	}
 
 	constexpr size_t ARENA_GUARD_BYTES = 256; // 0xA5 behind the last face of every arena, checked by tsom_debug_check_guards
@@ -1018,6 +1051,8 @@ extern "C"
 		TSOM_CUDA(cudaMemset(c->dInvalid, 0, maskBytes));
 		TSOM_CUDA(cudaMemset(c->dSummary, 0, maskBytes));
 		TSOM_CUDA(cudaMemset(c->dSync, 0, 64 * sizeof(uint32_t)));
+		TSOM_CUDA(cudaEventCreateWithFlags(&c->evGen, cudaEventDisableTiming));
+		TSOM_CUDA(cudaEventCreateWithFlags(&c->evPull, cudaEventDisableTiming));
 		c->summaryTableEpoch = ctx->tableEpoch;
 		c->idxOf.resize(capacity_chunks);
 		c->exists.assign(capacity_chunks, 0);
@@ -1051,6 +1086,10 @@ extern "C"
 		cudaFree(c->dSummary);
 		cudaFree(c->dNbr);
 		cudaFree(c->dSync);
+		if (c->evGen)
+			cudaEventDestroy(c->evGen);
+		if (c->evPull)
+			cudaEventDestroy(c->evPull);
 		cudaFree(c->dPerm);
 		if (c->hPerm)
 			cudaFreeHost(c->hPerm);
@@ -2501,6 +2540,7 @@ extern "C"
 		p.xslabs = peer->dXslabs;
 		p.sync = peer->dSync;
 		p.ipc = false;
+		p.local = peer;
 		c->peers[rank] = p;
 		c->peerFlagsDirty = true;
 		TopoChanged(c);
@@ -2516,8 +2556,19 @@ extern "C"
 		tsomk::launch_flag_publish(c->dSync + 0, c->epoch, ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(c->evGen, ctx->stream));
+		c->evGenEpoch.store(c->epoch);
 		c->published = true;
 		c->dirtySincePublish = false;
+		return TSOM_OK;
+	}
+
+	int tsom_halo_set_timeout(tsom_container* c, uint32_t milliseconds)
+	{
+		if (!c || milliseconds == 0)
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		TSOM_LOCK(c->ctx);
+		c->exchangeTimeoutMs = milliseconds;
 		return TSOM_OK;
 	}
 
@@ -2539,19 +2590,13 @@ extern "C"
 		int rc = SyncTopology(c);
 		if (rc != TSOM_OK)
 			return rc;
-		if ((rc = SyncPeerFlags(c)) != TSOM_OK)
-			return rc;
 		if (!c->published || c->dirtySincePublish)
 			if ((rc = HaloPublish(c)) != TSOM_OK)
 				return rc;
 		TSOM_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
-		if (!c->peers.empty())
-		{
-			// wait, on the device, until every peer's blocks are final for this round
-			tsomk::launch_flag_wait(c->peerGenFlags.ptr, uint32_t(c->peers.size()), c->epoch, EXCHANGE_TIMEOUT_NS, ctx->dSmall + 8, ctx->stream);
-			ctx->launches += 1;
-			TSOM_CUDA(cudaGetLastError());
-		}
+		// wait, on the device, until every peer's blocks are final for this round
+		if ((rc = WaitForPeers(c, 0, c->epoch)) != TSOM_OK)
+			return rc;
 		if (c->nGhost)
 		{
 			tsomk::launch_halo_pull(c->ghostDescs.ptr, c->nGhost, c->ghostSlabs.ptr, ctx->stream);
@@ -2561,6 +2606,8 @@ extern "C"
 		tsomk::launch_flag_publish(c->dSync + 1, c->epoch, ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
+		TSOM_CUDA(cudaEventRecord(c->evPull, ctx->stream));
+		c->evPullEpoch.store(c->epoch);
 		TSOM_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
 		ctx->pendingHalo = true;
 		c->pulledEpoch = c->epoch;
