@@ -142,25 +142,15 @@ namespace tsomk
 		for (int i = 0; i < 4; ++i)
 		{
 			F3 dir = quat_rotate(qw, qv, pos[i] - blockCenter);
-			float mag, uu, vv;
-			if (texDir == D_BACK || texDir == D_FRONT)
-			{
-				mag = 0.5f / fabsf(dir.x);
-				uu = dir.x < 0.f ? -dir.z : dir.z;
-				vv = -dir.y;
-			}
-			else if (texDir == D_DOWN || texDir == D_UP)
-			{
-				mag = 0.5f / fabsf(dir.y);
-				uu = dir.x;
-				vv = dir.y < 0.f ? -dir.z : dir.z;
-			}
-			else
-			{
-				mag = 0.5f / fabsf(dir.z);
-				uu = dir.z < 0.f ? dir.x : -dir.x;
-				vv = -dir.y;
-			}
+			// the three cases of Chunk.cpp:52-88 as selects (texDir differs from lane to lane: no divergent branches)
+			const bool zFace = texDir == D_BACK || texDir == D_FRONT, yFace = texDir == D_DOWN || texDir == D_UP;
+			const float major = zFace ? dir.x : (yFace ? dir.y : dir.z);
+			const float mag = 0.5f / fabsf(major);
+			const float uz = dir.x < 0.f ? -dir.z : dir.z;  // Back / Front
+			const float ux = dir.z < 0.f ? dir.x : -dir.x;  // Left / Right
+			const float vy = dir.y < 0.f ? -dir.z : dir.z;  // Down / Up
+			const float uu = zFace ? uz : (yFace ? dir.x : ux);
+			const float vv = yFace ? vy : -dir.y;
 			u[i] = uu * mag + 0.5f;
 			v[i] = vv * mag + 0.5f;
 		}
@@ -369,6 +359,8 @@ namespace tsomk
 		float4 stage[FUSED_WARPS][HALF_FACES * STAGE_FACE_F4];
 		uint16_t desc[FUSED_WARPS][WIN];  // x | slot << 5 | twin << 8 | (compact row - first compact row of the window) << 9
 		uint32_t lut32[LUTN];
+		// collider positions: output float4 i of a 16-face staging round (i < 48) = floats colOff[i].x .. .w of the staging tile
+		ushort4 colOff[HALF_FACES * 3];
 		alignas(16) FaceTable table;
 		uint32_t warpSum[FUSED_WARPS];
 		uint32_t job, slot, hasContent;   // the ticket and what it names (written by the lane that took the ticket)
@@ -810,15 +802,8 @@ namespace tsomk
 					const uint32_t n4 = nh * 3u;
 					for (uint32_t i = lane; i < n4; i += 32u)
 					{
-						const uint32_t face = i / 3u, j = i % 3u;
-						float e[4];
-#pragma unroll
-						for (int m = 0; m < 4; ++m)
-						{
-							const uint32_t q = j * 4u + m; // float q of the face's 12 position floats
-							e[m] = sf[face * (STAGE_FACE_F4 * 4) + (q / 3u) * 12u + (q % 3u)];
-						}
-						dst[i] = make_float4(e[0], e[1], e[2], e[3]);
+						const ushort4 o = sm.colOff[i];
+						dst[i] = make_float4(sf[o.x], sf[o.y], sf[o.z], sf[o.w]);
 					}
 				}
 				__syncwarp();
@@ -940,6 +925,19 @@ namespace tsomk
 			uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.table);
 			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += FUSED_THREADS)
 				dst[i] = src[i];
+		}
+		if (tid < HALF_FACES * 3)
+		{
+			// float q (0 .. 11) of a face's 12 position floats sits at vertex q / 3, component q % 3 of its 13-float4 staging slot
+			const uint32_t face = uint32_t(tid) / 3u, j = uint32_t(tid) % 3u;
+			unsigned short off[4];
+#pragma unroll
+			for (uint32_t m = 0; m < 4; ++m)
+			{
+				const uint32_t q = j * 4u + m;
+				off[m] = (unsigned short)(face * (STAGE_FACE_F4 * 4) + (q / 3u) * 12u + (q % 3u));
+			}
+			sm.colOff[tid] = make_ushort4(off[0], off[1], off[2], off[3]);
 		}
 		const LaneConst lc = lane_constants(lane);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;

@@ -373,6 +373,8 @@ struct tsom_container
 		int lo[3], hi[3], sumMin, sumMax;
 	} genPlan{};
 	DevBuf<uint16_t> templates;
+	std::vector<int32_t> planetIdx;          // chunk list of the last tsom_planet_generate (GenerateChunks order)
+	uint32_t planetIdxCount[3] = { 0, 0, 0 };
 
 	// remote neighbours (other ranks) and the ghost slabs that mirror their boundary layers
 	struct Remote
@@ -1653,17 +1655,25 @@ extern "C"
 		const uint64_t n = uint64_t(chunk_count[0]) * chunk_count[1] * chunk_count[2];
 		if (n == 0 || n > c->capacity)
 			return Fail(TSOM_ERR_CAPACITY, "chunk_count exceeds the container capacity");
-		std::vector<int32_t> idx;
-		idx.reserve(n * 3);
-		// Planet.cpp:387-393: z, y, x loops; indices = (x, y, z) - chunkCount / 2
-		for (int cz = 0; cz < int(chunk_count[2]); ++cz)
-			for (int cy = 0; cy < int(chunk_count[1]); ++cy)
-				for (int cx = 0; cx < int(chunk_count[0]); ++cx)
-				{
-					idx.push_back(cx - int(chunk_count[0] / 2));
-					idx.push_back(cy - int(chunk_count[1] / 2));
-					idx.push_back(cz - int(chunk_count[2] / 2));
-				}
+		// Planet.cpp:387-393: z, y, x loops; indices = (x, y, z) - chunkCount / 2 (the list is kept: a regenerate names the same chunks)
+		std::vector<int32_t>& idx = c->planetIdx;
+		{
+			TSOM_LOCK(c->ctx);
+			if (idx.size() != n * 3 || std::memcmp(c->planetIdxCount, chunk_count, sizeof(c->planetIdxCount)) != 0)
+			{
+				idx.clear();
+				idx.reserve(n * 3);
+				for (int cz = 0; cz < int(chunk_count[2]); ++cz)
+					for (int cy = 0; cy < int(chunk_count[1]); ++cy)
+						for (int cx = 0; cx < int(chunk_count[0]); ++cx)
+						{
+							idx.push_back(cx - int(chunk_count[0] / 2));
+							idx.push_back(cy - int(chunk_count[1] / 2));
+							idx.push_back(cz - int(chunk_count[2] / 2));
+						}
+				std::memcpy(c->planetIdxCount, chunk_count, sizeof(c->planetIdxCount));
+			}
+		}
 		return tsom_planet_generate_chunks(c, seed, chunk_count, ids, idx.data(), uint32_t(n));
 	}
 
