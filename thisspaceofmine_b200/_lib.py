@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libtsom_b200.so")
+SO_PATH = os.environ.get("TSOM_B200_SO") or os.path.join(_HERE, "libtsom_b200.so")  # the override is a development aid (kernel variants)
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CAPACITY, ERR_INTERNAL = range(7)
