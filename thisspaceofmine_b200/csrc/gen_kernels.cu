@@ -310,6 +310,71 @@ namespace tsomk
 		unsigned v[8];
 	};
 
+	// Per pass (order +X Right, -X Left, +Y Up, -Y Down, +Z Back, -Z Front): blockDepth of the chunk's reference layer and the global tile
+	// number of its 32 x 32 column tile (Planet.cpp:237,262,287,312,337,362)
+	struct PassGeom
+	{
+		int blockDepth[6];
+		size_t tileNo[6];
+	};
+
+	__device__ __forceinline__ PassGeom pass_geometry(const GenArgs& a, int cx, int cy, int cz)
+	{
+		const int wx0 = cx * CS - CS / 2, wy0 = cy * CS - CS / 2, wz0 = cz * CS - CS / 2;
+		const int Hx = a.maxH[0], Hy = a.maxH[1], Hz = a.maxH[2];
+		PassGeom g;
+		g.blockDepth[0] = Hx - wx0 + 1;
+		g.blockDepth[1] = Hx + (wx0 + CS - 1) + 1;
+		g.blockDepth[2] = Hy - wy0 + 1;
+		g.blockDepth[3] = Hy + (wy0 + CS - 1) + 1;
+		g.blockDepth[4] = Hz - wz0 + 1;
+		g.blockDepth[5] = Hz + (wz0 + CS - 1) + 1;
+		const int tx = cx - a.tileOrigin[0], ty = cy - a.tileOrigin[1], tz = cz - a.tileOrigin[2];
+		const size_t tYZ = size_t(tz) * a.tileCount[1] + ty; // (A = Y, B = Z)
+		const size_t tXZ = size_t(tz) * a.tileCount[0] + tx; // (A = X, B = Z)
+		const size_t tXY = size_t(ty) * a.tileCount[0] + tx; // (A = X, B = Y)
+		g.tileNo[0] = a.terrainOffset[D_RIGHT] / SLAB + tYZ;
+		g.tileNo[1] = a.terrainOffset[D_LEFT] / SLAB + tYZ;
+		g.tileNo[2] = a.terrainOffset[D_UP] / SLAB + tXZ;
+		g.tileNo[3] = a.terrainOffset[D_DOWN] / SLAB + tXZ;
+		g.tileNo[4] = a.terrainOffset[D_BACK] / SLAB + tXY;
+		g.tileNo[5] = a.terrainOffset[D_FRONT] / SLAB + tXY;
+		return g;
+	}
+
+	// One thread per job, between terrain_kernel and generate_kernel: everything generate_kernel's CTA would otherwise find through a
+	// chain of dependent global loads (job -> slot -> chunk index -> six tile ranges) in ONE 16-byte descriptor — chunk index, slot, and
+	// which of the six terrain passes can touch the chunk (some column has blockDepth >= terrainDepth and blockDepth - terrainDepth < 32).
+	constexpr uint32_t GEN_SLOT_MASK = 0x03FFFFFFu; // descriptor.w = slot | active passes << 26
+
+	__global__ void __launch_bounds__(256) gen_classify_kernel(const GenArgs a, int4* __restrict__ desc)
+	{
+		const uint32_t job = blockIdx.x * 256u + threadIdx.x;
+		if (job >= a.nJobs)
+			return;
+		const uint32_t slot = a.jobSlot[job];
+		const int4 ci = a.chunkIdx[slot];
+		const PassGeom g = pass_geometry(a, ci.x, ci.y, ci.z);
+		const int passDir[6] = { D_RIGHT, D_LEFT, D_UP, D_DOWN, D_BACK, D_FRONT };
+		uint32_t act = 0u;
+#pragma unroll
+		for (int p = 0; p < 6; ++p)
+		{
+			if (!((a.dirMask >> passDir[p]) & 1u))
+				continue; // no tables: the host proved that no chunk of this call reaches the terrain band from this side
+			const int tdMin = a.tileRange[g.tileNo[p] * 2], tdMax = a.tileRange[g.tileNo[p] * 2 + 1];
+			if (g.blockDepth[p] >= tdMin && g.blockDepth[p] - tdMax < CS)
+				act |= 1u << p;
+		}
+		desc[job] = make_int4(ci.x, ci.y, ci.z, int(slot | (act << 26)));
+	}
+
+	void launch_gen_classify(const GenArgs& a, int4* desc, cudaStream_t st)
+	{
+		if (a.nJobs)
+			gen_classify_kernel<<<(a.nJobs + 255u) / 256u, 256, 0, st>>>(a, desc);
+	}
+
 #ifndef GEN_OCC
 #define GEN_OCC 6 // 40 registers, 6 CTAs per SM: the per-chunk prologue is a chain of dependent global loads, more CTAs in flight hide it (47^3: 2.00 -> 1.87 ms)
 #endif
@@ -320,8 +385,9 @@ namespace tsomk
 		const uint32_t job = blockIdx.x;
 		if (job >= a.nJobs)
 			return;
-		const uint32_t slot = a.jobSlot[job];
-		const int4 ci = a.chunkIdx[slot];
+		const int4 ci = a.jobDesc[job]; // chunk index, slot | active passes << 26 (gen_classify_kernel)
+		const uint32_t slot = uint32_t(ci.w) & GEN_SLOT_MASK;
+		const uint32_t actBits = uint32_t(ci.w) >> 26;
 
 		// world coordinates of local (0,0,0): GetBlockIndices = chunk * 32 + (x, z, y) - 16
 		const int wx0 = ci.x * CS - CS / 2; // + local x
@@ -333,29 +399,13 @@ namespace tsomk
 		// pass order in sm.start: 0 +X(Right) 1 -X(Left) 2 +Y(Up) 3 -Y(Down) 4 +Z(Back) 5 -Z(Front)
 		bool act[6];
 		{
-			const int passDir[6] = { D_RIGHT, D_LEFT, D_UP, D_DOWN, D_BACK, D_FRONT };
-			const int blockDepth[6] = {
-				Hx - wx0 + 1, Hx + (wx0 + CS - 1) + 1,
-				Hy - wy0 + 1, Hy + (wy0 + CS - 1) + 1,
-				Hz - wz0 + 1, Hz + (wz0 + CS - 1) + 1,
-			};
-			const int tx = ci.x - a.tileOrigin[0], ty = ci.y - a.tileOrigin[1], tz = ci.z - a.tileOrigin[2];
-			const size_t tileIdx[6] = {
-				size_t(tz) * a.tileCount[1] + ty, size_t(tz) * a.tileCount[1] + ty, // (A = Y, B = Z)
-				size_t(tz) * a.tileCount[0] + tx, size_t(tz) * a.tileCount[0] + tx, // (A = X, B = Z)
-				size_t(ty) * a.tileCount[0] + tx, size_t(ty) * a.tileCount[0] + tx, // (A = X, B = Y)
-			};
+			const PassGeom g = pass_geometry(a, ci.x, ci.y, ci.z);
 #pragma unroll
 			for (int p = 0; p < 6; ++p)
 			{
-				act[p] = false;
-				if (!((a.dirMask >> passDir[p]) & 1u))
-					continue; // no tables: the host proved that no chunk of this call reaches the terrain band from this side
-				const size_t tileNo = a.terrainOffset[passDir[p]] / SLAB + tileIdx[p];
-				const int tdMin = a.tileRange[tileNo * 2], tdMax = a.tileRange[tileNo * 2 + 1];
-				const int bd = blockDepth[p];
-				// some column has blockDepth >= terrainDepth and start = blockDepth - terrainDepth < 32 ?
-				act[p] = (bd >= tdMin) && (bd - tdMax < CS);
+				act[p] = ((actBits >> p) & 1u) != 0u;
+				const size_t tileNo = g.tileNo[p];
+				const int bd = g.blockDepth[p];
 				if (act[p])
 				{
 					const int16_t* tile = a.terrain + tileNo * SLAB;

@@ -373,6 +373,7 @@ struct tsom_container
 		int lo[3], hi[3], sumMin, sumMax;
 	} genPlan{};
 	DevBuf<uint16_t> templates;
+	DevBuf<int4> genDesc; // per-job descriptors of the last generate call (gen_classify_kernel)
 	std::vector<int32_t> planetIdx;          // chunk list of the last tsom_planet_generate (GenerateChunks order)
 	uint32_t planetIdxCount[3] = { 0, 0, 0 };
 
@@ -1102,6 +1103,7 @@ extern "C"
 		c->genCache.jobs.Free();
 		c->meshCache.jobs.Free();
 		c->templates.Free();
+		c->genDesc.Free();
 		c->terrain.Free();
 		c->tileRange.Free();
 		c->slotGrid.Free();
@@ -1613,8 +1615,12 @@ extern "C"
 			TSOM_CUDA(cudaGetLastError());
 			ga.templates = c->templates.ptr;
 		}
+		// one descriptor per job (chunk index, slot, active passes): the dependent loads a CTA would start with, done by n threads at once
+		TSOM_CUDA(c->genDesc.Ensure(n));
+		ga.jobDesc = c->genDesc.ptr;
+		tsomk::launch_gen_classify(ga, c->genDesc.ptr, ctx->stream);
 		tsomk::launch_generate(ga, int(n), ctx->stream);
-		ctx->launches += 1;
+		ctx->launches += 2;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
 		TSOM_CUDA(cudaMemcpyAsync(ctx->hSmall + 8, ctx->dSmall + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

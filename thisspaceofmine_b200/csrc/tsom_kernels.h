@@ -79,6 +79,7 @@ namespace tsomk
 		uint16_t* xslabs;        // [capacity][2][1024]
 		const int4* chunkIdx;    // [capacity]
 		const uint32_t* jobSlot; // [nJobs]
+		const int4* jobDesc;     // [nJobs] (cx, cy, cz, slot | active passes << 26), written by gen_classify_kernel
 		uint32_t nJobs;
 		uint32_t seed;
 		int maxH[3];             // ((chunkCount + 1) / 2) * 32 per axis
@@ -117,6 +118,7 @@ namespace tsomk
 	void launch_terrain(const TerrainArgs& a, cudaStream_t st);
 	void launch_generate(const GenArgs& a, int grid, cudaStream_t st);
 	void launch_templates(const GenArgs& a, uint16_t* templates, cudaStream_t st);
+	void launch_gen_classify(const GenArgs& a, int4* desc, cudaStream_t st);
 
 	// ---- chunk maintenance ----
 	void launch_build_xslabs(const uint16_t* blocks, uint16_t* xslabs, uint8_t* summary, const uint32_t* slots, uint32_t n, cudaStream_t st);
