@@ -896,8 +896,9 @@ namespace tsomk
 		const uint32_t j = atomicAdd(a.jobCounter, 1u);
 		const uint32_t entry = j < a.nJobs ? a.jobSlot[j] : 0u;
 		sm.slot = entry & JOB_SLOT_MASK;
-		// a chunk whose summary proves that it has no face (job_classify_kernel) is treated like one without content: 0 faces, no stage
-		sm.hasContent = (entry & (JOB_HAS_CONTENT | JOB_SKIP)) == JOB_HAS_CONTENT ? 1u : 0u;
+		// a chunk whose summary proves that it has no face (job_classify_kernel) is treated like one without content: 0 faces, no stage;
+		// 2 = all opaque: the row masks are known up front
+		sm.hasContent = (entry & (JOB_HAS_CONTENT | JOB_SKIP)) == JOB_HAS_CONTENT ? ((entry & JOB_OPAQUE) ? 2u : 1u) : 0u;
 		sm.job = j;
 	}
 
@@ -961,6 +962,10 @@ namespace tsomk
 				break;
 			const uint32_t slot = sm.slot;
 			const bool hasContent = sm.hasContent != 0u;
+			// every block non-Empty, opaque, single sided (the producer's summary): mT = 0, mE = all ones, mD = 0 without looking at the ids.
+			// The ids are still staged (the emission reads the id of every face for its texture slice), but nothing waits for them before
+			// the faces are counted: the copy runs behind the halo classification, the count and the scan.
+			const bool opaque = sm.hasContent == 2u;
 
 			uint32_t F = 0, K = 0;
 			if (hasContent)
@@ -976,10 +981,22 @@ namespace tsomk
 						tma_load_1d(sm.ids + p * (NB / 4), src + p * (NB / 4), NB / 2, &sm.bar);
 				}
 				build_halo_masks<FUSED_THREADS>(a, sm.lut32, slot, sm.hT, tid);
-				mbar_wait(&sm.bar, parity);
-				parity ^= 1;
-
-				build_masks_fused<FUSED_THREADS>(a, sm.lut32, sm, tid);
+				if (!opaque)
+				{
+					mbar_wait(&sm.bar, parity);
+					parity ^= 1;
+					build_masks_fused<FUSED_THREADS>(a, sm.lut32, sm, tid);
+				}
+				else
+				{
+#pragma unroll
+					for (int k = 0; k < ROWS / FUSED_THREADS; ++k)
+					{
+						sm.mT[k * FUSED_THREADS + tid] = 0u;
+						sm.mE[k * FUSED_THREADS + tid] = 0xFFFFFFFFu;
+						sm.mD[k * FUSED_THREADS + tid] = 0u;
+					}
+				}
 				__syncthreads();
 
 				// ---- faces per row (thread t owns rows 4t .. 4t+3) and one packed scan: faces | rows-with-faces << 20
@@ -1028,6 +1045,11 @@ namespace tsomk
 			}
 
 			__syncthreads(); // ne[] is complete; sm.job has been read by everyone
+			if (hasContent && opaque)
+			{
+				mbar_wait(&sm.bar, parity); // the ids of an all-opaque chunk are first needed here
+				parity ^= 1;
+			}
 
 			// Unordered mode: no chunk waits on another, so the next ticket (and the dependent load behind it) can be taken
 			// now and its latency hides behind this chunk's emission.  (In ordered mode a ticket held during an emission would
@@ -1288,7 +1310,7 @@ namespace tsomk
 		const uint32_t j = blockIdx.x * 256u + threadIdx.x;
 		if (j >= n)
 			return;
-		uint32_t entry = src[j] & ~JOB_SKIP;
+		uint32_t entry = src[j] & ~(JOB_SKIP | JOB_OPAQUE);
 		if (entry & JOB_HAS_CONTENT)
 		{
 			const uint32_t slot = entry & JOB_SLOT_MASK;
@@ -1306,6 +1328,8 @@ namespace tsomk
 			}
 			if (skip)
 				entry |= JOB_SKIP;
+			else if (s == SUM_OPAQUE)
+				entry |= JOB_OPAQUE;
 		}
 		dst[j] = entry;
 	}

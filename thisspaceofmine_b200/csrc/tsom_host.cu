@@ -1596,7 +1596,7 @@ extern "C"
 		ga.aStar = ctx->aStar;
 		ga.aInv = ctx->aInv;
 		// chunk summaries the generator may write, from the block table (none without a table: everything stays SUM_UNKNOWN)
-		auto opaque = [&](uint16_t id) { return id != 0 && id < ctx->hostFlags.size() && !(ctx->hostFlags[id] & 4u /* BF_TRANSPARENT */); };
+		auto opaque = [&](uint16_t id) { return id != 0 && id < ctx->hostFlags.size() && !(ctx->hostFlags[id] & (4u | 2u) /* BF_TRANSPARENT | BF_DOUBLE_SIDED */); };
 		ga.summary = c->dSummary;
 		ga.fastSummary = (opaque(ids->stone) && opaque(ids->stone_mossy)) ? tsomk::SUM_OPAQUE : tsomk::SUM_UNKNOWN;
 		ga.allOpaque = (opaque(ids->dirt) && opaque(ids->grass) && opaque(ids->stone) && opaque(ids->stone_mossy) && opaque(ids->snow)) ? 1 : 0;

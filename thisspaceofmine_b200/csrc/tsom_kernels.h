@@ -15,10 +15,11 @@ namespace tsomk
 	{
 		SUM_UNKNOWN = 0, // anything (every reset / edit puts a chunk back here)
 		SUM_EMPTY = 1,   // every block is Empty
-		SUM_OPAQUE = 2   // every block is non-Empty and not transparent
+		SUM_OPAQUE = 2   // every block is non-Empty, not transparent and not double sided
 	};
-	// job entry of the mesher: slot | JOB_SKIP (no face, proven from the summaries) | JOB_HAS_CONTENT
-	constexpr uint32_t JOB_SLOT_MASK = 0x3FFFFFFFu, JOB_SKIP = 0x40000000u, JOB_HAS_CONTENT = 0x80000000u;
+	// job entry of the mesher: slot | JOB_OPAQUE (summary SUM_OPAQUE: the row masks are known without reading the ids) | JOB_SKIP (no face,
+	// proven from the summaries) | JOB_HAS_CONTENT
+	constexpr uint32_t JOB_SLOT_MASK = 0x1FFFFFFFu, JOB_OPAQUE = 0x20000000u, JOB_SKIP = 0x40000000u, JOB_HAS_CONTENT = 0x80000000u;
 
 	// per-(faceUp, slot, twin) face attributes of a FlatChunk with a power-of-two block size (see mesh_kernels.cu)
 	struct FaceTable
