@@ -58,6 +58,13 @@ FACE_BYTES = 216  # 4 x 48 B vertices + 6 x 4 B indices
 METRIC = "chunks_generated_and_meshed_per_sec"
 
 
+def workload_config(edge, n_gpus):
+    """`config` of the JSON line: the same object on both arms (the reference arm times a bounded sample of THIS workload)."""
+    return {"workload": workload_name(edge), "chunk_count": [edge, edge, edge], "chunks": edge ** 3, "seed": PLANET_SEED,
+            "l2": "per step the GPUs write 6.8 GB of ids and 37.9 GB of vertices + indices between them: far beyond the 126 MB L2, no explicit flush",
+            "parallelism": f"chunks sharded by chunk index over {n_gpus} GPU(s): one box per GPU, P2P halo slabs, no collective on the data path"}
+
+
 def workload_name(edge):
     return (f"one {edge}^3-chunk planet ({edge ** 3} chunks, seed {PLANET_SEED}): Planet::GenerateChunks + halo exchange + Chunk::BuildMesh (render attributes, "
             f"48 B vertices + u32 indices) of every chunk, sharded by chunk index over the GPUs (BASELINE configs[2]/[4])")
@@ -231,7 +238,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16+f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.edge), "chunks_per_step": r["chunks"], "sample": "bounded"},
+        "config": workload_config(args.edge, args.gpus), "sample_chunks_per_step": r["chunks"],
         "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind, "sample": sample_note(kind, threads, r),
                          "gen_ms": 1e3 * sum(s["gen_s"] for s in steps) / len(steps), "mesh_ms": 1e3 * sum(s["mesh_s"] for s in steps) / len(steps)},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -319,12 +326,12 @@ def run_b200(args):
     nbr_local = int(neighbour_counts(sp.local_grid, edge).sum())
 
     def step(views=False):
-        sp.GenerateChunks(lib, PLANET_SEED)  # terrain_kernel + template_kernel + generate_kernel on this rank's box
-        tg = ctx.timings()
-        sp.PullHalos()                       # publish -> wait for the peers on the device -> halo_pull_kernel -> publish
-        batch = sp.BuildMeshes(views=views)  # job_classify_kernel + mesh_fused_kernel
+        # three calls, one host wait: generate and the exchange are only queued, the mesh call returns when all three are done
+        sp.GenerateChunks(lib, PLANET_SEED, wait=False)  # terrain + template + gen_classify + generate kernels on this rank's box
+        sp.PullHalos()                                   # publish -> wait for the peers on the device -> halo_pull_kernel -> publish
+        batch = sp.BuildMeshes(views=views)              # job_classify_kernel + mesh_fused_kernel
         tm = ctx.timings()
-        return batch, tg, tm
+        return batch, tm, tm
 
     # ---- first pass sizes the arenas (the kernel counts, the host grows the arenas, the kernel runs again) and gives the per-chunk faces
     first, _, _ = step(views=True)
@@ -411,9 +418,7 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ramp_steps": ramp_steps,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16+f32", "data": "synthetic",
-            "config": {"workload": workload_name(edge), "chunk_count": list(cc), "chunks": n_total, "faces": faces_total,
-                       "l2": "per step every GPU writes its share of 6.8 GB of ids and 37.9 GB of vertices + indices: far beyond the 126 MB L2, no explicit flush",
-                       "parallelism": f"chunks sharded by chunk index over {world} GPU(s): one box per GPU, P2P halo slabs, no collective on the data path"},
+            "config": workload_config(edge, world), "faces_per_step": faces_total,
             "e2e": {"value": n_total / e2e_s, "unit": "chunks/s", "h2d_bytes_per_step": n_total * 24 + 1536 * world, "d2h_bytes_per_step": faces_total * FACE_BYTES + n_total * 16,
                     "steps": args.e2e_steps, "ms_per_step": e2e_s * 1e3,
                     "note": "tsom_planet_generate_chunks + tsom_halo_pull + tsom_mesh + tsom_mesh_copy_to_host of every face (pinned host vertices + indices, 4 Mi-face slices)"

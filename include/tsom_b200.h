@@ -210,6 +210,11 @@ int tsom_planet_generate(tsom_container* c, uint32_t seed, const uint32_t chunk_
 /* Planet::GenerateChunk on chosen (existing or new) chunks — the /regenchunk caller, src/ServerLib/Session/PlayerSessionHandler.cpp:290 */
 int tsom_planet_generate_chunks(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids,
                                 const int32_t* chunk_indices, uint32_t n);
+/* The same, returning as soon as the work is queued on the context's stream (Planet::GenerateChunks itself blocks in WaitForTasks; a caller
+ * that goes straight on to tsom_halo_pull / tsom_mesh does not need the wait in between).  The next blocking call on the context —
+ * tsom_mesh, tsom_synchronize, tsom_chunks_get_content ... — completes it; chunk_indices must stay valid only for the duration of the call. */
+int tsom_planet_generate_chunks_async(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids,
+                                      const int32_t* chunk_indices, uint32_t n);
 /* Planet::GeneratePlatform (Planet.cpp:405-512), executed against the device-resident blocks */
 int tsom_planet_generate_platform(tsom_container* c, int up_direction, const int32_t platform_center[3], const tsom_platform_blocks* ids);
 

@@ -88,6 +88,7 @@ SYMBOLS = {
     "tsom_chunks_reset_lz4": (C.c_int, [_vp, _i32p, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
     "tsom_planet_generate": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks)]),
     "tsom_planet_generate_chunks": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks), _i32p, C.c_uint32]),
+    "tsom_planet_generate_chunks_async": (C.c_int, [_vp, C.c_uint32, _u32p, C.POINTER(GenBlocks), _i32p, C.c_uint32]),
     "tsom_planet_generate_platform": (C.c_int, [_vp, C.c_int, _i32p, C.POINTER(PlatformBlocks)]),
     "tsom_apply_edits": (C.c_int, [_vp, C.POINTER(Edit), C.c_uint32]),
     "tsom_collect_dirty": (C.c_int, [_vp, _i32p, C.c_uint32, _u32p, C.c_int]),

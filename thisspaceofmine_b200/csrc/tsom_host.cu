@@ -919,7 +919,14 @@ extern "C"
 		if (!ctx)
 			return Fail(TSOM_ERR_INVALID, "ctx is null");
 		TSOM_LOCK(ctx);
+		TSOM_CUDA(cudaSetDevice(ctx->device));
 		TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->pendingGenerate)
+		{
+			ctx->pendingGenerate = false;
+			cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_TERRAIN_MS], ctx->ev[0], ctx->ev[1]);
+			cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[2], ctx->ev[3]);
+		}
 		return TSOM_OK;
 	}
 
@@ -1654,6 +1661,16 @@ extern "C"
 		return GenerateFinish(c);
 	}
 
+	int tsom_planet_generate_chunks_async(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids, const int32_t* chunk_indices, uint32_t n)
+	{
+		if (!c || !chunk_count || !ids || (!chunk_indices && n))
+			return Fail(TSOM_ERR_INVALID, "bad arguments");
+		if (n == 0)
+			return TSOM_OK;
+		TSOM_LOCK(c->ctx);
+		return GenerateEnqueue(c, seed, chunk_count, ids, chunk_indices, n); // completed by the next blocking call on the context
+	}
+
 	int tsom_planet_generate(tsom_container* c, uint32_t seed, const uint32_t chunk_count[3], const tsom_gen_blocks* ids)
 	{
 		if (!c || !chunk_count || !ids)
@@ -2059,6 +2076,13 @@ extern "C"
 
 		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_CLASSIFY_MS], ctx->ev[8], ctx->ev[9]);
 		cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_MESH_EMIT_MS], ctx->ev[4], ctx->ev[5]);
+		if (ctx->pendingGenerate)
+		{
+			// a tsom_planet_generate_chunks_async in front of this call has finished with it
+			ctx->pendingGenerate = false;
+			cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_TERRAIN_MS], ctx->ev[0], ctx->ev[1]);
+			cudaEventElapsedTime(&ctx->timings[TSOM_TIMING_GENERATE_MS], ctx->ev[2], ctx->ev[3]);
+		}
 		ctx->timings[TSOM_TIMING_MESH_REEMIT] = 0.f;
 		if (ctx->pendingHalo)
 		{

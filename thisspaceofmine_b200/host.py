@@ -600,12 +600,14 @@ class Planet(ChunkContainer):
         ids = self._gen_ids(blockLibrary)
         L.check(L.lib().tsom_planet_generate(self._h, seed & 0xFFFFFFFF, _p(cc, C.c_uint32), C.byref(ids)))
 
-    def GenerateChunk(self, blockLibrary: BlockLibrary, indices, seed: int, chunkCount: Sequence[int]):
-        """Planet::GenerateChunk (Planet.cpp:160-383) on one or more chunks."""
+    def GenerateChunk(self, blockLibrary: BlockLibrary, indices, seed: int, chunkCount: Sequence[int], wait: bool = True):
+        """Planet::GenerateChunk (Planet.cpp:160-383) on one or more chunks.  wait=False: return once the work is queued
+        (tsom_planet_generate_chunks_async); the next blocking call on the context completes it."""
         cc = np.ascontiguousarray(chunkCount, dtype=np.uint32)
         idx = _idx(indices)
         ids = self._gen_ids(blockLibrary)
-        L.check(L.lib().tsom_planet_generate_chunks(self._h, seed & 0xFFFFFFFF, _p(cc, C.c_uint32), C.byref(ids), _p(idx, C.c_int32), len(idx)))
+        fn = L.lib().tsom_planet_generate_chunks if wait else L.lib().tsom_planet_generate_chunks_async
+        L.check(fn(self._h, seed & 0xFFFFFFFF, _p(cc, C.c_uint32), C.byref(ids), _p(idx, C.c_int32), len(idx)))
 
     def GeneratePlatform(self, blockLibrary: BlockLibrary, upDirection: int, platformCenter: Sequence[int]):
         """Planet::GeneratePlatform (Planet.cpp:405-512)."""

@@ -149,9 +149,10 @@ class ShardedPlanet:
         self.planet.close()
 
     # ---- phase 1: generation (no communication)
-    def GenerateChunks(self, blockLibrary, seed: int):
+    def GenerateChunks(self, blockLibrary, seed: int, wait: bool = True):
+        """wait=False: only queue the work; PullHalos + BuildMeshes behind it are ordered on the stream and the mesh call completes all three."""
         if len(self.local_grid):
-            self.planet.GenerateChunk(blockLibrary, self.local_grid, seed, self.plan.chunkCount)
+            self.planet.GenerateChunk(blockLibrary, self.local_grid, seed, self.plan.chunkCount, wait=wait)
 
     # ---- phase 1.5: halo exchange over P2P
     def _dist(self):
