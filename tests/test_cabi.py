@@ -125,3 +125,16 @@ def test_numpy_record_layouts_match_the_ctypes_mirror():
         assert EDIT_DTYPE.fields[name][1] == getattr(L.Edit, name).offset, name
     for name, _ in L.MeshView._fields_:
         assert VIEW_DTYPE.fields[name][1] == getattr(L.MeshView, name).offset, name
+
+
+def test_indices_for_faces_is_the_reference_pattern():
+    """tsom_mesh_indices_for_faces (host code, no device): 4k + {0, 2, 1, 1, 2, 3} per face (src/CommonLib/Chunk.cpp:95-101), also on
+    the multi-threaded path (> 2^20 faces)."""
+    lib = L.lib()
+    for faces in (0, 1, 7, (1 << 20) + 5):
+        out = np.full(6 * faces + 3, 0xDEADBEEF, np.uint32)
+        assert lib.tsom_mesh_indices_for_faces(faces, out.ctypes.data_as(C.POINTER(C.c_uint32))) == L.OK
+        want = (4 * np.arange(faces, dtype=np.uint32)[:, None] + np.array([0, 2, 1, 1, 2, 3], np.uint32)[None, :]).reshape(-1)
+        assert np.array_equal(out[: 6 * faces], want) and np.all(out[6 * faces:] == 0xDEADBEEF)
+    assert lib.tsom_mesh_indices_for_faces(1 << 31, out.ctypes.data_as(C.POINTER(C.c_uint32))) != L.OK  # vertex ordinals would not fit 32 bits
+    assert lib.tsom_mesh_indices_for_faces(3, None) != L.OK
