@@ -42,6 +42,35 @@ def test_generate_chunks_bit_exact(ctx, seed, count):
     _assert_blocks_equal(gp, op, T.Planet.chunk_grid(count))
 
 
+@pytest.mark.parametrize("seed,count", [(42, (9, 9, 9)), (2024, (11, 9, 9))])
+def test_template_and_masked_template_chunks_bit_exact(ctx, seed, count):
+    """Planets large enough that a chunk in which EVERY block draws also sits in the terrain band: the generator's masked template copy
+    (template chunk AND NOT "above a column start"), which the 5^3 fixtures never reach (there the drawing chunks and the carved chunks are
+    disjoint).  Every chunk's ids against the oracle; the classes the generator saw are checked to be the ones this test is about."""
+    gp, op = _planets(ctx, seed, count)
+    grid = T.Planet.chunk_grid(count)
+    _assert_blocks_equal(gp, op, grid)
+    # some full-draw chunk must have been carved (stone / stone_mossy chunk with Empty blocks above the terrain) and some must not
+    got = gp.GetContent(grid)
+    lib = ctx.blockLibrary
+    stone, mossy = lib.GetBlockIndex("stone"), lib.GetBlockIndex("stone_mossy")
+    only_draws = np.array([np.isin(b, (0, stone, mossy)).all() and (b != 0).any() for b in got])
+    carved = only_draws & np.array([(b == 0).any() for b in got])
+    not_shaft = ~((grid[:, 0] == 0) & (grid[:, 2] == 0))
+    assert (carved & not_shaft).sum() > 10, "no masked template chunk in this planet"
+    assert (only_draws & ~carved & not_shaft).sum() > 10, "no plain template chunk in this planet"
+    # and every mesh: the summaries the generator wrote let the mesher skip chunks (all opaque with all-opaque neighbours, all Empty) and
+    # know the row masks of all-opaque chunks up front — each of those shortcuts has to give what the oracle gives
+    batch = gp.BuildMeshes(grid, render=True, collider=True)
+    skipped = with_faces = 0
+    for i, idx in enumerate(grid):
+        st = assert_mesh_equal(batch.chunk(i), op.mesh(idx), f"chunk {tuple(idx)}")
+        with_faces += st["faces"] > 0
+        skipped += st["faces"] == 0 and only_draws[i] and not carved[i]
+    assert skipped > 20 and with_faces > 300, (skipped, with_faces)
+    gp.close()
+
+
 def test_bernoulli_tie_where_the_first_engine_output_decides(ctx):
     """std::bernoulli_distribution(0.9) over std::minstd_rand burns two engine outputs u1, u2 per draw and is decided by u2 alone
     (stone iff u2 - 1 < 1932735281) except when u2 - 1 == 1932735281, where u1 decides (about once in 2^31 draws; the kernel's slow
