@@ -133,47 +133,60 @@ def mesh_algo_bytes(n_chunks, nbr_total, faces, with_collider=False):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons of one GPU, polled through NVML every few milliseconds on a thread (the timed region of a multi-GPU
+    run lasts tens of milliseconds: `nvidia-smi -lms` cannot sample inside it).  start() before the warm-up, mark_begin() / mark_end()
+    around the timed region; the summary is over the samples taken between the two marks."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period_s=0.004):
+        self.rows, self.t0, self.t1, self.err = [], None, None, None
+        self.period = period_s
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # no NVML: say so in the line instead of failing the run
+            self.nv, self.err = None, str(e)
 
     def _run(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), mhz, reasons))
+            except Exception as e:
+                self.err = str(e)
+                return
+            self._stop.wait(self.period)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {self.err}"]}
+        self.t.join(timeout=1.0)
+        inside = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if len(inside) < 3:  # a very short region: the load is the same since the ramp began, so say what was sampled instead
+            inside = [r for r in self.rows if self.t0 is None or r[0] >= self.t0 - 0.5]
+            window = "timed region + the 0.5 s of identical steps before it"
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in inside) if inside else None, "sm_min_mhz": min((r[1] for r in inside), default=None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside), "window": window, "source": "NVML, 4 ms period"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -345,11 +358,13 @@ def run_b200(args):
     while allmax(1.0 if time.perf_counter() - t_ramp < args.ramp_seconds else 0.0) > 0.0:
         step()
         ramp_steps += 1
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launch_count
     barrier()
+    if sampler:
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kt = []
     e0.record(stream)
@@ -358,6 +373,8 @@ def run_b200(args):
         kt.append((tg["terrain_ms"], tg["generate_ms"], tm["halo_ms"], tm["classify_ms"], tm["mesh_emit_ms"]))
     e1.record(stream)
     barrier()
+    if sampler:
+        sampler.mark_end()
     elapsed_ms = allmax(e0.elapsed_time(e1))
     launches = allsum(ctx.launch_count - launches0)
     clocks = sampler.stop() if sampler else None

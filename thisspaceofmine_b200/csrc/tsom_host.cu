@@ -1474,6 +1474,8 @@ extern "C"
 	{
 		tsom_ctx* ctx = c->ctx;
 		TSOM_CUDA(cudaSetDevice(ctx->device));
+		if (ctx->pendingGenerate)
+			TSOM_CUDA(cudaStreamSynchronize(ctx->stream)); // an earlier asynchronous generate may not have consumed its pinned staging (permutation tables) yet
 
 		int maxH[3];
 		for (int k = 0; k < 3; ++k)
