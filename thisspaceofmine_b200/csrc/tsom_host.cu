@@ -1523,8 +1523,12 @@ extern "C"
 			c->genPlan = plan;
 			cache.hostSlots = std::move(slots);
 		}
-		for (uint32_t s : cache.hostSlots)
-			c->hostInvalid[s] = 0x80u | 0x3Fu; // OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37)
+		// OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37) for every generated chunk
+		if (n == c->slotOf.size() && c->freeSlots.empty())
+			std::fill(c->hostInvalid.begin(), c->hostInvalid.begin() + c->highWater, uint8_t(0x80u | 0x3Fu)); // the whole container: one fill
+		else
+			for (uint32_t s : cache.hostSlots)
+				c->hostInvalid[s] = 0x80u | 0x3Fu;
 		const tsom_container::GenPlan& plan = c->genPlan;
 
 		// generation reads chunkIdx on the device: make sure new chunks are there
