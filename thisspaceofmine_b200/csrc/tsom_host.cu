@@ -361,6 +361,7 @@ struct tsom_container
 		std::vector<int32_t> idx;
 		DevBuf<uint32_t> jobs;
 		std::vector<uint32_t> hostSlots;
+		bool coversAll = false; // the list names every chunk of the container exactly once
 		uint64_t version = 0;
 		uint32_t n = 0;
 		bool Matches(const int32_t* chunk_indices, uint32_t count, uint64_t ver) const
@@ -1522,9 +1523,17 @@ extern "C"
 			cache.version = c->topoVersion;
 			c->genPlan = plan;
 			cache.hostSlots = std::move(slots);
+			// does the list name every chunk of the container exactly once?
+			std::vector<uint8_t> seen(c->highWater, 0);
+			cache.coversAll = n == c->slotOf.size();
+			for (uint32_t s : cache.hostSlots)
+			{
+				cache.coversAll = cache.coversAll && !seen[s];
+				seen[s] = 1;
+			}
 		}
 		// OnReset -> OnChunkUpdated(DirectionMask_All) (Planet.cpp:34-37) for every generated chunk
-		if (n == c->slotOf.size() && c->freeSlots.empty())
+		if (cache.coversAll && n == c->slotOf.size() && c->freeSlots.empty())
 			std::fill(c->hostInvalid.begin(), c->hostInvalid.begin() + c->highWater, uint8_t(0x80u | 0x3Fu)); // the whole container: one fill
 		else
 			for (uint32_t s : cache.hostSlots)
