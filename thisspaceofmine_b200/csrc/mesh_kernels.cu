@@ -51,6 +51,11 @@ namespace tsomk
 		float radius;
 		bool deformed;
 		bool wantAttr; // normals + uv (render) — collider-only skips them like null SparsePtrs do (Chunk.cpp:33,39)
+		// Table-driven flat path only: faceCenter - gravityCenter is EXACT (power-of-two block size, container centre 0, chunk indices
+		// below 2^14: every coordinate is a multiple of tile / 2 far below 2^24), so DirectionFromNormal gives the same answer on the
+		// raw vector as on the normalised one — scaling by 1 / length keeps equal components equal and distinct ones (at least
+		// 2^-21 apart, relatively) distinct, and the largest component is >= 0 > the -1 the search starts from either way.
+		bool rawUp;
 	};
 
 	// DeformedChunk::DeformPosition (reference src/CommonLib/DeformedChunk.cpp:139-154)
@@ -312,7 +317,7 @@ namespace tsomk
 			for (int i = 0; i < 4; ++i)
 				fc = fc + o.pos[i];
 			fc = fc / 4.f;
-			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
+			const int faceUp = cx.rawUp ? direction_from_normal(fc - cx.gravity) : direction_from_normal(normalize(fc - cx.gravity));
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
 			n = tb.normal[slot];
@@ -1097,6 +1102,7 @@ namespace tsomk
 				cx.radius = a.deformRadius;
 				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
 				cx.wantAttr = wantRender;
+				cx.rawUp = false;
 				if (a.gravity)
 					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);
 				else
@@ -1104,6 +1110,7 @@ namespace tsomk
 					// container centre - GetChunkOffset(indices) (ClientChunkEntities.cpp:160, ChunkContainer.inl:53-56)
 					const int4 ci = a.chunkIdx[slot];
 					cx.gravity = f3(a.center[0] - float(ci.x) * float(CS) * a.tile, a.center[1] - float(ci.y) * float(CS) * a.tile, a.center[2] - float(ci.z) * float(CS) * a.tile);
+					cx.rawUp = fastFlat && a.center[0] == 0.f && a.center[1] == 0.f && a.center[2] == 0.f && max(max(abs(ci.x), abs(ci.y)), abs(ci.z)) < (1 << 14);
 				}
 
 				float4* stage = sm.stage[warp];
