@@ -151,6 +151,35 @@ def test_deformed_corners(ctx, radius):
     _compare_all(gc, op, list(chunks), deformed=True, deformRadius=radius, render=False, collider=True)
 
 
+@pytest.mark.parametrize("tile,radius", [(1.0, 16.0), (1.0, 7.5), (0.5, 3.0), (4.0, 0.0), (1.0, 200.0)])
+def test_deformed_table_shortcut_is_bit_identical_to_generic_math(ctx, tile, radius):
+    """DeformedChunk blocks whose 8 corners the deformation leaves in place take their normals / uvs from the flat path's table
+    (power-of-two block size); the call with genericMath=True evaluates DrawFace for every face.  Same bits either way, near the
+    planet's rounded edges (corner chunk), on its flat sides (face chunk) and inside the deformation radius (centre chunk)."""
+    rng = np.random.default_rng(23)
+    chunks = {(2, 2, 2): random_chunk(rng, 0.4, ids=(1, 3, 7, 13)), (0, 3, 0): random_chunk(rng, 0.3, ids=(1, 3)), (0, 0, 0): random_chunk(rng, 0.1)}
+    gc, op = _pair(ctx, chunks, tile=tile)
+    idx = list(chunks)
+    fast = gc.BuildMeshes(idx, deformed=True, deformRadius=radius)
+    meshes_fast = [fast.chunk(i) for i in range(len(idx))]
+    gen = gc.BuildMeshes(idx, deformed=True, deformRadius=radius, genericMath=True)
+    for i, k in enumerate(idx):
+        g = gen.chunk(i)
+        assert np.array_equal(meshes_fast[i].vertices.view(np.uint32), g.vertices.view(np.uint32)), f"tile {tile} radius {radius} chunk {k}"
+        assert np.array_equal(meshes_fast[i].indices, g.indices)
+        assert_mesh_equal(g, op.mesh(k, deformed=True, deform_radius=radius), f"tile {tile} radius {radius} chunk {k}")
+    # own centres (gravity and deformation): far along one axis on the 2^-10 grid (whole chunk undeformed), far but off the grid
+    # (per-corner check), and close by (really deformed)
+    centers = np.array([[-300.25, 3.0, 8.5], [0.3, 411.7, -2.9], [10.0, 12.0, 40.0]], np.float32)
+    fast = gc.BuildMeshes(idx, deformed=True, deformRadius=radius, gravityCenters=centers)
+    meshes_fast = [fast.chunk(i) for i in range(len(idx))]
+    gen = gc.BuildMeshes(idx, deformed=True, deformRadius=radius, gravityCenters=centers, genericMath=True)
+    for i, k in enumerate(idx):
+        g = gen.chunk(i)
+        assert np.array_equal(meshes_fast[i].vertices.view(np.uint32), g.vertices.view(np.uint32)), f"own centre: tile {tile} radius {radius} chunk {k}"
+        assert_mesh_equal(g, op.mesh(k, deformed=True, deform_radius=radius, gravity_center=centers[i]), f"own centre: tile {tile} radius {radius} chunk {k}")
+
+
 def test_batch_order_and_views(ctx):
     """One batched call: per-chunk views are dense, in job order, and each equals the single-chunk result."""
     rng = np.random.default_rng(21)

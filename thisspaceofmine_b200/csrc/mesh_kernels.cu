@@ -56,6 +56,10 @@ namespace tsomk
 		// raw vector as on the normalised one — scaling by 1 / length keeps equal components equal and distinct ones (at least
 		// 2^-21 apart, relatively) distinct, and the largest component is >= 0 > the -1 the search starts from either way.
 		bool rawUp;
+		// chunk-local index that maps to coordinate 0: size / 2 for a FlatChunk (FlatChunk.cpp:50-53), 0 for the corners of a
+		// DeformedChunk (DeformedChunk.cpp:117-119) when the table-driven path serves a chunk the deformation leaves untouched
+		float flatOrigin;
+		bool exactDeform; // deform_is_exact: regions may be classified as undeformed without evaluating DeformPosition
 	};
 
 	// DeformedChunk::DeformPosition (reference src/CommonLib/DeformedChunk.cpp:139-154)
@@ -94,6 +98,56 @@ namespace tsomk
 			p = deform_position(cx, p);
 		}
 		return p;
+	}
+
+	// DeformedChunk corner plus whether the deformation left it where it was (bit for bit up to the sign of a zero): true for every
+	// corner further than the deformation radius from two of the planet's faces, i.e. for most of a planet's surface
+	__device__ __forceinline__ F3 deformed_corner(const FaceCtx& cx, int x, int y, int z, unsigned code, bool& same)
+	{
+		const float s = cx.tile;
+		const float fx = float(unsigned(x)) * s;
+		const float fy = float(unsigned(y)) * s;
+		const float fz = float(unsigned(z)) * s;
+		const F3 p = f3((code & 1u) ? fx + s : fx, (code & 2u) ? fz + s : fz, (code & 4u) ? fy + s : fy);
+		const F3 d = deform_position(cx, p);
+		same = d.x == p.x && d.y == p.y && d.z == p.z;
+		return d;
+	}
+
+	// DeformPosition returns every point of an axis-aligned region unchanged, bit for bit, when
+	//   * one axis m dominates the whole region and the other two stay inside the inner box: max |p_j - c_j| <= min |p_m - c_m| - radius.
+	//     Then the clamp moves a point by exactly (+-radius, 0, 0) along m, the normalised offset is (+-1, 0, 0) and the point comes
+	//     back to where it was — most of a planet: everything further than the radius from two of its faces (region_is_undeformed);
+	//   * and the arithmetic on the way is exact (deform_is_exact): centre and radius are multiples of 2^-10 below 2^13 like every
+	//     corner coordinate (power-of-two block size: the caller checked), so no sum or difference rounds; sqrt(radius^2) == radius
+	//     in binary floating point, and radius * (1 / radius) == 1 is checked (it fails for a few radii).
+	// Conservative: whatever fails takes the per-corner path, which compares every deformed corner with the undeformed one.
+	__device__ __forceinline__ bool deform_is_exact(const FaceCtx& cx)
+	{
+		const float r = cx.radius, s = cx.tile;
+		auto gridded = [](float v) { return fabsf(v) < 8192.f && v * 1024.f == truncf(v * 1024.f); };
+		if (!(r >= 0.f) || !gridded(r) || !gridded(cx.gravity.x) || !gridded(cx.gravity.y) || !gridded(cx.gravity.z) || !(s >= 1.f / 1024.f) || !(float(CS) * s < 8192.f))
+			return false;
+		return r == 0.f || r * (1.f / r) == 1.f;
+	}
+
+	// region = [lo, lo + ext] on each axis, in the chunk's own coordinates
+	__device__ __forceinline__ bool region_is_undeformed(const FaceCtx& cx, float lox, float loy, float loz, float ext)
+	{
+		const float lo[3] = { lox - cx.gravity.x, loy - cx.gravity.y, loz - cx.gravity.z };
+		float qmin[3], qmax[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			const float hi = lo[k] + ext;
+			qmax[k] = fmaxf(fabsf(lo[k]), fabsf(hi));
+			qmin[k] = (lo[k] <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo[k]), fabsf(hi));
+		}
+		const float lead = fmaxf(fmaxf(qmin[0], qmin[1]), qmin[2]);
+		// the two non-leading axes: the largest qmax among the axes whose qmin is not the lead (ties: any one leads, the rest must fit)
+		const int m = qmin[0] == lead ? 0 : (qmin[1] == lead ? 1 : 2);
+		const float other = m == 0 ? fmaxf(qmax[1], qmax[2]) : (m == 1 ? fmaxf(qmax[0], qmax[2]) : fmaxf(qmax[0], qmax[1]));
+		return other <= lead - cx.radius;
 	}
 
 	// geometry of one face: block centre (mean of the 8 corners, summed in enum order, Chunk.cpp:186-188), the 4 quad corners
@@ -294,13 +348,13 @@ namespace tsomk
 
 	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st) { face_table_kernel<<<1, 96, 0, st>>>(table, tile, a); }
 
-	__device__ __forceinline__ void draw_face_flat_r(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, int x, int y, int z, int slot, bool twin, unsigned id, FaceOut& o)
+	__device__ __forceinline__ void draw_face_flat_r(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, float origin, int x, int y, int z, int slot, bool twin, unsigned id, FaceOut& o)
 	{
 		const float s = cx.tile;
 		// Boxf(blockPos.x, blockPos.z, blockPos.y, s, s, s) with blockPos = (indices - size / 2) * s (FlatChunk.cpp:50-53)
-		const float ox = (float(x) - float(CS) * 0.5f) * s;
-		const float oy = (float(z) - float(CS) * 0.5f) * s;
-		const float oz = (float(y) - float(CS) * 0.5f) * s;
+		const float ox = (float(x) - origin) * s;
+		const float oy = (float(z) - origin) * s;
+		const float oz = (float(y) - origin) * s;
 		const float ex = ox + s, ey = oy + s, ez = oz + s;
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
@@ -318,6 +372,36 @@ namespace tsomk
 				fc = fc + o.pos[i];
 			fc = fc / 4.f;
 			const int faceUp = cx.rawUp ? direction_from_normal(fc - cx.gravity) : direction_from_normal(normalize(fc - cx.gravity));
+			uv0 = tb.uv[faceUp][slot][twin][0];
+			uv1 = tb.uv[faceUp][slot][twin][1];
+			n = tb.normal[slot];
+			o.slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
+		}
+		o.n = f3(n.x, n.y, n.z);
+		o.u[0] = uv0.x; o.v[0] = uv0.y;
+		o.u[1] = uv0.z; o.v[1] = uv0.w;
+		o.u[2] = uv1.x; o.v[2] = uv1.y;
+		o.u[3] = uv1.z; o.v[3] = uv1.w;
+	}
+
+	// DrawFace of a DeformedChunk block whose 8 corners the deformation left in place (deformed_corner): with a power-of-two block
+	// size its corners are exact multiples of the block size, so normal, texture direction and uvs are the table's — the generic
+	// arithmetic on these inputs produces the very same bits (it is what filled the table)
+	__device__ __forceinline__ void draw_face_cached_table(const MeshArgs& a, const FaceCtx& cx, const FaceTable& tb, const F3 pos[4], int slot, bool twin, unsigned id, FaceOut& o)
+	{
+		F3 fc = f3(0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			o.pos[i] = pos[i];
+			fc = fc + pos[i];
+		}
+		fc = fc / 4.f;
+		float4 uv0 = make_float4(0.f, 0.f, 0.f, 0.f), uv1 = uv0, n = uv0;
+		o.slice = 0.f;
+		if (cx.wantAttr)
+		{
+			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
 			n = tb.normal[slot];
@@ -697,24 +781,31 @@ namespace tsomk
 				s = int((de >> 5) & 7u);
 				twin = ((de >> 8) & 1u) != 0u;
 			}
+			// a chunk the deformation touches still has plenty of blocks it leaves alone: their faces need no corner evaluation
+			bool flatFace = false;
+			if (!LEAN && !fastFlat && cx.exactDeform && valid)
+				flatFace = region_is_undeformed(cx, float(x) * cx.tile, float(row >> 5) * cx.tile, float(row & 31u) * cx.tile, cx.tile);
 			if (LEAN || fastFlat)
 			{
 				if (valid)
-					draw_face_flat_r(a, cx, table, x, int(row & 31u), int(row >> 5), s, twin, sm.ids[row * CS + x], fo);
+					draw_face_flat_r(a, cx, table, LEAN ? float(CS) * 0.5f : cx.flatOrigin, x, int(row & 31u), int(row >> 5), s, twin, sm.ids[row * CS + x], fo);
 			}
 			else
 			{
 				// Generic corner providers (DeformedChunk: a normalisation per corner): the 8 corners and the centre of a block are the
 				// same for all of its faces (up to 12), and the faces of a block are neighbours in the emission order.  The warp finds
-				// the distinct blocks of the tile, spreads their 8 * nBlocks corner evaluations over its 32 lanes and shares the
+				// the distinct blocks of the tile (those not already known to be undeformed), spreads their 8 * nBlocks corner evaluations over its 32 lanes and shares the
 				// results through the staging tile, which is idle at this point: [0, 32) block keys, then 9 F3 per block (8 corners by
-				// code dX | dY << 1 | dZ << 2, centre), 16 blocks per round.
+				// code dX | dY << 1 | dZ << 2, centre), 16 blocks per round, then 16 "block left undeformed" flags.
 				constexpr uint32_t FULLM = 0xffffffffu;
 				uint32_t* keys = reinterpret_cast<uint32_t*>(stage);
 				float* cache = reinterpret_cast<float*>(stage) + 32;
-				const uint32_t key = valid ? ((row << 5) | uint32_t(x)) : 0xFFFFFFFFu;
+				uint32_t* blockFlat = reinterpret_cast<uint32_t*>(stage) + 32 + 16 * 27; // 16 flags: all 8 corners of the block undeformed
+				const bool blockTable = cx.deformed && a.faceTable != nullptr;
+				const bool needGeo = valid && !flatFace;
+				const uint32_t key = needGeo ? ((row << 5) | uint32_t(x)) : 0xFFFFFFFFu;
 				const uint32_t prev = __shfl_up_sync(FULLM, key, 1);
-				const bool leader = valid && (lane == 0 || key != prev);
+				const bool leader = needGeo && (lane == 0 || key != prev);
 				const uint32_t leaders = __ballot_sync(FULLM, leader);
 				const uint32_t nBlocks = __popc(leaders);
 				const uint32_t myBlock = __popc(leaders & (0xFFFFFFFFu >> (31 - lane))) - 1u; // ordinal of this lane's block in the tile
@@ -725,17 +816,28 @@ namespace tsomk
 #pragma unroll
 				for (int i = 0; i < 4; ++i)
 					pos[i] = f3(0.f, 0.f, 0.f);
+				bool flatBlock = false;
 				for (uint32_t b0 = 0; b0 < nBlocks; b0 += 16u)
 				{
 					const uint32_t nb = min(16u, nBlocks - b0);
-					for (uint32_t e = uint32_t(lane); e < nb * 8u; e += 32u)
+					for (uint32_t e0 = 0; e0 < nb * 8u; e0 += 32u)
 					{
-						const uint32_t k = keys[b0 + (e >> 3)];
-						const F3 c = voxel_corner(cx, int(k & 31u), int((k >> 5) & 31u), int(k >> 10), e & 7u);
-						float* dst = cache + ((e >> 3) * 9u + (e & 7u)) * 3u;
-						dst[0] = c.x;
-						dst[1] = c.y;
-						dst[2] = c.z;
+						const uint32_t e = e0 + uint32_t(lane);
+						bool same = false;
+						if (e < nb * 8u)
+						{
+							const uint32_t k = keys[b0 + (e >> 3)];
+							const int bx = int(k & 31u), by = int((k >> 5) & 31u), bz = int(k >> 10);
+							const F3 c = blockTable ? deformed_corner(cx, bx, by, bz, e & 7u, same) : voxel_corner(cx, bx, by, bz, e & 7u);
+							float* dst = cache + ((e >> 3) * 9u + (e & 7u)) * 3u;
+							dst[0] = c.x;
+							dst[1] = c.y;
+							dst[2] = c.z;
+						}
+						// a block is flat when all 8 of its corners (8 neighbouring lanes) stayed in place
+						const uint32_t sameMask = __ballot_sync(FULLM, same);
+						if (e < nb * 8u && (e & 7u) == 0u)
+							blockFlat[e >> 3] = ((sameMask >> (lane & 24)) & 0xFFu) == 0xFFu ? 1u : 0u;
 					}
 					__syncwarp();
 					if (uint32_t(lane) < nb)
@@ -754,10 +856,11 @@ namespace tsomk
 						dst[2] = sum.z;
 					}
 					__syncwarp();
-					if (valid && myBlock >= b0 && myBlock < b0 + nb)
+					if (needGeo && myBlock >= b0 && myBlock < b0 + nb)
 					{
 						const float* cb = cache + (myBlock - b0) * 27u;
 						blockCenter = f3(cb[24], cb[25], cb[26]);
+						flatBlock = blockFlat[myBlock - b0] != 0u;
 #pragma unroll
 						for (int i = 0; i < 4; ++i)
 						{
@@ -767,8 +870,15 @@ namespace tsomk
 					}
 					__syncwarp();
 				}
-				if (valid)
-					draw_face_cached(a, cx, blockCenter, pos, sm.ids[row * CS + x], fo);
+				if (flatFace)
+					draw_face_flat_r(a, cx, table, cx.flatOrigin, x, int(row & 31u), int(row >> 5), s, twin, sm.ids[row * CS + x], fo);
+				else if (valid)
+				{
+					if (flatBlock)
+						draw_face_cached_table(a, cx, table, pos, s, twin, sm.ids[row * CS + x], fo);
+					else
+						draw_face_cached(a, cx, blockCenter, pos, sm.ids[row * CS + x], fo);
+				}
 			}
 			const unsigned long long face0 = firstFace + w0 + tt * 32u;
 #pragma unroll
@@ -924,8 +1034,9 @@ namespace tsomk
 		}
 		for (int i = tid; i < LUTN; i += FUSED_THREADS)
 			sm.lut32[i] = pack_flags(a.blkFlags[uint32_t(i) < a.nTypes ? i : a.nTypes - 1], unsigned(i));
-		const bool fastFlat = a.faceTable != nullptr;
-		if (fastFlat)
+		// the attribute table serves every face of a FlatChunk and, on a DeformedChunk, the faces of blocks the deformation left in place
+		const bool fastFlat = a.faceTable != nullptr && !(a.flags & MESH_F_DEFORMED);
+		if (a.faceTable != nullptr)
 		{
 			const uint32_t* src = reinterpret_cast<const uint32_t*>(a.faceTable);
 			uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.table);
@@ -1103,6 +1214,7 @@ namespace tsomk
 				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
 				cx.wantAttr = wantRender;
 				cx.rawUp = false;
+				cx.flatOrigin = float(CS) * 0.5f;
 				if (a.gravity)
 					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);
 				else
@@ -1111,6 +1223,21 @@ namespace tsomk
 					const int4 ci = a.chunkIdx[slot];
 					cx.gravity = f3(a.center[0] - float(ci.x) * float(CS) * a.tile, a.center[1] - float(ci.y) * float(CS) * a.tile, a.center[2] - float(ci.z) * float(CS) * a.tile);
 					cx.rawUp = fastFlat && a.center[0] == 0.f && a.center[1] == 0.f && a.center[2] == 0.f && max(max(abs(ci.x), abs(ci.y)), abs(ci.z)) < (1 << 14);
+				}
+
+				// A DeformedChunk the deformation leaves alone is a FlatChunk whose corners start at 0 instead of -size / 2
+				bool tableJob = fastFlat;
+				cx.exactDeform = false;
+				if (!LEAN && cx.deformed && a.faceTable != nullptr)
+				{
+					cx.flatOrigin = 0.f;
+					cx.exactDeform = deform_is_exact(cx);
+					tableJob = cx.exactDeform && region_is_undeformed(cx, 0.f, 0.f, 0.f, float(CS) * cx.tile);
+					// faceUp of an undeformed face from the raw centre-to-face vector (see FaceCtx::rawUp): exact and well separated when
+					// the centre sits on the half-block grid within 2^20 half-blocks, like the default centre (a multiple of 32 blocks)
+					const float toHalf = 2.f / cx.tile;
+					auto halfGrid = [toHalf](float v) { const float t = v * toHalf; return fabsf(t) < 1048576.f && t == truncf(t); };
+					cx.rawUp = cx.exactDeform && halfGrid(cx.gravity.x) && halfGrid(cx.gravity.y) && halfGrid(cx.gravity.z);
 				}
 
 				float4* stage = sm.stage[warp];
@@ -1138,7 +1265,7 @@ namespace tsomk
 					if (firstFace + F > a.arenaFaces)
 						break; // arena too small: this launch only counts (the host grows the arena and runs the kernel again)
 
-					store_window<LEAN>(a, sm, sm.table, fastFlat, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, wantTangents, lane);
+					store_window<LEAN>(a, sm, sm.table, tableJob, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, wantTangents, lane);
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}
@@ -1363,7 +1490,7 @@ namespace tsomk
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st)
 	{
 		// the lean instantiation: table-driven flat path, no tangents
-		if (a.faceTable != nullptr && !(a.flags & MESH_F_TANGENTS))
+		if (a.faceTable != nullptr && !(a.flags & (MESH_F_TANGENTS | MESH_F_DEFORMED)))
 			mesh_fused_kernel<true><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
 		else
 			mesh_fused_kernel<false><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);

@@ -2047,7 +2047,7 @@ extern "C"
 		int expo = 0;
 		const bool pow2Tile = c->tile > 0.f && std::isfinite(c->tile) && std::frexp(c->tile, &expo) == 0.5f && expo > -100 && expo < 100;
 		a.faceTable = nullptr;
-		if (!(flags & (TSOM_MESH_DEFORMED | TSOM_MESH_GENERIC_MATH)) && pow2Tile)
+		if (!(flags & TSOM_MESH_GENERIC_MATH) && pow2Tile)
 		{
 			if (ctx->faceTableTile != c->tile)
 			{
