@@ -431,6 +431,7 @@ namespace tsomk
 	//     faces, finds the first row by a two-level ballot search, and lanes walk one row each, writing 16-bit face descriptors
 	//     in the reference's emission order.  Faces are then built one per lane in registers and streamed out through a
 	//     16-face staging tile with fully coalesced 16-byte stores.
+	constexpr int MODE_LEAN = 0, MODE_GENERIC = 1, MODE_TANGENTS = 2;
 	constexpr int FUSED_THREADS = 256;
 	constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 	constexpr int WIN = 128;        // faces per descriptor window
@@ -755,9 +756,10 @@ namespace tsomk
 
 	// Build the faces of the window [w0, w0 + nw) from their descriptors, one per lane, and stream them out through the warp's 16-face
 	// staging tile with coalesced 16-byte stores (vertices, collider positions, indices).
-	// LEAN: the table-driven flat path without tangents, compiled without the generic corner / attribute / tangent code (the
-	// instantiation a planet remesh runs; the other one carries everything else)
-	template<bool LEAN, class B>
+	// MODE_LEAN: the table-driven flat path without tangents, compiled without the generic corner / attribute / tangent code (the
+	// instantiation a planet remesh runs); MODE_GENERIC adds the generic corner providers and per-face attribute math (deformed
+	// chunks, other block sizes); MODE_TANGENTS adds what GenerateTangents computes on top of that
+	template<int MODE, class B>
 	__device__ __forceinline__ void store_window(const MeshArgs& a, const B& sm, const FaceTable& table, bool fastFlat, const FaceCtx& cx, uint32_t w0, uint32_t nw, uint32_t kA,
 	                                             const uint16_t* desc, float4* stage, unsigned long long firstFace, const LaneConst& lc, bool wantRender, bool wantCollider, bool wantTangents,
 	                                             int lane)
@@ -783,6 +785,7 @@ namespace tsomk
 			}
 			// a chunk the deformation touches still has plenty of blocks it leaves alone: their faces need no corner evaluation
 			bool flatFace = false;
+			constexpr bool LEAN = MODE == MODE_LEAN;
 			if (!LEAN && !fastFlat && cx.exactDeform && valid)
 				flatFace = region_is_undeformed(cx, float(x) * cx.tile, float(row >> 5) * cx.tile, float(row & 31u) * cx.tile, cx.tile);
 			if (LEAN || fastFlat)
@@ -888,7 +891,7 @@ namespace tsomk
 					break;
 				const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
 				if (valid && (uint32_t(lane) >> 4) == h)
-					store_face(stage + (lane & 15) * STAGE_FACE_F4, fo, !LEAN && wantTangents);
+					store_face(stage + (lane & 15) * STAGE_FACE_F4, fo, MODE == MODE_TANGENTS && wantTangents);
 				__syncwarp();
 				const unsigned long long faceH = face0 + h * HALF_FACES;
 				if (wantRender)
@@ -1017,7 +1020,7 @@ namespace tsomk
 		sm.job = j;
 	}
 
-	template<bool LEAN>
+	template<int MODE>
 	__global__ void __launch_bounds__(FUSED_THREADS, 2) mesh_fused_kernel(const MeshArgs a)
 	{
 		extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -1228,7 +1231,7 @@ namespace tsomk
 				// A DeformedChunk the deformation leaves alone is a FlatChunk whose corners start at 0 instead of -size / 2
 				bool tableJob = fastFlat;
 				cx.exactDeform = false;
-				if (!LEAN && cx.deformed && a.faceTable != nullptr)
+				if (MODE != MODE_LEAN && cx.deformed && a.faceTable != nullptr)
 				{
 					cx.flatOrigin = 0.f;
 					cx.exactDeform = deform_is_exact(cx);
@@ -1265,7 +1268,7 @@ namespace tsomk
 					if (firstFace + F > a.arenaFaces)
 						break; // arena too small: this launch only counts (the host grows the arena and runs the kernel again)
 
-					store_window<LEAN>(a, sm, sm.table, tableJob, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, wantTangents, lane);
+					store_window<MODE>(a, sm, sm.table, tableJob, cx, w0, nw, kA, desc, stage, firstFace, lc, wantRender, wantCollider, wantTangents, lane);
 					__syncwarp(); // the descriptors are consumed before the next window overwrites them
 				}
 			}
@@ -1477,22 +1480,28 @@ namespace tsomk
 	// ---- launchers ----
 	size_t mesh_fused_smem_bytes() { return sizeof(FusedSmem); }
 
+	template<int MODE>
+	static cudaError_t init_fused()
+	{
+		cudaError_t e = cudaFuncSetAttribute(mesh_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)));
+		return e != cudaSuccess ? e : cudaFuncSetAttribute(mesh_fused_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+	}
+
 	cudaError_t mesh_kernels_init()
 	{
 		cudaError_t e;
-		if ((e = cudaFuncSetAttribute(mesh_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)))) != cudaSuccess ||
-		    (e = cudaFuncSetAttribute(mesh_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess ||
-		    (e = cudaFuncSetAttribute(mesh_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(FusedSmem)))) != cudaSuccess)
+		if ((e = init_fused<MODE_LEAN>()) != cudaSuccess || (e = init_fused<MODE_GENERIC>()) != cudaSuccess)
 			return e;
-		return cudaFuncSetAttribute(mesh_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+		return init_fused<MODE_TANGENTS>();
 	}
 
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st)
 	{
-		// the lean instantiation: table-driven flat path, no tangents
-		if (a.faceTable != nullptr && !(a.flags & (MESH_F_TANGENTS | MESH_F_DEFORMED)))
-			mesh_fused_kernel<true><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+		if (a.flags & MESH_F_TANGENTS)
+			mesh_fused_kernel<MODE_TANGENTS><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+		else if (a.faceTable != nullptr && !(a.flags & MESH_F_DEFORMED))
+			mesh_fused_kernel<MODE_LEAN><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
 		else
-			mesh_fused_kernel<false><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
+			mesh_fused_kernel<MODE_GENERIC><<<grid, FUSED_THREADS, sizeof(FusedSmem), st>>>(a);
 	}
 }
