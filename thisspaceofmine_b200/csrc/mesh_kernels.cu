@@ -431,6 +431,9 @@ namespace tsomk
 	//     faces, finds the first row by a two-level ballot search, and lanes walk one row each, writing 16-bit face descriptors
 	//     in the reference's emission order.  Faces are then built one per lane in registers and streamed out through a
 	//     16-face staging tile with fully coalesced 16-byte stores.
+	// The arenas are written once and read by someone else much later (a copy to the host, a renderer): streaming stores
+	// (st.global.cs, evict-first in L2) keep 40 GB of output from pushing the ids the mesher still has to read out of L2 (47^3: 8.44 -> 8.34 ms)
+#define ST_OUT(ptr, val) __stcs((ptr), (val))
 	constexpr int MODE_LEAN = 0, MODE_GENERIC = 1, MODE_TANGENTS = 2;
 	constexpr int FUSED_THREADS = 256;
 	constexpr int FUSED_WARPS = FUSED_THREADS / 32;
@@ -901,7 +904,7 @@ namespace tsomk
 					{
 #pragma unroll
 						for (int k = 0; k < 6; ++k)
-							dst[32 * k] = stage[lc.stageOff[k]];
+							ST_OUT(dst + 32 * k, stage[lc.stageOff[k]]);
 					}
 					else
 					{
@@ -909,7 +912,7 @@ namespace tsomk
 #pragma unroll
 						for (int k = 0; k < 6; ++k)
 							if (uint32_t(lane) + 32u * k < n4)
-								dst[32 * k] = stage[lc.stageOff[k]];
+								ST_OUT(dst + 32 * k, stage[lc.stageOff[k]]);
 					}
 				}
 				if (wantCollider)
@@ -921,7 +924,7 @@ namespace tsomk
 					for (uint32_t i = lane; i < n4; i += 32u)
 					{
 						const ushort4 o = sm.colOff[i];
-						dst[i] = make_float4(sf[o.x], sf[o.y], sf[o.z], sf[o.w]);
+						ST_OUT(dst + i, make_float4(sf[o.x], sf[o.y], sf[o.z], sf[o.w]));
 					}
 				}
 				__syncwarp();
@@ -934,7 +937,7 @@ namespace tsomk
 #pragma unroll
 				for (int k = 0; k < 3; ++k)
 					if (nf == 32u || uint32_t(lane) + 32u * k < n2)
-						dst[32 * k] = make_uint2(lc.idxPat[k].x + base, lc.idxPat[k].y + base);
+						ST_OUT(dst + 32 * k, make_uint2(lc.idxPat[k].x + base, lc.idxPat[k].y + base));
 			}
 		}
 	}
