@@ -716,17 +716,41 @@ namespace tsomk
 		for (uint32_t k0 = kA; k0 <= kB; k0 += 32u >> lgS)
 		{
 			const uint32_t k = k0 + (uint32_t(lane) >> lgS);
+			uint32_t v[6] = { 0u, 0u, 0u, 0u, 0u, 0u };
+			uint32_t d = 0u, p = 0u, base = 0u, any = 0u;
 			if (k <= kB)
 			{
 				const uint32_t en = sm.ne[k];
-				uint32_t v[6];
-				const uint32_t d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
-				uint32_t p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
+				d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
+				p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
 #pragma unroll
 				for (int s = 0; s < 6; ++s)
 					p += __popc(v[s] & below) + __popc(v[s] & d & below);
-				const uint32_t base = (k - kA) << 9;
-				uint32_t any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+				base = (k - kA) << 9;
+				any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+			}
+			// no double-sided block in any of these rows (a planet has none): half the loop body
+			if (!__any_sync(FULL, d != 0u))
+			{
+				while (any && int(p) < int(nw))
+				{
+					const uint32_t x = uint32_t(__ffs(any) - 1);
+					any &= any - 1u;
+					const uint32_t bit = 1u << x;
+#pragma unroll
+					for (uint32_t s = 0; s < 6; ++s)
+					{
+						if (v[s] & bit)
+						{
+							if (p < nw)
+								desc[p] = uint16_t(base | x | (s << 5));
+							++p;
+						}
+					}
+				}
+			}
+			else
+			{
 				while (any && int(p) < int(nw))
 				{
 					const uint32_t x = uint32_t(__ffs(any) - 1);
