@@ -636,7 +636,8 @@ def microbench(args, T, ctx, torch, device, peak):
     res = {"workload": "config[1]: 4096 independent 32^3 chunks, random solid/air fill p=0.5 (stone), mesh-only, render attributes", "chunks": n, "faces": faces, "kernel_ms": t,
            "value": n / (t / 1e3), "unit": "chunks/s",
            "roofline": {"bound": "hbm", "kernel": "mesh_fused_kernel", "achieved": algo / (t / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (t / 1e3) / 1e9 / peak,
-                        "algorithmic_bytes_per_launch": algo, "traffic": ncu_traffic("config1_4096")}}
+                        "algorithmic_bytes_per_launch": algo, "traffic": ncu_traffic("config1_4096"),
+                        "note": "the measured peak is a COPY (half reads, half writes); this launch is 94 % writes issued as streaming stores, so it can land a little above it"}}
     # the two other fills of SURVEY.md §8(d) config 2 (1024 chunks): sparse p = 0.05, and ids uniform over {0, 2, 3, 7, 8, 9, 13}
     m = 1024
     sub = np.ascontiguousarray(idx[:m])
