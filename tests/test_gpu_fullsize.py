@@ -197,3 +197,28 @@ def test_planet_full_size_properties(ctx, edge):
     assert np.array_equal(batch2.face_counts, batch.face_counts)
     assert checksum() == ck1, "regenerate + remesh must be idempotent"
     planet.close()
+
+
+def test_deformed_planet_shortcuts_equal_generic_math_on_every_chunk(ctx):
+    """31^3 planet, DeformedChunk corners (radius 16) + collider: the run that sends undeformed chunks / blocks through the flat
+    path's attribute table must write the same bytes as the run that evaluates DrawFace for every face (TSOM_MESH_GENERIC_MATH) —
+    device checksums of every chunk's vertex words and indices, plus the face counts; and the same for the collider positions of a
+    collider-only run."""
+    import thisspaceofmine_b200 as T
+
+    cc = (31, 31, 31)
+    planet = T.Planet(ctx, capacity=31 ** 3)
+    try:
+        planet.GenerateChunks(ctx.blockLibrary, 42, cc)
+        grid = T.Planet.chunk_grid(cc)
+        for kw in (dict(render=True, collider=True), dict(render=False, collider=True)):
+            fast = planet.BuildMeshes(grid, deformed=True, deformRadius=16.0, ordered=True, **kw)
+            fc, fs = np.asarray(fast.face_counts).copy(), fast.checksums()
+            gen = planet.BuildMeshes(grid, deformed=True, deformRadius=16.0, ordered=True, genericMath=True, **kw)
+            assert np.array_equal(fc, gen.face_counts)
+            gs = gen.checksums()
+            bad = np.nonzero((fs != gs).any(axis=1))[0]
+            assert len(bad) == 0, f"{kw}: {len(bad)} chunks differ, first {grid[bad[0]].tolist()}"
+            assert int(fc.sum()) == 53483600
+    finally:
+        planet.close()
