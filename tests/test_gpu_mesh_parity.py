@@ -180,6 +180,37 @@ def test_deformed_table_shortcut_is_bit_identical_to_generic_math(ctx, tile, rad
         assert_mesh_equal(g, op.mesh(k, deformed=True, deform_radius=radius, gravity_center=centers[i]), f"own centre: tile {tile} radius {radius} chunk {k}")
 
 
+def test_deformed_table_shortcut_random_centres_and_radii(ctx):
+    """Forty random (radius, centre) pairs — on and off the 2^-10 grid, near and far, radii with r * (1 / r) != 1 among them — over chunks
+    at the corner, on an edge, on a face and in the middle of a planet: the shortcut run and the generic-math run write the same bits."""
+    rng = np.random.default_rng(41)
+    keys = [(2, 2, 2), (2, -2, 0), (0, 3, 0), (0, 0, 0), (-3, 1, 0), (1, 0, -3)]
+    chunks = {k: random_chunk(rng, 0.35, ids=(1, 3, 7, 13)) for k in keys}
+    gc, op = _pair(ctx, chunks)
+    idx = list(chunks)
+    taken = 0
+    for trial in range(40):
+        radius = float(rng.choice([0.0, 1.0, 3.0, 7.5, 16.0, 41.0, 49.0, 0.3, 100.0 / 3.0, 12.125]))
+        kw = dict(deformed=True, deformRadius=radius)
+        if trial % 2:
+            c = rng.normal(0, 150, (len(idx), 3))
+            c = np.round(c * 4) / 4 if trial % 4 == 1 else c  # quarter-block grid or arbitrary
+            kw["gravityCenters"] = c.astype(np.float32)
+        fast = gc.BuildMeshes(idx, **kw)
+        meshes_fast = [fast.chunk(i) for i in range(len(idx))]
+        gen = gc.BuildMeshes(idx, genericMath=True, **kw)
+        meshes_gen = [gen.chunk(i) for i in range(len(idx))]  # a batch's views die with the next BuildMeshes call
+        for i, k in enumerate(idx):
+            g = meshes_gen[i]
+            assert np.array_equal(meshes_fast[i].vertices.view(np.uint32), g.vertices.view(np.uint32)), f"trial {trial} radius {radius} chunk {k}"
+            assert np.array_equal(meshes_fast[i].indices, g.indices)
+        # how often the geometry really was left in place (the shortcut is exercised, not just skipped)
+        if "gravityCenters" not in kw:
+            flat = gc.BuildMeshes(idx)
+            taken += sum(int(np.array_equal(flat.chunk(i).normal, meshes_gen[i].normal)) for i in range(len(idx)))
+    assert taken > 0
+
+
 def test_batch_order_and_views(ctx):
     """One batched call: per-chunk views are dense, in job order, and each equals the single-chunk result."""
     rng = np.random.default_rng(21)
