@@ -610,8 +610,10 @@ namespace tsomk
 	}
 
 	// visibility masks of row r in emission-slot order; returns the row's double-sided mask.  Thread-local (no warp collectives).
+	// The same-type suppression of transparent blocks is applied to the blocks of `fixMask` only (a lane that shares a row with others
+	// fixes its own segment); `hadNeed` says whether the row has transparent non-empty blocks at all.
 	template<class B>
-	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const B& sm, uint32_t slot, int r, uint32_t v[6])
+	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const B& sm, uint32_t slot, int r, uint32_t v[6], uint32_t fixMask, bool& hadNeed)
 	{
 		const int z = r >> 5, y = r & 31;
 		const uint32_t t = sm.mT[r], e = sm.mE[r];
@@ -630,6 +632,8 @@ namespace tsomk
 
 		// transparent non-empty blocks (glass, forcefield): no face towards a neighbour of the same type (Chunk.cpp:192-194)
 		uint32_t need = e & t;
+		hadNeed = need != 0u;
+		need &= fixMask;
 		while (need)
 		{
 			const int x = __ffs(need) - 1;
@@ -656,6 +660,13 @@ namespace tsomk
 					v[5] &= ~bit;
 		}
 		return sm.mD[r];
+	}
+
+	template<class B>
+	__device__ __forceinline__ uint32_t row_vis(const MeshArgs& a, const B& sm, uint32_t slot, int r, uint32_t v[6])
+	{
+		bool hadNeed;
+		return row_vis(a, sm, slot, r, v, 0xFFFFFFFFu, hadNeed);
 	}
 
 	// per-lane write-out constants: a staging round is 16 faces = 192 float4; an index tile is 32 faces = 96 uint2
@@ -718,16 +729,39 @@ namespace tsomk
 			const uint32_t k = k0 + (uint32_t(lane) >> lgS);
 			uint32_t v[6] = { 0u, 0u, 0u, 0u, 0u, 0u };
 			uint32_t d = 0u, p = 0u, base = 0u, any = 0u;
+			bool hadNeed = false;
 			if (k <= kB)
 			{
 				const uint32_t en = sm.ne[k];
-				d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v);
+				d = row_vis(a, sm, slot, int(en >> NE_ROW_SHIFT), v, segMask, hadNeed);
 				p = (en & NE_OFF_MASK) - w0; // wraps for the part of the first row that precedes the window
+				base = (k - kA) << 9;
+				any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+			}
+			if (!__any_sync(FULL, hadNeed))
+			{
+				// nothing to suppress in these rows: the masks are final everywhere, the faces in front of this lane's segment are counted directly
 #pragma unroll
 				for (int s = 0; s < 6; ++s)
 					p += __popc(v[s] & below) + __popc(v[s] & d & below);
-				base = (k - kA) << 9;
-				any = (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) & segMask;
+			}
+			else
+			{
+				// rows with transparent non-empty blocks (glass next to glass shows no face): every lane has run the suppression for its own
+				// segment only, so the faces in front of it are the sum over the lanes to its left in the row's group
+				uint32_t cnt = 0u;
+#pragma unroll
+				for (int s = 0; s < 6; ++s)
+					cnt += __popc(v[s] & segMask) + __popc(v[s] & d & segMask);
+				uint32_t incl = cnt;
+				const uint32_t sub = uint32_t(lane) & ((1u << lgS) - 1u);
+				for (uint32_t o = 1u; o < (1u << lgS); o <<= 1)
+				{
+					const uint32_t n = __shfl_up_sync(FULL, incl, o);
+					if (sub >= o)
+						incl += n;
+				}
+				p += incl - cnt;
 			}
 			// no double-sided block in any of these rows (a planet has none): half the loop body
 			if (!__any_sync(FULL, d != 0u))
