@@ -60,7 +60,9 @@ namespace tsomk
 		// DeformedChunk (DeformedChunk.cpp:117-119) when the table-driven path serves a chunk the deformation leaves untouched
 		float flatOrigin;
 		bool exactDeform; // deform_is_exact: regions may be classified as undeformed without evaluating DeformPosition
+		const uint8_t* tex8; // shared-memory copy of the texture-slice table ([TEX8N][6] bytes) or nullptr
 	};
+	constexpr int TEX8N = 128;
 
 	// DeformedChunk::DeformPosition (reference src/CommonLib/DeformedChunk.cpp:139-154)
 	__device__ __forceinline__ F3 deform_position(const FaceCtx& cx, F3 p)
@@ -215,8 +217,11 @@ namespace tsomk
 		}
 	}
 
-	__device__ __forceinline__ unsigned tex_slice(const MeshArgs& a, unsigned id, int texDir)
+	__device__ __forceinline__ unsigned tex_slice(const MeshArgs& a, const FaceCtx& cx, unsigned id, int texDir)
 	{
+		// the texture slices of the first TEX8N block types as bytes in shared memory (when they all fit a byte)
+		if (cx.tex8 != nullptr && id < unsigned(TEX8N))
+			return cx.tex8[id * 6u + unsigned(texDir)];
 		return __ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir);
 	}
 
@@ -288,7 +293,7 @@ namespace tsomk
 			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
 			int texDir;
 			face_attrs(a.quat, faceUp, blockCenter, o.pos, fc, o.n, texDir, o.u, o.v);
-			o.slice = float(tex_slice(a, id, texDir));
+			o.slice = float(tex_slice(a, cx, id, texDir));
 		}
 	}
 
@@ -313,7 +318,7 @@ namespace tsomk
 			const int faceUp = direction_from_normal(normalize(fc - cx.gravity));
 			int texDir;
 			face_attrs(a.quat, faceUp, blockCenter, o.pos, fc, o.n, texDir, o.u, o.v);
-			o.slice = float(tex_slice(a, id, texDir));
+			o.slice = float(tex_slice(a, cx, id, texDir));
 		}
 	}
 
@@ -375,7 +380,7 @@ namespace tsomk
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
 			n = tb.normal[slot];
-			o.slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
+			o.slice = float(tex_slice(a, cx, id, int(tb.texDir[faceUp][slot])));
 		}
 		o.n = f3(n.x, n.y, n.z);
 		o.u[0] = uv0.x; o.v[0] = uv0.y;
@@ -405,7 +410,7 @@ namespace tsomk
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
 			n = tb.normal[slot];
-			o.slice = float(tex_slice(a, id, int(tb.texDir[faceUp][slot])));
+			o.slice = float(tex_slice(a, cx, id, int(tb.texDir[faceUp][slot])));
 		}
 		o.n = f3(n.x, n.y, n.z);
 		o.u[0] = uv0.x; o.v[0] = uv0.y;
@@ -452,6 +457,7 @@ namespace tsomk
 		float4 stage[FUSED_WARPS][HALF_FACES * STAGE_FACE_F4];
 		uint16_t desc[FUSED_WARPS][WIN];  // x | slot << 5 | twin << 8 | (compact row - first compact row of the window) << 9
 		uint32_t lut32[LUTN];
+		uint8_t tex8[TEX8N * 6];          // texture slice per (block type, direction) when MeshArgs::texFits8
 		alignas(16) FaceTable table;
 		uint32_t warpSum[FUSED_WARPS];
 		uint32_t job, slot, hasContent;   // the ticket and what it names (written by the lane that took the ticket)
@@ -1103,6 +1109,9 @@ namespace tsomk
 			for (int i = tid; i < int(sizeof(FaceTable) / 4); i += FUSED_THREADS)
 				dst[i] = src[i];
 		}
+		if (a.texFits8)
+			for (int i = tid; i < TEX8N * 6; i += FUSED_THREADS)
+				sm.tex8[i] = uint8_t(a.blkTex[size_t(uint32_t(i / 6) < a.nTypes ? i / 6 : a.nTypes - 1) * 6 + i % 6]);
 		const LaneConst lc = lane_constants(lane);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
@@ -1261,6 +1270,7 @@ namespace tsomk
 				cx.deformed = (a.flags & MESH_F_DEFORMED) != 0;
 				cx.wantAttr = wantRender;
 				cx.rawUp = false;
+				cx.tex8 = a.texFits8 ? sm.tex8 : nullptr;
 				cx.flatOrigin = float(CS) * 0.5f;
 				if (a.gravity)
 					cx.gravity = f3(a.gravity[size_t(job) * 3 + 0], a.gravity[size_t(job) * 3 + 1], a.gravity[size_t(job) * 3 + 2]);

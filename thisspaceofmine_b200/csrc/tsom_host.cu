@@ -255,6 +255,7 @@ struct tsom_ctx
 	// block table
 	uint8_t* dFlags = nullptr;
 	uint32_t* dTex = nullptr;
+	bool texFits8 = false; // every texture slice < 256: the mesher keeps the table as bytes in shared memory
 	uint32_t nTypes = 0;
 	std::vector<uint8_t> hostFlags; // BF_* per type, host copy (the generator derives the chunk summaries it may write from it)
 	uint32_t tableEpoch = 0;        // bumped by tsom_set_block_table: chunk summaries made under another table are void
@@ -983,6 +984,7 @@ extern "C"
 		TSOM_CUDA(cudaMemcpy(ctx->dFlags, flags.data(), n, cudaMemcpyHostToDevice));
 		TSOM_CUDA(cudaMemcpy(ctx->dTex, tex.data(), tex.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		ctx->nTypes = n;
+		ctx->texFits8 = std::all_of(tex.begin(), tex.end(), [](uint32_t t) { return t < 256u; });
 		ctx->hostFlags = flags;
 		++ctx->tableEpoch; // chunk summaries made under the previous table no longer hold
 		return TSOM_OK;
@@ -2034,6 +2036,7 @@ extern "C"
 		a.nJobs = n;
 		a.blkFlags = ctx->dFlags;
 		a.blkTex = ctx->dTex;
+		a.texFits8 = ctx->texFits8 ? 1u : 0u;
 		a.nTypes = ctx->nTypes;
 		a.faceCount = ctx->faceCount.ptr;
 		a.overflow = ctx->dSmall + 3;

@@ -43,6 +43,7 @@ namespace tsomk
 		const uint8_t* blkFlags;
 		const uint32_t* blkTex;          // [nTypes][6]
 		uint32_t nTypes;
+		uint32_t texFits8;               // every texture slice of the table is below 256
 		// results per job + the chained scan over the jobs (decoupled look-back)
 		uint32_t* faceCount;                   // [nJobs]
 		uint32_t* jobCounter;                  // work-stealing ticket, zeroed before each launch
