@@ -348,7 +348,13 @@ namespace tsomk
 		table->uv[faceUp][slot][twin][1] = make_float4(u[2], v[2], u[3], v[3]);
 		table->texDir[faceUp][slot] = uint32_t(texDir);
 		if (faceUp == 0 && !twin)
-			table->normal[slot] = make_float4(normal.x, normal.y, normal.z, 0.f);
+		{
+			// .w: the corner codes of the slot's four vertices, 3 bits each, in emission order (bits 0-11) and in the twin's order (bits 16-27)
+			uint32_t packed = 0u;
+			for (int i = 0; i < 4; ++i)
+				packed |= (uint32_t(c_faceCorners[slot][i]) << (3 * i)) | (uint32_t(c_faceCorners[slot][i ^ 1]) << (16 + 3 * i));
+			table->normal[slot] = make_float4(normal.x, normal.y, normal.z, __uint_as_float(packed));
+		}
 	}
 
 	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st) { face_table_kernel<<<1, 96, 0, st>>>(table, tile, a); }
@@ -361,12 +367,12 @@ namespace tsomk
 		const float oy = (float(z) - origin) * s;
 		const float oz = (float(y) - origin) * s;
 		const float ex = ox + s, ey = oy + s, ez = oz + s;
+		// one shared-memory load instead of four constant-bank loads at a per-lane index (the slot differs from lane to lane)
+		const float4 nc = tb.normal[slot];
+		const uint32_t codes = twin ? __float_as_uint(nc.w) >> 16 : __float_as_uint(nc.w);
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
-		{
-			const unsigned code = c_faceCorners[slot][twin ? (i ^ 1) : i];
-			o.pos[i] = f3((code & 1u) ? ex : ox, (code & 2u) ? ey : oy, (code & 4u) ? ez : oz);
-		}
+			o.pos[i] = f3((codes >> (3 * i)) & 1u ? ex : ox, (codes >> (3 * i + 1)) & 1u ? ey : oy, (codes >> (3 * i + 2)) & 1u ? ez : oz);
 		float4 uv0 = make_float4(0.f, 0.f, 0.f, 0.f), uv1 = uv0, n = uv0;
 		o.slice = 0.f;
 		if (cx.wantAttr)
@@ -379,7 +385,7 @@ namespace tsomk
 			const int faceUp = cx.rawUp ? direction_from_normal(fc - cx.gravity) : direction_from_normal(normalize(fc - cx.gravity));
 			uv0 = tb.uv[faceUp][slot][twin][0];
 			uv1 = tb.uv[faceUp][slot][twin][1];
-			n = tb.normal[slot];
+			n = nc;
 			o.slice = float(tex_slice(a, cx, id, int(tb.texDir[faceUp][slot])));
 		}
 		o.n = f3(n.x, n.y, n.z);
