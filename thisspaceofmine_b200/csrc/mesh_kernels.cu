@@ -277,6 +277,18 @@ namespace tsomk
 		}
 	}
 
+	// the same face without tangents in 9 float4: the third float4 {w 0 0 0} of the four vertices is staged once
+	__device__ __forceinline__ void store_face_compact(float4* out, const FaceOut& f)
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			out[i] = make_float4(f.pos[i].x, f.pos[i].y, f.pos[i].z, f.n.x);
+			out[4 + i] = make_float4(f.n.y, f.n.z, f.u[i], f.v[i]);
+		}
+		out[8] = make_float4(f.slice, 0.f, 0.f, 0.f);
+	}
+
 	// DrawFace (Chunk.cpp:22-102), generic arithmetic
 	__device__ __forceinline__ void draw_face_r(const MeshArgs& a, const FaceCtx& cx, int x, int y, int z, int slot, bool twin, unsigned id, FaceOut& o)
 	{
@@ -686,14 +698,17 @@ namespace tsomk
 		uint2 idxPat[3];
 	};
 
-	__device__ __forceinline__ LaneConst lane_constants(int lane)
+	// `compact`: the staging slot of a face without tangents holds 9 float4 — 4 x {px py pz nx}, 4 x {ny nz u v} and ONE {w 0 0 0}
+	// that all four vertices read (store_face_compact)
+	__device__ __forceinline__ LaneConst lane_constants(int lane, bool compact)
 	{
 		LaneConst lc;
 #pragma unroll
 		for (int k = 0; k < 6; ++k)
 		{
 			const uint32_t i = uint32_t(lane) + 32u * k;
-			lc.stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (i % 12u);
+			const uint32_t e = i % 12u, v = e / 3u, part = e % 3u;
+			lc.stageOff[k] = (i / 12u) * STAGE_FACE_F4 + (compact ? (part == 0u ? v : (part == 1u ? 4u + v : 8u)) : e);
 		}
 #pragma unroll
 		for (int k = 0; k < 3; ++k)
@@ -964,7 +979,12 @@ namespace tsomk
 						break;
 					const uint32_t nh = min(uint32_t(HALF_FACES), nf - h * HALF_FACES);
 					if (valid && (uint32_t(lane) >> 4) == h)
-						store_face(stage + (lane & 15) * STAGE_FACE_F4, fo, MODE == MODE_TANGENTS && wantTangents);
+					{
+						if (MODE == MODE_TANGENTS)
+							store_face(stage + (lane & 15) * STAGE_FACE_F4, fo, wantTangents);
+						else
+							store_face_compact(stage + (lane & 15) * STAGE_FACE_F4, fo);
+					}
 					__syncwarp();
 					float4* dst = a.vertices + (face0 + h * HALF_FACES) * 12ull + lane;
 					if (nh == HALF_FACES)
@@ -1118,7 +1138,7 @@ namespace tsomk
 		if (a.texFits8)
 			for (int i = tid; i < TEX8N * 6; i += FUSED_THREADS)
 				sm.tex8[i] = uint8_t(a.blkTex[size_t(uint32_t(i / 6) < a.nTypes ? i / 6 : a.nTypes - 1) * 6 + i % 6]);
-		const LaneConst lc = lane_constants(lane);
+		const LaneConst lc = lane_constants(lane, MODE != MODE_TANGENTS);
 		const bool wantRender = (a.flags & MESH_F_RENDER) != 0;
 		const bool wantCollider = (a.flags & MESH_F_COLLIDER) != 0;
 		const bool wantTangents = (a.flags & MESH_F_TANGENTS) != 0;
