@@ -217,12 +217,18 @@ namespace tsomk
 		}
 	}
 
+	// out of line so that the shared-memory path below is a real branch around the global load (inlined, both loads were issued)
+	__device__ __noinline__ unsigned tex_slice_global(const uint32_t* blkTex, uint32_t nTypes, unsigned id, int texDir)
+	{
+		return __ldg(blkTex + size_t(id < nTypes ? id : nTypes - 1) * 6 + texDir);
+	}
+
 	__device__ __forceinline__ unsigned tex_slice(const MeshArgs& a, const FaceCtx& cx, unsigned id, int texDir)
 	{
 		// the texture slices of the first TEX8N block types as bytes in shared memory (when they all fit a byte)
 		if (cx.tex8 != nullptr && id < unsigned(TEX8N))
 			return cx.tex8[id * 6u + unsigned(texDir)];
-		return __ldg(a.blkTex + size_t(id < a.nTypes ? id : a.nTypes - 1) * 6 + texDir);
+		return tex_slice_global(a.blkTex, a.nTypes, id, texDir);
 	}
 
 	// one face held in registers: 4 positions, the shared normal, 4 uv pairs and the texture slice
