@@ -434,6 +434,8 @@ struct tsom_container
 	// dense chunk-index -> slot grid over the bounding box of the existing chunks (O(1) lookups for per-tick batches: edits,
 	// dirty sets, mesh jobs); rebuilt lazily after the set of chunks changed, skipped for very sparse containers
 	mutable std::vector<uint32_t> hostGrid;
+	mutable std::vector<uint32_t> gridOrderXYZ; // the slots of the grid in (x, y, z) order of their chunk indices (tsom_collect_dirty's output order)
+	std::vector<uint8_t> dirtySeen;             // scratch of tsom_collect_dirty
 	mutable int32_t gridOrigin[3] = { 0, 0, 0 }, gridDim[3] = { 0, 0, 0 };
 	mutable bool hostGridValid = false, hostGridUsable = false;
 
@@ -468,6 +470,16 @@ struct tsom_container
 		hostGrid.assign(size_t(cells), 0xFFFFFFFFu);
 		for (auto& kv : slotOf)
 			hostGrid[(size_t(kv.first.z - lo[2]) * gridDim[1] + size_t(kv.first.y - lo[1])) * gridDim[0] + size_t(kv.first.x - lo[0])] = kv.second;
+		gridOrderXYZ.clear();
+		gridOrderXYZ.reserve(slotOf.size());
+		for (size_t x = 0; x < size_t(gridDim[0]); ++x)
+			for (size_t y = 0; y < size_t(gridDim[1]); ++y)
+				for (size_t z = 0; z < size_t(gridDim[2]); ++z)
+				{
+					const uint32_t sl = hostGrid[(z * size_t(gridDim[1]) + y) * size_t(gridDim[0]) + x];
+					if (sl != 0xFFFFFFFFu)
+						gridOrderXYZ.push_back(sl);
+				}
 		hostGridUsable = true;
 	}
 
@@ -1835,74 +1847,81 @@ extern "C"
 		TSOM_LOCK(ctx);
 		TSOM_CUDA(cudaSetDevice(ctx->device));
 		const uint32_t n = c->highWater;
-		std::vector<uint8_t> mask(n, 0);
+		const uint8_t* mask = nullptr; // the device's invalidation bytes (edits), read where the copy lands: pinned memory
 		if (n)
 		{
 			TSOM_CUDA(ctx->EnsurePinned(n));
 			TSOM_CUDA(cudaMemcpyAsync(ctx->hPinned, c->dInvalid, n, cudaMemcpyDeviceToHost, ctx->stream));
 			TSOM_CUDA(cudaStreamSynchronize(ctx->stream));
-			std::memcpy(mask.data(), ctx->hPinned, n);
+			mask = static_cast<const uint8_t*>(ctx->hPinned);
 		}
 		const bool wantClear = clear != 0;
-		clear = 0; // decided below: a list that does not fit the caller's buffer must not be lost
-		std::vector<Key> dirty;
-		std::vector<uint8_t> seen(n, 0);
+		// ChunkEntities::Update's set: every invalidated chunk with content plus the neighbours its mask names (ChunkEntities.cpp:73-112)
+		std::vector<uint8_t>& seen = c->dirtySeen;
+		seen.assign(n, 0);
+		c->EnsureHostGrid();
+		uint32_t count = 0;
 		for (uint32_t s = 0; s < n; ++s)
 		{
 			const uint8_t m = mask[s] | c->hostInvalid[s];
 			if (!(m & 0x80u) || !c->exists[s] || !c->hasContent[s])
 				continue;
-			if (!seen[s])
-			{
-				seen[s] = 1;
-				dirty.push_back(c->idxOf[s]);
-			}
+			count += seen[s] ? 0u : 1u;
+			seen[s] = 1;
+			if (!(m & 0x3Fu))
+				continue;
 			const Key k = c->idxOf[s];
 			for (int d = 0; d < 6; ++d)
 			{
 				if (!(m & (1u << d)))
 					continue;
-				uint32_t ns = c->SlotOf(Key{ k.x + kChunkDirOffset[d][0], k.y + kChunkDirOffset[d][1], k.z + kChunkDirOffset[d][2] });
+				const uint32_t ns = c->SlotOf(Key{ k.x + kChunkDirOffset[d][0], k.y + kChunkDirOffset[d][1], k.z + kChunkDirOffset[d][2] });
 				if (ns == 0xFFFFFFFFu || !c->hasContent[ns] || seen[ns])
 					continue;
 				seen[ns] = 1;
-				dirty.push_back(c->idxOf[ns]);
+				++count;
 			}
 		}
-		c->EnsureHostGrid();
-		if (c->hostGridUsable && dirty.size() * 8 > c->hostGrid.size())
+		*n_out = count;
+		// a list that does not fit the caller's buffer must not be lost
+		if (wantClear && chunk_indices_out && count > cap)
+			return Fail(TSOM_ERR_CAPACITY, "chunk_indices_out holds " + std::to_string(cap) + " chunks, " + std::to_string(count) + " are invalidated; nothing was cleared");
+		if (chunk_indices_out)
 		{
-			// many dirty chunks: emit them in (x, y, z) order by walking the dense slot grid with x outermost instead of sorting
-			dirty.clear();
-			const size_t nx = size_t(c->gridDim[0]), ny = size_t(c->gridDim[1]), nz = size_t(c->gridDim[2]);
-			for (size_t x = 0; x < nx; ++x)
-				for (size_t y = 0; y < ny; ++y)
-					for (size_t z = 0; z < nz; ++z)
-					{
-						const uint32_t s = c->hostGrid[(z * ny + y) * nx + x];
-						if (s != 0xFFFFFFFFu && seen[s])
-							dirty.push_back(c->idxOf[s]);
-					}
+			// sorted by (x, y, z): the slots of the dense grid are kept in that order; without a grid (scattered chunks) sort the set
+			uint32_t i = 0;
+			auto put = [&](const Key& k) {
+				if (i < cap)
+				{
+					chunk_indices_out[i * 3 + 0] = k.x;
+					chunk_indices_out[i * 3 + 1] = k.y;
+					chunk_indices_out[i * 3 + 2] = k.z;
+				}
+				++i;
+			};
+			if (c->hostGridUsable)
+			{
+				for (uint32_t sl : c->gridOrderXYZ)
+					if (sl < n && seen[sl])
+						put(c->idxOf[sl]);
+			}
+			else
+			{
+				std::vector<Key> dirty;
+				dirty.reserve(count);
+				for (uint32_t s = 0; s < n; ++s)
+					if (seen[s])
+						dirty.push_back(c->idxOf[s]);
+				std::sort(dirty.begin(), dirty.end());
+				for (const Key& k : dirty)
+					put(k);
+			}
 		}
-		else
-			std::sort(dirty.begin(), dirty.end());
-		*n_out = uint32_t(dirty.size());
 		if (wantClear)
 		{
-			if (chunk_indices_out && dirty.size() > cap)
-				return Fail(TSOM_ERR_CAPACITY, "chunk_indices_out holds " + std::to_string(cap) + " chunks, " + std::to_string(dirty.size()) + " are invalidated; nothing was cleared");
 			std::fill(c->hostInvalid.begin(), c->hostInvalid.begin() + n, uint8_t(0));
 			if (n)
 				TSOM_CUDA(cudaMemsetAsync(c->dInvalid, 0, n, ctx->stream));
-		}
-		if (chunk_indices_out)
-		{
-			for (uint32_t i = 0; i < dirty.size() && i < cap; ++i)
-			{
-				chunk_indices_out[i * 3 + 0] = dirty[i].x;
-				chunk_indices_out[i * 3 + 1] = dirty[i].y;
-				chunk_indices_out[i * 3 + 2] = dirty[i].z;
-			}
 		}
 		return TSOM_OK;
 	}
