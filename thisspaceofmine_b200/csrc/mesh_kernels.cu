@@ -1106,7 +1106,23 @@ namespace tsomk
 	// load behind the atomic)
 	__device__ __forceinline__ void take_ticket(const MeshArgs& a, FusedSmem& sm)
 	{
-		const uint32_t j = atomicAdd(a.jobCounter, 1u);
+		uint32_t j = atomicAdd(a.jobCounter, 1u);
+		if (a.order != nullptr && j < a.nJobs)
+		{
+			// ticket -> job through the bucket lists (heavy chunks first)
+			uint32_t t = j, q = 0u;
+#pragma unroll
+			for (int b = 0; b < JOB_BUCKETS - 1; ++b)
+			{
+				const uint32_t cnt = a.bucketCount[b];
+				if (q == uint32_t(b) && t >= cnt)
+				{
+					t -= cnt;
+					q = uint32_t(b) + 1u;
+				}
+			}
+			j = a.order[size_t(q) * a.nJobs + t];
+		}
 		const uint32_t entry = j < a.nJobs ? a.jobSlot[j] : 0u;
 		sm.slot = entry & JOB_SLOT_MASK;
 		// a chunk whose summary proves that it has no face (job_classify_kernel) is treated like one without content: 0 faces, no stage;
@@ -1285,6 +1301,7 @@ namespace tsomk
 					*reinterpret_cast<volatile uint32_t*>(&sm.ffSeq) = job + 1u;
 					a.faceCount[job] = F;
 					a.firstFaceOut[job] = excl;
+					a.lastFaces[slot] = F;
 					if (ordered && job == a.nJobs - 1u)
 						*a.totalFacesOut = excl + F;
 					if (F > 0 && excl + F > a.arenaFaces)
@@ -1527,14 +1544,17 @@ namespace tsomk
 	// job_classify_kernel — one thread per job: a chunk that is all Empty, or all opaque with six all-opaque neighbours, has no face
 	// (Chunk.cpp:190-201: a face needs a non-Empty block next to a transparent one or to a missing chunk).  The summaries come for free
 	// from the producers (generate_kernel); two thirds of a large planet are such chunks and skip their 64 KiB stage this way.
+	// It also deals the tickets of the unordered mode: jobs go into JOB_BUCKETS lists by the face count their chunk had the last time it
+	// was meshed (heavy first, jobs without faces last), so that the persistent CTAs of mesh_fused_kernel end on small chunks instead of
+	// on whatever the caller's list ends with (a planet's list ends with its +z surface).  One atomic per warp and bucket.
 	__global__ void __launch_bounds__(256) job_classify_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n, const uint8_t* __restrict__ summary,
-	                                                           const int32_t* __restrict__ nbrSlot)
+	                                                           const int32_t* __restrict__ nbrSlot, const uint32_t* __restrict__ lastFaces, uint32_t* __restrict__ order,
+	                                                           uint32_t* __restrict__ bucketCount)
 	{
 		const uint32_t j = blockIdx.x * 256u + threadIdx.x;
-		if (j >= n)
-			return;
-		uint32_t entry = src[j] & ~(JOB_SKIP | JOB_OPAQUE);
-		if (entry & JOB_HAS_CONTENT)
+		const bool live = j < n;
+		uint32_t entry = live ? src[j] & ~(JOB_SKIP | JOB_OPAQUE) : 0u;
+		if (live && (entry & JOB_HAS_CONTENT))
 		{
 			const uint32_t slot = entry & JOB_SLOT_MASK;
 			const uint8_t s = summary[slot];
@@ -1554,13 +1574,38 @@ namespace tsomk
 			else if (s == SUM_OPAQUE)
 				entry |= JOB_OPAQUE;
 		}
-		dst[j] = entry;
+		if (live)
+			dst[j] = entry;
+		if (order != nullptr)
+		{
+			int b = JOB_BUCKETS - 1;
+			if (live && (entry & (JOB_HAS_CONTENT | JOB_SKIP)) == JOB_HAS_CONTENT)
+			{
+				const uint32_t lf = lastFaces[entry & JOB_SLOT_MASK];
+				b = lf >= 4096u ? 0 : (lf >= 512u ? 1 : 2);
+			}
+			const int lane = threadIdx.x & 31;
+#pragma unroll
+			for (int q = 0; q < JOB_BUCKETS; ++q)
+			{
+				const uint32_t members = __ballot_sync(0xffffffffu, live && b == q);
+				if (members == 0u)
+					continue;
+				uint32_t base = 0u;
+				if (lane == __ffs(members) - 1)
+					base = atomicAdd(&bucketCount[q], uint32_t(__popc(members)));
+				base = __shfl_sync(0xffffffffu, base, __ffs(members) - 1);
+				if (live && b == q)
+					order[size_t(q) * n + base + __popc(members & ((1u << lane) - 1u))] = j;
+			}
+		}
 	}
 
-	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, cudaStream_t st)
+	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, const uint32_t* lastFaces, uint32_t* order,
+	                         uint32_t* bucketCount, cudaStream_t st)
 	{
 		if (n)
-			job_classify_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(src, dst, n, summary, nbrSlot);
+			job_classify_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(src, dst, n, summary, nbrSlot, lastFaces, order, bucketCount);
 	}
 
 	// ---- launchers ----

@@ -270,6 +270,7 @@ struct tsom_ctx
 
 	// per-call scratch
 	DevBuf<uint32_t> jobSlot, faceCount;
+	DevBuf<uint32_t> jobOrder; // ticket order of the unordered mesher: tsomk::JOB_BUCKETS lists of n jobs (job_classify_kernel)
 	DevBuf<unsigned long long> firstFace, status;
 	DevBuf<float> gravity;
 	DevBuf<tsomk::EditDev> edits;
@@ -343,6 +344,7 @@ struct tsom_container
 	int4* dChunkIdx = nullptr;
 	uint8_t* dInvalid = nullptr;
 	uint8_t* dSummary = nullptr;  // [capacity] tsomk::SUM_*
+	uint32_t* dLastFaces = nullptr; // [capacity] faces of the chunk's last mesh (orders the mesher's tickets)
 	int32_t* dNbr = nullptr;      // [capacity][6] slot of the face-adjacent local chunk with content, -1 otherwise
 	uint32_t* dSync = nullptr;    // [0] blocks-final epoch [1] slabs-pulled epoch (polled by the peers over NVLink)
 	uint32_t summaryTableEpoch = 0;
@@ -897,6 +899,7 @@ extern "C"
 		cudaFree(ctx->dCollider);
 		ctx->jobSlot.Free();
 		ctx->faceCount.Free();
+		ctx->jobOrder.Free();
 		ctx->firstFace.Free();
 		ctx->status.Free();
 		ctx->editKeys.Free();
@@ -1057,6 +1060,7 @@ extern "C"
 		    (e = cudaMalloc(&c->dChunkIdx, size_t(capacity_chunks) * sizeof(int4))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dInvalid, maskBytes)) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dSummary, maskBytes)) != cudaSuccess ||
+		    (e = cudaMalloc(&c->dLastFaces, size_t(capacity_chunks) * sizeof(uint32_t))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dNbr, size_t(capacity_chunks) * 6 * sizeof(int32_t))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dSync, 64 * sizeof(uint32_t))) != cudaSuccess ||
 		    (e = cudaMalloc(&c->dPerm, 6 * 256)) != cudaSuccess ||
@@ -1068,6 +1072,7 @@ extern "C"
 			cudaFree(c->dChunkIdx);
 			cudaFree(c->dInvalid);
 			cudaFree(c->dSummary);
+			cudaFree(c->dLastFaces);
 			cudaFree(c->dNbr);
 			cudaFree(c->dSync);
 			cudaFree(c->dPerm);
@@ -1075,6 +1080,7 @@ extern "C"
 		}
 		TSOM_CUDA(cudaMemset(c->dInvalid, 0, maskBytes));
 		TSOM_CUDA(cudaMemset(c->dSummary, 0, maskBytes));
+		TSOM_CUDA(cudaMemset(c->dLastFaces, 0, size_t(capacity_chunks) * sizeof(uint32_t)));
 		TSOM_CUDA(cudaMemset(c->dSync, 0, 64 * sizeof(uint32_t)));
 		TSOM_CUDA(cudaEventCreateWithFlags(&c->evGen, cudaEventDisableTiming));
 		TSOM_CUDA(cudaEventCreateWithFlags(&c->evPull, cudaEventDisableTiming));
@@ -1109,6 +1115,7 @@ extern "C"
 		cudaFree(c->dChunkIdx);
 		cudaFree(c->dInvalid);
 		cudaFree(c->dSummary);
+		cudaFree(c->dLastFaces);
 		cudaFree(c->dNbr);
 		cudaFree(c->dSync);
 		if (c->evGen)
@@ -2040,7 +2047,14 @@ extern "C"
 
 		// ---- chunks that provably have no face (summaries of the producers) are marked and skip their 64 KiB stage
 		TSOM_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
-		tsomk::launch_job_classify(cache.jobs.ptr, ctx->jobSlot.ptr, n, c->dSummary, c->dNbr, ctx->stream);
+		// ... and, for the unordered mode, deals the tickets heavy chunks first (JOB_BUCKETS lists of n entries, counters in dSmall[9..12])
+		const bool dealt = !(flags & TSOM_MESH_ORDERED);
+		if (dealt)
+		{
+			TSOM_CUDA(ctx->jobOrder.Ensure(size_t(n) * tsomk::JOB_BUCKETS));
+			TSOM_CUDA(cudaMemsetAsync(ctx->dSmall + 9, 0, tsomk::JOB_BUCKETS * sizeof(uint32_t), ctx->stream));
+		}
+		tsomk::launch_job_classify(cache.jobs.ptr, ctx->jobSlot.ptr, n, c->dSummary, c->dNbr, c->dLastFaces, dealt ? ctx->jobOrder.ptr : nullptr, ctx->dSmall + 9, ctx->stream);
 		ctx->launches += 1;
 		TSOM_CUDA(cudaGetLastError());
 		TSOM_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
@@ -2058,6 +2072,9 @@ extern "C"
 		a.texFits8 = ctx->texFits8 ? 1u : 0u;
 		a.nTypes = ctx->nTypes;
 		a.faceCount = ctx->faceCount.ptr;
+		a.order = dealt ? ctx->jobOrder.ptr : nullptr;
+		a.bucketCount = ctx->dSmall + 9;
+		a.lastFaces = c->dLastFaces;
 		a.overflow = ctx->dSmall + 3;
 		a.flags = flags;
 		a.tile = c->tile;

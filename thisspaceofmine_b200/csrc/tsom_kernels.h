@@ -63,7 +63,13 @@ namespace tsomk
 		float center[3];  // ChunkContainer::GetCenter()
 		float quat[6][4]; // RotationBetween(s_dirNormals[d], Up) as (w, x, y, z)
 		const FaceTable* faceTable; // non-null: table-driven flat path
+		// unordered mode: tickets are dealt heavy chunks first — order[b * nJobs + i] = i-th job of bucket b (by the face count of the
+		// chunk's previous mesh), bucketCount[b] jobs in bucket b (job_classify_kernel); nullptr: ticket == job
+		const uint32_t* order;
+		const uint32_t* bucketCount;
+		uint32_t* lastFaces; // [capacity] face count of the last mesh of every chunk slot
 	};
+	constexpr int JOB_BUCKETS = 4; // >= 4096 faces, >= 512, the rest, no face at all (skipped jobs)
 
 	void launch_face_table(FaceTable* table, float tile, const MeshArgs& a, cudaStream_t st);
 
@@ -72,7 +78,8 @@ namespace tsomk
 	void launch_mesh_fused(const MeshArgs& a, int grid, cudaStream_t st);
 	// dst[j] = src[j] | JOB_SKIP when the chunk of job j provably has no face: it is SUM_EMPTY, or SUM_OPAQUE with six existing
 	// SUM_OPAQUE neighbours (nbrSlot: [capacity][6] slot of the face-adjacent chunk with content in this container, -1 otherwise)
-	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, cudaStream_t st);
+	void launch_job_classify(const uint32_t* src, uint32_t* dst, uint32_t n, const uint8_t* summary, const int32_t* nbrSlot, const uint32_t* lastFaces, uint32_t* order,
+	                         uint32_t* bucketCount, cudaStream_t st);
 
 	// ---- generation ----
 	struct GenArgs
